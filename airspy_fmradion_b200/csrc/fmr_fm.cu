@@ -1,0 +1,498 @@
+// fmr_fm.cu — FM broadcast handle: the C ABI of include/fmradion_b200.h for the path
+// FourthConverterIQ -> IfResampler -> FmDecoder::process (main.cpp:912-956,
+// FmDecode.cpp:85-221), many channels per launch.
+#include <complex>
+#include <cmath>
+
+#include "fmr_host.cuh"
+#include "fmr_mpf.cuh"
+
+namespace fmr {
+thread_local std::string g_err;
+}
+
+using namespace fmr;
+
+struct fmr_fm {
+  fmr_fm_config cfg;
+  int C = 0;
+  const ChainDesc *ifc = nullptr; // null when input_rate == 384000 (no IfResampler, main.cpp:778)
+  const ChainDesc *auc = nullptr;
+  DevMem mem;
+  PinnedSlots slots;
+  cudaStream_t own_stream = nullptr;
+
+  Resampler<float> ifres;
+  Resampler<double> aures;
+  float2 *hist[2] = {nullptr, nullptr};
+  int hist_cur = 0;
+  Ring<float2> r_if{nullptr, 0};   // 384 kHz decoder input
+  Ring<float2> r_iff{nullptr, 0};  // after the optional IF filter
+  Ring<float2> r_agc{nullptr, 0};  // after AGC (multipath path only)
+  Ring<float2> r_mpf{nullptr, 0};  // after multipath filter
+  Ring<double2> r_384{nullptr, 0}; // (mono, L-R) after deemphasis
+  Ring<double2> r_48a{nullptr, 0}; // audio resampler output
+  Ring<double2> r_48b{nullptr, 0}; // after pilot-cut FIR
+  FmChanState *d_state = nullptr;
+  uint8_t *d_flags = nullptr;
+  PpsEventDev *d_pps = nullptr;
+  uint32_t *d_e384 = nullptr, *d_e48 = nullptr;
+  float *d_fmfilter = nullptr;
+  int fmfilter_taps = 0;
+  double *d_pilotcut = nullptr;
+  float *d_atan = nullptr;
+  MpfDev mpf;
+  FmCoreParams core;
+  FmTailParams tail;
+
+  int64_t cum_in = 0, cum384 = 0, cum48 = 0;
+  uint32_t last_blocks = 0;
+  uint32_t last_launches = 0;
+  int64_t last_t0 = 0, last_t1 = 0;
+
+  // host staging for the *_host entry point
+  float *d_iq = nullptr;
+  double *d_audio = nullptr;
+  size_t audio_cap = 0; // doubles per channel
+};
+
+static int64_t if_out_total(const fmr_fm *h, int64_t n) { return h->ifc ? chain_out(h->ifc, n) : n; }
+
+static void hp_coeffs(double cutoff, double *b0, double *b1, double *b2, double *a1, double *a2) {
+  // HighPassFilterIir::HighPassFilterIir (Filter.cpp:254-290)
+  using CD = std::complex<double>;
+  const double w = 2 * M_PI * cutoff;
+  const CD p1s = w / std::exp((2 * 1 + 2 - 1) / double(2 * 2) * CD(0, M_PI));
+  const CD p1z = std::exp(p1s);
+  double B0 = 1, B1 = -2, B2 = 1;
+  const double A1 = -2 * std::real(p1z);
+  const double A2 = std::abs(p1z * p1z);
+  const double g = (B0 - B1 + B2) / (1 - A1 + A2);
+  *b0 = B0 / g;
+  *b1 = B1 / g;
+  *b2 = B2 / g;
+  *a1 = A1;
+  *a2 = A2;
+}
+
+extern "C" const char *fmr_last_error(void) { return g_err.c_str(); }
+extern "C" const char *fmr_version(void) { return "fmradion_b200 0.1 (sm_100a)"; }
+extern "C" int fmr_device_sm_count(int device) {
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+  return n;
+}
+
+static fmr_status fm_build(fmr_fm *h) {
+  const fmr_fm_config &cfg = h->cfg;
+  FMR_CUDA(cudaSetDevice(cfg.device));
+  const int C = h->C = (int)cfg.n_channels;
+  const int64_t max_in = cfg.max_samples_per_call;
+  const int max_blocks = (int)cfg.max_blocks_per_call;
+  if (cfg.input_rate != 384000.0) {
+    h->ifc = find_chain(cfg.input_rate, 384000.0, 0);
+    if (!h->ifc) return fail(FMR_ERR_UNSUPPORTED, "no resampler tables for this input_rate -> 384000");
+  }
+  h->auc = find_chain(384000.0, 48000.0, 1);
+  if (!h->auc) return fail(FMR_ERR_UNSUPPORTED, "audio resampler tables missing");
+  FMR_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  FMR_CUDA(h->slots.init(2 * sizeof(uint32_t) * (size_t)max_blocks));
+
+  int64_t max384 = max_in + 8;
+  if (h->ifc) {
+    fmr_status s = h->ifres.init(h->ifc, C, max_in, true, h->mem);
+    if (s != FMR_OK) return s;
+    max384 = chain_out(h->ifc, max_in) - chain_out(h->ifc, 0) + 8;
+    // the per-call maximum can exceed the from-zero count by the start-up latency
+    max384 = (int64_t)std::ceil((double)max_in * 384000.0 / cfg.input_rate) + 8;
+  } else {
+    HbTaps<float> t;
+    memset(&t, 0, sizeof(t));
+    FMR_CUDA((cudaFuncSetAttribute(k_hb_cascade<float, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)Resampler<float>::hb_smem(t, 0))));
+  }
+  FMR_CUDA(h->mem.alloc(&h->hist[0], (size_t)C * kHist));
+  FMR_CUDA(h->mem.alloc(&h->hist[1], (size_t)C * kHist));
+  h->r_if.cap = pow2ceil((uint64_t)max384 + 512);
+  FMR_CUDA(h->mem.alloc(&h->r_if.base, (size_t)C * h->r_if.cap));
+  h->r_iff = h->r_if;
+  if (cfg.fmfilter) {
+    const float *tbl = (cfg.fmfilter == 1) ? k_jj1bdx_fm_384kHz_medium : k_jj1bdx_fm_384kHz_narrow;
+    h->fmfilter_taps = 127;
+    FMR_CUDA(h->mem.alloc(&h->d_fmfilter, 127, false));
+    FMR_CUDA(cudaMemcpy(h->d_fmfilter, tbl, 127 * sizeof(float), cudaMemcpyHostToDevice));
+    h->r_iff.cap = h->r_if.cap;
+    FMR_CUDA(h->mem.alloc(&h->r_iff.base, (size_t)C * h->r_iff.cap));
+  }
+  if (cfg.multipath_stages > 0) {
+    h->r_agc.cap = h->r_if.cap;
+    FMR_CUDA(h->mem.alloc(&h->r_agc.base, (size_t)C * h->r_agc.cap));
+    h->r_mpf.cap = h->r_if.cap;
+    FMR_CUDA(h->mem.alloc(&h->r_mpf.base, (size_t)C * h->r_mpf.cap));
+    fmr_status s = h->mpf.init(cfg.multipath_stages, C, h->mem);
+    if (s != FMR_OK) return s;
+  }
+  h->r_384.cap = pow2ceil((uint64_t)max384 + 512);
+  FMR_CUDA(h->mem.alloc(&h->r_384.base, (size_t)C * h->r_384.cap));
+  {
+    fmr_status s = h->aures.init(h->auc, C, max384, false, h->mem);
+    if (s != FMR_OK) return s;
+  }
+  const int64_t max48 = max384 / 8 + 16;
+  h->r_48a.cap = pow2ceil((uint64_t)max48 + 512);
+  FMR_CUDA(h->mem.alloc(&h->r_48a.base, (size_t)C * h->r_48a.cap));
+  h->r_48b.cap = h->r_48a.cap;
+  FMR_CUDA(h->mem.alloc(&h->r_48b.base, (size_t)C * h->r_48b.cap));
+  FMR_CUDA(h->mem.alloc(&h->d_state, (size_t)C));
+  FMR_CUDA(h->mem.alloc(&h->d_flags, (size_t)C * max_blocks));
+  FMR_CUDA(h->mem.alloc(&h->d_pps, (size_t)C * kMaxPps));
+  FMR_CUDA(h->mem.alloc(&h->d_e384, (size_t)max_blocks));
+  FMR_CUDA(h->mem.alloc(&h->d_e48, (size_t)max_blocks));
+  FMR_CUDA(h->mem.alloc(&h->d_pilotcut, 127, false));
+  FMR_CUDA(cudaMemcpy(h->d_pilotcut, k_jj1bdx_48khz_fmaudio, 127 * sizeof(double), cudaMemcpyHostToDevice));
+  FMR_CUDA(h->mem.alloc(&h->d_atan, 257, false));
+  FMR_CUDA(cudaMemcpy(h->d_atan, k_fast_atan_table, 257 * sizeof(float), cudaMemcpyHostToDevice));
+
+  // initial state (constructors: FmDecode.cpp:25-83, PilotPhaseLock.cpp:35-54, IfSimpleAgc.cpp:22-32)
+  {
+    std::vector<FmChanState> st(C);
+    memset(st.data(), 0, sizeof(FmChanState) * C);
+    for (int c = 0; c < C; c++) {
+      st[c].agc_gain = 1.0f;
+      st[c].mpf_wait = 100; // FmDecode.cpp:33
+      st[c].pll_freq = (19000.0 / 384000.0) * 2.0 * M_PI;
+    }
+    FMR_CUDA(cudaMemcpy(h->d_state, st.data(), sizeof(FmChanState) * C, cudaMemcpyHostToDevice));
+  }
+  FmCoreParams &P = h->core;
+  memset(&P, 0, sizeof(P));
+  P.agc_max = 100000.0f;
+  P.agc_rate = 0.0001f;
+  {
+    const double max_freq_dev = 75000.0 / 384000.0; // FmDecode.cpp:52
+    const double norm = max_freq_dev * 2.0 * M_PI;  // PhaseDiscriminator.cpp:27
+    P.disc_inv_norm = 1.0f / (float)norm;
+    P.disc_bound = (float)(1.0 / (max_freq_dev * 2.0)); // PhaseDiscriminator.cpp:29
+  }
+  {
+    const double freq = 19000.0 / 384000.0, bw = 30.0 / 384000.0;
+    P.pll_minfreq = (freq - bw) * 2.0 * M_PI;
+    P.pll_maxfreq = (freq + bw) * 2.0 * M_PI;
+    P.lock_delay = int(15.0 / bw);
+  }
+  P.bq_b0 = 1.46974784e-06;
+  P.bq_a1 = -1.99682419;
+  P.bq_a2 = 0.996825659;
+  P.lf_b0 = 0.000304341788;
+  P.lf_b1 = -0.000304324564;
+  P.minsignal = 0.001;
+  {
+    const double tc = (cfg.deemphasis_us == 0) ? 1.0 : (cfg.deemphasis_us * 384000.0 * 1.0e-6); // FmDecode.cpp:67-70
+    P.de_a1 = -std::exp(-1 / tc);
+    P.de_b0 = 1 + P.de_a1;
+  }
+  P.stereo = cfg.stereo ? 1 : 0;
+  P.pilot_shift = cfg.pilot_shift ? 1 : 0;
+  P.deemph_on_stereo = cfg.pilot_shift ? 0 : 1;
+  P.n_channels = C;
+  FmTailParams &T = h->tail;
+  hp_coeffs(0.0001, &T.b0, &T.b1, &T.b2, &T.a1, &T.a2);
+  T.stereo = P.stereo;
+  T.pilot_shift = P.pilot_shift;
+  T.n_channels = C;
+
+  h->audio_cap = (size_t)(max48 * (cfg.stereo ? 2 : 1));
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_fm_create(const fmr_fm_config *cfg, fmr_fm **out) {
+  if (!cfg || !out) return fail(FMR_ERR_INVALID, "null argument");
+  if (cfg->n_channels == 0 || cfg->max_samples_per_call == 0 || cfg->max_blocks_per_call == 0) {
+    return fail(FMR_ERR_INVALID, "n_channels, max_samples_per_call and max_blocks_per_call must be > 0");
+  }
+  if (cfg->fmfilter < 0 || cfg->fmfilter > 2) return fail(FMR_ERR_INVALID, "fmfilter must be 0, 1 or 2");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    return fail(FMR_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  }
+  fmr_fm *h = new fmr_fm();
+  h->cfg = *cfg;
+  fmr_status s = fm_build(h);
+  if (s != FMR_OK) {
+    std::string keep = g_err;
+    fmr_fm_destroy(h);
+    g_err = keep;
+    return s;
+  }
+  *out = h;
+  return FMR_OK;
+}
+
+extern "C" void fmr_fm_destroy(fmr_fm *h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  h->mem.release();
+  h->slots.release();
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+static fmr_status fm_schedule(const fmr_fm *h, const uint32_t *block_len, uint32_t n_blocks, uint32_t *e384,
+                              uint32_t *e48, uint64_t *total_in) {
+  int64_t n = 0;
+  const int64_t base384 = if_out_total(h, h->cum_in);
+  const int64_t base48 = chain_out(h->auc, h->cum384);
+  if (base384 != h->cum384) return fail(FMR_ERR_INVALID, "internal: stream position mismatch");
+  for (uint32_t b = 0; b < n_blocks; b++) {
+    // IfResampler asserts input <= 65536 per call (IfResampler.cpp:41, IfResampler.h:31)
+    if (h->ifc && block_len[b] > 65536) return fail(FMR_ERR_INVALID, "block_len > 65536 (IfResampler limit)");
+    n += block_len[b];
+    const int64_t c384 = if_out_total(h, h->cum_in + n);
+    e384[b] = (uint32_t)(c384 - base384);
+    // AudioResampler asserts input <= 32768 per call (AudioResampler.cpp:41)
+    const uint32_t prev = b ? e384[b - 1] : 0;
+    if (e384[b] - prev > 32768) return fail(FMR_ERR_INVALID, "block yields > 32768 IF samples (AudioResampler limit)");
+    e48[b] = (uint32_t)(chain_out(h->auc, c384) - base48);
+  }
+  *total_in = (uint64_t)n;
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_fm_query_output(fmr_fm *h, const uint32_t *block_len, uint32_t n_blocks,
+                                          uint64_t *audio_doubles_total, uint32_t *audio_len) {
+  if (!h || !block_len) return fail(FMR_ERR_INVALID, "null argument");
+  std::vector<uint32_t> e384(n_blocks), e48(n_blocks);
+  uint64_t tot = 0;
+  fmr_status s = fm_schedule(h, block_len, n_blocks, e384.data(), e48.data(), &tot);
+  if (s != FMR_OK) return s;
+  const uint32_t w = h->cfg.stereo ? 2 : 1;
+  if (audio_len) {
+    for (uint32_t b = 0; b < n_blocks; b++) audio_len[b] = (e48[b] - (b ? e48[b - 1] : 0)) * w;
+  }
+  if (audio_doubles_total) *audio_doubles_total = n_blocks ? (uint64_t)e48[n_blocks - 1] * w : 0;
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t iq_stride,
+                                            const uint32_t *block_len, uint32_t n_blocks, double *d_audio,
+                                            size_t audio_stride, uint32_t *audio_len, void *stream) {
+  if (!h || !d_iq || !block_len || !d_audio) return fail(FMR_ERR_INVALID, "null argument");
+  if (n_blocks == 0) return FMR_OK;
+  if (n_blocks > h->cfg.max_blocks_per_call) return fail(FMR_ERR_CAPACITY, "n_blocks > max_blocks_per_call");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = h->C;
+  int slot = 0;
+  uint32_t *tab = (uint32_t *)h->slots.acquire(&slot);
+  uint32_t *e384 = tab, *e48 = tab + h->cfg.max_blocks_per_call;
+  uint64_t total_in = 0;
+  fmr_status s = fm_schedule(h, block_len, n_blocks, e384, e48, &total_in);
+  if (s != FMR_OK) return s;
+  if (total_in > h->cfg.max_samples_per_call) return fail(FMR_ERR_CAPACITY, "sum(block_len) > max_samples_per_call");
+  if (total_in > iq_stride) return fail(FMR_ERR_INVALID, "iq_stride < sum(block_len)");
+  const uint32_t w = h->cfg.stereo ? 2 : 1;
+  const uint32_t n384 = e384[n_blocks - 1], n48 = e48[n_blocks - 1];
+  if ((size_t)n48 * w > audio_stride) return fail(FMR_ERR_CAPACITY, "audio_stride too small for this call");
+  if (audio_len) {
+    for (uint32_t b = 0; b < n_blocks; b++) audio_len[b] = (e48[b] - (b ? e48[b - 1] : 0)) * w;
+  }
+  FMR_CUDA(cudaMemcpyAsync(h->d_e384, e384, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
+  FMR_CUDA(cudaMemcpyAsync(h->d_e48, e48, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
+  h->slots.commit(slot, st);
+
+  int launches = 0;
+  // ---- front end: Fs/4 shift + IF resampler -> r_if[t0, t1)
+  InSrc<float2> src;
+  src.lin = reinterpret_cast<const float2 *>(d_iq);
+  src.stride = iq_stride;
+  src.hist = h->hist[h->hist_cur];
+  src.start = h->cum_in;
+  src.n_new = (int64_t)total_in;
+  src.ring = Ring<float2>{nullptr, 0};
+  int64_t t0 = h->cum384, t1 = h->cum384 + n384;
+  if (h->ifc) {
+    int64_t o0, o1;
+    s = h->ifres.run(src, (int64_t)total_in, h->r_if, h->cfg.fs4_shift, st, &o0, &o1, &launches);
+    if (s != FMR_OK) return s;
+    if (o0 != t0 || o1 != t1) return fail(FMR_ERR_INVALID, "internal: IF schedule mismatch");
+  } else if (total_in > 0) {
+    HbTaps<float> t;
+    memset(&t, 0, sizeof(t));
+    dim3 grid((unsigned)((total_in + kHbTile - 1) / kHbTile), C);
+    k_hb_cascade<float, 0, true><<<grid, kHbThreads, Resampler<float>::hb_smem(t, 0), st>>>(
+        src, h->r_if, t, t0, (int)total_in, h->cfg.fs4_shift);
+    launches++;
+  }
+  if (h->ifc && total_in > 0) {
+    k_save_hist<float2><<<C, 128, 0, st>>>(src.lin, iq_stride, (int64_t)total_in, h->hist[h->hist_cur],
+                                           h->hist[h->hist_cur ^ 1]);
+    h->hist_cur ^= 1;
+    launches++;
+  }
+  if (n384 > 0) {
+    // ---- optional IF filter (FmDecode.cpp:98-102)
+    if (h->cfg.fmfilter) {
+      dim3 grid((n384 + 127) / 128, C);
+      k_fir_quirk<float><<<grid, 128, 0, st>>>(h->r_if, h->r_iff, h->d_fmfilter, h->fmfilter_taps, t0, (int)n384,
+                                               h->d_e384, (int)n_blocks);
+      launches++;
+    }
+    // ---- 384 kHz serial core
+    dim3 cgrid((C + 31) / 32);
+    if (h->cfg.multipath_stages == 0) {
+      k_fm_core<0><<<cgrid, 32, 0, st>>>(h->r_if, h->r_iff, h->r_iff, h->r_384, h->d_state, h->d_flags, h->d_pps,
+                                         h->d_e384, (int)n_blocks, t0, h->core, h->d_atan);
+      launches++;
+    } else {
+      k_fm_core<1><<<cgrid, 32, 0, st>>>(h->r_if, h->r_iff, h->r_agc, h->r_384, h->d_state, h->d_flags, h->d_pps,
+                                         h->d_e384, (int)n_blocks, t0, h->core, h->d_atan);
+      h->mpf.run(h->r_agc, h->r_mpf, h->d_state, h->d_e384, (int)n_blocks, t0, st);
+      k_fm_core<2><<<cgrid, 32, 0, st>>>(h->r_if, h->r_mpf, h->r_mpf, h->r_384, h->d_state, h->d_flags, h->d_pps,
+                                         h->d_e384, (int)n_blocks, t0, h->core, h->d_atan);
+      launches += 3;
+    }
+    // ---- audio resamplers (mono and L-R in lock step, FmDecode.cpp:172-183)
+    InSrc<double2> asrc;
+    memset(&asrc, 0, sizeof(asrc));
+    asrc.ring = h->r_384;
+    int64_t j0, j1;
+    s = h->aures.run(asrc, (int64_t)n384, h->r_48a, 0, st, &j0, &j1, &launches);
+    if (s != FMR_OK) return s;
+    if (j0 != h->cum48 || j1 != h->cum48 + n48) return fail(FMR_ERR_INVALID, "internal: audio schedule mismatch");
+    if (n48 > 0) {
+      // ---- pilot-cut FIR (FmDecode.cpp:190,196) then DC block + matrix
+      dim3 grid((n48 + 127) / 128, C);
+      k_fir_quirk<double><<<grid, 128, 0, st>>>(h->r_48a, h->r_48b, h->d_pilotcut, 127, j0, (int)n48, h->d_e48,
+                                                (int)n_blocks);
+      k_fm_tail<<<cgrid, 32, 0, st>>>(h->r_48b, d_audio, audio_stride, h->d_state, h->d_flags, h->d_e48,
+                                      (int)n_blocks, j0, h->tail);
+      launches += 2;
+    }
+  }
+  FMR_CUDA(cudaGetLastError());
+  h->cum_in += (int64_t)total_in;
+  h->cum384 += n384;
+  h->cum48 += n48;
+  h->last_blocks = n_blocks;
+  h->last_launches = (uint32_t)launches;
+  h->last_t0 = t0;
+  h->last_t1 = t1;
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_fm_process_host(fmr_fm *h, const float *iq, size_t iq_stride, const uint32_t *block_len,
+                                          uint32_t n_blocks, double *audio, size_t audio_stride,
+                                          uint32_t *audio_len) {
+  if (!h || !iq || !block_len || !audio) return fail(FMR_ERR_INVALID, "null argument");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < n_blocks; b++) total += block_len[b];
+  if (total > h->cfg.max_samples_per_call) return fail(FMR_ERR_CAPACITY, "sum(block_len) > max_samples_per_call");
+  if (total > iq_stride) return fail(FMR_ERR_INVALID, "iq_stride < sum(block_len)");
+  const int C = h->C;
+  if (!h->d_iq) {
+    FMR_CUDA(h->mem.alloc(&h->d_iq, (size_t)C * h->cfg.max_samples_per_call * 2, false));
+    FMR_CUDA(h->mem.alloc(&h->d_audio, (size_t)C * h->audio_cap, false));
+  }
+  cudaStream_t st = h->own_stream;
+  if (total > 0) {
+    FMR_CUDA(cudaMemcpy2DAsync(h->d_iq, (size_t)total * 8, iq, iq_stride * 8, (size_t)total * 8, C,
+                               cudaMemcpyHostToDevice, st));
+  }
+  uint64_t out_total = 0;
+  fmr_status s = fmr_fm_query_output(h, block_len, n_blocks, &out_total, nullptr);
+  if (s != FMR_OK) return s;
+  if (out_total > audio_stride) return fail(FMR_ERR_CAPACITY, "audio_stride too small for this call");
+  s = fmr_fm_process_device(h, h->d_iq, (size_t)total, block_len, n_blocks, h->d_audio, h->audio_cap, audio_len,
+                            (void *)st);
+  if (s != FMR_OK) return s;
+  if (out_total > 0) {
+    FMR_CUDA(cudaMemcpy2DAsync(audio, audio_stride * 8, h->d_audio, h->audio_cap * 8, (size_t)out_total * 8, C,
+                               cudaMemcpyDeviceToHost, st));
+  }
+  FMR_CUDA(cudaStreamSynchronize(st));
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_fm_stats(fmr_fm *h, uint32_t channel, fmr_fm_stats_t *out) {
+  if (!h || !out || channel >= (uint32_t)h->C) return fail(FMR_ERR_INVALID, "bad argument");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  FMR_CUDA(cudaDeviceSynchronize());
+  FmChanState s;
+  FMR_CUDA(cudaMemcpy(&s, h->d_state + channel, sizeof(s), cudaMemcpyDeviceToHost));
+  out->stereo_detected = s.stereo_detected;
+  out->tuning_offset = s.baseband_mean * 75000.0f; // FmDecode.h:80
+  out->baseband_level = s.baseband_level;
+  out->pilot_level = 2 * s.pilot_level; // PilotPhaseLock.h:66
+  out->if_rms = s.if_rms;
+  out->multipath_error = s.mpf_error;
+  out->if_agc_gain = s.agc_gain;
+  out->pll_freq = s.pll_freq;
+  out->pll_phase = s.pll_phase;
+  out->pll_lock_cnt = s.lock_cnt;
+  out->decoder_calls = s.decoder_calls;
+  out->n_pps = s.n_pps;
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_fm_pps_events(fmr_fm *h, uint32_t channel, fmr_pps_event_t *out, uint32_t cap,
+                                        uint32_t *n) {
+  if (!h || !n || channel >= (uint32_t)h->C) return fail(FMR_ERR_INVALID, "bad argument");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  FMR_CUDA(cudaDeviceSynchronize());
+  FmChanState s;
+  FMR_CUDA(cudaMemcpy(&s, h->d_state + channel, sizeof(s), cudaMemcpyDeviceToHost));
+  PpsEventDev ev[kMaxPps];
+  FMR_CUDA(cudaMemcpy(ev, h->d_pps + (size_t)channel * kMaxPps, sizeof(ev), cudaMemcpyDeviceToHost));
+  uint32_t cnt = s.n_pps < (uint32_t)kMaxPps ? s.n_pps : (uint32_t)kMaxPps;
+  *n = cnt;
+  for (uint32_t i = 0; i < cnt && i < cap && out; i++) {
+    out[i].pps_index = ev[i].pps_index;
+    out[i].sample_index = ev[i].sample_index;
+    out[i].block_position = ev[i].block_position;
+    out[i].block = ev[i].block;
+  }
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_fm_coeffs(fmr_fm *h, uint32_t channel, float *re_im, size_t n_complex) {
+  if (!h || !re_im || channel >= (uint32_t)h->C) return fail(FMR_ERR_INVALID, "bad argument");
+  if (h->cfg.multipath_stages == 0) return fail(FMR_ERR_INVALID, "multipath filter is disabled");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  FMR_CUDA(cudaDeviceSynchronize());
+  return h->mpf.read_coeffs(channel, re_im, n_complex);
+}
+
+extern "C" fmr_status fmr_fm_block_flags(fmr_fm *h, uint32_t channel, uint8_t *stereo, uint32_t n_blocks) {
+  if (!h || !stereo || channel >= (uint32_t)h->C || n_blocks != h->last_blocks) {
+    return fail(FMR_ERR_INVALID, "bad argument (n_blocks must equal the last call's)");
+  }
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  FMR_CUDA(cudaDeviceSynchronize());
+  FMR_CUDA(cudaMemcpy(stereo, h->d_flags + (size_t)channel * n_blocks, n_blocks, cudaMemcpyDeviceToHost));
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_fm_tap_if(fmr_fm *h, uint32_t channel, float *re_im, size_t cap_complex,
+                                    uint64_t *n_complex) {
+  if (!h || !n_complex || channel >= (uint32_t)h->C) return fail(FMR_ERR_INVALID, "bad argument");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  FMR_CUDA(cudaDeviceSynchronize());
+  const int64_t n = h->last_t1 - h->last_t0;
+  *n_complex = (uint64_t)n;
+  if (!re_im) return FMR_OK;
+  const uint32_t cap = h->r_if.cap;
+  for (int64_t i = 0; i < n && (size_t)i < cap_complex;) {
+    const uint32_t pos = (uint32_t)((h->last_t0 + i) & (cap - 1));
+    int64_t run = cap - pos;
+    if (run > n - i) run = n - i;
+    if ((size_t)(i + run) > cap_complex) run = (int64_t)cap_complex - i;
+    FMR_CUDA(cudaMemcpy(re_im + 2 * i, h->r_if.base + (size_t)channel * cap + pos, (size_t)run * 8,
+                        cudaMemcpyDeviceToHost));
+    i += run;
+  }
+  return FMR_OK;
+}
+
+extern "C" uint32_t fmr_fm_last_launches(fmr_fm *h) { return h ? h->last_launches : 0; }

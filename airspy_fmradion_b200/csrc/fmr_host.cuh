@@ -1,0 +1,230 @@
+// fmr_host.cuh — host-side plumbing shared by the FM and AM handles: error reporting,
+// device buffers, the generic streaming resampler (half-band cascade -> long low-pass ->
+// polyphase bank) that stands in for r8b::CDSPResampler (IfResampler.cpp:25-79,
+// AudioResampler.cpp:25-61), and pinned staging for the per-call tables.
+#ifndef FMR_HOST_CUH
+#define FMR_HOST_CUH
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fmradion_b200.h"
+#include "fmr_kernels.cuh"
+#include "fmr_tables.h"
+
+namespace fmr {
+
+extern thread_local std::string g_err;
+
+inline fmr_status fail(fmr_status code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define FMR_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      return fmr::fail(FMR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+    }                                                                                          \
+  } while (0)
+
+inline uint32_t pow2ceil(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return (uint32_t)p;
+}
+
+struct DevMem {
+  std::vector<void *> ptrs;
+  size_t total = 0;
+  template <typename T> cudaError_t alloc(T **p, size_t count, bool zero = true) {
+    void *q = nullptr;
+    const size_t bytes = count * sizeof(T);
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(q);
+    total += bytes;
+    if (zero && bytes) {
+      e = cudaMemset(q, 0, bytes);
+      if (e != cudaSuccess) return e;
+    }
+    *p = reinterpret_cast<T *>(q);
+    return cudaSuccess;
+  }
+  void release() {
+    for (void *q : ptrs) cudaFree(q);
+    ptrs.clear();
+  }
+};
+
+// Pinned staging slots for small per-call tables; a slot is reused only after the copy
+// that read it has completed.
+struct PinnedSlots {
+  static const int kSlots = 8;
+  void *host[kSlots] = {nullptr};
+  cudaEvent_t ev[kSlots] = {nullptr};
+  bool used[kSlots] = {false};
+  size_t bytes = 0;
+  int next = 0;
+  cudaError_t init(size_t b) {
+    bytes = b;
+    for (int i = 0; i < kSlots; i++) {
+      cudaError_t e = cudaMallocHost(&host[i], b ? b : 1);
+      if (e != cudaSuccess) return e;
+      e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  void *acquire(int *slot) {
+    const int s = next;
+    next = (next + 1) % kSlots;
+    if (used[s]) cudaEventSynchronize(ev[s]);
+    used[s] = true;
+    *slot = s;
+    return host[s];
+  }
+  void commit(int slot, cudaStream_t st) { cudaEventRecord(ev[slot], st); }
+  void release() {
+    for (int i = 0; i < kSlots; i++) {
+      if (host[i]) cudaFreeHost(host[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+      host[i] = nullptr;
+      ev[i] = nullptr;
+    }
+  }
+};
+
+template <typename S> struct Resampler {
+  using V = typename V2<S>::type;
+  const ChainDesc *d = nullptr;
+  int C = 0;
+  bool linear_in = false;
+  Ring<V> r_hb{nullptr, 0}, r_bc{nullptr, 0};
+  S *d_bc = nullptr, *d_fi = nullptr;
+  HbTaps<S> hbt;
+  int64_t cum_in = 0;
+  size_t smem_hb = 0, smem_fir = 0;
+
+  static size_t hb_smem(const HbTaps<S> &t, int nst) {
+    size_t total = 0;
+    for (int s = 0; s <= nst; s++) {
+      size_t full = kHbTile;
+      for (int q = nst; q > s; q--) full = 2 * full + 4 * t.n[q - 1] - 3;
+      total += full;
+    }
+    return total * sizeof(V);
+  }
+
+  template <int NST, bool LIN> static cudaError_t set_hb_attr(size_t smem) {
+    return cudaFuncSetAttribute(k_hb_cascade<S, NST, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem);
+  }
+
+  fmr_status init(const ChainDesc *desc, int channels, int64_t max_in, bool lin, DevMem &mem) {
+    d = desc;
+    C = channels;
+    linear_in = lin;
+    cum_in = 0;
+    memset(&hbt, 0, sizeof(hbt));
+    for (int s = 0; s < d->n_hb; s++) {
+      hbt.n[s] = d->hb[s].ntaps;
+      if (hbt.n[s] > 14) return fail(FMR_ERR_UNSUPPORTED, "half-band stage longer than 14 taps");
+      for (int k = 0; k < hbt.n[s]; k++) hbt.t[s][k] = (S)d->hb[s].taps[k];
+    }
+    smem_hb = hb_smem(hbt, d->n_hb);
+    cudaError_t e = cudaSuccess;
+    switch (d->n_hb) {
+    case 0: e = lin ? set_hb_attr<0, true>(smem_hb) : set_hb_attr<0, false>(smem_hb); break;
+    case 1: e = lin ? set_hb_attr<1, true>(smem_hb) : set_hb_attr<1, false>(smem_hb); break;
+    case 2: e = lin ? set_hb_attr<2, true>(smem_hb) : set_hb_attr<2, false>(smem_hb); break;
+    default: e = lin ? set_hb_attr<3, true>(smem_hb) : set_hb_attr<3, false>(smem_hb); break;
+    }
+    FMR_CUDA(e);
+    const int64_t max_hb = (max_in >> d->n_hb) + 4;
+    if (d->n_hb > 0 || lin) {
+      r_hb.cap = pow2ceil((uint64_t)(max_hb + d->bc.latency + d->bc.klen + 64));
+      FMR_CUDA(mem.alloc(&r_hb.base, (size_t)C * r_hb.cap));
+    }
+    {
+      std::vector<S> h(d->bc.klen);
+      for (int i = 0; i < d->bc.klen; i++) h[i] = (S)d->bc.taps[i];
+      FMR_CUDA(mem.alloc(&d_bc, h.size(), false));
+      FMR_CUDA(cudaMemcpy(d_bc, h.data(), h.size() * sizeof(S), cudaMemcpyHostToDevice));
+    }
+    smem_fir = ((size_t)(kFirTile - 1) * d->bc.down + d->bc.klen) * sizeof(V) + (size_t)d->bc.klen * sizeof(S);
+    FMR_CUDA(cudaFuncSetAttribute(k_fir_long<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fir));
+    if (d->has_fi) {
+      const int64_t max_bc = max_hb / d->bc.down + 4;
+      r_bc.cap = pow2ceil((uint64_t)(max_bc + 4 * d->fi.flen + 64));
+      FMR_CUDA(mem.alloc(&r_bc.base, (size_t)C * r_bc.cap));
+      const size_t nt = (size_t)d->fi.outstep * d->fi.flen;
+      std::vector<S> h(nt);
+      for (size_t i = 0; i < nt; i++) h[i] = (S)d->fi.taps[i];
+      FMR_CUDA(mem.alloc(&d_fi, nt, false));
+      FMR_CUDA(cudaMemcpy(d_fi, h.data(), nt * sizeof(S), cudaMemcpyHostToDevice));
+    }
+    return FMR_OK;
+  }
+
+  int64_t max_out(int64_t max_in) const { return chain_out(d, max_in + (int64_t)1) + 8; }
+
+  template <int NST, bool LIN>
+  void launch_hb(const InSrc<V> &src, int64_t o0, int n_out, int fs4, cudaStream_t st) {
+    dim3 grid((n_out + kHbTile - 1) / kHbTile, C);
+    k_hb_cascade<S, NST, LIN><<<grid, kHbThreads, smem_hb, st>>>(src, r_hb, hbt, o0, n_out, fs4);
+  }
+
+  // Consume n_new more input samples; produce the reference's output index range into `out`.
+  fmr_status run(InSrc<V> src, int64_t n_new, Ring<V> out, int fs4, cudaStream_t st, int64_t *o0,
+                 int64_t *o1, int *launches) {
+    const int64_t N0 = cum_in, N1 = cum_in + n_new;
+    const int64_t h0 = hb_out(d, N0), h1 = hb_out(d, N1);
+    const int64_t b0 = bc_out(d, h0), b1 = bc_out(d, h1);
+    const int64_t f0 = fi_out(d, b0), f1 = fi_out(d, b1);
+    Ring<V> bc_in = src.ring;
+    if (d->n_hb > 0 || linear_in) {
+      const int n = (int)(h1 - h0);
+      if (n > 0) {
+        switch (d->n_hb) {
+        case 0: linear_in ? launch_hb<0, true>(src, h0, n, fs4, st) : launch_hb<0, false>(src, h0, n, fs4, st); break;
+        case 1: linear_in ? launch_hb<1, true>(src, h0, n, fs4, st) : launch_hb<1, false>(src, h0, n, fs4, st); break;
+        case 2: linear_in ? launch_hb<2, true>(src, h0, n, fs4, st) : launch_hb<2, false>(src, h0, n, fs4, st); break;
+        default: linear_in ? launch_hb<3, true>(src, h0, n, fs4, st) : launch_hb<3, false>(src, h0, n, fs4, st); break;
+        }
+        (*launches)++;
+      }
+      bc_in = r_hb;
+    }
+    {
+      const int n = (int)(b1 - b0);
+      if (n > 0) {
+        dim3 grid((n + kFirTile - 1) / kFirTile, C);
+        k_fir_long<S><<<grid, kFirThreads, smem_fir, st>>>(bc_in, d->has_fi ? r_bc : out, d_bc, d->bc.klen,
+                                                            d->bc.down, b0, n);
+        (*launches)++;
+      }
+    }
+    if (d->has_fi) {
+      const int n = (int)(f1 - f0);
+      if (n > 0) {
+        dim3 grid((n + 127) / 128, C);
+        k_frac_interp<S><<<grid, 128, 0, st>>>(r_bc, out, d_fi, d->fi.instep, d->fi.outstep, d->fi.flen, f0, n);
+        (*launches)++;
+      }
+    }
+    cum_in = N1;
+    *o0 = f0;
+    *o1 = f1;
+    FMR_CUDA(cudaGetLastError());
+    return FMR_OK;
+  }
+};
+
+} // namespace fmr
+#endif

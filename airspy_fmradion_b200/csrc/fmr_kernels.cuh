@@ -1,0 +1,664 @@
+// fmr_kernels.cuh — sm_100a device code of the demodulation hot path.
+//
+// Data layout in HBM: every inter-stage stream is a channel-major ring, element (c, i)
+// at base[c*cap + (i & (cap-1))] where i is the ABSOLUTE sample index of that stream since
+// the handle was created. Absolute indexing makes every stage a pure function of
+// (input stream, output index range); the host's integer schedule (fmr_tables.h) decides
+// which index ranges a process call covers. Samples at negative absolute indices are zero
+// (the reference's zero-initialised delay lines).
+#ifndef FMR_KERNELS_CUH
+#define FMR_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fmr {
+
+template <typename S> struct V2;
+template <> struct V2<float> {
+  using type = float2;
+};
+template <> struct V2<double> {
+  using type = double2;
+};
+
+template <typename V> struct Ring {
+  V *base;
+  uint32_t cap; // power of two, per channel
+  __device__ __forceinline__ V ld(uint32_t c, int64_t i) const {
+    if (i < 0) {
+      V z;
+      z.x = 0;
+      z.y = 0;
+      return z;
+    }
+    return base[(size_t)c * cap + ((uint32_t)i & (cap - 1))];
+  }
+  __device__ __forceinline__ void st(uint32_t c, int64_t i, V v) const {
+    base[(size_t)c * cap + ((uint32_t)i & (cap - 1))] = v;
+  }
+};
+
+// Input of a resampler: either the caller's linear buffer for this call plus a short
+// history of the previous call's tail, or a ring.
+template <typename V> struct InSrc {
+  const V *lin;      // [C][stride], sample 0 has absolute index `start`
+  size_t stride;
+  const V *hist;     // [C][HIST], absolute indices start-HIST .. start-1
+  int64_t start;
+  int64_t n_new;
+  Ring<V> ring;
+};
+constexpr int kHist = 256;
+
+template <typename V, bool LINEAR>
+__device__ __forceinline__ V src_ld(const InSrc<V> &s, uint32_t c, int64_t i) {
+  if (LINEAR) {
+    V z;
+    z.x = 0;
+    z.y = 0;
+    if (i < 0) return z;
+    int64_t r = i - s.start;
+    if (r < 0) {
+      return (r >= -kHist) ? s.hist[(size_t)c * kHist + (kHist + r)] : z;
+    }
+    return (r < s.n_new) ? s.lin[(size_t)c * s.stride + r] : z;
+  } else {
+    return s.ring.ld(c, i);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Half-band decimator cascade (reference: r8b::CDSPHBDownsampler::process,
+// CDSPHBDownsampler.h:137-239; kernel form CDSPHBDownsampler.inc:620-629):
+//   y[m] = x[2m] + sum_k t[k] * (x[2m+2k+1] + x[2m-2k-1]),   zero-phase, gain 2 per stage.
+// NST = 0 degenerates to a copy (used for rates that need no half-band stage and to apply
+// the Fs/4 shift of FourthConverterIQ, include/FourthConverterIQ.h:38-82: y[n] = x[n](-j)^n).
+// One CTA computes kHbTile final-rate outputs of one channel; all intermediate rates live
+// in shared memory, so the input is read from HBM exactly once.
+template <typename S> struct HbTaps {
+  int n[3];
+  S t[3][14];
+};
+constexpr int kHbTile = 512;
+constexpr int kHbThreads = 256;
+
+template <typename S, int NST, bool LINEAR>
+__global__ void __launch_bounds__(kHbThreads)
+    k_hb_cascade(InSrc<typename V2<S>::type> in, Ring<typename V2<S>::type> out, HbTaps<S> taps,
+                 int64_t o0, int n_out, int fs4) {
+  using V = typename V2<S>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V *lvl[4];
+  const uint32_t c = blockIdx.y;
+  const int64_t a_fin = o0 + (int64_t)blockIdx.x * kHbTile;
+  int cnt_fin = n_out - (int)(blockIdx.x * kHbTile);
+  if (cnt_fin > kHbTile) cnt_fin = kHbTile;
+  if (cnt_fin <= 0) return;
+
+  // index ranges per level: level NST = final outputs, level 0 = raw input
+  int64_t a[4];
+  int len[4];
+  a[NST] = a_fin;
+  len[NST] = cnt_fin;
+#pragma unroll
+  for (int s = NST; s >= 1; s--) {
+    const int h = 2 * taps.n[s - 1] - 1;
+    a[s - 1] = 2 * a[s] - h;
+    len[s - 1] = 2 * len[s] + 2 * h - 1;
+  }
+  {
+    V *p = reinterpret_cast<V *>(smem_raw);
+#pragma unroll
+    for (int s = 0; s <= NST; s++) {
+      lvl[s] = p;
+      // sizes use the full tile so that the carve-up does not depend on cnt_fin
+      int full = kHbTile;
+      for (int q = NST; q > s; q--) full = 2 * full + 4 * taps.n[q - 1] - 3;
+      p += full;
+    }
+  }
+  // level 0: load raw input (coalesced), apply Fs/4 shift
+  for (int i = threadIdx.x; i < len[0]; i += kHbThreads) {
+    const int64_t ai = a[0] + i;
+    V v = src_ld<V, LINEAR>(in, c, ai);
+    if (fs4) {
+      const int ph = (int)(ai & 3);
+      V w;
+      if (ph == 0) {
+        w = v;
+      } else if (ph == 1) {
+        w.x = v.y;
+        w.y = -v.x;
+      } else if (ph == 2) {
+        w.x = -v.x;
+        w.y = -v.y;
+      } else {
+        w.x = -v.y;
+        w.y = v.x;
+      }
+      v = w;
+    }
+    if (NST == 0) {
+      out.st(c, ai, v);
+    } else {
+      lvl[0][i] = v;
+    }
+  }
+  if (NST == 0) return;
+  __syncthreads();
+#pragma unroll
+  for (int s = 1; s <= NST; s++) {
+    const int n = taps.n[s - 1];
+    const int h = 2 * n - 1;
+    const V *src = lvl[s - 1];
+    for (int i = threadIdx.x; i < len[s]; i += kHbThreads) {
+      const int64_t m = a[s] + i;
+      V y;
+      y.x = 0;
+      y.y = 0;
+      if (m >= 0) {
+        const int p = 2 * i + h; // position of x[2m] in the source level
+        y = src[p];
+        for (int k = 0; k < n; k++) {
+          const S t = taps.t[s - 1][k];
+          const V u = src[p + 2 * k + 1];
+          const V w = src[p - 2 * k - 1];
+          y.x += t * (u.x + w.x);
+          y.y += t * (u.y + w.y);
+        }
+      }
+      if (s == NST) {
+        out.st(c, m, y);
+      } else {
+        lvl[s][i] = y;
+      }
+    }
+    if (s < NST) __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Long zero-phase low-pass, direct form (reference: r8b::CDSPBlockConvolver::process,
+// CDSPBlockConvolver.h:252-353 — overlap-save FFT there; same linear convolution here):
+//   y[q] = sum_j h[j] * x[q*down - fl2 + j],  j = 0..klen-1,  fl2 = (klen-1)/2.
+constexpr int kFirThreads = 256;
+constexpr int kFirR = 4;
+constexpr int kFirTile = kFirThreads * kFirR;
+
+template <typename S>
+__global__ void __launch_bounds__(kFirThreads)
+    k_fir_long(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out, const S *__restrict__ taps,
+               int klen, int down, int64_t q0, int n_out) {
+  using V = typename V2<S>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t c = blockIdx.y;
+  const int tile0 = blockIdx.x * kFirTile;
+  int cnt = n_out - tile0;
+  if (cnt > kFirTile) cnt = kFirTile;
+  if (cnt <= 0) return;
+  const int span = (kFirTile - 1) * down + klen;
+  V *xs = reinterpret_cast<V *>(smem_raw);
+  S *hs = reinterpret_cast<S *>(xs + span);
+  const int fl2 = (klen - 1) / 2;
+  const int64_t x0 = (q0 + tile0) * down - fl2;
+  const int need = (cnt - 1) * down + klen;
+  for (int i = threadIdx.x; i < span; i += kFirThreads) {
+    V v;
+    v.x = 0;
+    v.y = 0;
+    if (i < need) v = in.ld(c, x0 + i);
+    xs[i] = v;
+  }
+  for (int i = threadIdx.x; i < klen; i += kFirThreads) hs[i] = taps[i];
+  __syncthreads();
+  V acc[kFirR];
+#pragma unroll
+  for (int r = 0; r < kFirR; r++) {
+    acc[r].x = 0;
+    acc[r].y = 0;
+  }
+  const int base = threadIdx.x * down;
+  const int rstep = kFirThreads * down;
+  for (int k = 0; k < klen; k++) {
+    const S h = hs[k];
+#pragma unroll
+    for (int r = 0; r < kFirR; r++) {
+      const V x = xs[base + r * rstep + k];
+      acc[r].x += h * x.x;
+      acc[r].y += h * x.y;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kFirR; r++) {
+    const int q = threadIdx.x + r * kFirThreads;
+    if (q < cnt) out.st(c, q0 + tile0 + q, acc[r]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Whole-step polyphase interpolator (reference: r8b::CDSPFracInterpolator::convolve0,
+// CDSPFracInterpolator.h:992-1060): output m reads flen inputs starting at
+// floor(m*instep/outstep) - (flen/2 - 1) with the bank row (m*instep) mod outstep.
+template <typename S>
+__global__ void k_frac_interp(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out,
+                              const S *__restrict__ bank, int instep, int outstep, int flen, int64_t m0,
+                              int n_out) {
+  using V = typename V2<S>::type;
+  const uint32_t c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const int64_t m = m0 + i;
+  const int64_t pos = m * instep;
+  const int64_t ip = pos / outstep;
+  const int ph = (int)(pos - ip * outstep);
+  const S *row = bank + (size_t)ph * flen;
+  const int64_t x0 = ip - (flen / 2 - 1);
+  V acc;
+  acc.x = 0;
+  acc.y = 0;
+  for (int k = 0; k < flen; k++) {
+    const V x = in.ld(c, x0 + k);
+    const S h = row[k];
+    acc.x += h * x.x;
+    acc.y += h * x.y;
+  }
+  out.st(c, m, acc);
+}
+
+// ---------------------------------------------------------------------------------------
+// Short symmetric FIR with the reference's per-call head-loop quirk (reference:
+// LowPassFilterFirIQ::process Filter.cpp:37-96 and LowPassFilterFirAudio::process
+// Filter.cpp:108-163): the first min(n, order) outputs of every process() call are
+// computed by a loop that starts at coefficient 1, i.e. the coeff[0]*x[p] term is never
+// added for them. call_end[] holds the cumulative per-call ends
+// (relative to j0) of this launch's range.
+__device__ __forceinline__ int find_call(const uint32_t *__restrict__ call_end, int n_calls, uint32_t rel) {
+  int lo = 0, hi = n_calls - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (call_end[mid] > rel) {
+      hi = mid;
+    } else {
+      lo = mid + 1;
+    }
+  }
+  return lo;
+}
+
+template <typename S>
+__global__ void k_fir_quirk(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out,
+                            const S *__restrict__ coeff, int ntaps, int64_t j0, int n_out,
+                            const uint32_t *__restrict__ call_end, int n_calls) {
+  using V = typename V2<S>::type;
+  const uint32_t c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const int order = ntaps - 1;
+  const int b = find_call(call_end, n_calls, (uint32_t)i);
+  const uint32_t cstart = (b == 0) ? 0u : call_end[b - 1];
+  const int p = i - (int)cstart; // index within the reference's process() call
+  const int k0 = (p < order) ? 1 : 0;
+  const int64_t j = j0 + i;
+  V acc;
+  acc.x = 0;
+  acc.y = 0;
+  for (int k = k0; k <= order; k++) {
+    const V x = in.ld(c, j - k);
+    const S h = coeff[k];
+    acc.x += h * x.x;
+    acc.y += h * x.y;
+  }
+  out.st(c, j, acc);
+}
+
+// ---------------------------------------------------------------------------------------
+// fast_atan2f of the reference (include/Utility.h:236-304; GNU Radio table method). It sits
+// inside the PLL feedback loop, so it is replicated operation for operation.
+__device__ __forceinline__ float fast_atan2f_dev(float y, float x, const float *__restrict__ tbl) {
+  const float y_abs = fabsf(y);
+  const float x_abs = fabsf(x);
+  if (!((y_abs > 0.0f) || (x_abs > 0.0f))) return 0.0f;
+  float z;
+  if (y_abs < x_abs) {
+    z = y_abs / x_abs;
+  } else {
+    z = x_abs / y_abs;
+  }
+  float base_angle;
+  if ((double)z < 0.003921569) {
+    base_angle = z;
+  } else {
+    float alpha = z * 255.0f;
+    const int index = ((int)alpha) & 0xff;
+    alpha -= (float)index;
+    base_angle = tbl[index];
+    base_angle += (tbl[index + 1] - tbl[index]) * alpha;
+  }
+  float angle;
+  if (x_abs > y_abs) {
+    if (x >= 0.0f) {
+      angle = (y >= 0.0f) ? base_angle : -base_angle;
+    } else {
+      angle = 3.14159265358979323846f;
+      if (y >= 0.0f) {
+        angle -= base_angle;
+      } else {
+        angle = base_angle - angle;
+      }
+    }
+  } else {
+    if (y >= 0.0f) {
+      angle = 1.57079632679489661923f;
+      if (x >= 0.0f) {
+        angle -= base_angle;
+      } else {
+        angle += base_angle;
+      }
+    } else {
+      angle = -1.57079632679489661923f;
+      if (x >= 0.0f) {
+        angle += base_angle;
+      } else {
+        angle -= base_angle;
+      }
+    }
+  }
+  return angle;
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-channel persistent state of the FM decoder (reference: FmDecoder members,
+// include/FmDecode.h:127-163, and the members of the blocks it owns).
+struct FmChanState {
+  // IfSimpleAgc (IfSimpleAgc.h:55-60)
+  float agc_gain;
+  // PhaseDiscriminator m_save_value (PhaseDiscriminator.h:44-48)
+  float disc_prev;
+  // FmDecoder statistics (FmDecode.h:134-137)
+  float baseband_mean, baseband_level, if_rms;
+  int stereo_detected;
+  uint32_t mpf_wait; // m_wait_multipath_blocks
+  int lock_cnt;      // PilotPhaseLock m_lock_cnt
+  int pilot_periods;
+  uint32_t n_pps; // events recorded in the last process call
+  // PilotPhaseLock (PilotPhaseLock.h:81-95)
+  double pll_phase, pll_freq;
+  double bi_x1, bi_x2, bq_x1, bq_x2; // biquad delay lines (I, Q)
+  double lf_x1;                      // loop filter delay
+  double pilot_level;                // m_pilot_level (not doubled)
+  double freq_err;
+  unsigned long long pps_cnt, sample_cnt;
+  // LowPassFilterRC delay lines (mono, L-R)
+  double de_m_x1, de_s_x1;
+  // HighPassFilterIir delay lines (mono, L-R)
+  double dc_m_x1, dc_m_x2, dc_s_x1, dc_s_x2;
+  // MultipathFilter m_error
+  double mpf_error;
+  unsigned long long decoder_calls;
+};
+
+struct PpsEventDev {
+  unsigned long long pps_index, sample_index;
+  double block_position;
+  uint32_t block;
+  uint32_t pad;
+};
+constexpr int kMaxPps = 16;
+
+struct FmCoreParams {
+  // constants
+  float agc_max, agc_rate;         // IfSimpleAgc(1.0, 100000.0, 0.0001)  FmDecode.cpp:74
+  float disc_inv_norm, disc_bound; // PhaseDiscriminator.cpp:27-30
+  double pll_minfreq, pll_maxfreq; // PilotPhaseLock.cpp:35-36
+  double bq_b0, bq_a1, bq_a2;      // PilotPhaseLock.cpp:48-49
+  double lf_b0, lf_b1;             // PilotPhaseLock.cpp:51
+  int lock_delay;                  // PilotPhaseLock.cpp:43
+  double minsignal;                // PilotPhaseLock.h:37
+  double de_a1, de_b0;             // LowPassFilterRC  Filter.cpp:186-188
+  int stereo, pilot_shift, deemph_on_stereo;
+  int n_channels;
+};
+
+// The serial 384 kHz core, one lane per channel (reference: FmDecoder::process
+// FmDecode.cpp:85-183 up to the audio resamplers). PHASE selects what runs:
+//   0 = everything (no multipath filter); 1 = IF RMS + AGC only (writes IQ to `iq_out`);
+//   2 = discriminator onwards (reads IQ from `iq_in` = multipath filter output).
+template <int PHASE>
+__global__ void k_fm_core(Ring<float2> if_raw, Ring<float2> iq_in, Ring<float2> iq_out, Ring<double2> out384,
+                          FmChanState *__restrict__ st, uint8_t *__restrict__ flags,
+                          PpsEventDev *__restrict__ pps, const uint32_t *__restrict__ call_end, int n_calls,
+                          int64_t t0, FmCoreParams P, const float *__restrict__ atan_tbl) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.n_channels) return;
+  FmChanState s = st[c];
+  if (PHASE != 1) s.n_pps = 0;
+  uint32_t prev_end = 0;
+  for (int b = 0; b < n_calls; b++) {
+    const uint32_t end = call_end[b];
+    const int n = (int)(end - prev_end);
+    if (n == 0) continue; // main.cpp:933-936: the decoder is not called
+    const int64_t tb = t0 + prev_end;
+    prev_end = end;
+    if (PHASE != 2) {
+      s.decoder_calls++;
+      // Utility::rms_level_sample (Utility.h:118-132) on the decoder input
+      float sumsq = 0.0f;
+      for (int i = 0; i < n; i++) {
+        const float2 x = if_raw.ld(c, tb + i);
+        sumsq += x.x * x.x + x.y * x.y;
+      }
+      s.if_rms = sqrtf(sumsq / (float)n);
+    }
+    float vsum = 0.0f, vsumsq = 0.0f;
+    const bool was_locked = (s.lock_cnt >= P.lock_delay);
+    for (int i = 0; i < n; i++) {
+      const int64_t t = tb + i;
+      float2 x2;
+      if (PHASE != 2) {
+        // IfSimpleAgc::process (IfSimpleAgc.cpp:37-57)
+        const float2 x = iq_in.ld(c, t);
+        x2.x = x.x * s.agc_gain;
+        x2.y = x.y * s.agc_gain;
+        const float nrm = x2.x * x2.x + x2.y * x2.y;
+        const float z = (float)(1.0 + ((double)P.agc_rate * (1.0 - (double)nrm)));
+        s.agc_gain *= z;
+        if (!isfinite(s.agc_gain)) {
+          s.agc_gain = 1.0f;
+        } else if (s.agc_gain > P.agc_max) {
+          s.agc_gain = P.agc_max;
+        }
+        if (PHASE == 1) {
+          iq_out.st(c, t, x2);
+          continue;
+        }
+      } else {
+        x2 = iq_in.ld(c, t);
+      }
+      // PhaseDiscriminator::process (PhaseDiscriminator.cpp:33-46)
+      const float ph = atan2f(x2.y, x2.x) * P.disc_inv_norm;
+      float d = ph - s.disc_prev;
+      if (d > P.disc_bound) d -= 2 * P.disc_bound;
+      if (d < -P.disc_bound) d += 2 * P.disc_bound;
+      s.disc_prev = ph;
+      if (isnan(d)) d = 0.0f;
+      vsum += d;
+      vsumsq += d * d;
+      const double xd = (double)d;
+      double stereo = 0.0;
+      if (P.stereo) {
+        // PilotPhaseLock::process (PilotPhaseLock.cpp:56-171)
+        double psin, pcos;
+        sincos(s.pll_phase, &psin, &pcos);
+        const double tone = P.pilot_shift ? (2 * pcos * pcos - 1) : (2 * psin * pcos);
+        const double pi_in = psin * xd;
+        const double pq_in = pcos * xd;
+        const double i0 = pi_in - (P.bq_a1 * s.bi_x1 + P.bq_a2 * s.bi_x2);
+        const double q0 = pq_in - (P.bq_a1 * s.bq_x1 + P.bq_a2 * s.bq_x2);
+        const double new_i = P.bq_b0 * i0;
+        const double new_q = P.bq_b0 * q0;
+        s.bi_x2 = s.bi_x1;
+        s.bi_x1 = i0;
+        s.bq_x2 = s.bq_x1;
+        s.bq_x1 = q0;
+        const double perr = (double)fast_atan2f_dev((float)new_q, (float)new_i, atan_tbl);
+        s.pilot_level = sqrt(new_i * new_i + new_q * new_q);
+        const double ferr = P.lf_b0 * perr + P.lf_b1 * s.lf_x1;
+        s.lf_x1 = perr;
+        s.freq_err = ferr;
+        s.pll_freq += ferr;
+        s.pll_freq = fmax(P.pll_minfreq, fmin(P.pll_maxfreq, s.pll_freq));
+        s.pll_phase += s.pll_freq;
+        if (s.pll_phase > 2.0 * 3.14159265358979323846) {
+          s.pll_phase -= 2.0 * 3.14159265358979323846;
+          s.pilot_periods++;
+          if (s.pilot_periods == 19000) {
+            s.pilot_periods = 0;
+            if (was_locked) {
+              if (s.n_pps < (uint32_t)kMaxPps) {
+                PpsEventDev ev;
+                ev.pps_index = s.pps_cnt;
+                ev.sample_index = s.sample_cnt + (unsigned long long)i;
+                ev.block_position = (double)i / (double)n;
+                ev.block = (uint32_t)b;
+                ev.pad = 0;
+                pps[(size_t)c * kMaxPps + s.n_pps] = ev;
+              }
+              s.n_pps++;
+              s.pps_cnt++;
+            }
+          }
+        }
+        // FmDecoder::demod_stereo (FmDecode.cpp:224-239) and L-R deemphasis (:168-170)
+        stereo = (tone * xd) * 2.0;
+        if (P.deemph_on_stereo) {
+          const double x0 = stereo - P.de_a1 * s.de_s_x1;
+          stereo = P.de_b0 * x0;
+          s.de_s_x1 = x0;
+        }
+      }
+      // mono deemphasis (FmDecode.cpp:180)
+      const double m0 = xd - P.de_a1 * s.de_m_x1;
+      const double mono = P.de_b0 * m0;
+      s.de_m_x1 = m0;
+      double2 o;
+      o.x = mono;
+      o.y = stereo;
+      out384.st(c, t, o);
+    }
+    if (PHASE == 1) continue;
+    // Utility::samples_mean_rms + EMA (FmDecode.cpp:146-150)
+    {
+      const float mean = vsum / (float)n;
+      const float rms = sqrtf(vsumsq / (float)n);
+      s.baseband_mean = (float)(0.95 * (double)s.baseband_mean + 0.05 * (double)mean);
+      s.baseband_level = (float)(0.95 * (double)s.baseband_level + 0.05 * (double)rms);
+    }
+    if (P.stereo) {
+      // lock bookkeeping (PilotPhaseLock.cpp:153-170)
+      if (2 * s.pilot_level > P.minsignal) {
+        if (s.lock_cnt < P.lock_delay) s.lock_cnt += n;
+      } else {
+        s.lock_cnt = 0;
+      }
+      if (s.lock_cnt < P.lock_delay) {
+        s.pilot_periods = 0;
+        s.pps_cnt = 0;
+        // events of THIS call are dropped: rewind those recorded with block == b
+        while (s.n_pps > 0 && s.n_pps <= (uint32_t)kMaxPps && pps[(size_t)c * kMaxPps + s.n_pps - 1].block == (uint32_t)b) {
+          s.n_pps--;
+        }
+      }
+      s.sample_cnt += (unsigned long long)n;
+      s.stereo_detected = (s.lock_cnt >= P.lock_delay) ? 1 : 0;
+    }
+    flags[(size_t)c * n_calls + b] = (uint8_t)s.stereo_detected;
+  }
+  st[c] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// 48 kHz tail, one lane per channel: DC block (HighPassFilterIir::process_inplace,
+// Filter.cpp:304-311, biquad Filter.cpp:243-250) on mono and L-R, then the per-call
+// matrix (FmDecoder::process FmDecode.cpp:194-220, stereo_to_left_right :255-270).
+struct FmTailParams {
+  double b0, b1, b2, a1, a2; // HighPassFilterIir(0.0001) FmDecode.cpp:62
+  int stereo, pilot_shift;
+  int n_channels;
+};
+
+static __global__ void k_fm_tail(Ring<double2> in48, double *__restrict__ audio, size_t audio_stride,
+                          FmChanState *__restrict__ st, const uint8_t *__restrict__ flags,
+                          const uint32_t *__restrict__ call_end48, int n_calls, int64_t j0, FmTailParams P) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.n_channels) return;
+  double m1 = st[c].dc_m_x1, m2 = st[c].dc_m_x2, s1 = st[c].dc_s_x1, s2 = st[c].dc_s_x2;
+  double *o = audio + (size_t)c * audio_stride;
+  uint32_t prev_end = 0;
+  for (int b = 0; b < n_calls; b++) {
+    const uint32_t end = call_end48[b];
+    const int det = flags[(size_t)c * n_calls + b];
+    for (uint32_t r = prev_end; r < end; r++) {
+      const double2 x = in48.ld(c, j0 + r);
+      const double m0 = x.x - (P.a1 * m1 + P.a2 * m2);
+      const double mono = P.b0 * m0 + P.b1 * m1 + P.b2 * m2;
+      m2 = m1;
+      m1 = m0;
+      if (!P.stereo) {
+        o[r] = mono;
+        continue;
+      }
+      const double s0 = x.y - (P.a1 * s1 + P.a2 * s2);
+      const double ster = P.b0 * s0 + P.b1 * s1 + P.b2 * s2;
+      s2 = s1;
+      s1 = s0;
+      double l, rr;
+      if (det) {
+        if (P.pilot_shift) {
+          l = ster;
+          rr = ster;
+        } else {
+          const double sb = 1.017 * ster;
+          l = mono + sb;
+          rr = mono - sb;
+        }
+      } else {
+        if (P.pilot_shift) {
+          l = 0.0;
+          rr = 0.0;
+        } else {
+          l = mono;
+          rr = mono;
+        }
+      }
+      o[2 * (size_t)r] = l;
+      o[2 * (size_t)r + 1] = rr;
+    }
+    prev_end = end;
+  }
+  st[c].dc_m_x1 = m1;
+  st[c].dc_m_x2 = m2;
+  st[c].dc_s_x1 = s1;
+  st[c].dc_s_x2 = s2;
+}
+
+// Keep the last kHist input samples of every channel for the next call's halo.
+template <typename V>
+__global__ void k_save_hist(const V *__restrict__ lin, size_t stride, int64_t n_new, const V *__restrict__ hist_old,
+                            V *__restrict__ hist_new) {
+  const uint32_t c = blockIdx.x;
+  for (int i = threadIdx.x; i < kHist; i += blockDim.x) {
+    const int64_t r = n_new - kHist + i; // index into this call's samples
+    V v;
+    if (r >= 0) {
+      v = lin[(size_t)c * stride + r];
+    } else {
+      const int64_t h = kHist + r; // = i + n_new, < kHist
+      v = hist_old[(size_t)c * kHist + h];
+    }
+    hist_new[(size_t)c * kHist + i] = v;
+  }
+}
+
+} // namespace fmr
+#endif

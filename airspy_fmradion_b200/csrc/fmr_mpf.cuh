@@ -1,0 +1,206 @@
+// fmr_mpf.cuh — the multipath equaliser (reference: MultipathFilter, MultipathFilter.cpp:
+// 92-197; its use in FmDecoder::process, FmDecode.cpp:107-128).
+//
+// Sample-serial NLMS/CMA exactly as the reference runs it: FIR output for every sample,
+// coefficient update on every 4th sample OF THE CURRENT process() CALL ((i & 3) == 0),
+// step size renormalised from the instantaneous state energy, reference tap pinned to
+// 1+0j, failure (non-finite output or error) -> coefficients re-initialised and the whole
+// call passed through unfiltered. One warp owns one channel: the 4*stages+1 complex
+// coefficients live in registers (tap k on lane k%32), the delay line in a shared-memory
+// ring, the dot product is reduced with warp shuffles, so a sample costs no block barrier.
+#ifndef FMR_MPF_CUH
+#define FMR_MPF_CUH
+
+#include "fmr_host.cuh"
+
+namespace fmr {
+
+constexpr int kMpfRing = 1024;
+constexpr int kMpfWarps = 4;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int J>
+__global__ void __launch_bounds__(32 * kMpfWarps)
+    k_mpf(Ring<float2> in, Ring<float2> out, FmChanState *__restrict__ st, float2 *__restrict__ g_coeff,
+          float2 *__restrict__ g_state, int N, int ref_idx, const uint32_t *__restrict__ call_end, int n_calls,
+          int64_t t0, int C) {
+  __shared__ float2 ring_all[kMpfWarps][kMpfRing];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kMpfWarps + warp;
+  if (c >= C) return;
+  float2 *ring = ring_all[warp];
+  float2 cf[J];
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int k = lane + 32 * j;
+    cf[j] = (k < N) ? g_coeff[(size_t)c * kMpfRing + k] : make_float2(0.f, 0.f);
+  }
+  for (int k = lane; k < kMpfRing; k += 32) {
+    ring[k] = (k < N) ? g_state[(size_t)c * kMpfRing + k] : make_float2(0.f, 0.f);
+  }
+  __syncwarp();
+  uint32_t cnt = (uint32_t)(N - 1); // ring index of the newest sample
+  uint32_t wait = st[c].mpf_wait;
+  double err_keep = st[c].mpf_error;
+  uint32_t prev_end = 0;
+  for (int b = 0; b < n_calls; b++) {
+    const uint32_t end = call_end[b];
+    const int n = (int)(end - prev_end);
+    if (n == 0) continue;
+    const int64_t tb = t0 + prev_end;
+    prev_end = end;
+    if (wait > 0) {
+      // FmDecode.cpp:107-110: bypass, filter state untouched
+      wait--;
+      for (int q = lane; q < n; q += 32) out.st(c, tb + q, in.ld(c, tb + q));
+      continue;
+    }
+    bool ok = true;
+    for (int i = 0; i < n; i++) {
+      const float2 x = in.ld(c, tb + i);
+      cnt++;
+      if (lane == 0) ring[cnt & (kMpfRing - 1)] = x;
+      __syncwarp();
+      const bool upd = ((i & 3) == 0);
+      float yr = 0.f, yi = 0.f, ms = 0.f;
+#pragma unroll
+      for (int j = 0; j < J; j++) {
+        const int k = lane + 32 * j;
+        if (k < N) {
+          const float2 s = ring[(cnt - (uint32_t)(N - 1 - k)) & (kMpfRing - 1)];
+          yr += s.x * cf[j].x - s.y * cf[j].y;
+          yi += s.x * cf[j].y + s.y * cf[j].x;
+          ms += s.x * s.x + s.y * s.y;
+        }
+      }
+      yr = warp_sum(yr);
+      yi = warp_sum(yi);
+      if (!isfinite(yr) || !isfinite(yi)) {
+        ok = false;
+        break;
+      }
+      if (lane == 0) out.st(c, tb + i, make_float2(yr, yi));
+      if (upd) {
+        // MultipathFilter::update_coeff (MultipathFilter.cpp:108-161)
+        ms = warp_sum(ms);
+        const double env = (double)(yr * yr + yi * yi);
+        const double err = 1.0 - env;
+        const float mu = (float)(0.1 / ((double)ms + 1e-10));
+        const float factor = (float)(err * (double)mu);
+        const float fr = factor * yr, fi = factor * yi;
+#pragma unroll
+        for (int j = 0; j < J; j++) {
+          const int k = lane + 32 * j;
+          if (k < N) {
+            const float2 s = ring[(cnt - (uint32_t)(N - 1 - k)) & (kMpfRing - 1)];
+            cf[j].x += fr * s.x + fi * s.y;
+            cf[j].y += fi * s.x - fr * s.y;
+            if (k == ref_idx) cf[j] = make_float2(1.f, 0.f);
+          }
+        }
+        err_keep = err;
+        if (!isfinite(err)) {
+          ok = false;
+          break;
+        }
+      }
+    }
+    if (!ok) {
+      // FmDecode.cpp:114-123: reset coefficients, pass the call through unfiltered
+#pragma unroll
+      for (int j = 0; j < J; j++) {
+        const int k = lane + 32 * j;
+        cf[j] = (k == ref_idx) ? make_float2(1.f, 0.f) : make_float2(0.f, 0.f);
+      }
+      __syncwarp();
+      for (int q = lane; q < n; q += 32) out.st(c, tb + q, in.ld(c, tb + q));
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int k = lane + 32 * j;
+    if (k < N) g_coeff[(size_t)c * kMpfRing + k] = cf[j];
+  }
+  // linearise the delay line: entry k is the sample N-1-k steps behind the newest
+  float2 tmp[J];
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int k = lane + 32 * j;
+    tmp[j] = (k < N) ? ring[(cnt - (uint32_t)(N - 1 - k)) & (kMpfRing - 1)] : make_float2(0.f, 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int k = lane + 32 * j;
+    if (k < N) g_state[(size_t)c * kMpfRing + k] = tmp[j];
+  }
+  if (lane == 0) {
+    st[c].mpf_wait = wait;
+    st[c].mpf_error = err_keep;
+  }
+}
+
+struct MpfDev {
+  int N = 0, ref_idx = 0, C = 0, J = 0;
+  float2 *d_coeff = nullptr, *d_state = nullptr;
+
+  fmr_status init(uint32_t stages, int channels, DevMem &mem) {
+    // MultipathFilter::MultipathFilter (MultipathFilter.cpp:35-75)
+    N = (int)stages * 4 + 1;
+    ref_idx = (int)stages * 3 + 1;
+    C = channels;
+    if (N > kMpfRing - 3) return fail(FMR_ERR_UNSUPPORTED, "multipath_stages > 255 is not supported");
+    const int need = (N + 31) / 32;
+    const int opts[] = {4, 8, 13, 16, 20, 26, 32};
+    J = 32;
+    for (int o : opts) {
+      if (o >= need) {
+        J = o;
+        break;
+      }
+    }
+    FMR_CUDA(mem.alloc(&d_coeff, (size_t)C * kMpfRing));
+    FMR_CUDA(mem.alloc(&d_state, (size_t)C * kMpfRing));
+    std::vector<float2> init((size_t)C * kMpfRing, make_float2(0.f, 0.f));
+    for (int c = 0; c < C; c++) init[(size_t)c * kMpfRing + ref_idx] = make_float2(1.f, 0.f);
+    FMR_CUDA(cudaMemcpy(d_coeff, init.data(), init.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    return FMR_OK;
+  }
+
+  void run(Ring<float2> in, Ring<float2> out, FmChanState *st, const uint32_t *call_end, int n_calls, int64_t t0,
+           cudaStream_t s) {
+    dim3 grid((C + kMpfWarps - 1) / kMpfWarps);
+    dim3 block(32 * kMpfWarps);
+#define FMR_MPF_CASE(j)                                                                                          \
+  case j:                                                                                                        \
+    k_mpf<j><<<grid, block, 0, s>>>(in, out, st, d_coeff, d_state, N, ref_idx, call_end, n_calls, t0, C);         \
+    break;
+    switch (J) {
+      FMR_MPF_CASE(4)
+      FMR_MPF_CASE(8)
+      FMR_MPF_CASE(13)
+      FMR_MPF_CASE(16)
+      FMR_MPF_CASE(20)
+      FMR_MPF_CASE(26)
+    default:
+      k_mpf<32><<<grid, block, 0, s>>>(in, out, st, d_coeff, d_state, N, ref_idx, call_end, n_calls, t0, C);
+      break;
+    }
+#undef FMR_MPF_CASE
+  }
+
+  fmr_status read_coeffs(uint32_t channel, float *re_im, size_t n_complex) {
+    if ((int)n_complex < N) return fail(FMR_ERR_CAPACITY, "coefficient buffer smaller than 4*stages+1");
+    FMR_CUDA(cudaMemcpy(re_im, d_coeff + (size_t)channel * kMpfRing, (size_t)N * sizeof(float2),
+                        cudaMemcpyDeviceToHost));
+    return FMR_OK;
+  }
+};
+
+} // namespace fmr
+#endif

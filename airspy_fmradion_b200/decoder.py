@@ -1,0 +1,198 @@
+"""Host-side mirror of the reference's decoder block API over the C ABI.
+
+`FmDecoder` / `AmDecoder` keep the reference's names, constructor argument meaning and
+getters (include/FmDecode.h:34-105, include/AmDecode.h:32-65) so that tests read like the
+reference's usage in main.cpp:812-830,953-974. Differences, all additive:
+  * a decoder holds `n_channels` independent streams decoded in lock step;
+  * the front end the reference runs just before the decoder (FourthConverterIQ, IfResampler;
+    main.cpp:912-926) is part of the object (`input_rate`, `fs4_shift`), because the GPU
+    path absorbs it;
+  * `process_blocks` hands over many source blocks at once together with the block
+    partition; `process` is the one-block form with the reference's signature.
+No torch types here; device-pointer entry points take integer addresses.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import check
+
+
+class _Base:
+    _h = None
+
+    def close(self):
+        if self._h:
+            self._destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- shared process plumbing -------------------------------------------------------
+    def _blocks(self, block_len):
+        bl = np.ascontiguousarray(block_len, dtype=np.uint32)
+        return bl, int(bl.sum())
+
+    def query_output(self, block_len):
+        bl, _ = self._blocks(block_len)
+        tot = C.c_uint64(0)
+        lens = np.zeros(len(bl), dtype=np.uint32)
+        check(self._query(self._h, bl.ctypes.data, len(bl), C.byref(tot), lens.ctypes.data))
+        return int(tot.value), lens
+
+    def process_blocks(self, iq, block_len):
+        """iq: complex64 [C, T] (or [T] for one channel); returns (audio [C, n], audio_len[n_blocks])."""
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        if iq.ndim == 1:
+            iq = iq[None, :]
+        assert iq.shape[0] == self.n_channels
+        bl, total = self._blocks(block_len)
+        assert total <= iq.shape[1]
+        out_total, _ = self.query_output(bl)
+        audio = np.zeros((self.n_channels, max(out_total, 1)), dtype=np.float64)
+        lens = np.zeros(len(bl), dtype=np.uint32)
+        check(self._process_host(self._h, iq.ctypes.data, iq.shape[1], bl.ctypes.data, len(bl),
+                                 audio.ctypes.data, audio.shape[1], lens.ctypes.data))
+        return audio[:, :out_total], lens
+
+    def process_device(self, d_iq_ptr, iq_stride, block_len, d_audio_ptr, audio_stride, stream=0):
+        """Device-pointer form (addresses as ints, e.g. torch.Tensor.data_ptr()); asynchronous on
+        `stream` (a cudaStream_t handle as int). Returns audio_len per block."""
+        bl, _ = self._blocks(block_len)
+        lens = np.zeros(len(bl), dtype=np.uint32)
+        check(self._process_device(self._h, d_iq_ptr, iq_stride, bl.ctypes.data, len(bl), d_audio_ptr,
+                                   audio_stride, lens.ctypes.data, stream))
+        return lens
+
+    def process(self, samples_in):
+        """Reference signature: one block in, audio out (FmDecode.h:74 / AmDecode.h:55)."""
+        samples_in = np.asarray(samples_in)
+        n = samples_in.shape[-1]
+        audio, _ = self.process_blocks(samples_in, [n])
+        return audio[0] if samples_in.ndim == 1 else audio
+
+
+class FmDecoder(_Base):
+    # Static constants (include/FmDecode.h:38-47)
+    sample_rate_if = 384000.0
+    sample_rate_pcm = 48000.0
+    freq_dev = 75000.0
+    bandwidth_pcm = 15000.0
+    pilot_freq = 19000.0
+    deemphasis_time_eu = 50.0
+    deemphasis_time_na = 75.0
+
+    def __init__(self, fmfilter=0, stereo=True, deemphasis=50.0, pilot_shift=False, multipath_stages=0, *,
+                 input_rate=384000.0, fs4_shift=False, n_channels=1, max_samples_per_call=1 << 20,
+                 max_blocks_per_call=4096, device=0):
+        """fmfilter: 0 none (FilterType Default/Wide), 1 medium, 2 narrow (main.cpp:785-810); the other
+        arguments are FmDecoder's (FmDecode.h:49-64)."""
+        L = _capi.lib()
+        self._destroy, self._query = L.fmr_fm_destroy, L.fmr_fm_query_output
+        self._process_host, self._process_device = L.fmr_fm_process_host, L.fmr_fm_process_device
+        self.n_channels = int(n_channels)
+        self.stereo = bool(stereo)
+        self.multipath_stages = int(multipath_stages)
+        cfg = _capi.FmConfig(float(input_rate), int(fs4_shift), int(fmfilter), int(stereo), float(deemphasis),
+                             int(pilot_shift), int(multipath_stages), int(n_channels),
+                             int(max_samples_per_call), int(max_blocks_per_call), int(device))
+        h = C.c_void_p()
+        check(L.fmr_fm_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def stats(self, channel=0):
+        s = _capi.FmStats()
+        check(_capi.lib().fmr_fm_stats(self._h, channel, C.byref(s)))
+        return s
+
+    def stereo_detected(self, channel=0):
+        return bool(self.stats(channel).stereo_detected)
+
+    def get_tuning_offset(self, channel=0):
+        return self.stats(channel).tuning_offset
+
+    def get_baseband_level(self, channel=0):
+        return self.stats(channel).baseband_level
+
+    def get_pilot_level(self, channel=0):
+        return self.stats(channel).pilot_level
+
+    def get_if_rms(self, channel=0):
+        return self.stats(channel).if_rms
+
+    def get_multipath_error(self, channel=0):
+        return self.stats(channel).multipath_error
+
+    def get_pps_events(self, channel=0):
+        ev = (_capi.PpsEvent * 16)()
+        n = C.c_uint32(0)
+        check(_capi.lib().fmr_fm_pps_events(self._h, channel, ev, 16, C.byref(n)))
+        return [(e.pps_index, e.sample_index, e.block_position, e.block) for e in ev[:n.value]]
+
+    def get_multipath_coefficients(self, channel=0):
+        n = 4 * self.multipath_stages + 1
+        buf = np.zeros(2 * n, dtype=np.float32)
+        check(_capi.lib().fmr_fm_coeffs(self._h, channel, buf.ctypes.data, n))
+        return buf.view(np.complex64)
+
+    def block_flags(self, n_blocks, channel=0):
+        f = np.zeros(n_blocks, dtype=np.uint8)
+        check(_capi.lib().fmr_fm_block_flags(self._h, channel, f.ctypes.data, n_blocks))
+        return f
+
+    def tap_if(self, channel=0):
+        n = C.c_uint64(0)
+        check(_capi.lib().fmr_fm_tap_if(self._h, channel, None, 0, C.byref(n)))
+        buf = np.zeros(2 * max(int(n.value), 1), dtype=np.float32)
+        check(_capi.lib().fmr_fm_tap_if(self._h, channel, buf.ctypes.data, int(n.value), C.byref(n)))
+        return buf[:2 * int(n.value)].view(np.complex64)
+
+    def last_launches(self):
+        return int(_capi.lib().fmr_fm_last_launches(self._h))
+
+
+class AmDecoder(_Base):
+    # Static constants (include/AmDecode.h:35-40)
+    sample_rate_pcm = 48000.0
+    internal_rate_pcm = 48000.0
+    bandwidth_pcm = 4500.0
+    deemphasis_time = 100.0
+    MODTYPE_AM = 2  # include/SoftFM.h:56
+
+    def __init__(self, amfilter=0, mode=2, *, input_rate=48000.0, fs4_shift=False, n_channels=1,
+                 max_samples_per_call=1 << 20, max_blocks_per_call=4096, device=0):
+        """amfilter: 0 default, 1 medium, 2 narrow, 3 wide (main.cpp:785-810); mode: ModType value."""
+        L = _capi.lib()
+        self._destroy, self._query = L.fmr_am_destroy, L.fmr_am_query_output
+        self._process_host, self._process_device = L.fmr_am_process_host, L.fmr_am_process_device
+        self.n_channels = int(n_channels)
+        cfg = _capi.AmConfig(float(input_rate), int(fs4_shift), int(amfilter), int(mode), int(n_channels),
+                             int(max_samples_per_call), int(max_blocks_per_call), int(device))
+        h = C.c_void_p()
+        check(L.fmr_am_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def stats(self, channel=0):
+        s = _capi.AmStats()
+        check(_capi.lib().fmr_am_stats(self._h, channel, C.byref(s)))
+        return s
+
+    def get_baseband_level(self, channel=0):
+        return self.stats(channel).baseband_level
+
+    def get_af_agc_current_gain(self, channel=0):
+        return self.stats(channel).af_agc_gain
+
+    def get_if_agc_current_gain(self, channel=0):
+        return self.stats(channel).if_agc_gain
+
+    def get_if_rms(self, channel=0):
+        return self.stats(channel).if_rms
+
+    def last_launches(self):
+        return int(_capi.lib().fmr_am_last_launches(self._h))

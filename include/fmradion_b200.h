@@ -1,0 +1,180 @@
+/*
+ * fmradion_b200.h — C ABI of the B200-native demodulation hot path.
+ *
+ * This is the drop-in boundary for the block API the reference exposes as C++ classes:
+ *
+ *   FmDecoder::FmDecoder(...)                     include/FmDecode.h:63-64
+ *   void FmDecoder::process(IQSampleVector, SampleVector&)          include/FmDecode.h:74
+ *   stereo_detected / get_tuning_offset / get_baseband_level /
+ *   get_pilot_level / get_if_rms                  include/FmDecode.h:77-89
+ *   get_pps_events / erase_first_pps_event        include/FmDecode.h:92-97
+ *   get_multipath_error / get_multipath_coefficients   include/FmDecode.h:100-105
+ *   AmDecoder::AmDecoder(...), process, getters   include/AmDecode.h:48-65
+ *
+ * plus the two front-end objects the reference's block loop runs immediately before the
+ * decoder and which the GPU path absorbs because that is where the bytes are:
+ *
+ *   FourthConverterIQ::process                    include/FourthConverterIQ.h:38-82  (main.cpp:912-919)
+ *   IfResampler::process                          sfmbase/IfResampler.cpp:37-79      (main.cpp:921-926)
+ *
+ * One handle decodes `n_channels` independent IQ streams in lock step (same block lengths
+ * for every channel). A call hands over `n_blocks` consecutive source blocks per channel
+ * (a "super-block"); `block_len[]` carries the reference's block partition so that every
+ * behaviour that depends on where the reference's process() calls begin and end (stereo
+ * switch-over, per-call statistics, the FIR head-loop quirk, LMS update phase, multipath
+ * warm-up count) is reproduced inside one launch sequence.
+ *
+ * Conventions: plain pointers and sizes, integer status codes, no exceptions cross the ABI,
+ * caller-owned buffers, one caller thread per handle. There is NO CPU fallback: every entry
+ * point that computes fails with FMR_ERR_CUDA if the device or kernels are unavailable.
+ */
+#ifndef FMRADION_B200_H
+#define FMRADION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int fmr_status;
+enum {
+  FMR_OK = 0,
+  FMR_ERR_INVALID = 1,     /* bad argument */
+  FMR_ERR_UNSUPPORTED = 2, /* rate pair or option outside the shipped tables */
+  FMR_ERR_CUDA = 3,        /* CUDA runtime error; see fmr_last_error() */
+  FMR_ERR_CAPACITY = 4     /* output buffer or max_samples_per_call too small */
+};
+
+/* Human-readable description of the last error on this thread. */
+const char *fmr_last_error(void);
+/* Library version string and number of multiprocessors of `device` (<=0 on failure). */
+const char *fmr_version(void);
+int fmr_device_sm_count(int device);
+
+/* ------------------------------------------------------------------ FM broadcast ---- */
+
+typedef struct fmr_fm fmr_fm;
+
+typedef struct fmr_fm_config {
+  double input_rate;          /* IQ sample rate in Hz: 384000, 1e6, 2.5e6, 6e6, 1e7      */
+  int fs4_shift;              /* 1: FourthConverterIQ(false) first (zero-IF sources)      */
+  int fmfilter;               /* 0 none (default/wide), 1 medium, 2 narrow (main.cpp:785) */
+  int stereo;                 /* FmDecoder ctor `stereo`                                  */
+  double deemphasis_us;       /* 50 (EU/JP), 75 (NA), 0 = off                             */
+  int pilot_shift;            /* FmDecoder ctor `pilot_shift` (-X)                        */
+  uint32_t multipath_stages;  /* FmDecoder ctor `multipath_stages` (-E), 0 = off          */
+  uint32_t n_channels;        /* independent streams decoded by this handle               */
+  uint32_t max_samples_per_call; /* largest sum(block_len) a process call may carry       */
+  uint32_t max_blocks_per_call;  /* largest n_blocks                                       */
+  int device;                 /* CUDA device ordinal                                      */
+} fmr_fm_config;
+
+typedef struct fmr_fm_stats_t {
+  int stereo_detected;      /* FmDecoder::stereo_detected()      */
+  float tuning_offset;      /* FmDecoder::get_tuning_offset()    */
+  float baseband_level;     /* FmDecoder::get_baseband_level()   */
+  double pilot_level;       /* FmDecoder::get_pilot_level()      */
+  float if_rms;             /* FmDecoder::get_if_rms()           */
+  double multipath_error;   /* FmDecoder::get_multipath_error()  */
+  float if_agc_gain;        /* IfSimpleAgc::get_current_gain()   */
+  double pll_freq;          /* PilotPhaseLock m_freq (rad/sample) */
+  double pll_phase;         /* PilotPhaseLock m_phase            */
+  int pll_lock_cnt;         /* PilotPhaseLock m_lock_cnt         */
+  uint64_t decoder_calls;   /* non-empty FmDecoder::process calls so far */
+  uint32_t n_pps;           /* PPS events recorded during the last process call */
+} fmr_fm_stats_t;
+
+typedef struct fmr_pps_event_t { /* PilotPhaseLock::PpsEvent + the block it fell in */
+  uint64_t pps_index;
+  uint64_t sample_index;
+  double block_position;
+  uint32_t block; /* index into block_len[] of the last process call */
+} fmr_pps_event_t;
+
+fmr_status fmr_fm_create(const fmr_fm_config *cfg, fmr_fm **out);
+void fmr_fm_destroy(fmr_fm *h);
+
+/*
+ * Decode n_blocks source blocks for every channel.
+ *   iq            : interleaved (re,im) float pairs, channel-major:
+ *                   channel c occupies iq[2*c*iq_stride .. 2*c*iq_stride + 2*sum(block_len));
+ *                   iq_stride is in complex samples (>= sum(block_len)).
+ *   audio         : channel-major, channel c at audio[c*audio_stride ..]; stereo handles write
+ *                   interleaved L,R doubles, mono handles one double per frame (FmDecode.h:66-74).
+ *   audio_stride  : capacity per channel in doubles.
+ *   audio_len     : [n_blocks] doubles produced by each block (identical for all channels;
+ *                   0 while the resamplers fill, exactly as the reference's per-call sizes).
+ * The *_host form takes pageable or pinned host pointers and does the copies itself; the
+ * *_device form takes device pointers and enqueues on `stream` (a cudaStream_t, 0 = default)
+ * without synchronising; audio_len is always a host pointer and is filled before return.
+ */
+fmr_status fmr_fm_process_host(fmr_fm *h, const float *iq, size_t iq_stride,
+                               const uint32_t *block_len, uint32_t n_blocks,
+                               double *audio, size_t audio_stride, uint32_t *audio_len);
+fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t iq_stride,
+                                 const uint32_t *block_len, uint32_t n_blocks,
+                                 double *d_audio, size_t audio_stride, uint32_t *audio_len,
+                                 void *stream);
+
+/* Audio doubles per channel the next process call with these block lengths will produce
+ * (lets the caller size `audio`); does not advance the stream. */
+fmr_status fmr_fm_query_output(fmr_fm *h, const uint32_t *block_len, uint32_t n_blocks,
+                               uint64_t *audio_doubles_total, uint32_t *audio_len);
+
+fmr_status fmr_fm_stats(fmr_fm *h, uint32_t channel, fmr_fm_stats_t *out);
+/* Copies up to cap events of the last process call; returns the count in *n. */
+fmr_status fmr_fm_pps_events(fmr_fm *h, uint32_t channel, fmr_pps_event_t *out, uint32_t cap,
+                             uint32_t *n);
+/* Multipath filter coefficients as (re,im) float pairs; n_complex = 4*stages+1. */
+fmr_status fmr_fm_coeffs(fmr_fm *h, uint32_t channel, float *re_im, size_t n_complex);
+/* Per-block stereo flags of the last process call, channel-major [n_blocks]. */
+fmr_status fmr_fm_block_flags(fmr_fm *h, uint32_t channel, uint8_t *stereo, uint32_t n_blocks);
+/* Debug/parity tap: the 384 kHz IF samples (decoder input) of the last process call. */
+fmr_status fmr_fm_tap_if(fmr_fm *h, uint32_t channel, float *re_im, size_t cap_complex,
+                         uint64_t *n_complex);
+/* Kernel launches issued by the last process call (for bench accounting). */
+uint32_t fmr_fm_last_launches(fmr_fm *h);
+
+/* ------------------------------------------------------------------------- AM ------- */
+
+typedef struct fmr_am fmr_am;
+
+typedef struct fmr_am_config {
+  double input_rate;    /* 48000 or 384000 */
+  int fs4_shift;
+  int amfilter;         /* 0 default, 1 medium, 2 narrow, 3 wide (main.cpp:785-810) */
+  int mode;             /* ModType value; only 2 (AM) is implemented */
+  uint32_t n_channels;
+  uint32_t max_samples_per_call;
+  uint32_t max_blocks_per_call;
+  int device;
+} fmr_am_config;
+
+typedef struct fmr_am_stats_t {
+  double baseband_level;  /* AmDecoder::get_baseband_level()        */
+  float af_agc_gain;      /* AmDecoder::get_af_agc_current_gain()   */
+  float if_agc_gain;      /* AmDecoder::get_if_agc_current_gain()   */
+  float if_rms;           /* AmDecoder::get_if_rms()                */
+  uint64_t decoder_calls;
+} fmr_am_stats_t;
+
+fmr_status fmr_am_create(const fmr_am_config *cfg, fmr_am **out);
+void fmr_am_destroy(fmr_am *h);
+fmr_status fmr_am_process_host(fmr_am *h, const float *iq, size_t iq_stride,
+                               const uint32_t *block_len, uint32_t n_blocks,
+                               double *audio, size_t audio_stride, uint32_t *audio_len);
+fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t iq_stride,
+                                 const uint32_t *block_len, uint32_t n_blocks,
+                                 double *d_audio, size_t audio_stride, uint32_t *audio_len,
+                                 void *stream);
+fmr_status fmr_am_query_output(fmr_am *h, const uint32_t *block_len, uint32_t n_blocks,
+                               uint64_t *audio_doubles_total, uint32_t *audio_len);
+fmr_status fmr_am_stats(fmr_am *h, uint32_t channel, fmr_am_stats_t *out);
+uint32_t fmr_am_last_launches(fmr_am *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMRADION_B200_H */

@@ -169,6 +169,19 @@ def filter_table(name):
     return buf[:n].copy()
 
 
+def fast_atan_table():
+    buf = np.empty(512, dtype=np.float32)
+    L = lib()
+    L.ref_fast_atan_table.restype = C.c_int
+    L.ref_fast_atan_table.argtypes = [C.c_void_p, C.c_int]
+    n = L.ref_fast_atan_table(buf.ctypes.data, len(buf))
+    return buf[:n].copy()
+
+
+def fast_atan2f(y, x):
+    return float(lib().ref_fast_atan2f(float(y), float(x)))
+
+
 def r8b_dump(src, dst, kind):
     """Return the stage list of the r8brain chain for (src, dst); kind 0 = IF (24-bit spec),
     1 = audio (default spec)."""

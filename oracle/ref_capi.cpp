@@ -426,6 +426,15 @@ int ref_filter_table(const char *name, double *out, int cap) {
 
 float ref_fast_atan2f(float y, float x) { return Utility::fast_atan2f(y, x); }
 
+// The 257-entry table behind fast_atan2f (include/Utility.h:165-217).
+int ref_fast_atan_table(float *out, int cap) {
+  const int n = (int)(sizeof(Utility::fast_atan_table) / sizeof(float));
+  for (int i = 0; i < n && i < cap; i++) {
+    out[i] = Utility::fast_atan_table[i];
+  }
+  return n;
+}
+
 // ---- CPU baseline: nthreads independent chains, each consuming `blocks` blocks of
 // `blklen` samples read cyclically from iq[0..n_iq). Returns wall seconds (all threads).
 // mode 0 = FM (stereo, deemph 50, given mpf stages), 1 = AM default filter.
