@@ -42,6 +42,8 @@ struct fmr_fm {
   double *d_pilotcut = nullptr;
   float *d_atan = nullptr;
   MpfDev mpf;
+  Prof prof;
+  int p_hist = -1, p_fmf = -1, p_core = -1, p_agc = -1, p_mpf = -1, p_core2 = -1, p_pcut = -1, p_tail = -1;
   FmCoreParams core;
   FmTailParams tail;
 
@@ -202,6 +204,22 @@ static fmr_status fm_build(fmr_fm *h) {
   T.n_channels = C;
 
   h->audio_cap = (size_t)(max48 * (cfg.stereo ? 2 : 1));
+  // profiling stage registry (order = pipeline order)
+  h->ifres.prof = &h->prof;
+  h->ifres.p_hb = h->prof.add("if_halfband_cascade");
+  h->ifres.p_bc = h->prof.add("if_lowpass");
+  h->ifres.p_fi = h->prof.add("if_polyphase");
+  h->p_hist = h->prof.add("save_hist");
+  h->p_fmf = h->prof.add("fm_if_filter");
+  h->p_core = h->prof.add("fm_core_384k");
+  h->p_agc = h->prof.add("fm_agc");
+  h->p_mpf = h->prof.add("fm_multipath");
+  h->p_core2 = h->prof.add("fm_core_384k_post");
+  h->aures.prof = &h->prof;
+  h->aures.p_hb = h->prof.add("audio_halfband_cascade");
+  h->aures.p_bc = h->prof.add("audio_lowpass");
+  h->p_pcut = h->prof.add("pilot_cut_fir");
+  h->p_tail = h->prof.add("dcblock_matrix");
   return FMR_OK;
 }
 
@@ -234,6 +252,7 @@ extern "C" void fmr_fm_destroy(fmr_fm *h) {
   cudaDeviceSynchronize();
   h->mem.release();
   h->slots.release();
+  h->prof.release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -302,6 +321,8 @@ extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t
   h->slots.commit(slot, st);
 
   int launches = 0;
+  Prof &pf = h->prof;
+  pf.reset();
   // ---- front end: Fs/4 shift + IF resampler -> r_if[t0, t1)
   InSrc<float2> src;
   src.lin = reinterpret_cast<const float2 *>(d_iq);
@@ -320,13 +341,17 @@ extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t
     HbTaps<float> t;
     memset(&t, 0, sizeof(t));
     dim3 grid((unsigned)((total_in + kHbTile - 1) / kHbTile), C);
+    pf.begin(h->ifres.p_hb, st);
     k_hb_cascade<float, 0, true><<<grid, kHbThreads, Resampler<float>::hb_smem(t, 0), st>>>(
         src, h->r_if, t, t0, (int)total_in, h->cfg.fs4_shift);
+    pf.end(h->ifres.p_hb, st);
     launches++;
   }
   if (h->ifc && total_in > 0) {
+    pf.begin(h->p_hist, st);
     k_save_hist<float2><<<C, 128, 0, st>>>(src.lin, iq_stride, (int64_t)total_in, h->hist[h->hist_cur],
                                            h->hist[h->hist_cur ^ 1]);
+    pf.end(h->p_hist, st);
     h->hist_cur ^= 1;
     launches++;
   }
@@ -334,22 +359,32 @@ extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t
     // ---- optional IF filter (FmDecode.cpp:98-102)
     if (h->cfg.fmfilter) {
       dim3 grid((n384 + 127) / 128, C);
+      pf.begin(h->p_fmf, st);
       k_fir_quirk<float><<<grid, 128, 0, st>>>(h->r_if, h->r_iff, h->d_fmfilter, h->fmfilter_taps, t0, (int)n384,
                                                h->d_e384, (int)n_blocks);
+      pf.end(h->p_fmf, st);
       launches++;
     }
     // ---- 384 kHz serial core
     dim3 cgrid((C + 31) / 32);
     if (h->cfg.multipath_stages == 0) {
+      pf.begin(h->p_core, st);
       k_fm_core<0><<<cgrid, 32, 0, st>>>(h->r_if, h->r_iff, h->r_iff, h->r_384, h->d_state, h->d_flags, h->d_pps,
                                          h->d_e384, (int)n_blocks, t0, h->core, h->d_atan);
+      pf.end(h->p_core, st);
       launches++;
     } else {
+      pf.begin(h->p_agc, st);
       k_fm_core<1><<<cgrid, 32, 0, st>>>(h->r_if, h->r_iff, h->r_agc, h->r_384, h->d_state, h->d_flags, h->d_pps,
                                          h->d_e384, (int)n_blocks, t0, h->core, h->d_atan);
+      pf.end(h->p_agc, st);
+      pf.begin(h->p_mpf, st);
       h->mpf.run(h->r_agc, h->r_mpf, h->d_state, h->d_e384, (int)n_blocks, t0, st);
+      pf.end(h->p_mpf, st);
+      pf.begin(h->p_core2, st);
       k_fm_core<2><<<cgrid, 32, 0, st>>>(h->r_if, h->r_mpf, h->r_mpf, h->r_384, h->d_state, h->d_flags, h->d_pps,
                                          h->d_e384, (int)n_blocks, t0, h->core, h->d_atan);
+      pf.end(h->p_core2, st);
       launches += 3;
     }
     // ---- audio resamplers (mono and L-R in lock step, FmDecode.cpp:172-183)
@@ -363,10 +398,14 @@ extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t
     if (n48 > 0) {
       // ---- pilot-cut FIR (FmDecode.cpp:190,196) then DC block + matrix
       dim3 grid((n48 + 127) / 128, C);
+      pf.begin(h->p_pcut, st);
       k_fir_quirk<double><<<grid, 128, 0, st>>>(h->r_48a, h->r_48b, h->d_pilotcut, 127, j0, (int)n48, h->d_e48,
                                                 (int)n_blocks);
+      pf.end(h->p_pcut, st);
+      pf.begin(h->p_tail, st);
       k_fm_tail<<<cgrid, 32, 0, st>>>(h->r_48b, d_audio, audio_stride, h->d_state, h->d_flags, h->d_e48,
                                       (int)n_blocks, j0, h->tail);
+      pf.end(h->p_tail, st);
       launches += 2;
     }
   }
@@ -496,3 +535,20 @@ extern "C" fmr_status fmr_fm_tap_if(fmr_fm *h, uint32_t channel, float *re_im, s
 }
 
 extern "C" uint32_t fmr_fm_last_launches(fmr_fm *h) { return h ? h->last_launches : 0; }
+
+extern "C" fmr_status fmr_fm_set_profiling(fmr_fm *h, int enable) {
+  if (!h) return fail(FMR_ERR_INVALID, "null handle");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  if (enable) {
+    h->prof.enable();
+  } else {
+    h->prof.release();
+  }
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_fm_stage_times(fmr_fm *h, float *ms, const char **names, uint32_t cap, uint32_t *n) {
+  if (!h || !ms || !names || !n) return fail(FMR_ERR_INVALID, "null argument");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  return h->prof.read(ms, names, cap, n);
+}

@@ -100,6 +100,63 @@ struct PinnedSlots {
   }
 };
 
+// Optional per-stage timing with CUDA events on the launching stream.
+struct Prof {
+  static const int kMax = 16;
+  bool on = false;
+  const char *names[kMax] = {nullptr};
+  cudaEvent_t a[kMax] = {nullptr}, b[kMax] = {nullptr};
+  bool ran[kMax] = {false};
+  int n = 0;
+  int add(const char *name) {
+    names[n] = name;
+    return n++;
+  }
+  void enable() {
+    if (on) return;
+    for (int i = 0; i < n; i++) {
+      cudaEventCreate(&a[i]);
+      cudaEventCreate(&b[i]);
+    }
+    on = true;
+  }
+  void reset() {
+    for (int i = 0; i < n; i++) ran[i] = false;
+  }
+  void begin(int i, cudaStream_t st) {
+    if (on && i >= 0) cudaEventRecord(a[i], st);
+  }
+  void end(int i, cudaStream_t st) {
+    if (on && i >= 0) {
+      cudaEventRecord(b[i], st);
+      ran[i] = true;
+    }
+  }
+  fmr_status read(float *ms, const char **nm, uint32_t cap, uint32_t *cnt) {
+    uint32_t k = 0;
+    for (int i = 0; i < n && k < cap; i++) {
+      if (!on || !ran[i]) continue;
+      float t = 0;
+      if (cudaEventSynchronize(b[i]) != cudaSuccess || cudaEventElapsedTime(&t, a[i], b[i]) != cudaSuccess) {
+        return fail(FMR_ERR_CUDA, "event timing failed");
+      }
+      ms[k] = t;
+      nm[k] = names[i];
+      k++;
+    }
+    *cnt = k;
+    return FMR_OK;
+  }
+  void release() {
+    if (!on) return;
+    for (int i = 0; i < n; i++) {
+      cudaEventDestroy(a[i]);
+      cudaEventDestroy(b[i]);
+    }
+    on = false;
+  }
+};
+
 template <typename S> struct Resampler {
   using V = typename V2<S>::type;
   const ChainDesc *d = nullptr;
@@ -110,6 +167,8 @@ template <typename S> struct Resampler {
   HbTaps<S> hbt;
   int64_t cum_in = 0;
   size_t smem_hb = 0, smem_fir = 0;
+  Prof *prof = nullptr;
+  int p_hb = -1, p_bc = -1, p_fi = -1;
 
   static size_t hb_smem(const HbTaps<S> &t, int nst) {
     size_t total = 0;
@@ -191,6 +250,7 @@ template <typename S> struct Resampler {
     if (d->n_hb > 0 || linear_in) {
       const int n = (int)(h1 - h0);
       if (n > 0) {
+        if (prof) prof->begin(p_hb, st);
         switch (d->n_hb) {
         case 0: linear_in ? launch_hb<0, true>(src, h0, n, fs4, st) : launch_hb<0, false>(src, h0, n, fs4, st); break;
         case 1: linear_in ? launch_hb<1, true>(src, h0, n, fs4, st) : launch_hb<1, false>(src, h0, n, fs4, st); break;
@@ -198,6 +258,7 @@ template <typename S> struct Resampler {
         default: linear_in ? launch_hb<3, true>(src, h0, n, fs4, st) : launch_hb<3, false>(src, h0, n, fs4, st); break;
         }
         (*launches)++;
+        if (prof) prof->end(p_hb, st);
       }
       bc_in = r_hb;
     }
@@ -205,8 +266,10 @@ template <typename S> struct Resampler {
       const int n = (int)(b1 - b0);
       if (n > 0) {
         dim3 grid((n + kFirTile - 1) / kFirTile, C);
+        if (prof) prof->begin(p_bc, st);
         k_fir_long<S><<<grid, kFirThreads, smem_fir, st>>>(bc_in, d->has_fi ? r_bc : out, d_bc, d->bc.klen,
                                                             d->bc.down, b0, n);
+        if (prof) prof->end(p_bc, st);
         (*launches)++;
       }
     }
@@ -214,7 +277,9 @@ template <typename S> struct Resampler {
       const int n = (int)(f1 - f0);
       if (n > 0) {
         dim3 grid((n + 127) / 128, C);
+        if (prof) prof->begin(p_fi, st);
         k_frac_interp<S><<<grid, 128, 0, st>>>(r_bc, out, d_fi, d->fi.instep, d->fi.outstep, d->fi.flen, f0, n);
+        if (prof) prof->end(p_fi, st);
         (*launches)++;
       }
     }

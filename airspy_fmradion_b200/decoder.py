@@ -69,6 +69,17 @@ class _Base:
                                    audio_stride, lens.ctypes.data, stream))
         return lens
 
+    def set_profiling(self, enable=True):
+        check(self._set_profiling(self._h, int(enable)))
+
+    def stage_times(self):
+        """{stage name: ms} of the last process call (needs set_profiling(True))."""
+        ms = (C.c_float * 16)()
+        names = (C.c_char_p * 16)()
+        n = C.c_uint32(0)
+        check(self._stage_times(self._h, ms, names, 16, C.byref(n)))
+        return {names[i].decode(): float(ms[i]) for i in range(n.value)}
+
     def process(self, samples_in):
         """Reference signature: one block in, audio out (FmDecode.h:74 / AmDecode.h:55)."""
         samples_in = np.asarray(samples_in)
@@ -95,6 +106,7 @@ class FmDecoder(_Base):
         L = _capi.lib()
         self._destroy, self._query = L.fmr_fm_destroy, L.fmr_fm_query_output
         self._process_host, self._process_device = L.fmr_fm_process_host, L.fmr_fm_process_device
+        self._set_profiling, self._stage_times = L.fmr_fm_set_profiling, L.fmr_fm_stage_times
         self.n_channels = int(n_channels)
         self.stereo = bool(stereo)
         self.multipath_stages = int(multipath_stages)
@@ -170,6 +182,7 @@ class AmDecoder(_Base):
         L = _capi.lib()
         self._destroy, self._query = L.fmr_am_destroy, L.fmr_am_query_output
         self._process_host, self._process_device = L.fmr_am_process_host, L.fmr_am_process_device
+        self._set_profiling, self._stage_times = L.fmr_am_set_profiling, L.fmr_am_stage_times
         self.n_channels = int(n_channels)
         cfg = _capi.AmConfig(float(input_rate), int(fs4_shift), int(amfilter), int(mode), int(n_channels),
                              int(max_samples_per_call), int(max_blocks_per_call), int(device))

@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the demodulation hot path on B200 (and of the reference on CPU).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+    torchrun ... bench.py --gpus N ...                       # one rank per GPU
+
+A "step" is one pass of the hot path over one batch of synthetic IQ: every channel of the
+handle consumes `--blocks` source blocks of 2048 samples (FileSource's default block,
+FileSource.h:34). Streams are continuous across steps (filter/PLL/AGC state carries over).
+Metric = IQ Msamples/s consumed, summed over channels and GPUs (BASELINE.json).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (input_rate, stereo, multipath_stages, mode)
+    "cfg2_fm_stereo_10Msps": (1.0e7, True, 0, "fm"),
+    "cfg3_fm_stereo_10Msps_E200": (1.0e7, True, 200, "fm"),
+    "cfg4_fm_stereo_1Msps": (1.0e6, True, 0, "fm"),
+    "cfg5_am_384ksps": (384000.0, False, 0, "am"),
+}
+BLK = 2048
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_iq_device(torch, dev, fs, C, T, mode, chunk=32):
+    """Synthetic IQ on the device, [C, T] complex64 (SURVEY.md §8(d) signal model; torch RNG)."""
+    out = torch.empty((C, T), dtype=torch.complex64, device=dev)
+    t = torch.arange(T, dtype=torch.float64, device=dev) / fs
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    for c0 in range(0, C, chunk):
+        c1 = min(C, c0 + chunk)
+        ch = torch.arange(c0, c1, dtype=torch.float64, device=dev)[:, None]
+        if mode == "fm":
+            L = torch.sin(2 * np.pi * (1000.0 + 37.0 * ch) * t)
+            R = torch.sin(2 * np.pi * (2500.0 + 53.0 * ch) * t)
+            mpx = 0.45 * (L + R) + 0.45 * (L - R) * torch.sin(2 * np.pi * 38000.0 * t) \
+                + 0.1 * torch.sin(2 * np.pi * 19000.0 * t)
+            del L, R
+            phi = torch.cumsum(2 * np.pi * 75000.0 * mpx / fs, dim=1)
+            del mpx
+            re, im, sigma = 0.5 * torch.cos(phi), 0.5 * torch.sin(phi), 0.01
+            del phi
+        else:
+            re = 0.3 * (1.0 + 0.5 * torch.sin(2 * np.pi * (1000.0 + 11.0 * ch) * t))
+            im, sigma = torch.zeros_like(re), 0.005
+        noise = torch.randn((c1 - c0, T, 2), dtype=torch.float32, device=dev, generator=g) * sigma
+        out[c0:c1] = torch.complex(re.float() + noise[..., 0], im.float() + noise[..., 1])
+        del re, im, noise
+    return out
+
+
+def make_decoder(wl, C, T, nblk, device):
+    from airspy_fmradion_b200 import AmDecoder, FmDecoder
+    fs, stereo, mpf, mode = WORKLOADS[wl]
+    if mode == "fm":
+        return FmDecoder(stereo=stereo, multipath_stages=mpf, input_rate=fs, n_channels=C,
+                         max_samples_per_call=T, max_blocks_per_call=nblk, device=device)
+    return AmDecoder(input_rate=fs, n_channels=C, max_samples_per_call=T, max_blocks_per_call=nblk, device=device)
+
+
+def cpu_reference(wl, seconds, threads):
+    """Reference CPU path (oracle/_ref = the reference's own classes) on the host cores."""
+    from oracle import ref, siggen
+    fs, stereo, mpf, mode = WORKLOADS[wl]
+    if not ref.available():
+        return None
+    n_iq = BLK * 2048
+    iq = siggen.fm_stereo_iq(fs, n_iq, 0) if mode == "fm" else siggen.am_iq(fs, n_iq, 0)
+    m = 0 if mode == "fm" else 1
+    # calibrate on one thread, then size the sample for ~`seconds` of wall time per thread
+    probe = 400 if mpf == 0 else 100
+    t = ref.bench(m, fs, stereo, mpf, 1, probe, BLK, iq)
+    rate1 = probe * BLK / t
+    blocks = max(200, int(rate1 * seconds / BLK))
+    t1 = ref.bench(m, fs, stereo, mpf, 1, blocks, BLK, iq)
+    one = blocks * BLK / t1 / 1e6
+    tn = ref.bench(m, fs, stereo, mpf, threads, blocks, BLK, iq)
+    allc = threads * blocks * BLK / tn / 1e6
+    return {"value": allc, "unit": "Msamples/s", "cores": threads, "kind": "reference",
+            "one_core_value": one,
+            "sample": "%d threads x %d blocks of %d IQ samples (%s), reference classes compiled from "
+                      "/root/reference with a generic-C VOLK shim, unthrottled" % (threads, blocks, BLK, wl),
+            "seconds": tn}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2_fm_stereo_10Msps", choices=sorted(WORKLOADS))
+    ap.add_argument("--channels", type=int, default=0, help="channels per GPU (default per workload)")
+    ap.add_argument("--blocks", type=int, default=128, help="source blocks of 2048 samples per channel per step")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=6.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = args.workload
+    fs, stereo, mpf, mode = WORKLOADS[wl]
+    metric = "IQ Msamples/s (%s)" % wl
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        vals, secs = [], 0.0
+        res = None
+        for _ in range(max(1, min(args.steps, 3))):
+            res = cpu_reference(wl, max(1.0, args.cpu_seconds / 2), threads)
+            if res is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfmref.so was not built"}))
+                return 0
+            vals.append(res["value"])
+            secs += res["seconds"]
+        v = float(np.median(vals))
+        res["value"] = v
+        line = {"impl": "reference", "metric": metric, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs / len(vals),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32",
+                "data": "synthetic", "config": {"workload": wl, "block": BLK},
+                "cpu_baseline": res,
+                "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev_index = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev_index)
+    dev = torch.device("cuda", dev_index)
+
+    nblk = args.blocks
+    T = nblk * BLK
+    C = args.channels or {"fm": 1024 if fs >= 5e6 else 2048, "am": 4096}[mode]
+    if mpf:
+        C = args.channels or 512
+    dec = make_decoder(wl, C, T, nblk, dev_index)
+    iq = gen_iq_device(torch, dev, fs, C, T, mode)
+    width = 2 if (mode == "fm" and stereo) else 1
+    audio_cap = int(T * 48000.0 / fs) * width + 64
+    audio = torch.zeros((C, audio_cap), dtype=torch.float64, device=dev)
+    bl = [BLK] * nblk
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+
+    def step():
+        return dec.process_device(iq.data_ptr(), T, bl, audio.data_ptr(), audio_cap, sh)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(dev_index)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        lens = step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = dec.last_launches() * args.steps
+    if dist is not None:
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    total_samples = world * C * T * args.steps
+    value = total_samples / (ms * 1e-3) / 1e6
+
+    # per-stage device times of one step (CUDA events inside the library, same stream)
+    dec.set_profiling(True)
+    stage = {}
+    reps = 3
+    for _ in range(reps):
+        step()
+        torch.cuda.synchronize()
+        for k, v in dec.stage_times().items():
+            stage[k] = stage.get(k, 0.0) + v / reps
+    dec.set_profiling(False)
+    dom = max(stage, key=stage.get) if stage else None
+    peak, peak_src = peaks()
+    alg_bytes = C * T * 8 + C * int(lens.sum()) * 8  # IQ read + audio written, per launch/step
+    roof = None
+    if dom:
+        ach = alg_bytes / (stage[dom] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": stage[dom],
+                "whole_step_frac": (alg_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
+                "stage_ms": {k: round(v, 4) for k, v in stage.items()}}
+
+    # end to end through the host-buffer entry point (pinned host memory, H2D + D2H inside)
+    e2e = None
+    if not args.no_e2e:
+        Ce = min(C, 256)
+        dec2 = make_decoder(wl, Ce, T, nblk, dev_index)
+        h_iq = torch.empty((Ce, T), dtype=torch.complex64, pin_memory=True)
+        h_iq.copy_(iq[:Ce])
+        h_np = h_iq.numpy()
+        for _ in range(3):
+            a, l = dec2.process_blocks(h_np, bl)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            a, l = dec2.process_blocks(h_np, bl)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": world * Ce * T * args.e2e_steps / dt / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": Ce * T * 8, "d2h_bytes_per_step": int(a.shape[1]) * 8 * Ce,
+               "channels": Ce, "note": "fmr_fm_process_host: pinned host IQ -> device -> audio back to host"}
+        dec2.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cpu = cpu_reference(wl, args.cpu_seconds, os.cpu_count() or 1)
+        except Exception as ex:  # the bench line must still print
+            cpu = {"error": str(ex)}
+
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (IF) / f64 (PLL, audio)",
+                "data": "synthetic",
+                "config": {"workload": wl, "channels_per_gpu": C, "samples_per_channel_per_step": T,
+                           "block": BLK, "blocks_per_step": nblk, "input_bytes_per_step": C * T * 8,
+                           "l2": "input per step (%.0f MB) exceeds the 126 MB L2" % (C * T * 8 / 1e6),
+                           "parallelism": "channels sharded %d per GPU, no data-path collective" % C},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

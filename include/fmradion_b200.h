@@ -136,6 +136,10 @@ fmr_status fmr_fm_tap_if(fmr_fm *h, uint32_t channel, float *re_im, size_t cap_c
                          uint64_t *n_complex);
 /* Kernel launches issued by the last process call (for bench accounting). */
 uint32_t fmr_fm_last_launches(fmr_fm *h);
+/* Per-stage device timing (CUDA events on the launching stream). Enable, run a process
+ * call, synchronise, then read: ms[i] is the duration of stage names[i] in the last call. */
+fmr_status fmr_fm_set_profiling(fmr_fm *h, int enable);
+fmr_status fmr_fm_stage_times(fmr_fm *h, float *ms, const char **names, uint32_t cap, uint32_t *n);
 
 /* ------------------------------------------------------------------------- AM ------- */
 
@@ -173,6 +177,8 @@ fmr_status fmr_am_query_output(fmr_am *h, const uint32_t *block_len, uint32_t n_
                                uint64_t *audio_doubles_total, uint32_t *audio_len);
 fmr_status fmr_am_stats(fmr_am *h, uint32_t channel, fmr_am_stats_t *out);
 uint32_t fmr_am_last_launches(fmr_am *h);
+fmr_status fmr_am_set_profiling(fmr_am *h, int enable);
+fmr_status fmr_am_stage_times(fmr_am *h, float *ms, const char **names, uint32_t cap, uint32_t *n);
 
 #ifdef __cplusplus
 }

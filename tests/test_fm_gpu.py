@@ -106,3 +106,35 @@ def test_fmfilter_and_pilot_shift_384k():
         d = audio[0] - ref_audio
         print(kw, "max %.3e rms %.3e" % (np.abs(d).max(), np.sqrt(np.mean(d * d))))
         assert np.abs(d).max() <= TOL_MAX and np.sqrt(np.mean(d * d)) <= TOL_RMS
+
+
+def test_cfg3_multipath_E200():
+    """10 Msps stereo with a static 20 us echo and -E 200 (801-tap NLMS/CMA). Tolerance for the
+    adaptive path: max 1e-4, rms 2e-5, coefficient vector relative L2 <= 1e-3."""
+    from airspy_fmradion_b200 import FmDecoder
+    fs, blk, nblk = 1.0e7, 2048, 1500
+    echo = (200, 0.3 * np.exp(1j * 0.7))
+    iq = siggen.fm_stereo_iq(fs, blk * nblk, 0, echo=echo)[None, :]
+    dec = FmDecoder(stereo=True, multipath_stages=200, input_rate=fs, n_channels=1, max_samples_per_call=blk * 500)
+    audio, lens = _run_gpu(dec, iq, blk, 500)
+    c = None
+    from oracle import ref
+    if ref.available():
+        c = ref.RefChain("fm", fs, stereo=True, mpf_stages=200)
+        ref_audio, ref_lens, _ = c.run(iq[0], blk)
+        ref_coef = c.mpf_coeffs()
+        ref_err = c.stats().mpf_error
+    else:
+        ref_audio, ref_lens, _, st = oracle_fm_run(iq[0], fs, blk, stereo=True, mpf_stages=200, taps=("if",))
+        ref_coef, ref_err = st.mpf_coeffs, st.mpf_error
+    assert list(lens) == list(ref_lens)
+    d = audio[0] - ref_audio
+    coef = dec.get_multipath_coefficients(0)
+    rel = np.linalg.norm(coef - ref_coef) / np.linalg.norm(ref_coef)
+    print("cfg3 max %.3e rms %.3e coef rel L2 %.3e  err gpu %.4e ref %.4e  |coef-delta| %.3f" % (
+        np.abs(d).max(), np.sqrt(np.mean(d * d)), rel, dec.get_multipath_error(0), ref_err,
+        np.linalg.norm(ref_coef) - 1))
+    assert np.abs(d).max() <= 1e-4 and np.sqrt(np.mean(d * d)) <= 2e-5
+    assert rel <= 1e-3
+    # the filter really adapted (it is not the identity any more)
+    assert np.abs(ref_coef).sum() > 1.05
