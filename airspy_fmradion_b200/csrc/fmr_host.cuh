@@ -13,6 +13,10 @@
 #include <vector>
 
 #include "../../include/fmradion_b200.h"
+#include <cmath>
+#include <complex>
+
+#include "fmr_fft.cuh"
 #include "fmr_kernels.cuh"
 #include "fmr_tables.h"
 
@@ -157,6 +161,32 @@ struct Prof {
   }
 };
 
+// Host-side double-precision radix-2 FFT (only used once per handle to build the filter
+// spectrum for k_fir_fft).
+inline void host_fft(std::vector<std::complex<double>> &a) {
+  const size_t n = a.size();
+  for (size_t i = 1, j = 0; i < n; i++) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(a[i], a[j]);
+  }
+  for (size_t len = 2; len <= n; len <<= 1) {
+    const double ang = -2.0 * M_PI / (double)len;
+    for (size_t i = 0; i < n; i += len) {
+      for (size_t k = 0; k < len / 2; k++) {
+        const std::complex<double> w(std::cos(ang * (double)k), std::sin(ang * (double)k));
+        const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * w;
+        a[i + k] = u + v;
+        a[i + k + len / 2] = u - v;
+      }
+    }
+  }
+}
+
+// Outputs per launch below which the direct-form kernel is used instead of the FFT one.
+constexpr int kFftMinOut = 3000;
+
 template <typename S> struct Resampler {
   using V = typename V2<S>::type;
   const ChainDesc *d = nullptr;
@@ -169,6 +199,8 @@ template <typename S> struct Resampler {
   size_t smem_hb = 0, smem_fir = 0;
   Prof *prof = nullptr;
   int p_hb = -1, p_bc = -1, p_fi = -1;
+  float2 *d_H = nullptr; // filter spectrum for k_fir_fft (float chains only)
+  bool use_fft = false;
 
   static size_t hb_smem(const HbTaps<S> &t, int nst) {
     size_t total = 0;
@@ -216,6 +248,19 @@ template <typename S> struct Resampler {
       FMR_CUDA(mem.alloc(&d_bc, h.size(), false));
       FMR_CUDA(cudaMemcpy(d_bc, h.data(), h.size() * sizeof(S), cudaMemcpyHostToDevice));
     }
+    if (sizeof(S) == sizeof(float) && d->bc.klen < kFftN / 2) {
+      std::vector<std::complex<double>> hc(kFftN, std::complex<double>(0.0, 0.0));
+      for (int i = 0; i < d->bc.klen; i++) hc[i] = d->bc.taps[i];
+      host_fft(hc);
+      std::vector<float2> hf(kFftN);
+      for (int i = 0; i < kFftN; i++) {
+        hf[i] = make_float2((float)(hc[i].real() / kFftN), (float)(hc[i].imag() / kFftN));
+      }
+      FMR_CUDA(mem.alloc(&d_H, (size_t)kFftN, false));
+      FMR_CUDA(cudaMemcpy(d_H, hf.data(), sizeof(float2) * kFftN, cudaMemcpyHostToDevice));
+      FMR_CUDA(cudaFuncSetAttribute(k_fir_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemBytes));
+      use_fft = true;
+    }
     smem_fir = ((size_t)(kFirTile - 1) * d->bc.down + d->bc.klen) * sizeof(V) + (size_t)d->bc.klen * sizeof(S);
     FMR_CUDA(cudaFuncSetAttribute(k_fir_long<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fir));
     if (d->has_fi) {
@@ -238,6 +283,13 @@ template <typename S> struct Resampler {
     dim3 grid((n_out + kHbTile - 1) / kHbTile, C);
     k_hb_cascade<S, NST, LIN><<<grid, kHbThreads, smem_hb, st>>>(src, r_hb, hbt, o0, n_out, fs4);
   }
+
+  void launch_fft(Ring<float2> in, Ring<float2> o, int64_t q0, int n, int64_t avail, cudaStream_t st) {
+    const int lq = (kFftN - d->bc.klen + 1) / d->bc.down;
+    dim3 grid((n + lq - 1) / lq, C);
+    k_fir_fft<<<grid, kFftThreads, kFftSmemBytes, st>>>(in, o, d_H, d->bc.klen, d->bc.down, q0, n, avail, lq);
+  }
+  void launch_fft(Ring<double2>, Ring<double2>, int64_t, int, int64_t, cudaStream_t) {}
 
   // Consume n_new more input samples; produce the reference's output index range into `out`.
   fmr_status run(InSrc<V> src, int64_t n_new, Ring<V> out, int fs4, cudaStream_t st, int64_t *o0,
@@ -265,10 +317,14 @@ template <typename S> struct Resampler {
     {
       const int n = (int)(b1 - b0);
       if (n > 0) {
-        dim3 grid((n + kFirTile - 1) / kFirTile, C);
         if (prof) prof->begin(p_bc, st);
-        k_fir_long<S><<<grid, kFirThreads, smem_fir, st>>>(bc_in, d->has_fi ? r_bc : out, d_bc, d->bc.klen,
-                                                            d->bc.down, b0, n);
+        if (use_fft && n >= kFftMinOut) {
+          launch_fft(bc_in, d->has_fi ? r_bc : out, b0, n, h1, st);
+        } else {
+          dim3 grid((n + kFirTile - 1) / kFirTile, C);
+          k_fir_long<S><<<grid, kFirThreads, smem_fir, st>>>(bc_in, d->has_fi ? r_bc : out, d_bc, d->bc.klen,
+                                                              d->bc.down, b0, n);
+        }
         if (prof) prof->end(p_bc, st);
         (*launches)++;
       }

@@ -136,13 +136,14 @@ def cpu_reference(wl, seconds, threads):
     n_iq = BLK * 2048
     iq = siggen.fm_stereo_iq(fs, n_iq, 0) if mode == "fm" else siggen.am_iq(fs, n_iq, 0)
     m = 0 if mode == "fm" else 1
-    # calibrate on one thread, then size the sample for ~`seconds` of wall time per thread
+    # calibrate (1 thread and all threads), then size both samples for ~`seconds` of wall time
     probe = 400 if mpf == 0 else 100
     t = ref.bench(m, fs, stereo, mpf, 1, probe, BLK, iq)
-    rate1 = probe * BLK / t
-    blocks = max(200, int(rate1 * seconds / BLK))
-    t1 = ref.bench(m, fs, stereo, mpf, 1, blocks, BLK, iq)
-    one = blocks * BLK / t1 / 1e6
+    blocks1 = max(200, int(probe / t * seconds / 2))
+    t1 = ref.bench(m, fs, stereo, mpf, 1, blocks1, BLK, iq)
+    one = blocks1 * BLK / t1 / 1e6
+    t = ref.bench(m, fs, stereo, mpf, threads, probe, BLK, iq)
+    blocks = max(200, int(probe / t * seconds))
     tn = ref.bench(m, fs, stereo, mpf, threads, blocks, BLK, iq)
     allc = threads * blocks * BLK / tn / 1e6
     return {"value": allc, "unit": "Msamples/s", "cores": threads, "kind": "reference",
