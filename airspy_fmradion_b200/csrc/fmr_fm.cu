@@ -30,6 +30,8 @@ struct fmr_fm {
   Ring<float2> r_iff{nullptr, 0};  // after the optional IF filter
   Ring<float2> r_agc{nullptr, 0};  // after AGC (multipath path only)
   Ring<float2> r_mpf{nullptr, 0};  // after multipath filter
+  Ring<float> r_mpx{nullptr, 0};   // discriminator output
+  float *d_stats = nullptr;        // per (channel, block): if_rms, baseband mean, baseband rms
   Ring<double2> r_384{nullptr, 0}; // (mono, L-R) after deemphasis
   Ring<double2> r_48a{nullptr, 0}; // audio resampler output
   Ring<double2> r_48b{nullptr, 0}; // after pilot-cut FIR
@@ -126,9 +128,12 @@ static fmr_status fm_build(fmr_fm *h) {
     h->r_iff.cap = h->r_if.cap;
     FMR_CUDA(h->mem.alloc(&h->r_iff.base, (size_t)C * h->r_iff.cap));
   }
+  h->r_agc.cap = h->r_if.cap;
+  FMR_CUDA(h->mem.alloc(&h->r_agc.base, (size_t)C * h->r_agc.cap));
+  h->r_mpx.cap = h->r_if.cap;
+  FMR_CUDA(h->mem.alloc(&h->r_mpx.base, (size_t)C * h->r_mpx.cap));
+  FMR_CUDA(h->mem.alloc(&h->d_stats, (size_t)C * max_blocks * 3));
   if (cfg.multipath_stages > 0) {
-    h->r_agc.cap = h->r_if.cap;
-    FMR_CUDA(h->mem.alloc(&h->r_agc.base, (size_t)C * h->r_agc.cap));
     h->r_mpf.cap = h->r_if.cap;
     FMR_CUDA(h->mem.alloc(&h->r_mpf.base, (size_t)C * h->r_mpf.cap));
     fmr_status s = h->mpf.init(cfg.multipath_stages, C, h->mem);
@@ -211,10 +216,10 @@ static fmr_status fm_build(fmr_fm *h) {
   h->ifres.p_fi = h->prof.add("if_polyphase");
   h->p_hist = h->prof.add("save_hist");
   h->p_fmf = h->prof.add("fm_if_filter");
-  h->p_core = h->prof.add("fm_core_384k");
   h->p_agc = h->prof.add("fm_agc");
   h->p_mpf = h->prof.add("fm_multipath");
-  h->p_core2 = h->prof.add("fm_core_384k_post");
+  h->p_core = h->prof.add("fm_discriminator_stats");
+  h->p_core2 = h->prof.add("fm_pll_stereo_deemph");
   h->aures.prof = &h->prof;
   h->aures.p_hb = h->prof.add("audio_halfband_cascade");
   h->aures.p_bc = h->prof.add("audio_lowpass");
@@ -365,28 +370,33 @@ extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t
       pf.end(h->p_fmf, st);
       launches++;
     }
-    // ---- 384 kHz serial core
+    // ---- 384 kHz core: AGC (serial) -> [multipath] -> discriminator + statistics (parallel) -> PLL (serial)
     dim3 cgrid((C + 31) / 32);
-    if (h->cfg.multipath_stages == 0) {
-      pf.begin(h->p_core, st);
-      k_fm_core<0><<<cgrid, 32, 0, st>>>(h->r_if, h->r_iff, h->r_iff, h->r_384, h->d_state, h->d_flags, h->d_pps,
-                                         h->d_e384, (int)n_blocks, t0, h->core, h->d_atan);
-      pf.end(h->p_core, st);
-      launches++;
-    } else {
-      pf.begin(h->p_agc, st);
-      k_fm_core<1><<<cgrid, 32, 0, st>>>(h->r_if, h->r_iff, h->r_agc, h->r_384, h->d_state, h->d_flags, h->d_pps,
-                                         h->d_e384, (int)n_blocks, t0, h->core, h->d_atan);
-      pf.end(h->p_agc, st);
+    pf.begin(h->p_agc, st);
+    k_fm_agc<<<cgrid, 32, 0, st>>>(h->r_iff, h->r_agc, h->d_state, (int)n384, t0, h->core);
+    pf.end(h->p_agc, st);
+    launches++;
+    Ring<float2> disc_in = h->r_agc;
+    if (h->cfg.multipath_stages > 0) {
       pf.begin(h->p_mpf, st);
       h->mpf.run(h->r_agc, h->r_mpf, h->d_state, h->d_e384, (int)n_blocks, t0, st);
       pf.end(h->p_mpf, st);
-      pf.begin(h->p_core2, st);
-      k_fm_core<2><<<cgrid, 32, 0, st>>>(h->r_if, h->r_mpf, h->r_mpf, h->r_384, h->d_state, h->d_flags, h->d_pps,
-                                         h->d_e384, (int)n_blocks, t0, h->core, h->d_atan);
-      pf.end(h->p_core2, st);
-      launches += 3;
+      launches++;
+      disc_in = h->r_mpf;
     }
+    pf.begin(h->p_core, st);
+    {
+      dim3 g((n384 + 255) / 256, C);
+      k_fm_disc<<<g, 256, 0, st>>>(disc_in, h->r_mpx, (int)n384, t0, h->core);
+      dim3 g2((n_blocks + 3) / 4, C);
+      k_fm_call_stats<<<g2, 128, 0, st>>>(h->r_if, h->r_mpx, h->d_stats, h->d_e384, (int)n_blocks, t0);
+    }
+    pf.end(h->p_core, st);
+    pf.begin(h->p_core2, st);
+    k_fm_pll<<<cgrid, 32, 0, st>>>(h->r_mpx, h->r_384, h->d_state, h->d_flags, h->d_pps, h->d_stats, h->d_e384,
+                                   (int)n_blocks, t0, h->core, h->d_atan);
+    pf.end(h->p_core2, st);
+    launches += 3;
     // ---- audio resamplers (mono and L-R in lock step, FmDecode.cpp:172-183)
     InSrc<double2> asrc;
     memset(&asrc, 0, sizeof(asrc));

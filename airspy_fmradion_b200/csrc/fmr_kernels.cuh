@@ -420,19 +420,126 @@ struct FmCoreParams {
   int n_channels;
 };
 
-// The serial 384 kHz core, one lane per channel (reference: FmDecoder::process
-// FmDecode.cpp:85-183 up to the audio resamplers). PHASE selects what runs:
-//   0 = everything (no multipath filter); 1 = IF RMS + AGC only (writes IQ to `iq_out`);
-//   2 = discriminator onwards (reads IQ from `iq_in` = multipath filter output).
-template <int PHASE>
-__global__ void k_fm_core(Ring<float2> if_raw, Ring<float2> iq_in, Ring<float2> iq_out, Ring<double2> out384,
-                          FmChanState *__restrict__ st, uint8_t *__restrict__ flags,
-                          PpsEventDev *__restrict__ pps, const uint32_t *__restrict__ call_end, int n_calls,
-                          int64_t t0, FmCoreParams P, const float *__restrict__ atan_tbl) {
+// The 384 kHz core (reference: FmDecoder::process FmDecode.cpp:85-183 up to the audio
+// resamplers) is split by data dependence into three launches:
+//   k_fm_agc  — IfSimpleAgc, a float recurrence of a handful of instructions per sample,
+//               one lane per channel;
+//   k_fm_disc — everything between the recurrences that is parallel in time: phase
+//               discriminator, and the per-call statistics (IF RMS, baseband mean/RMS);
+//   k_fm_pll  — PilotPhaseLock + L-R mix + both deemphasis filters, one lane per channel.
+// With the multipath filter enabled k_mpf runs between k_fm_agc and k_fm_disc.
+constexpr int kCoreChunk = 8;
+
+static __global__ void k_fm_agc(Ring<float2> iq_in, Ring<float2> iq_out, FmChanState *__restrict__ st, int n_total,
+                         int64_t t0, FmCoreParams P) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.n_channels) return;
+  float g = st[c].agc_gain;
+  for (int i0 = 0; i0 < n_total; i0 += kCoreChunk) {
+    float2 xin[kCoreChunk];
+#pragma unroll
+    for (int u = 0; u < kCoreChunk; u++) {
+      xin[u] = (i0 + u < n_total) ? iq_in.ld(c, t0 + i0 + u) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kCoreChunk; u++) {
+      if (i0 + u >= n_total) break;
+      // IfSimpleAgc::process (IfSimpleAgc.cpp:37-57)
+      float2 x2;
+      x2.x = xin[u].x * g;
+      x2.y = xin[u].y * g;
+      const float nrm = x2.x * x2.x + x2.y * x2.y;
+      const float z = (float)(1.0 + ((double)P.agc_rate * (1.0 - (double)nrm)));
+      g *= z;
+      if (!isfinite(g)) {
+        g = 1.0f;
+      } else if (g > P.agc_max) {
+        g = P.agc_max;
+      }
+      iq_out.st(c, t0 + i0 + u, x2);
+    }
+  }
+  st[c].agc_gain = g;
+}
+
+// One thread per 384 kHz sample: PhaseDiscriminator::process (PhaseDiscriminator.cpp:33-46).
+// The previous sample's phase is recomputed from the ring (bit-identical to the value the
+// serial loop would have carried); before the very first sample m_save_value is 0.
+static __global__ void k_fm_disc(Ring<float2> iq, Ring<float> mpx, int n_total, int64_t t0, FmCoreParams P) {
+  const uint32_t c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  const int64_t t = t0 + i;
+  const float2 x = iq.base[(size_t)c * iq.cap + ((uint32_t)t & (iq.cap - 1))];
+  const float ph = atan2f(x.y, x.x) * P.disc_inv_norm;
+  float prev = 0.0f;
+  if (t > 0) {
+    const float2 xp = iq.base[(size_t)c * iq.cap + ((uint32_t)(t - 1) & (iq.cap - 1))];
+    prev = atan2f(xp.y, xp.x) * P.disc_inv_norm;
+  }
+  float d = ph - prev;
+  if (d > P.disc_bound) d -= 2 * P.disc_bound;
+  if (d < -P.disc_bound) d += 2 * P.disc_bound;
+  if (isnan(d)) d = 0.0f;
+  mpx.base[(size_t)c * mpx.cap + ((uint32_t)t & (mpx.cap - 1))] = d;
+}
+
+// One warp per (call, channel): Utility::rms_level_sample on the decoder input
+// (FmDecode.cpp:95, Utility.h:118-132) and Utility::samples_mean_rms on the MPX
+// (FmDecode.cpp:146, Utility.h:135-152). stats[(c*n_calls + b)*3 + {0,1,2}] = if_rms, mean, rms.
+static __global__ void k_fm_call_stats(Ring<float2> if_raw, Ring<float> mpx, float *__restrict__ stats,
+                                const uint32_t *__restrict__ call_end, int n_calls, int64_t t0) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int b = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const uint32_t c = blockIdx.y;
+  if (b >= n_calls) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t beg = b ? call_end[b - 1] : 0u, end = call_end[b];
+  const int n = (int)(end - beg);
+  float sq = 0.f, vs = 0.f, vq = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const int64_t t = t0 + beg + i;
+    const float2 x = if_raw.ld(c, t);
+    sq += x.x * x.x + x.y * x.y;
+    const float d = mpx.base[(size_t)c * mpx.cap + ((uint32_t)t & (mpx.cap - 1))];
+    vs += d;
+    vq += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    vs += __shfl_xor_sync(0xffffffffu, vs, o);
+    vq += __shfl_xor_sync(0xffffffffu, vq, o);
+  }
+  if (lane == 0 && n > 0) {
+    float *o = stats + ((size_t)c * n_calls + b) * 3;
+    o[0] = sqrtf(sq / (float)n);
+    o[1] = vs / (float)n;
+    o[2] = sqrtf(vq / (float)n);
+  }
+}
+
+// PilotPhaseLock::process (PilotPhaseLock.cpp:56-171), FmDecoder::demod_stereo
+// (FmDecode.cpp:224-239), both LowPassFilterRC deemphasis filters (FmDecode.cpp:168-170,180),
+// per-call statistics EMA (FmDecode.cpp:147-150) and lock bookkeeping, one lane per channel.
+//
+// The reference evaluates sin/cos of the accumulated phase with libm every sample. Here the
+// pilot phasor (sin, cos) is advanced by a rotation through m_freq each sample — the small
+// correction to the 19 kHz centre frequency is |d| < 5e-4 rad, so sin d, cos d come from
+// three-term series with error < 3e-19 — and re-anchored with an exact sincos(m_phase) at
+// the start of every reference call, so rounding cannot accumulate beyond one call. m_phase
+// itself is accumulated and wrapped exactly as the reference does.
+static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanState *__restrict__ st,
+                         uint8_t *__restrict__ flags, PpsEventDev *__restrict__ pps,
+                         const float *__restrict__ stats, const uint32_t *__restrict__ call_end, int n_calls,
+                         int64_t t0, FmCoreParams P, const float *__restrict__ atan_tbl) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= P.n_channels) return;
   FmChanState s = st[c];
-  if (PHASE != 1) s.n_pps = 0;
+  s.n_pps = 0;
+  const double f0 = (19000.0 / 384000.0) * 2.0 * 3.14159265358979323846;
+  double sf0, cf0;
+  sincos(f0, &sf0, &cf0);
   uint32_t prev_end = 0;
   for (int b = 0; b < n_calls; b++) {
     const uint32_t end = call_end[b];
@@ -440,121 +547,101 @@ __global__ void k_fm_core(Ring<float2> if_raw, Ring<float2> iq_in, Ring<float2> 
     if (n == 0) continue; // main.cpp:933-936: the decoder is not called
     const int64_t tb = t0 + prev_end;
     prev_end = end;
-    if (PHASE != 2) {
-      s.decoder_calls++;
-      // Utility::rms_level_sample (Utility.h:118-132) on the decoder input
-      float sumsq = 0.0f;
-      for (int i = 0; i < n; i++) {
-        const float2 x = if_raw.ld(c, tb + i);
-        sumsq += x.x * x.x + x.y * x.y;
-      }
-      s.if_rms = sqrtf(sumsq / (float)n);
-    }
-    float vsum = 0.0f, vsumsq = 0.0f;
+    s.decoder_calls++;
     const bool was_locked = (s.lock_cnt >= P.lock_delay);
-    for (int i = 0; i < n; i++) {
-      const int64_t t = tb + i;
-      float2 x2;
-      if (PHASE != 2) {
-        // IfSimpleAgc::process (IfSimpleAgc.cpp:37-57)
-        const float2 x = iq_in.ld(c, t);
-        x2.x = x.x * s.agc_gain;
-        x2.y = x.y * s.agc_gain;
-        const float nrm = x2.x * x2.x + x2.y * x2.y;
-        const float z = (float)(1.0 + ((double)P.agc_rate * (1.0 - (double)nrm)));
-        s.agc_gain *= z;
-        if (!isfinite(s.agc_gain)) {
-          s.agc_gain = 1.0f;
-        } else if (s.agc_gain > P.agc_max) {
-          s.agc_gain = P.agc_max;
-        }
-        if (PHASE == 1) {
-          iq_out.st(c, t, x2);
-          continue;
-        }
-      } else {
-        x2 = iq_in.ld(c, t);
+    double last_i = 0.0, last_q = 0.0;
+    double psin = 0.0, pcos = 1.0;
+    if (P.stereo) sincos(s.pll_phase, &psin, &pcos);
+    for (int i0 = 0; i0 < n; i0 += kCoreChunk) {
+      float din[kCoreChunk];
+#pragma unroll
+      for (int u = 0; u < kCoreChunk; u++) {
+        din[u] = (i0 + u < n) ? mpx.base[(size_t)c * mpx.cap + ((uint32_t)(tb + i0 + u) & (mpx.cap - 1))] : 0.f;
       }
-      // PhaseDiscriminator::process (PhaseDiscriminator.cpp:33-46)
-      const float ph = atan2f(x2.y, x2.x) * P.disc_inv_norm;
-      float d = ph - s.disc_prev;
-      if (d > P.disc_bound) d -= 2 * P.disc_bound;
-      if (d < -P.disc_bound) d += 2 * P.disc_bound;
-      s.disc_prev = ph;
-      if (isnan(d)) d = 0.0f;
-      vsum += d;
-      vsumsq += d * d;
-      const double xd = (double)d;
-      double stereo = 0.0;
-      if (P.stereo) {
-        // PilotPhaseLock::process (PilotPhaseLock.cpp:56-171)
-        double psin, pcos;
-        sincos(s.pll_phase, &psin, &pcos);
-        const double tone = P.pilot_shift ? (2 * pcos * pcos - 1) : (2 * psin * pcos);
-        const double pi_in = psin * xd;
-        const double pq_in = pcos * xd;
-        const double i0 = pi_in - (P.bq_a1 * s.bi_x1 + P.bq_a2 * s.bi_x2);
-        const double q0 = pq_in - (P.bq_a1 * s.bq_x1 + P.bq_a2 * s.bq_x2);
-        const double new_i = P.bq_b0 * i0;
-        const double new_q = P.bq_b0 * q0;
-        s.bi_x2 = s.bi_x1;
-        s.bi_x1 = i0;
-        s.bq_x2 = s.bq_x1;
-        s.bq_x1 = q0;
-        const double perr = (double)fast_atan2f_dev((float)new_q, (float)new_i, atan_tbl);
-        s.pilot_level = sqrt(new_i * new_i + new_q * new_q);
-        const double ferr = P.lf_b0 * perr + P.lf_b1 * s.lf_x1;
-        s.lf_x1 = perr;
-        s.freq_err = ferr;
-        s.pll_freq += ferr;
-        s.pll_freq = fmax(P.pll_minfreq, fmin(P.pll_maxfreq, s.pll_freq));
-        s.pll_phase += s.pll_freq;
-        if (s.pll_phase > 2.0 * 3.14159265358979323846) {
-          s.pll_phase -= 2.0 * 3.14159265358979323846;
-          s.pilot_periods++;
-          if (s.pilot_periods == 19000) {
-            s.pilot_periods = 0;
-            if (was_locked) {
-              if (s.n_pps < (uint32_t)kMaxPps) {
-                PpsEventDev ev;
-                ev.pps_index = s.pps_cnt;
-                ev.sample_index = s.sample_cnt + (unsigned long long)i;
-                ev.block_position = (double)i / (double)n;
-                ev.block = (uint32_t)b;
-                ev.pad = 0;
-                pps[(size_t)c * kMaxPps + s.n_pps] = ev;
+#pragma unroll
+      for (int u = 0; u < kCoreChunk; u++) {
+        const int i = i0 + u;
+        if (i >= n) break;
+        const double xd = (double)din[u];
+        double stereo = 0.0;
+        if (P.stereo) {
+          const double tone = P.pilot_shift ? (2 * pcos * pcos - 1) : (2 * psin * pcos);
+          const double i0v = psin * xd - (P.bq_a1 * s.bi_x1 + P.bq_a2 * s.bi_x2);
+          const double q0v = pcos * xd - (P.bq_a1 * s.bq_x1 + P.bq_a2 * s.bq_x2);
+          const double new_i = P.bq_b0 * i0v;
+          const double new_q = P.bq_b0 * q0v;
+          s.bi_x2 = s.bi_x1;
+          s.bi_x1 = i0v;
+          s.bq_x2 = s.bq_x1;
+          s.bq_x1 = q0v;
+          const double perr = (double)fast_atan2f_dev((float)new_q, (float)new_i, atan_tbl);
+          last_i = new_i;
+          last_q = new_q;
+          const double ferr = P.lf_b0 * perr + P.lf_b1 * s.lf_x1;
+          s.lf_x1 = perr;
+          s.freq_err = ferr;
+          s.pll_freq += ferr;
+          s.pll_freq = fmax(P.pll_minfreq, fmin(P.pll_maxfreq, s.pll_freq));
+          s.pll_phase += s.pll_freq;
+          // advance the phasor by m_freq = f0 + dl
+          {
+            const double dl = s.pll_freq - f0;
+            const double d2 = dl * dl;
+            const double sd = dl * (1.0 - d2 * (1.0 / 6.0) * (1.0 - d2 * (1.0 / 20.0)));
+            const double cd = 1.0 - d2 * 0.5 * (1.0 - d2 * (1.0 / 12.0));
+            const double sr = sf0 * cd + cf0 * sd; // sin(f0 + dl)
+            const double cr = cf0 * cd - sf0 * sd; // cos(f0 + dl)
+            const double ns = psin * cr + pcos * sr;
+            const double nc = pcos * cr - psin * sr;
+            psin = ns;
+            pcos = nc;
+          }
+          if (s.pll_phase > 2.0 * 3.14159265358979323846) {
+            s.pll_phase -= 2.0 * 3.14159265358979323846;
+            s.pilot_periods++;
+            if (s.pilot_periods == 19000) {
+              s.pilot_periods = 0;
+              if (was_locked) {
+                if (s.n_pps < (uint32_t)kMaxPps) {
+                  PpsEventDev ev;
+                  ev.pps_index = s.pps_cnt;
+                  ev.sample_index = s.sample_cnt + (unsigned long long)i;
+                  ev.block_position = (double)i / (double)n;
+                  ev.block = (uint32_t)b;
+                  ev.pad = 0;
+                  pps[(size_t)c * kMaxPps + s.n_pps] = ev;
+                }
+                s.n_pps++;
+                s.pps_cnt++;
               }
-              s.n_pps++;
-              s.pps_cnt++;
             }
           }
+          stereo = (tone * xd) * 2.0;
+          if (P.deemph_on_stereo) {
+            const double x0 = stereo - P.de_a1 * s.de_s_x1;
+            stereo = P.de_b0 * x0;
+            s.de_s_x1 = x0;
+          }
         }
-        // FmDecoder::demod_stereo (FmDecode.cpp:224-239) and L-R deemphasis (:168-170)
-        stereo = (tone * xd) * 2.0;
-        if (P.deemph_on_stereo) {
-          const double x0 = stereo - P.de_a1 * s.de_s_x1;
-          stereo = P.de_b0 * x0;
-          s.de_s_x1 = x0;
-        }
+        const double m0 = xd - P.de_a1 * s.de_m_x1;
+        const double mono = P.de_b0 * m0;
+        s.de_m_x1 = m0;
+        double2 o;
+        o.x = mono;
+        o.y = stereo;
+        out384.st(c, tb + i, o);
       }
-      // mono deemphasis (FmDecode.cpp:180)
-      const double m0 = xd - P.de_a1 * s.de_m_x1;
-      const double mono = P.de_b0 * m0;
-      s.de_m_x1 = m0;
-      double2 o;
-      o.x = mono;
-      o.y = stereo;
-      out384.st(c, t, o);
     }
-    if (PHASE == 1) continue;
-    // Utility::samples_mean_rms + EMA (FmDecode.cpp:146-150)
+    // per-call statistics (FmDecode.cpp:95,146-150)
     {
-      const float mean = vsum / (float)n;
-      const float rms = sqrtf(vsumsq / (float)n);
-      s.baseband_mean = (float)(0.95 * (double)s.baseband_mean + 0.05 * (double)mean);
-      s.baseband_level = (float)(0.95 * (double)s.baseband_level + 0.05 * (double)rms);
+      const float *sv = stats + ((size_t)c * n_calls + b) * 3;
+      s.if_rms = sv[0];
+      s.baseband_mean = (float)(0.95 * (double)s.baseband_mean + 0.05 * (double)sv[1]);
+      s.baseband_level = (float)(0.95 * (double)s.baseband_level + 0.05 * (double)sv[2]);
     }
     if (P.stereo) {
+      // m_pilot_level is the value of the call's last sample (PilotPhaseLock.cpp:106)
+      s.pilot_level = sqrt(last_i * last_i + last_q * last_q);
       // lock bookkeeping (PilotPhaseLock.cpp:153-170)
       if (2 * s.pilot_level > P.minsignal) {
         if (s.lock_cnt < P.lock_delay) s.lock_cnt += n;
@@ -564,8 +651,9 @@ __global__ void k_fm_core(Ring<float2> if_raw, Ring<float2> iq_in, Ring<float2> 
       if (s.lock_cnt < P.lock_delay) {
         s.pilot_periods = 0;
         s.pps_cnt = 0;
-        // events of THIS call are dropped: rewind those recorded with block == b
-        while (s.n_pps > 0 && s.n_pps <= (uint32_t)kMaxPps && pps[(size_t)c * kMaxPps + s.n_pps - 1].block == (uint32_t)b) {
+        // events of THIS call are dropped
+        while (s.n_pps > 0 && s.n_pps <= (uint32_t)kMaxPps &&
+               pps[(size_t)c * kMaxPps + s.n_pps - 1].block == (uint32_t)b) {
           s.n_pps--;
         }
       }
