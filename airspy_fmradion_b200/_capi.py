@@ -57,7 +57,7 @@ class AmStats(C.Structure):
 EXPORTS = [
     "fmr_last_error", "fmr_version", "fmr_device_sm_count",
     "fmr_fm_create", "fmr_fm_destroy", "fmr_fm_process_host", "fmr_fm_process_device",
-    "fmr_fm_query_output", "fmr_fm_stats", "fmr_fm_pps_events", "fmr_fm_coeffs",
+    "fmr_fm_query_output", "fmr_fm_schedule", "fmr_am_schedule", "fmr_fm_stats", "fmr_fm_pps_events", "fmr_fm_coeffs",
     "fmr_fm_block_flags", "fmr_fm_tap_if", "fmr_fm_last_launches", "fmr_fm_set_profiling",
     "fmr_fm_stage_times",
     "fmr_am_create", "fmr_am_destroy", "fmr_am_process_host", "fmr_am_process_device",
@@ -99,6 +99,8 @@ def lib():
     L.fmr_fm_stage_times.argtypes = [vp, vp, vp, C.c_uint32, u32p]
     L.fmr_am_set_profiling.argtypes = [vp, C.c_int]
     L.fmr_am_stage_times.argtypes = [vp, vp, vp, C.c_uint32, u32p]
+    L.fmr_fm_schedule.argtypes = [C.c_double, C.c_int, C.c_uint64, vp, C.c_uint32, vp, vp]
+    L.fmr_am_schedule.argtypes = [C.c_double, C.c_uint64, vp, C.c_uint32, vp]
     L.fmr_am_create.argtypes = [C.POINTER(AmConfig), C.POINTER(vp)]
     L.fmr_am_destroy.argtypes = [vp]
     L.fmr_am_destroy.restype = None

@@ -1,14 +1,437 @@
-// fmr_am.cu — AM handle (AmDecoder::process, AmDecode.cpp:96-218). Placeholder until the
-// AM kernels land: every entry point reports FMR_ERR_UNSUPPORTED.
+// fmr_am.cu — AM handle: FourthConverterIQ -> IfResampler -> AmDecoder::process for
+// ModType::AM (main.cpp:912-971, AmDecode.cpp:96-218), many channels per launch.
+#include <complex>
+#include <cmath>
+
 #include "fmr_host.cuh"
+
 using namespace fmr;
-struct fmr_am { int dummy; };
-extern "C" fmr_status fmr_am_create(const fmr_am_config *, fmr_am **) { return fail(FMR_ERR_UNSUPPORTED, "AM path not built yet"); }
-extern "C" void fmr_am_destroy(fmr_am *) {}
-extern "C" fmr_status fmr_am_process_host(fmr_am *, const float *, size_t, const uint32_t *, uint32_t, double *, size_t, uint32_t *) { return fail(FMR_ERR_UNSUPPORTED, "AM path not built yet"); }
-extern "C" fmr_status fmr_am_process_device(fmr_am *, const float *, size_t, const uint32_t *, uint32_t, double *, size_t, uint32_t *, void *) { return fail(FMR_ERR_UNSUPPORTED, "AM path not built yet"); }
-extern "C" fmr_status fmr_am_query_output(fmr_am *, const uint32_t *, uint32_t, uint64_t *, uint32_t *) { return fail(FMR_ERR_UNSUPPORTED, "AM path not built yet"); }
-extern "C" fmr_status fmr_am_stats(fmr_am *, uint32_t, fmr_am_stats_t *) { return fail(FMR_ERR_UNSUPPORTED, "AM path not built yet"); }
-extern "C" uint32_t fmr_am_last_launches(fmr_am *) { return 0; }
-extern "C" fmr_status fmr_am_set_profiling(fmr_am *, int) { return fail(FMR_ERR_UNSUPPORTED, "AM path not built yet"); }
-extern "C" fmr_status fmr_am_stage_times(fmr_am *, float *, const char **, uint32_t, uint32_t *) { return fail(FMR_ERR_UNSUPPORTED, "AM path not built yet"); }
+
+namespace {
+
+struct AmChanState {
+  float if_gain;                          // IfSimpleAgc m_current_gain
+  float baseband_mean, baseband_level, if_rms;
+  double af_gain;                         // AfSimpleAgc m_current_gain
+  double dc_x1, dc_x2;                    // HighPassFilterIir delay line
+  double de_x1;                           // LowPassFilterRC delay line
+  unsigned long long decoder_calls;
+};
+
+struct AmCoreParams {
+  float if_max, if_rate;                  // IfSimpleAgc(1.0, 1000000.0, 0.0003)  AmDecode.cpp:71-77
+  double af_max, af_ref, af_rate;         // AfSimpleAgc(1.0, 1.5, 0.6, 0.001)    AmDecode.cpp:54-66
+  double b0, b1, b2, a1, a2;              // HighPassFilterIir(60/48000)          AmDecode.cpp:45
+  double de_a1, de_b0;                    // LowPassFilterRC(100us * 48 kHz)      AmDecode.cpp:49
+  int n_channels;
+};
+
+// AmDecoder::process after the channel filter (AmDecode.cpp:153-217): IF RMS, IF AGC,
+// envelope detector, DC block, AF AGC, statistics, deemphasis. All of it is a chain of short
+// recurrences at 48 kHz, so one lane per channel runs it serially.
+__global__ void k_am_core(Ring<float2> in, double *__restrict__ audio, size_t audio_stride,
+                          AmChanState *__restrict__ st, const uint32_t *__restrict__ call_end, int n_calls,
+                          int64_t t0, AmCoreParams P) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.n_channels) return;
+  AmChanState s = st[c];
+  double *o = audio + (size_t)c * audio_stride;
+  uint32_t prev_end = 0;
+  for (int b = 0; b < n_calls; b++) {
+    const uint32_t end = call_end[b];
+    const int n = (int)(end - prev_end);
+    if (n == 0) continue;
+    const int64_t tb = t0 + prev_end;
+    const uint32_t ob = prev_end;
+    prev_end = end;
+    s.decoder_calls++;
+    float sumsq = 0.f, vsum = 0.f, vsq = 0.f;
+    for (int i0 = 0; i0 < n; i0 += kCoreChunk) {
+      float2 xin[kCoreChunk];
+#pragma unroll
+      for (int u = 0; u < kCoreChunk; u++) xin[u] = (i0 + u < n) ? in.ld(c, tb + i0 + u) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kCoreChunk; u++) {
+        const int i = i0 + u;
+        if (i >= n) break;
+        const float2 x = xin[u];
+        sumsq += x.x * x.x + x.y * x.y; // Utility::rms_level_sample (AmDecode.cpp:154)
+        // IfSimpleAgc::process (IfSimpleAgc.cpp:37-57)
+        const float xr = x.x * s.if_gain, xi = x.y * s.if_gain;
+        const float nrm = xr * xr + xi * xi;
+        const float z = (float)(1.0 + ((double)P.if_rate * (1.0 - (double)nrm)));
+        s.if_gain *= z;
+        if (!isfinite(s.if_gain)) {
+          s.if_gain = 1.0f;
+        } else if (s.if_gain > P.if_max) {
+          s.if_gain = P.if_max;
+        }
+        // demodulate_am (AmDecode.cpp:221-226): volk_32fc_magnitude_32f
+        const float mag = sqrtf(xr * xr + xi * xi);
+        vsum += mag;
+        vsq += mag * mag;
+        // DC block (AmDecode.cpp:194; Filter.cpp:243-250)
+        const double d0 = (double)mag - (P.a1 * s.dc_x1 + P.a2 * s.dc_x2);
+        const double v = P.b0 * d0 + P.b1 * s.dc_x1 + P.b2 * s.dc_x2;
+        s.dc_x2 = s.dc_x1;
+        s.dc_x1 = d0;
+        // AfSimpleAgc::process (AfSimpleAgc.cpp:36-58)
+        const double x2 = v * s.af_gain;
+        const double y = x2 * P.af_ref;
+        const double za = 1.0 + (P.af_rate * (1.0 - (x2 * x2)));
+        s.af_gain *= za;
+        if (!isfinite(s.af_gain)) {
+          s.af_gain = 1.0;
+        } else if (s.af_gain > P.af_max) {
+          s.af_gain = P.af_max;
+        }
+        // deemphasis (AmDecode.cpp:212-214)
+        const double e0 = y - P.de_a1 * s.de_x1;
+        o[ob + i] = P.de_b0 * e0;
+        s.de_x1 = e0;
+      }
+    }
+    s.if_rms = sqrtf(sumsq / (float)n);
+    const float mean = vsum / (float)n, rms = sqrtf(vsq / (float)n);
+    s.baseband_mean = (float)(0.95 * (double)s.baseband_mean + 0.05 * (double)mean);
+    s.baseband_level = (float)(0.95 * (double)s.baseband_level + 0.05 * (double)rms);
+  }
+  st[c] = s;
+}
+
+} // namespace
+
+struct fmr_am {
+  fmr_am_config cfg;
+  int C = 0;
+  const ChainDesc *ifc = nullptr; // null when input_rate == 48000
+  DevMem mem;
+  PinnedSlots slots;
+  cudaStream_t own_stream = nullptr;
+  Resampler<float> ifres;
+  float2 *hist[2] = {nullptr, nullptr};
+  int hist_cur = 0;
+  Ring<float2> r_if{nullptr, 0};  // 48 kHz decoder input
+  Ring<float2> r_flt{nullptr, 0}; // after the channel filter
+  AmChanState *d_state = nullptr;
+  uint32_t *d_e48 = nullptr;
+  float *d_amfilter = nullptr;
+  int amfilter_taps = 0;
+  Prof prof;
+  int p_hist = -1, p_flt = -1, p_core = -1;
+  AmCoreParams core;
+  int64_t cum_in = 0, cum48 = 0;
+  uint32_t last_launches = 0;
+  float *d_iq = nullptr;
+  double *d_audio = nullptr;
+  size_t audio_cap = 0;
+};
+
+static int64_t am_out_total(const ChainDesc *ifc, int64_t n) { return ifc ? chain_out(ifc, n) : n; }
+
+extern "C" fmr_status fmr_am_schedule(double input_rate, uint64_t start_sample, const uint32_t *block_len,
+                                      uint32_t n_blocks, uint32_t *audio_len) {
+  if (!block_len || !audio_len) return fail(FMR_ERR_INVALID, "null argument");
+  const ChainDesc *ifc = nullptr;
+  if (input_rate != 48000.0) {
+    ifc = find_chain(input_rate, 48000.0, 0);
+    if (!ifc) return fail(FMR_ERR_UNSUPPORTED, "no resampler tables for this input_rate -> 48000");
+  }
+  int64_t n = (int64_t)start_sample;
+  int64_t prev = am_out_total(ifc, n);
+  for (uint32_t b = 0; b < n_blocks; b++) {
+    n += block_len[b];
+    const int64_t cur = am_out_total(ifc, n);
+    audio_len[b] = (uint32_t)(cur - prev);
+    prev = cur;
+  }
+  return FMR_OK;
+}
+
+static fmr_status am_build(fmr_am *h) {
+  const fmr_am_config &cfg = h->cfg;
+  FMR_CUDA(cudaSetDevice(cfg.device));
+  const int C = h->C = (int)cfg.n_channels;
+  const int64_t max_in = cfg.max_samples_per_call;
+  const int max_blocks = (int)cfg.max_blocks_per_call;
+  if (cfg.mode != 2) return fail(FMR_ERR_UNSUPPORTED, "only ModType::AM (2) is implemented");
+  if (cfg.input_rate != 48000.0) {
+    h->ifc = find_chain(cfg.input_rate, 48000.0, 0);
+    if (!h->ifc) return fail(FMR_ERR_UNSUPPORTED, "no resampler tables for this input_rate -> 48000");
+  }
+  FMR_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  FMR_CUDA(h->slots.init(sizeof(uint32_t) * (size_t)max_blocks));
+  int64_t max48 = max_in + 8;
+  if (h->ifc) {
+    fmr_status s = h->ifres.init(h->ifc, C, max_in, true, h->mem);
+    if (s != FMR_OK) return s;
+    max48 = (int64_t)std::ceil((double)max_in * 48000.0 / cfg.input_rate) + 8;
+  } else {
+    HbTaps<float> t;
+    memset(&t, 0, sizeof(t));
+    FMR_CUDA((cudaFuncSetAttribute(k_hb_cascade<float, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)Resampler<float>::hb_smem(t, 0))));
+  }
+  FMR_CUDA(h->mem.alloc(&h->hist[0], (size_t)C * kHist));
+  FMR_CUDA(h->mem.alloc(&h->hist[1], (size_t)C * kHist));
+  h->r_if.cap = pow2ceil((uint64_t)max48 + 1024);
+  FMR_CUDA(h->mem.alloc(&h->r_if.base, (size_t)C * h->r_if.cap));
+  h->r_flt.cap = h->r_if.cap;
+  FMR_CUDA(h->mem.alloc(&h->r_flt.base, (size_t)C * h->r_flt.cap));
+  {
+    const float *tbl = k_jj1bdx_am_48khz_default; // main.cpp:785-810
+    h->amfilter_taps = 255;
+    if (cfg.amfilter == 1) tbl = k_jj1bdx_am_48khz_medium;
+    if (cfg.amfilter == 2) tbl = k_jj1bdx_am_48khz_narrow;
+    if (cfg.amfilter == 3) {
+      tbl = k_jj1bdx_am_48khz_wide;
+      h->amfilter_taps = 127;
+    }
+    FMR_CUDA(h->mem.alloc(&h->d_amfilter, (size_t)h->amfilter_taps, false));
+    FMR_CUDA(cudaMemcpy(h->d_amfilter, tbl, h->amfilter_taps * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  FMR_CUDA(h->mem.alloc(&h->d_state, (size_t)C));
+  FMR_CUDA(h->mem.alloc(&h->d_e48, (size_t)max_blocks));
+  {
+    std::vector<AmChanState> st(C);
+    memset(st.data(), 0, sizeof(AmChanState) * C);
+    for (int c = 0; c < C; c++) {
+      st[c].if_gain = 1.0f;
+      st[c].af_gain = 1.0;
+    }
+    FMR_CUDA(cudaMemcpy(h->d_state, st.data(), sizeof(AmChanState) * C, cudaMemcpyHostToDevice));
+  }
+  AmCoreParams &P = h->core;
+  memset(&P, 0, sizeof(P));
+  P.if_max = 1000000.0f;
+  P.if_rate = 0.0003f;
+  P.af_max = 1.5;
+  P.af_ref = 0.6;
+  P.af_rate = 0.001;
+  {
+    // HighPassFilterIir::HighPassFilterIir (Filter.cpp:254-290), cutoff 60/48000
+    using CD = std::complex<double>;
+    const double w = 2 * M_PI * (60.0 / 48000.0);
+    const CD p1s = w / std::exp((2 * 1 + 2 - 1) / double(2 * 2) * CD(0, M_PI));
+    const CD p1z = std::exp(p1s);
+    const double A1 = -2 * std::real(p1z), A2 = std::abs(p1z * p1z);
+    const double g = (1.0 + 2.0 + 1.0) / (1 - A1 + A2);
+    P.b0 = 1.0 / g;
+    P.b1 = -2.0 / g;
+    P.b2 = 1.0 / g;
+    P.a1 = A1;
+    P.a2 = A2;
+  }
+  {
+    const double tc = 100.0 * 48000.0 * 1.0e-6;
+    P.de_a1 = -std::exp(-1 / tc);
+    P.de_b0 = 1 + P.de_a1;
+  }
+  P.n_channels = C;
+  h->audio_cap = (size_t)max48;
+  h->ifres.prof = &h->prof;
+  h->ifres.p_hb = h->prof.add("if_halfband_cascade");
+  h->ifres.p_bc = h->prof.add("if_lowpass");
+  h->ifres.p_fi = h->prof.add("if_polyphase");
+  h->p_hist = h->prof.add("save_hist");
+  h->p_flt = h->prof.add("am_channel_filter");
+  h->p_core = h->prof.add("am_core_48k");
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_am_create(const fmr_am_config *cfg, fmr_am **out) {
+  if (!cfg || !out) return fail(FMR_ERR_INVALID, "null argument");
+  if (cfg->n_channels == 0 || cfg->max_samples_per_call == 0 || cfg->max_blocks_per_call == 0) {
+    return fail(FMR_ERR_INVALID, "n_channels, max_samples_per_call and max_blocks_per_call must be > 0");
+  }
+  if (cfg->amfilter < 0 || cfg->amfilter > 3) return fail(FMR_ERR_INVALID, "amfilter must be 0..3");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    return fail(FMR_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  }
+  fmr_am *h = new fmr_am();
+  h->cfg = *cfg;
+  fmr_status s = am_build(h);
+  if (s != FMR_OK) {
+    std::string keep = g_err;
+    fmr_am_destroy(h);
+    g_err = keep;
+    return s;
+  }
+  *out = h;
+  return FMR_OK;
+}
+
+extern "C" void fmr_am_destroy(fmr_am *h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  h->mem.release();
+  h->slots.release();
+  h->prof.release();
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+extern "C" fmr_status fmr_am_query_output(fmr_am *h, const uint32_t *block_len, uint32_t n_blocks,
+                                          uint64_t *audio_doubles_total, uint32_t *audio_len) {
+  if (!h || !block_len) return fail(FMR_ERR_INVALID, "null argument");
+  std::vector<uint32_t> tmp(n_blocks);
+  fmr_status s = fmr_am_schedule(h->cfg.input_rate, (uint64_t)h->cum_in, block_len, n_blocks, tmp.data());
+  if (s != FMR_OK) return s;
+  uint64_t tot = 0;
+  for (uint32_t b = 0; b < n_blocks; b++) {
+    tot += tmp[b];
+    if (audio_len) audio_len[b] = tmp[b];
+  }
+  if (audio_doubles_total) *audio_doubles_total = tot;
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t iq_stride,
+                                            const uint32_t *block_len, uint32_t n_blocks, double *d_audio,
+                                            size_t audio_stride, uint32_t *audio_len, void *stream) {
+  if (!h || !d_iq || !block_len || !d_audio) return fail(FMR_ERR_INVALID, "null argument");
+  if (n_blocks == 0) return FMR_OK;
+  if (n_blocks > h->cfg.max_blocks_per_call) return fail(FMR_ERR_CAPACITY, "n_blocks > max_blocks_per_call");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = h->C;
+  int slot = 0;
+  uint32_t *e48 = (uint32_t *)h->slots.acquire(&slot);
+  int64_t n = 0;
+  const int64_t base48 = am_out_total(h->ifc, h->cum_in);
+  for (uint32_t b = 0; b < n_blocks; b++) {
+    if (h->ifc && block_len[b] > 65536) return fail(FMR_ERR_INVALID, "block_len > 65536 (IfResampler limit)");
+    n += block_len[b];
+    e48[b] = (uint32_t)(am_out_total(h->ifc, h->cum_in + n) - base48);
+  }
+  const uint64_t total_in = (uint64_t)n;
+  if (total_in > h->cfg.max_samples_per_call) return fail(FMR_ERR_CAPACITY, "sum(block_len) > max_samples_per_call");
+  if (total_in > iq_stride) return fail(FMR_ERR_INVALID, "iq_stride < sum(block_len)");
+  const uint32_t n48 = e48[n_blocks - 1];
+  if ((size_t)n48 > audio_stride) return fail(FMR_ERR_CAPACITY, "audio_stride too small for this call");
+  if (audio_len) {
+    for (uint32_t b = 0; b < n_blocks; b++) audio_len[b] = e48[b] - (b ? e48[b - 1] : 0);
+  }
+  FMR_CUDA(cudaMemcpyAsync(h->d_e48, e48, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
+  h->slots.commit(slot, st);
+  int launches = 0;
+  Prof &pf = h->prof;
+  pf.reset();
+  InSrc<float2> src;
+  src.lin = reinterpret_cast<const float2 *>(d_iq);
+  src.stride = iq_stride;
+  src.hist = h->hist[h->hist_cur];
+  src.start = h->cum_in;
+  src.n_new = (int64_t)total_in;
+  src.ring = Ring<float2>{nullptr, 0};
+  const int64_t t0 = h->cum48;
+  if (h->ifc) {
+    int64_t o0, o1;
+    fmr_status s = h->ifres.run(src, (int64_t)total_in, h->r_if, h->cfg.fs4_shift, st, &o0, &o1, &launches);
+    if (s != FMR_OK) return s;
+    if (o0 != t0 || o1 != t0 + n48) return fail(FMR_ERR_INVALID, "internal: IF schedule mismatch");
+    if (total_in > 0) {
+      pf.begin(h->p_hist, st);
+      k_save_hist<float2><<<C, 128, 0, st>>>(src.lin, iq_stride, (int64_t)total_in, h->hist[h->hist_cur],
+                                             h->hist[h->hist_cur ^ 1]);
+      pf.end(h->p_hist, st);
+      h->hist_cur ^= 1;
+      launches++;
+    }
+  } else if (total_in > 0) {
+    HbTaps<float> t;
+    memset(&t, 0, sizeof(t));
+    dim3 grid((unsigned)((total_in + kHbTile - 1) / kHbTile), C);
+    pf.begin(h->ifres.p_hb, st);
+    k_hb_cascade<float, 0, true><<<grid, kHbThreads, Resampler<float>::hb_smem(t, 0), st>>>(
+        src, h->r_if, t, t0, (int)total_in, h->cfg.fs4_shift);
+    pf.end(h->ifres.p_hb, st);
+    launches++;
+  }
+  if (n48 > 0) {
+    dim3 grid((n48 + 127) / 128, C);
+    pf.begin(h->p_flt, st);
+    k_fir_quirk<float><<<grid, 128, 0, st>>>(h->r_if, h->r_flt, h->d_amfilter, h->amfilter_taps, t0, (int)n48,
+                                             h->d_e48, (int)n_blocks);
+    pf.end(h->p_flt, st);
+    pf.begin(h->p_core, st);
+    k_am_core<<<(C + 31) / 32, 32, 0, st>>>(h->r_flt, d_audio, audio_stride, h->d_state, h->d_e48, (int)n_blocks, t0,
+                                            h->core);
+    pf.end(h->p_core, st);
+    launches += 2;
+  }
+  FMR_CUDA(cudaGetLastError());
+  h->cum_in += (int64_t)total_in;
+  h->cum48 += n48;
+  h->last_launches = (uint32_t)launches;
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_am_process_host(fmr_am *h, const float *iq, size_t iq_stride, const uint32_t *block_len,
+                                          uint32_t n_blocks, double *audio, size_t audio_stride,
+                                          uint32_t *audio_len) {
+  if (!h || !iq || !block_len || !audio) return fail(FMR_ERR_INVALID, "null argument");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < n_blocks; b++) total += block_len[b];
+  if (total > h->cfg.max_samples_per_call) return fail(FMR_ERR_CAPACITY, "sum(block_len) > max_samples_per_call");
+  if (total > iq_stride) return fail(FMR_ERR_INVALID, "iq_stride < sum(block_len)");
+  const int C = h->C;
+  if (!h->d_iq) {
+    FMR_CUDA(h->mem.alloc(&h->d_iq, (size_t)C * h->cfg.max_samples_per_call * 2, false));
+    FMR_CUDA(h->mem.alloc(&h->d_audio, (size_t)C * h->audio_cap, false));
+  }
+  cudaStream_t st = h->own_stream;
+  if (total > 0) {
+    FMR_CUDA(cudaMemcpy2DAsync(h->d_iq, (size_t)total * 8, iq, iq_stride * 8, (size_t)total * 8, C,
+                               cudaMemcpyHostToDevice, st));
+  }
+  uint64_t out_total = 0;
+  fmr_status s = fmr_am_query_output(h, block_len, n_blocks, &out_total, nullptr);
+  if (s != FMR_OK) return s;
+  if (out_total > audio_stride) return fail(FMR_ERR_CAPACITY, "audio_stride too small for this call");
+  s = fmr_am_process_device(h, h->d_iq, (size_t)total, block_len, n_blocks, h->d_audio, h->audio_cap, audio_len,
+                            (void *)st);
+  if (s != FMR_OK) return s;
+  if (out_total > 0) {
+    FMR_CUDA(cudaMemcpy2DAsync(audio, audio_stride * 8, h->d_audio, h->audio_cap * 8, (size_t)out_total * 8, C,
+                               cudaMemcpyDeviceToHost, st));
+  }
+  FMR_CUDA(cudaStreamSynchronize(st));
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_am_stats(fmr_am *h, uint32_t channel, fmr_am_stats_t *out) {
+  if (!h || !out || channel >= (uint32_t)h->C) return fail(FMR_ERR_INVALID, "bad argument");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  FMR_CUDA(cudaDeviceSynchronize());
+  AmChanState s;
+  FMR_CUDA(cudaMemcpy(&s, h->d_state + channel, sizeof(s), cudaMemcpyDeviceToHost));
+  out->baseband_level = s.baseband_level;
+  out->af_agc_gain = (float)s.af_gain;
+  out->if_agc_gain = s.if_gain;
+  out->if_rms = s.if_rms;
+  out->decoder_calls = s.decoder_calls;
+  return FMR_OK;
+}
+
+extern "C" uint32_t fmr_am_last_launches(fmr_am *h) { return h ? h->last_launches : 0; }
+
+extern "C" fmr_status fmr_am_set_profiling(fmr_am *h, int enable) {
+  if (!h) return fail(FMR_ERR_INVALID, "null handle");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  if (enable) {
+    h->prof.enable();
+  } else {
+    h->prof.release();
+  }
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_am_stage_times(fmr_am *h, float *ms, const char **names, uint32_t cap, uint32_t *n) {
+  if (!h || !ms || !names || !n) return fail(FMR_ERR_INVALID, "null argument");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  return h->prof.read(ms, names, cap, n);
+}

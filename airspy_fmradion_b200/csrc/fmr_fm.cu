@@ -283,6 +283,31 @@ static fmr_status fm_schedule(const fmr_fm *h, const uint32_t *block_len, uint32
   return FMR_OK;
 }
 
+extern "C" fmr_status fmr_fm_schedule(double input_rate, int stereo, uint64_t start_sample, const uint32_t *block_len,
+                                      uint32_t n_blocks, uint32_t *if_len, uint32_t *audio_len) {
+  if (!block_len) return fail(FMR_ERR_INVALID, "null argument");
+  const ChainDesc *ifc = nullptr;
+  if (input_rate != 384000.0) {
+    ifc = find_chain(input_rate, 384000.0, 0);
+    if (!ifc) return fail(FMR_ERR_UNSUPPORTED, "no resampler tables for this input_rate -> 384000");
+  }
+  const ChainDesc *auc = find_chain(384000.0, 48000.0, 1);
+  int64_t n = (int64_t)start_sample;
+  int64_t p384 = ifc ? chain_out(ifc, n) : n;
+  int64_t p48 = chain_out(auc, p384);
+  const uint32_t w = stereo ? 2 : 1;
+  for (uint32_t b = 0; b < n_blocks; b++) {
+    n += block_len[b];
+    const int64_t c384 = ifc ? chain_out(ifc, n) : n;
+    const int64_t c48 = chain_out(auc, c384);
+    if (if_len) if_len[b] = (uint32_t)(c384 - p384);
+    if (audio_len) audio_len[b] = (uint32_t)(c48 - p48) * w;
+    p384 = c384;
+    p48 = c48;
+  }
+  return FMR_OK;
+}
+
 extern "C" fmr_status fmr_fm_query_output(fmr_fm *h, const uint32_t *block_len, uint32_t n_blocks,
                                           uint64_t *audio_doubles_total, uint32_t *audio_len) {
   if (!h || !block_len) return fail(FMR_ERR_INVALID, "null argument");

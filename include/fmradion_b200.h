@@ -123,6 +123,12 @@ fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t iq_stride,
 fmr_status fmr_fm_query_output(fmr_fm *h, const uint32_t *block_len, uint32_t n_blocks,
                                uint64_t *audio_doubles_total, uint32_t *audio_len);
 
+/* Pure host bookkeeping, no device needed: the IF (384 kHz) and audio (doubles) lengths the
+ * reference produces per block for a stream that has already consumed start_sample samples.
+ * Same integer model fmr_fm_process_* uses (r8brain's release schedule, see csrc/fmr_tables.h). */
+fmr_status fmr_fm_schedule(double input_rate, int stereo, uint64_t start_sample, const uint32_t *block_len,
+                           uint32_t n_blocks, uint32_t *if_len, uint32_t *audio_len);
+
 fmr_status fmr_fm_stats(fmr_fm *h, uint32_t channel, fmr_fm_stats_t *out);
 /* Copies up to cap events of the last process call; returns the count in *n. */
 fmr_status fmr_fm_pps_events(fmr_fm *h, uint32_t channel, fmr_pps_event_t *out, uint32_t cap,
@@ -175,6 +181,8 @@ fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t iq_stride,
                                  void *stream);
 fmr_status fmr_am_query_output(fmr_am *h, const uint32_t *block_len, uint32_t n_blocks,
                                uint64_t *audio_doubles_total, uint32_t *audio_len);
+fmr_status fmr_am_schedule(double input_rate, uint64_t start_sample, const uint32_t *block_len,
+                           uint32_t n_blocks, uint32_t *audio_len);
 fmr_status fmr_am_stats(fmr_am *h, uint32_t channel, fmr_am_stats_t *out);
 uint32_t fmr_am_last_launches(fmr_am *h);
 fmr_status fmr_am_set_profiling(fmr_am *h, int enable);
