@@ -201,15 +201,12 @@ template <typename S> struct Resampler {
   int p_hb = -1, p_bc = -1, p_fi = -1;
   float2 *d_H = nullptr; // filter spectrum for k_fir_fft (float chains only)
   bool use_fft = false;
+  bool use_dec2 = false; // double chains with a decimate-by-2 low-pass (audio resampler)
 
   static size_t hb_smem(const HbTaps<S> &t, int nst) {
     size_t total = 0;
-    for (int s = 0; s <= nst; s++) {
-      size_t full = kHbTile;
-      for (int q = nst; q > s; q--) full = 2 * full + 4 * t.n[q - 1] - 3;
-      total += full;
-    }
-    return total * sizeof(V);
+    for (int s = 0; s < nst; s++) total += 2 * (size_t)hb_half(hb_level_len(t.n, nst, s));
+    return total * sizeof(V) + 16;
   }
 
   template <int NST, bool LIN> static cudaError_t set_hb_attr(size_t smem) {
@@ -261,6 +258,11 @@ template <typename S> struct Resampler {
       FMR_CUDA(cudaFuncSetAttribute(k_fir_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemBytes));
       use_fft = true;
     }
+    if (sizeof(S) == sizeof(double) && d->bc.down == 2 && (d->bc.klen + 1) / 2 <= kDecMaxTaps) {
+      FMR_CUDA(cudaFuncSetAttribute(k_fir_dec2_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)dec2_smem(d->bc.klen)));
+      use_dec2 = true;
+    }
     smem_fir = ((size_t)(kFirTile - 1) * d->bc.down + d->bc.klen) * sizeof(V) + (size_t)d->bc.klen * sizeof(S);
     FMR_CUDA(cudaFuncSetAttribute(k_fir_long<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fir));
     if (d->has_fi) {
@@ -290,6 +292,11 @@ template <typename S> struct Resampler {
     k_fir_fft<<<grid, kFftThreads, kFftSmemBytes, st>>>(in, o, d_H, d->bc.klen, d->bc.down, q0, n, avail, lq);
   }
   void launch_fft(Ring<double2>, Ring<double2>, int64_t, int, int64_t, cudaStream_t) {}
+  void launch_dec2(Ring<double2> in, Ring<double2> o, int64_t q0, int n, cudaStream_t st) {
+    dim3 grid((n + kDecTile - 1) / kDecTile, C);
+    k_fir_dec2_f64<<<grid, kDecThreads, dec2_smem(d->bc.klen), st>>>(in, o, d_bc, d->bc.klen, q0, n);
+  }
+  void launch_dec2(Ring<float2>, Ring<float2>, int64_t, int, cudaStream_t) {}
 
   // Consume n_new more input samples; produce the reference's output index range into `out`.
   fmr_status run(InSrc<V> src, int64_t n_new, Ring<V> out, int fs4, cudaStream_t st, int64_t *o0,
@@ -320,6 +327,8 @@ template <typename S> struct Resampler {
         if (prof) prof->begin(p_bc, st);
         if (use_fft && n >= kFftMinOut) {
           launch_fft(bc_in, d->has_fi ? r_bc : out, b0, n, h1, st);
+        } else if (use_dec2) {
+          launch_dec2(bc_in, d->has_fi ? r_bc : out, b0, n, st);
         } else {
           dim3 grid((n + kFirTile - 1) / kFirTile, C);
           k_fir_long<S><<<grid, kFirThreads, smem_fir, st>>>(bc_in, d->has_fi ? r_bc : out, d_bc, d->bc.klen,

@@ -80,8 +80,37 @@ template <typename S> struct HbTaps {
   int n[3];
   S t[3][14];
 };
-constexpr int kHbTile = 512;
+constexpr int kHbTile = 256;
 constexpr int kHbThreads = 256;
+
+// Shared-memory footprint (elements of V) of one CTA: every level keeps its even- and
+// odd-indexed samples in two separate arrays (E[m] = x[2m], O[j] = x[2j+1]), because a
+// half-band output reads x[2m] and only ODD neighbours: with the split, consecutive threads
+// read consecutive words of E and O (no 2-way bank conflict of a stride-2 walk).
+__host__ __device__ inline int hb_level_len(const int *ntaps, int nst, int s) {
+  int full = kHbTile; // number of samples of level s needed by a full tile
+  for (int q = nst; q > s; q--) full = 2 * full + 4 * ntaps[q - 1] - 3;
+  return full;
+}
+__host__ __device__ inline int hb_half(int len) { return len / 2 + 2; }
+
+template <typename V> __device__ __forceinline__ V fs4_rot(V v, int64_t ai) {
+  const int ph = (int)(ai & 3);
+  V w;
+  if (ph == 0) {
+    w = v;
+  } else if (ph == 1) {
+    w.x = v.y;
+    w.y = -v.x;
+  } else if (ph == 2) {
+    w.x = -v.x;
+    w.y = -v.y;
+  } else {
+    w.x = -v.y;
+    w.y = v.x;
+  }
+  return w;
+}
 
 template <typename S, int NST, bool LINEAR>
 __global__ void __launch_bounds__(kHbThreads)
@@ -89,81 +118,98 @@ __global__ void __launch_bounds__(kHbThreads)
                  int64_t o0, int n_out, int fs4) {
   using V = typename V2<S>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  V *lvl[4];
   const uint32_t c = blockIdx.y;
   const int64_t a_fin = o0 + (int64_t)blockIdx.x * kHbTile;
   int cnt_fin = n_out - (int)(blockIdx.x * kHbTile);
   if (cnt_fin > kHbTile) cnt_fin = kHbTile;
   if (cnt_fin <= 0) return;
 
+  if (NST == 0) { // plain copy (+ Fs/4 shift)
+    for (int i = threadIdx.x; i < cnt_fin; i += kHbThreads) {
+      const int64_t ai = a_fin + i;
+      V v = src_ld<V, LINEAR>(in, c, ai);
+      if (fs4) v = fs4_rot(v, ai);
+      out.st(c, ai, v);
+    }
+    return;
+  }
   // index ranges per level: level NST = final outputs, level 0 = raw input
-  int64_t a[4];
+  int64_t lo[4];
   int len[4];
-  a[NST] = a_fin;
+  lo[NST] = a_fin;
   len[NST] = cnt_fin;
 #pragma unroll
   for (int s = NST; s >= 1; s--) {
     const int h = 2 * taps.n[s - 1] - 1;
-    a[s - 1] = 2 * a[s] - h;
+    lo[s - 1] = 2 * lo[s] - h;
     len[s - 1] = 2 * len[s] + 2 * h - 1;
   }
+  V *E[3], *O[3];
   {
     V *p = reinterpret_cast<V *>(smem_raw);
 #pragma unroll
-    for (int s = 0; s <= NST; s++) {
-      lvl[s] = p;
-      // sizes use the full tile so that the carve-up does not depend on cnt_fin
-      int full = kHbTile;
-      for (int q = NST; q > s; q--) full = 2 * full + 4 * taps.n[q - 1] - 3;
-      p += full;
+    for (int s = 0; s < NST; s++) {
+      const int hl = hb_half(hb_level_len(taps.n, NST, s));
+      E[s] = p;
+      O[s] = p + hl;
+      p += 2 * hl;
     }
   }
-  // level 0: load raw input (coalesced), apply Fs/4 shift
-  for (int i = threadIdx.x; i < len[0]; i += kHbThreads) {
-    const int64_t ai = a[0] + i;
-    V v = src_ld<V, LINEAR>(in, c, ai);
-    if (fs4) {
-      const int ph = (int)(ai & 3);
-      V w;
-      if (ph == 0) {
-        w = v;
-      } else if (ph == 1) {
-        w.x = v.y;
-        w.y = -v.x;
-      } else if (ph == 2) {
-        w.x = -v.x;
-        w.y = -v.y;
-      } else {
-        w.x = -v.y;
-        w.y = v.x;
+  // ---- level 0: pairs (x[2p], x[2p+1]) -> E0[p - eb], O0[p - eb]
+  {
+    const int64_t eb = lo[0] >> 1; // floor
+    const int npairs = (int)(((lo[0] + len[0] - 1) >> 1) - eb) + 1;
+    for (int i = threadIdx.x; i < npairs; i += kHbThreads) {
+      const int64_t p = eb + i;
+      const int64_t a0 = 2 * p;
+      V v0, v1;
+      bool fast = false;
+      if (LINEAR) {
+        const int64_t r = a0 - in.start;
+        const float2 *pp = reinterpret_cast<const float2 *>(in.lin) + (size_t)c * in.stride + r;
+        if (r >= 0 && r + 1 < in.n_new && sizeof(V) == 8 && ((reinterpret_cast<uintptr_t>(pp) & 15) == 0)) {
+          // 16-byte aligned pair inside this call's buffer: one 128-bit load
+          const float4 q = *reinterpret_cast<const float4 *>(pp);
+          v0.x = q.x;
+          v0.y = q.y;
+          v1.x = q.z;
+          v1.y = q.w;
+          fast = true;
+        }
       }
-      v = w;
-    }
-    if (NST == 0) {
-      out.st(c, ai, v);
-    } else {
-      lvl[0][i] = v;
+      if (!fast) {
+        v0 = src_ld<V, LINEAR>(in, c, a0);
+        v1 = src_ld<V, LINEAR>(in, c, a0 + 1);
+      }
+      if (fs4) {
+        v0 = fs4_rot(v0, a0);
+        v1 = fs4_rot(v1, a0 + 1);
+      }
+      E[0][i] = v0;
+      O[0][i] = v1;
     }
   }
-  if (NST == 0) return;
   __syncthreads();
 #pragma unroll
   for (int s = 1; s <= NST; s++) {
     const int n = taps.n[s - 1];
-    const int h = 2 * n - 1;
-    const V *src = lvl[s - 1];
+    const V *Es = E[s - 1];
+    const V *Os = O[s - 1];
+    const int64_t ebp = lo[s - 1] >> 1;        // base of the source level's E/O arrays
+    const int64_t ebn = (s < NST) ? (lo[s] >> 1) : 0;
     for (int i = threadIdx.x; i < len[s]; i += kHbThreads) {
-      const int64_t m = a[s] + i;
+      const int64_t m = lo[s] + i;
       V y;
       y.x = 0;
       y.y = 0;
       if (m >= 0) {
-        const int p = 2 * i + h; // position of x[2m] in the source level
-        y = src[p];
+        const int q = (int)(m - ebp);
+        y = Es[q];
+#pragma unroll 4
         for (int k = 0; k < n; k++) {
           const S t = taps.t[s - 1][k];
-          const V u = src[p + 2 * k + 1];
-          const V w = src[p - 2 * k - 1];
+          const V u = Os[q + k];
+          const V w = Os[q - k - 1];
           y.x += t * (u.x + w.x);
           y.y += t * (u.y + w.y);
         }
@@ -171,7 +217,12 @@ __global__ void __launch_bounds__(kHbThreads)
       if (s == NST) {
         out.st(c, m, y);
       } else {
-        lvl[s][i] = y;
+        const int idx = (int)((m >> 1) - ebn);
+        if (m & 1) {
+          O[s][idx] = y;
+        } else {
+          E[s][idx] = y;
+        }
       }
     }
     if (s < NST) __syncthreads();
@@ -233,6 +284,88 @@ __global__ void __launch_bounds__(kFirThreads)
   for (int r = 0; r < kFirR; r++) {
     const int q = threadIdx.x + r * kFirThreads;
     if (q < cnt) out.st(c, q0 + tile0 + q, acc[r]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Double-precision decimate-by-2 low-pass for the audio resamplers (reference:
+// r8b::CDSPBlockConvolver with DownFactor 2 inside AudioResampler, AudioResampler.cpp:37-61;
+// 1621 taps at 96 kHz, both audio lanes (mono, L-R) ride as one double2 stream).
+// Polyphase form: y[u] = sum_i h0[i] X0[u+i] + sum_i h1[i] X1[u+i] with X0/X1 the even/odd
+// input samples, so every output costs klen FMAs per lane instead of 2*klen. Each thread
+// owns kDecR consecutive outputs and keeps a sliding window of inputs in registers (one new
+// shared-memory load per tap for 2*kDecR FMAs); the input phases are stored kDecR-way
+// interleaved so that the window loads of a warp are contiguous (bank-conflict free).
+constexpr int kDecR = 8;
+constexpr int kDecThreads = 64;
+constexpr int kDecTile = kDecR * kDecThreads; // outputs per CTA
+constexpr int kDecMaxTaps = 1024;             // per phase, padded to a multiple of kDecR
+
+__host__ __device__ inline int dec2_len(int ntp) { return kDecThreads + ntp / kDecR + 3; }
+__host__ inline size_t dec2_smem(int klen) {
+  const int ntp = ((klen + 1) / 2 + kDecR - 1) / kDecR * kDecR;
+  return (size_t)2 * kDecR * dec2_len(ntp) * sizeof(double2) + (size_t)2 * ntp * sizeof(double);
+}
+
+static __global__ void __launch_bounds__(kDecThreads)
+    k_fir_dec2_f64(Ring<double2> in, Ring<double2> out, const double *__restrict__ taps, int klen, int64_t q0,
+                   int n_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t c = blockIdx.y;
+  const int tile0 = blockIdx.x * kDecTile;
+  int cnt = n_out - tile0;
+  if (cnt > kDecTile) cnt = kDecTile;
+  if (cnt <= 0) return;
+  const int nt0 = (klen + 1) / 2;                       // taps of the even phase
+  const int ntp = (nt0 + kDecR - 1) / kDecR * kDecR;    // padded taps per phase
+  const int LEN = dec2_len(ntp);
+  double2 *xs = reinterpret_cast<double2 *>(smem_raw);  // [2][kDecR][LEN]
+  double *hs = reinterpret_cast<double *>(xs + 2 * kDecR * LEN); // [2][ntp]
+  const int fl2 = (klen - 1) / 2;
+  const int64_t B = 2 * (q0 + tile0) - fl2;
+  const int span = 2 * (kDecTile + ntp + kDecR);        // X[0..span)
+  const int need = 2 * (cnt - 1) + klen;
+  for (int i = threadIdx.x; i < span; i += kDecThreads) {
+    double2 v = make_double2(0.0, 0.0);
+    if (i < need) v = in.ld(c, B + i);
+    const int rho = i & 1, m = i >> 1;
+    if (m / kDecR < LEN) xs[(rho * kDecR + (m % kDecR)) * LEN + m / kDecR] = v;
+  }
+  for (int i = threadIdx.x; i < 2 * ntp; i += kDecThreads) {
+    const int rho = i / ntp, k = i - rho * ntp;
+    const int j = 2 * k + rho;
+    hs[i] = (j < klen) ? taps[j] : 0.0;
+  }
+  __syncthreads();
+  double2 acc[kDecR];
+#pragma unroll
+  for (int r = 0; r < kDecR; r++) acc[r] = make_double2(0.0, 0.0);
+  const int tid = threadIdx.x;
+#pragma unroll 1
+  for (int rho = 0; rho < 2; rho++) {
+    const double2 *xp = xs + (size_t)rho * kDecR * LEN;
+    const double *hp = hs + rho * ntp;
+    double2 w[kDecR];
+#pragma unroll
+    for (int r = 0; r < kDecR; r++) w[r] = xp[r * LEN + tid];
+    for (int i0 = 0; i0 < ntp; i0 += kDecR) {
+#pragma unroll
+      for (int ii = 0; ii < kDecR; ii++) {
+        const double h = hp[i0 + ii];
+#pragma unroll
+        for (int r = 0; r < kDecR; r++) {
+          const double2 x = w[(r + ii) % kDecR];
+          acc[r].x = fma(h, x.x, acc[r].x);
+          acc[r].y = fma(h, x.y, acc[r].y);
+        }
+        w[ii] = xp[ii * LEN + tid + i0 / kDecR + 1];
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kDecR; r++) {
+    const int u = kDecR * tid + r;
+    if (u < cnt) out.st(c, q0 + tile0 + u, acc[r]);
   }
 }
 
