@@ -26,7 +26,7 @@ class FmConfig(C.Structure):
                 ("stereo", C.c_int), ("deemphasis_us", C.c_double), ("pilot_shift", C.c_int),
                 ("multipath_stages", C.c_uint32), ("n_channels", C.c_uint32),
                 ("max_samples_per_call", C.c_uint32), ("max_blocks_per_call", C.c_uint32),
-                ("device", C.c_int)]
+                ("device", C.c_int), ("fmfilter_coeff", C.c_void_p), ("fmfilter_ntaps", C.c_uint32)]
 
 
 class FmStats(C.Structure):
@@ -45,7 +45,8 @@ class PpsEvent(C.Structure):
 class AmConfig(C.Structure):
     _fields_ = [("input_rate", C.c_double), ("fs4_shift", C.c_int), ("amfilter", C.c_int),
                 ("mode", C.c_int), ("n_channels", C.c_uint32), ("max_samples_per_call", C.c_uint32),
-                ("max_blocks_per_call", C.c_uint32), ("device", C.c_int)]
+                ("max_blocks_per_call", C.c_uint32), ("device", C.c_int), ("amfilter_coeff", C.c_void_p),
+                ("amfilter_ntaps", C.c_uint32)]
 
 
 class AmStats(C.Structure):

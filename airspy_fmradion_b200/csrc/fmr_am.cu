@@ -169,7 +169,7 @@ static fmr_status am_build(fmr_am *h) {
   } else {
     HbTaps<float> t;
     memset(&t, 0, sizeof(t));
-    FMR_CUDA((cudaFuncSetAttribute(k_hb_cascade<float, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FMR_CUDA((cudaFuncSetAttribute(k_hb_cascade<float, 0, true, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)Resampler<float>::hb_smem(t, 0))));
   }
   FMR_CUDA(h->mem.alloc(&h->hist[0], (size_t)C * kHist));
@@ -186,6 +186,13 @@ static fmr_status am_build(fmr_am *h) {
     if (cfg.amfilter == 3) {
       tbl = k_jj1bdx_am_48khz_wide;
       h->amfilter_taps = 127;
+    }
+    if (cfg.amfilter == 4) {
+      if (!cfg.amfilter_coeff || cfg.amfilter_ntaps < 2 || cfg.amfilter_ntaps > 4096) {
+        return fail(FMR_ERR_INVALID, "amfilter == 4 needs amfilter_coeff with 2..4096 taps");
+      }
+      tbl = cfg.amfilter_coeff;
+      h->amfilter_taps = (int)cfg.amfilter_ntaps;
     }
     FMR_CUDA(h->mem.alloc(&h->d_amfilter, (size_t)h->amfilter_taps, false));
     FMR_CUDA(cudaMemcpy(h->d_amfilter, tbl, h->amfilter_taps * sizeof(float), cudaMemcpyHostToDevice));
@@ -244,7 +251,7 @@ extern "C" fmr_status fmr_am_create(const fmr_am_config *cfg, fmr_am **out) {
   if (cfg->n_channels == 0 || cfg->max_samples_per_call == 0 || cfg->max_blocks_per_call == 0) {
     return fail(FMR_ERR_INVALID, "n_channels, max_samples_per_call and max_blocks_per_call must be > 0");
   }
-  if (cfg->amfilter < 0 || cfg->amfilter > 3) return fail(FMR_ERR_INVALID, "amfilter must be 0..3");
+  if (cfg->amfilter < 0 || cfg->amfilter > 4) return fail(FMR_ERR_INVALID, "amfilter must be 0..4");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
     return fail(FMR_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
@@ -345,7 +352,7 @@ extern "C" fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t
     memset(&t, 0, sizeof(t));
     dim3 grid((unsigned)((total_in + kHbTile - 1) / kHbTile), C);
     pf.begin(h->ifres.p_hb, st);
-    k_hb_cascade<float, 0, true><<<grid, kHbThreads, Resampler<float>::hb_smem(t, 0), st>>>(
+    k_hb_cascade<float, 0, true, 0, 0, 0><<<grid, kHbThreads, Resampler<float>::hb_smem(t, 0), st>>>(
         src, h->r_if, t, t0, (int)total_in, h->cfg.fs4_shift);
     pf.end(h->ifres.p_hb, st);
     launches++;

@@ -13,6 +13,9 @@ thread_local std::string g_err;
 
 using namespace fmr;
 
+constexpr int kMaxGroups = 4;  // channel groups (streams) per process call
+constexpr int kGroupMin = 1 << 28; // channel groups are disabled: measured slower (all groups hit their serial phase together)
+
 struct fmr_fm {
   fmr_fm_config cfg;
   int C = 0;
@@ -44,6 +47,8 @@ struct fmr_fm {
   double *d_pilotcut = nullptr;
   float *d_atan = nullptr;
   MpfDev mpf;
+  cudaStream_t gstream[kMaxGroups] = {nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {nullptr};
   Prof prof;
   int p_hist = -1, p_fmf = -1, p_core = -1, p_agc = -1, p_mpf = -1, p_core2 = -1, p_pcut = -1, p_tail = -1;
   FmCoreParams core;
@@ -101,6 +106,11 @@ static fmr_status fm_build(fmr_fm *h) {
   if (!h->auc) return fail(FMR_ERR_UNSUPPORTED, "audio resampler tables missing");
   FMR_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   FMR_CUDA(h->slots.init(2 * sizeof(uint32_t) * (size_t)max_blocks));
+  for (int g = 0; g < kMaxGroups; g++) {
+    FMR_CUDA(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+    FMR_CUDA(cudaEventCreateWithFlags(&h->ev_join[g], cudaEventDisableTiming));
+  }
+  FMR_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
 
   int64_t max384 = max_in + 8;
   if (h->ifc) {
@@ -112,7 +122,7 @@ static fmr_status fm_build(fmr_fm *h) {
   } else {
     HbTaps<float> t;
     memset(&t, 0, sizeof(t));
-    FMR_CUDA((cudaFuncSetAttribute(k_hb_cascade<float, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FMR_CUDA((cudaFuncSetAttribute(k_hb_cascade<float, 0, true, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)Resampler<float>::hb_smem(t, 0))));
   }
   FMR_CUDA(h->mem.alloc(&h->hist[0], (size_t)C * kHist));
@@ -123,8 +133,15 @@ static fmr_status fm_build(fmr_fm *h) {
   if (cfg.fmfilter) {
     const float *tbl = (cfg.fmfilter == 1) ? k_jj1bdx_fm_384kHz_medium : k_jj1bdx_fm_384kHz_narrow;
     h->fmfilter_taps = 127;
-    FMR_CUDA(h->mem.alloc(&h->d_fmfilter, 127, false));
-    FMR_CUDA(cudaMemcpy(h->d_fmfilter, tbl, 127 * sizeof(float), cudaMemcpyHostToDevice));
+    if (cfg.fmfilter == 3) {
+      if (!cfg.fmfilter_coeff || cfg.fmfilter_ntaps < 2 || cfg.fmfilter_ntaps > 4096) {
+        return fail(FMR_ERR_INVALID, "fmfilter == 3 needs fmfilter_coeff with 2..4096 taps");
+      }
+      tbl = cfg.fmfilter_coeff;
+      h->fmfilter_taps = (int)cfg.fmfilter_ntaps;
+    }
+    FMR_CUDA(h->mem.alloc(&h->d_fmfilter, (size_t)h->fmfilter_taps, false));
+    FMR_CUDA(cudaMemcpy(h->d_fmfilter, tbl, h->fmfilter_taps * sizeof(float), cudaMemcpyHostToDevice));
     h->r_iff.cap = h->r_if.cap;
     FMR_CUDA(h->mem.alloc(&h->r_iff.base, (size_t)C * h->r_iff.cap));
   }
@@ -233,7 +250,7 @@ extern "C" fmr_status fmr_fm_create(const fmr_fm_config *cfg, fmr_fm **out) {
   if (cfg->n_channels == 0 || cfg->max_samples_per_call == 0 || cfg->max_blocks_per_call == 0) {
     return fail(FMR_ERR_INVALID, "n_channels, max_samples_per_call and max_blocks_per_call must be > 0");
   }
-  if (cfg->fmfilter < 0 || cfg->fmfilter > 2) return fail(FMR_ERR_INVALID, "fmfilter must be 0, 1 or 2");
+  if (cfg->fmfilter < 0 || cfg->fmfilter > 3) return fail(FMR_ERR_INVALID, "fmfilter must be 0..3");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
     return fail(FMR_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
@@ -258,6 +275,11 @@ extern "C" void fmr_fm_destroy(fmr_fm *h) {
   h->mem.release();
   h->slots.release();
   h->prof.release();
+  for (int g = 0; g < kMaxGroups; g++) {
+    if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
+    if (h->ev_join[g]) cudaEventDestroy(h->ev_join[g]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -353,97 +375,137 @@ extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t
   int launches = 0;
   Prof &pf = h->prof;
   pf.reset();
-  // ---- front end: Fs/4 shift + IF resampler -> r_if[t0, t1)
-  InSrc<float2> src;
-  src.lin = reinterpret_cast<const float2 *>(d_iq);
-  src.stride = iq_stride;
-  src.hist = h->hist[h->hist_cur];
-  src.start = h->cum_in;
-  src.n_new = (int64_t)total_in;
-  src.ring = Ring<float2>{nullptr, 0};
-  int64_t t0 = h->cum384, t1 = h->cum384 + n384;
-  if (h->ifc) {
-    int64_t o0, o1;
-    s = h->ifres.run(src, (int64_t)total_in, h->r_if, h->cfg.fs4_shift, st, &o0, &o1, &launches);
-    if (s != FMR_OK) return s;
-    if (o0 != t0 || o1 != t1) return fail(FMR_ERR_INVALID, "internal: IF schedule mismatch");
-  } else if (total_in > 0) {
-    HbTaps<float> t;
-    memset(&t, 0, sizeof(t));
-    dim3 grid((unsigned)((total_in + kHbTile - 1) / kHbTile), C);
-    pf.begin(h->ifres.p_hb, st);
-    k_hb_cascade<float, 0, true><<<grid, kHbThreads, Resampler<float>::hb_smem(t, 0), st>>>(
-        src, h->r_if, t, t0, (int)total_in, h->cfg.fs4_shift);
-    pf.end(h->ifres.p_hb, st);
-    launches++;
+  const int64_t t0 = h->cum384, t1 = h->cum384 + n384;
+  const int64_t j0 = h->cum48;
+  // Channels are independent, so the handle works through them in groups, each group on its
+  // own stream: the latency-bound serial kernels (AGC, PLL, DC block) of one group overlap the
+  // throughput kernels (half-band cascade, FFT low-pass, audio FIR) of the others.
+  int n_groups = 1;
+  if (!pf.on && C >= 2 * kGroupMin) {
+    n_groups = C / kGroupMin;
+    if (n_groups > kMaxGroups) n_groups = kMaxGroups;
   }
-  if (h->ifc && total_in > 0) {
-    pf.begin(h->p_hist, st);
-    k_save_hist<float2><<<C, 128, 0, st>>>(src.lin, iq_stride, (int64_t)total_in, h->hist[h->hist_cur],
-                                           h->hist[h->hist_cur ^ 1]);
-    pf.end(h->p_hist, st);
-    h->hist_cur ^= 1;
-    launches++;
+  if (n_groups > 1) {
+    FMR_CUDA(cudaEventRecord(h->ev_fork, st));
+    for (int g = 0; g < n_groups; g++) FMR_CUDA(cudaStreamWaitEvent(h->gstream[g], h->ev_fork, 0));
   }
-  if (n384 > 0) {
-    // ---- optional IF filter (FmDecode.cpp:98-102)
-    if (h->cfg.fmfilter) {
-      dim3 grid((n384 + 127) / 128, C);
-      pf.begin(h->p_fmf, st);
-      k_fir_quirk<float><<<grid, 128, 0, st>>>(h->r_if, h->r_iff, h->d_fmfilter, h->fmfilter_taps, t0, (int)n384,
-                                               h->d_e384, (int)n_blocks);
-      pf.end(h->p_fmf, st);
+  for (int g = 0; g < n_groups; g++) {
+    const int c0 = (int)((int64_t)C * g / n_groups), c1 = (int)((int64_t)C * (g + 1) / n_groups);
+    const int cn = c1 - c0;
+    cudaStream_t gs = (n_groups > 1) ? h->gstream[g] : st;
+    const bool last = (g == n_groups - 1);
+    auto subf2 = [&](Ring<float2> r) { return Ring<float2>{r.base ? r.base + (size_t)c0 * r.cap : nullptr, r.cap}; };
+    auto subd2 = [&](Ring<double2> r) { return Ring<double2>{r.base + (size_t)c0 * r.cap, r.cap}; };
+    const Ring<float2> r_if = subf2(h->r_if), r_iff = subf2(h->r_iff), r_agc = subf2(h->r_agc), r_mpf = subf2(h->r_mpf);
+    const Ring<float> r_mpx{h->r_mpx.base + (size_t)c0 * h->r_mpx.cap, h->r_mpx.cap};
+    const Ring<double2> r_384 = subd2(h->r_384), r_48a = subd2(h->r_48a), r_48b = subd2(h->r_48b);
+    FmChanState *d_state = h->d_state + c0;
+    uint8_t *d_flags = h->d_flags + (size_t)c0 * n_blocks;
+    PpsEventDev *d_pps = h->d_pps + (size_t)c0 * kMaxPps;
+    float *d_stats = h->d_stats + (size_t)c0 * n_blocks * 3;
+    FmCoreParams core = h->core;
+    core.n_channels = cn;
+    FmTailParams tail = h->tail;
+    tail.n_channels = cn;
+    // ---- front end: Fs/4 shift + IF resampler -> r_if[t0, t1)
+    InSrc<float2> src;
+    src.lin = reinterpret_cast<const float2 *>(d_iq) + (size_t)c0 * iq_stride;
+    src.stride = iq_stride;
+    src.hist = h->hist[h->hist_cur] + (size_t)c0 * kHist;
+    src.start = h->cum_in;
+    src.n_new = (int64_t)total_in;
+    src.ring = Ring<float2>{nullptr, 0};
+    if (h->ifc) {
+      int64_t o0, o1;
+      h->ifres.gc0 = c0;
+      h->ifres.gcn = cn;
+      s = h->ifres.run(src, (int64_t)total_in, r_if, h->cfg.fs4_shift, gs, &o0, &o1, &launches, last);
+      if (s != FMR_OK) return s;
+      if (o0 != t0 || o1 != t1) return fail(FMR_ERR_INVALID, "internal: IF schedule mismatch");
+    } else if (total_in > 0) {
+      HbTaps<float> t;
+      memset(&t, 0, sizeof(t));
+      dim3 grid((unsigned)((total_in + kHbTile - 1) / kHbTile), cn);
+      pf.begin(h->ifres.p_hb, gs);
+      k_hb_cascade<float, 0, true, 0, 0, 0><<<grid, kHbThreads, Resampler<float>::hb_smem(t, 0), gs>>>(
+          src, r_if, t, t0, (int)total_in, h->cfg.fs4_shift);
+      pf.end(h->ifres.p_hb, gs);
       launches++;
     }
-    // ---- 384 kHz core: AGC (serial) -> [multipath] -> discriminator + statistics (parallel) -> PLL (serial)
-    dim3 cgrid((C + 31) / 32);
-    pf.begin(h->p_agc, st);
-    k_fm_agc<<<cgrid, 32, 0, st>>>(h->r_iff, h->r_agc, h->d_state, (int)n384, t0, h->core);
-    pf.end(h->p_agc, st);
-    launches++;
-    Ring<float2> disc_in = h->r_agc;
-    if (h->cfg.multipath_stages > 0) {
-      pf.begin(h->p_mpf, st);
-      h->mpf.run(h->r_agc, h->r_mpf, h->d_state, h->d_e384, (int)n_blocks, t0, st);
-      pf.end(h->p_mpf, st);
+    if (h->ifc && total_in > 0) {
+      pf.begin(h->p_hist, gs);
+      k_save_hist<float2><<<cn, 128, 0, gs>>>(src.lin, iq_stride, (int64_t)total_in, src.hist,
+                                              h->hist[h->hist_cur ^ 1] + (size_t)c0 * kHist);
+      pf.end(h->p_hist, gs);
       launches++;
-      disc_in = h->r_mpf;
     }
-    pf.begin(h->p_core, st);
-    {
-      dim3 g((n384 + 255) / 256, C);
-      k_fm_disc<<<g, 256, 0, st>>>(disc_in, h->r_mpx, (int)n384, t0, h->core);
-      dim3 g2((n_blocks + 3) / 4, C);
-      k_fm_call_stats<<<g2, 128, 0, st>>>(h->r_if, h->r_mpx, h->d_stats, h->d_e384, (int)n_blocks, t0);
+    if (n384 > 0) {
+      // ---- optional IF filter (FmDecode.cpp:98-102)
+      if (h->cfg.fmfilter) {
+        dim3 grid((n384 + 127) / 128, cn);
+        pf.begin(h->p_fmf, gs);
+        k_fir_quirk<float><<<grid, 128, 0, gs>>>(r_if, r_iff, h->d_fmfilter, h->fmfilter_taps, t0, (int)n384,
+                                                 h->d_e384, (int)n_blocks);
+        pf.end(h->p_fmf, gs);
+        launches++;
+      }
+      // ---- 384 kHz core: AGC (serial) -> [multipath] -> discriminator + statistics (parallel) -> PLL (serial)
+      dim3 cgrid((cn + 31) / 32);
+      pf.begin(h->p_agc, gs);
+      k_fm_agc<<<cgrid, 32, 0, gs>>>(r_iff, r_agc, d_state, (int)n384, t0, core);
+      pf.end(h->p_agc, gs);
+      launches++;
+      Ring<float2> disc_in = r_agc;
+      if (h->cfg.multipath_stages > 0) {
+        pf.begin(h->p_mpf, gs);
+        h->mpf.run(r_agc, r_mpf, d_state, h->d_e384, (int)n_blocks, t0, gs, c0, cn);
+        pf.end(h->p_mpf, gs);
+        launches++;
+        disc_in = r_mpf;
+      }
+      pf.begin(h->p_core, gs);
+      {
+        dim3 g1((n384 + 255) / 256, cn);
+        k_fm_disc<<<g1, 256, 0, gs>>>(disc_in, r_mpx, (int)n384, t0, core);
+        dim3 g2((n_blocks + 3) / 4, cn);
+        k_fm_call_stats<<<g2, 128, 0, gs>>>(r_if, r_mpx, d_stats, h->d_e384, (int)n_blocks, t0);
+      }
+      pf.end(h->p_core, gs);
+      pf.begin(h->p_core2, gs);
+      k_fm_pll<<<cgrid, 32, 0, gs>>>(r_mpx, r_384, d_state, d_flags, d_pps, d_stats, h->d_e384, (int)n_blocks, t0,
+                                     core, h->d_atan);
+      pf.end(h->p_core2, gs);
+      launches += 3;
+      // ---- audio resamplers (mono and L-R in lock step, FmDecode.cpp:172-183)
+      InSrc<double2> asrc;
+      memset(&asrc, 0, sizeof(asrc));
+      asrc.ring = r_384;
+      int64_t a0, a1;
+      h->aures.gc0 = c0;
+      h->aures.gcn = cn;
+      s = h->aures.run(asrc, (int64_t)n384, r_48a, 0, gs, &a0, &a1, &launches, last);
+      if (s != FMR_OK) return s;
+      if (a0 != j0 || a1 != j0 + n48) return fail(FMR_ERR_INVALID, "internal: audio schedule mismatch");
+      if (n48 > 0) {
+        // ---- pilot-cut FIR (FmDecode.cpp:190,196) then DC block + matrix
+        dim3 grid((n48 + 127) / 128, cn);
+        pf.begin(h->p_pcut, gs);
+        k_fir_quirk<double><<<grid, 128, 0, gs>>>(r_48a, r_48b, h->d_pilotcut, 127, j0, (int)n48, h->d_e48,
+                                                  (int)n_blocks);
+        pf.end(h->p_pcut, gs);
+        pf.begin(h->p_tail, gs);
+        k_fm_tail<<<cgrid, 32, 0, gs>>>(r_48b, d_audio + (size_t)c0 * audio_stride, audio_stride, d_state, d_flags,
+                                        h->d_e48, (int)n_blocks, j0, tail);
+        pf.end(h->p_tail, gs);
+        launches += 2;
+      }
     }
-    pf.end(h->p_core, st);
-    pf.begin(h->p_core2, st);
-    k_fm_pll<<<cgrid, 32, 0, st>>>(h->r_mpx, h->r_384, h->d_state, h->d_flags, h->d_pps, h->d_stats, h->d_e384,
-                                   (int)n_blocks, t0, h->core, h->d_atan);
-    pf.end(h->p_core2, st);
-    launches += 3;
-    // ---- audio resamplers (mono and L-R in lock step, FmDecode.cpp:172-183)
-    InSrc<double2> asrc;
-    memset(&asrc, 0, sizeof(asrc));
-    asrc.ring = h->r_384;
-    int64_t j0, j1;
-    s = h->aures.run(asrc, (int64_t)n384, h->r_48a, 0, st, &j0, &j1, &launches);
-    if (s != FMR_OK) return s;
-    if (j0 != h->cum48 || j1 != h->cum48 + n48) return fail(FMR_ERR_INVALID, "internal: audio schedule mismatch");
-    if (n48 > 0) {
-      // ---- pilot-cut FIR (FmDecode.cpp:190,196) then DC block + matrix
-      dim3 grid((n48 + 127) / 128, C);
-      pf.begin(h->p_pcut, st);
-      k_fir_quirk<double><<<grid, 128, 0, st>>>(h->r_48a, h->r_48b, h->d_pilotcut, 127, j0, (int)n48, h->d_e48,
-                                                (int)n_blocks);
-      pf.end(h->p_pcut, st);
-      pf.begin(h->p_tail, st);
-      k_fm_tail<<<cgrid, 32, 0, st>>>(h->r_48b, d_audio, audio_stride, h->d_state, h->d_flags, h->d_e48,
-                                      (int)n_blocks, j0, h->tail);
-      pf.end(h->p_tail, st);
-      launches += 2;
+    if (n_groups > 1) {
+      FMR_CUDA(cudaEventRecord(h->ev_join[g], gs));
+      FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[g], 0));
     }
   }
+  if (h->ifc && total_in > 0) h->hist_cur ^= 1;
   FMR_CUDA(cudaGetLastError());
   h->cum_in += (int64_t)total_in;
   h->cum384 += n384;

@@ -193,6 +193,9 @@ template <typename S> struct Resampler {
   int C = 0;
   bool linear_in = false;
   Ring<V> r_hb{nullptr, 0}, r_bc{nullptr, 0};
+  // channel group the next run() works on (the caller offsets `src` and `out` itself)
+  int gc0 = 0, gcn = 0;
+  Ring<V> sub(Ring<V> r) const { return Ring<V>{r.base + (size_t)gc0 * r.cap, r.cap}; }
   S *d_bc = nullptr, *d_fi = nullptr;
   HbTaps<S> hbt;
   int64_t cum_in = 0;
@@ -205,13 +208,34 @@ template <typename S> struct Resampler {
 
   static size_t hb_smem(const HbTaps<S> &t, int nst) {
     size_t total = 0;
-    for (int s = 0; s < nst; s++) total += 2 * (size_t)hb_half(hb_level_len(t.n, nst, s));
+    // levels 0 and 1 are live together; level 2 aliases level 0 (see k_hb_cascade)
+    for (int s = 0; s < nst && s < 2; s++) {
+      total += 2 * (size_t)kHbR * hb_sub_len(hb_level_len(t.n, nst, s), (int)sizeof(V));
+    }
     return total * sizeof(V) + 16;
   }
 
-  template <int NST, bool LIN> static cudaError_t set_hb_attr(size_t smem) {
-    return cudaFuncSetAttribute(k_hb_cascade<S, NST, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem);
+  // Dispatch over the half-band tap-count combinations of the shipped chains. F is called with
+  // the kernel's function pointer.
+  template <typename F> bool hb_dispatch(F &&f) const {
+    const int n1 = hbt.n[0], n2 = hbt.n[1], n3 = hbt.n[2];
+#define FMR_HB_COMBO(NST, A, B, Cc)                                                       \
+  if (d->n_hb == NST && n1 == A && n2 == B && n3 == Cc) {                                  \
+    if (linear_in) {                                                                      \
+      f(k_hb_cascade<S, NST, true, A, B, Cc>);                                            \
+    } else {                                                                              \
+      f(k_hb_cascade<S, NST, false, A, B, Cc>);                                           \
+    }                                                                                     \
+    return true;                                                                          \
+  }
+    FMR_HB_COMBO(0, 0, 0, 0)
+    FMR_HB_COMBO(3, 4, 5, 8)  // 10 MHz -> 384 kHz
+    FMR_HB_COMBO(2, 5, 8, 0)  // 6 MHz
+    FMR_HB_COMBO(1, 8, 0, 0)  // 2.5 MHz
+    FMR_HB_COMBO(2, 6, 11, 0) // 384 kHz -> 48 kHz (IfResampler spec, AM)
+    FMR_HB_COMBO(2, 7, 13, 0) // 384 kHz -> 48 kHz (AudioResampler spec)
+#undef FMR_HB_COMBO
+    return false;
   }
 
   fmr_status init(const ChainDesc *desc, int channels, int64_t max_in, bool lin, DevMem &mem) {
@@ -225,13 +249,14 @@ template <typename S> struct Resampler {
       if (hbt.n[s] > 14) return fail(FMR_ERR_UNSUPPORTED, "half-band stage longer than 14 taps");
       for (int k = 0; k < hbt.n[s]; k++) hbt.t[s][k] = (S)d->hb[s].taps[k];
     }
+    for (int s = 0; s < d->n_hb; s++) hbt.sl[s] = hb_sub_len(hb_level_len(hbt.n, d->n_hb, s), (int)sizeof(V));
     smem_hb = hb_smem(hbt, d->n_hb);
     cudaError_t e = cudaSuccess;
-    switch (d->n_hb) {
-    case 0: e = lin ? set_hb_attr<0, true>(smem_hb) : set_hb_attr<0, false>(smem_hb); break;
-    case 1: e = lin ? set_hb_attr<1, true>(smem_hb) : set_hb_attr<1, false>(smem_hb); break;
-    case 2: e = lin ? set_hb_attr<2, true>(smem_hb) : set_hb_attr<2, false>(smem_hb); break;
-    default: e = lin ? set_hb_attr<3, true>(smem_hb) : set_hb_attr<3, false>(smem_hb); break;
+    const size_t smem_need = smem_hb;
+    if (!hb_dispatch([&](auto kern) {
+          e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need);
+        })) {
+      return fail(FMR_ERR_UNSUPPORTED, "half-band tap combination not instantiated");
     }
     FMR_CUDA(e);
     const int64_t max_hb = (max_in >> d->n_hb) + 4;
@@ -280,27 +305,25 @@ template <typename S> struct Resampler {
 
   int64_t max_out(int64_t max_in) const { return chain_out(d, max_in + (int64_t)1) + 8; }
 
-  template <int NST, bool LIN>
-  void launch_hb(const InSrc<V> &src, int64_t o0, int n_out, int fs4, cudaStream_t st) {
-    dim3 grid((n_out + kHbTile - 1) / kHbTile, C);
-    k_hb_cascade<S, NST, LIN><<<grid, kHbThreads, smem_hb, st>>>(src, r_hb, hbt, o0, n_out, fs4);
-  }
-
   void launch_fft(Ring<float2> in, Ring<float2> o, int64_t q0, int n, int64_t avail, cudaStream_t st) {
     const int lq = (kFftN - d->bc.klen + 1) / d->bc.down;
-    dim3 grid((n + lq - 1) / lq, C);
+    dim3 grid((n + lq - 1) / lq, gcn);
     k_fir_fft<<<grid, kFftThreads, kFftSmemBytes, st>>>(in, o, d_H, d->bc.klen, d->bc.down, q0, n, avail, lq);
   }
   void launch_fft(Ring<double2>, Ring<double2>, int64_t, int, int64_t, cudaStream_t) {}
   void launch_dec2(Ring<double2> in, Ring<double2> o, int64_t q0, int n, cudaStream_t st) {
-    dim3 grid((n + kDecTile - 1) / kDecTile, C);
+    dim3 grid((n + kDecTile - 1) / kDecTile, gcn);
     k_fir_dec2_f64<<<grid, kDecThreads, dec2_smem(d->bc.klen), st>>>(in, o, d_bc, d->bc.klen, q0, n);
   }
   void launch_dec2(Ring<float2>, Ring<float2>, int64_t, int, cudaStream_t) {}
 
   // Consume n_new more input samples; produce the reference's output index range into `out`.
   fmr_status run(InSrc<V> src, int64_t n_new, Ring<V> out, int fs4, cudaStream_t st, int64_t *o0,
-                 int64_t *o1, int *launches) {
+                 int64_t *o1, int *launches, bool advance = true) {
+    if (gcn == 0) {
+      gc0 = 0;
+      gcn = C;
+    }
     const int64_t N0 = cum_in, N1 = cum_in + n_new;
     const int64_t h0 = hb_out(d, N0), h1 = hb_out(d, N1);
     const int64_t b0 = bc_out(d, h0), b1 = bc_out(d, h1);
@@ -310,28 +333,29 @@ template <typename S> struct Resampler {
       const int n = (int)(h1 - h0);
       if (n > 0) {
         if (prof) prof->begin(p_hb, st);
-        switch (d->n_hb) {
-        case 0: linear_in ? launch_hb<0, true>(src, h0, n, fs4, st) : launch_hb<0, false>(src, h0, n, fs4, st); break;
-        case 1: linear_in ? launch_hb<1, true>(src, h0, n, fs4, st) : launch_hb<1, false>(src, h0, n, fs4, st); break;
-        case 2: linear_in ? launch_hb<2, true>(src, h0, n, fs4, st) : launch_hb<2, false>(src, h0, n, fs4, st); break;
-        default: linear_in ? launch_hb<3, true>(src, h0, n, fs4, st) : launch_hb<3, false>(src, h0, n, fs4, st); break;
+        {
+          dim3 grid((n + kHbTile - 1) / kHbTile, gcn);
+          const Ring<V> hb_out_ring = sub(r_hb);
+          const HbTaps<S> tp = hbt;
+          const size_t sm = smem_hb;
+          hb_dispatch([&](auto kern) { kern<<<grid, kHbThreads, sm, st>>>(src, hb_out_ring, tp, h0, n, fs4); });
         }
         (*launches)++;
         if (prof) prof->end(p_hb, st);
       }
-      bc_in = r_hb;
+      bc_in = sub(r_hb);
     }
     {
       const int n = (int)(b1 - b0);
       if (n > 0) {
         if (prof) prof->begin(p_bc, st);
         if (use_fft && n >= kFftMinOut) {
-          launch_fft(bc_in, d->has_fi ? r_bc : out, b0, n, h1, st);
+          launch_fft(bc_in, d->has_fi ? sub(r_bc) : out, b0, n, h1, st);
         } else if (use_dec2) {
-          launch_dec2(bc_in, d->has_fi ? r_bc : out, b0, n, st);
+          launch_dec2(bc_in, d->has_fi ? sub(r_bc) : out, b0, n, st);
         } else {
-          dim3 grid((n + kFirTile - 1) / kFirTile, C);
-          k_fir_long<S><<<grid, kFirThreads, smem_fir, st>>>(bc_in, d->has_fi ? r_bc : out, d_bc, d->bc.klen,
+          dim3 grid((n + kFirTile - 1) / kFirTile, gcn);
+          k_fir_long<S><<<grid, kFirThreads, smem_fir, st>>>(bc_in, d->has_fi ? sub(r_bc) : out, d_bc, d->bc.klen,
                                                               d->bc.down, b0, n);
         }
         if (prof) prof->end(p_bc, st);
@@ -341,14 +365,14 @@ template <typename S> struct Resampler {
     if (d->has_fi) {
       const int n = (int)(f1 - f0);
       if (n > 0) {
-        dim3 grid((n + 127) / 128, C);
+        dim3 grid((n + 127) / 128, gcn);
         if (prof) prof->begin(p_fi, st);
-        k_frac_interp<S><<<grid, 128, 0, st>>>(r_bc, out, d_fi, d->fi.instep, d->fi.outstep, d->fi.flen, f0, n);
+        k_frac_interp<S><<<grid, 128, 0, st>>>(sub(r_bc), out, d_fi, d->fi.instep, d->fi.outstep, d->fi.flen, f0, n);
         if (prof) prof->end(p_fi, st);
         (*launches)++;
       }
     }
-    cum_in = N1;
+    if (advance) cum_in = N1;
     *o0 = f0;
     *o1 = f1;
     FMR_CUDA(cudaGetLastError());

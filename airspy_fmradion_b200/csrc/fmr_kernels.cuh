@@ -78,21 +78,34 @@ __device__ __forceinline__ V src_ld(const InSrc<V> &s, uint32_t c, int64_t i) {
 // in shared memory, so the input is read from HBM exactly once.
 template <typename S> struct HbTaps {
   int n[3];
+  int sl[3]; // shared-memory sub-array length per level (host-computed, hb_sub_len)
   S t[3][14];
 };
-constexpr int kHbTile = 256;
+constexpr int kHbTile = 512;
 constexpr int kHbThreads = 256;
+constexpr int kHbR = 4; // consecutive outputs per thread (register blocking)
 
-// Shared-memory footprint (elements of V) of one CTA: every level keeps its even- and
-// odd-indexed samples in two separate arrays (E[m] = x[2m], O[j] = x[2j+1]), because a
-// half-band output reads x[2m] and only ODD neighbours: with the split, consecutive threads
-// read consecutive words of E and O (no 2-way bank conflict of a stride-2 walk).
+// Shared-memory layout of one level: even- and odd-indexed samples in two separate arrays
+// (E[m] = x[2m], O[j] = x[2j+1]) because a half-band output reads x[2m] and only ODD
+// neighbours; each array is kHbR-way interleaved (element j lives in sub-array j % kHbR at
+// position j / kHbR) so that a thread that owns kHbR consecutive outputs, and whose window
+// of odd neighbours therefore advances kHbR elements per thread, still gives the warp
+// contiguous (bank-conflict-free) addresses for every window slot.
 __host__ __device__ inline int hb_level_len(const int *ntaps, int nst, int s) {
   int full = kHbTile; // number of samples of level s needed by a full tile
   for (int q = nst; q > s; q--) full = 2 * full + 4 * ntaps[q - 1] - 3;
   return full;
 }
-__host__ __device__ inline int hb_half(int len) { return len / 2 + 2; }
+// Per-sub-array length, padded so that the kHbR sub-arrays start 32 bytes apart modulo the
+// 128-byte bank window: threads that scatter consecutive samples over the sub-arrays (level
+// fill, stage write-back) then hit distinct banks. elem_bytes = sizeof(float2 / double2).
+__host__ __device__ inline int hb_sub_len(int len, int elem_bytes) {
+  int sl = (len / 2 + 2) / kHbR + 2;
+  const int mod = (elem_bytes == 8) ? 16 : 8, want = (elem_bytes == 8) ? 4 : 2;
+  while (sl % mod != want) sl++;
+  return sl;
+}
+__device__ __forceinline__ int hb_pos(int j, int sl) { return (j % kHbR) * sl + j / kHbR; }
 
 template <typename V> __device__ __forceinline__ V fs4_rot(V v, int64_t ai) {
   const int ph = (int)(ai & 3);
@@ -112,7 +125,60 @@ template <typename V> __device__ __forceinline__ V fs4_rot(V v, int64_t ai) {
   return w;
 }
 
-template <typename S, int NST, bool LINEAR>
+// One half-band stage with N taps: outputs [lo_out, lo_out+len_out) from the source level's
+// E/O arrays (base index ebp = lo_out - N), written to the next level's arrays or to `out`.
+template <typename S, int N, bool LAST>
+__device__ __forceinline__ void hb_stage(const typename V2<S>::type *__restrict__ Es,
+                                         const typename V2<S>::type *__restrict__ Os, int sl_src,
+                                         typename V2<S>::type *En, typename V2<S>::type *On, int sl_dst,
+                                         int64_t ebn, const S *__restrict__ t, int64_t lo_out, int len_out,
+                                         Ring<typename V2<S>::type> out, uint32_t c) {
+  using V = typename V2<S>::type;
+  constexpr int W = kHbR + 2 * N - 1; // odd-neighbour window of kHbR consecutive outputs
+  const int ngroups = (len_out + kHbR - 1) / kHbR;
+  for (int g = threadIdx.x; g < ngroups; g += kHbThreads) {
+    // local source index of output r's centre: q = kHbR*g + r + N
+    V w[W], e[kHbR];
+#pragma unroll
+    for (int sidx = 0; sidx < W; sidx++) w[sidx] = Os[(sidx % kHbR) * sl_src + g + sidx / kHbR];
+#pragma unroll
+    for (int r = 0; r < kHbR; r++) e[r] = Es[((r + N) % kHbR) * sl_src + g + (r + N) / kHbR];
+#pragma unroll
+    for (int r = 0; r < kHbR; r++) {
+      V y = e[r];
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        const V u = w[r + N + k];
+        const V v = w[r + N - k - 1];
+        y.x += t[k] * (u.x + v.x);
+        y.y += t[k] * (u.y + v.y);
+      }
+      const int i = kHbR * g + r;
+      if (i < len_out) {
+        const int64_t m = lo_out + i;
+        if (m < 0) {
+          y.x = 0;
+          y.y = 0;
+        }
+        if (LAST) {
+          out.st(c, m, y);
+        } else {
+          const int j = (int)((m >> 1) - ebn);
+          if (m & 1) {
+            On[hb_pos(j, sl_dst)] = y;
+          } else {
+            En[hb_pos(j, sl_dst)] = y;
+          }
+        }
+      }
+    }
+  }
+}
+
+// The tap counts are template parameters (N1, N2, N3; 0 = stage absent) so that every stage's
+// register window has a compile-time size; the host instantiates the combinations r8brain
+// produces for the shipped rates.
+template <typename S, int NST, bool LINEAR, int N1, int N2, int N3>
 __global__ void __launch_bounds__(kHbThreads)
     k_hb_cascade(InSrc<typename V2<S>::type> in, Ring<typename V2<S>::type> out, HbTaps<S> taps,
                  int64_t o0, int n_out, int fs4) {
@@ -145,87 +211,96 @@ __global__ void __launch_bounds__(kHbThreads)
     len[s - 1] = 2 * len[s] + 2 * h - 1;
   }
   V *E[3], *O[3];
+  int sl[3];
   {
     V *p = reinterpret_cast<V *>(smem_raw);
 #pragma unroll
     for (int s = 0; s < NST; s++) {
-      const int hl = hb_half(hb_level_len(taps.n, NST, s));
-      E[s] = p;
-      O[s] = p + hl;
-      p += 2 * hl;
+      sl[s] = taps.sl[s];
+      // level 2 re-uses level 0's storage: level 0 is dead once stage 1 has run
+      V *q = (s == 2) ? reinterpret_cast<V *>(smem_raw) : p;
+      E[s] = q;
+      O[s] = q + kHbR * sl[s];
+      if (s < 2) p += 2 * kHbR * sl[s];
     }
   }
   // ---- level 0: pairs (x[2p], x[2p+1]) -> E0[p - eb], O0[p - eb]
   {
     const int64_t eb = lo[0] >> 1; // floor
-    const int npairs = (int)(((lo[0] + len[0] - 1) >> 1) - eb) + 1;
-    for (int i = threadIdx.x; i < npairs; i += kHbThreads) {
-      const int64_t p = eb + i;
-      const int64_t a0 = 2 * p;
-      V v0, v1;
-      bool fast = false;
-      if (LINEAR) {
-        const int64_t r = a0 - in.start;
-        const float2 *pp = reinterpret_cast<const float2 *>(in.lin) + (size_t)c * in.stride + r;
-        if (r >= 0 && r + 1 < in.n_new && sizeof(V) == 8 && ((reinterpret_cast<uintptr_t>(pp) & 15) == 0)) {
-          // 16-byte aligned pair inside this call's buffer: one 128-bit load
-          const float4 q = *reinterpret_cast<const float4 *>(pp);
-          v0.x = q.x;
-          v0.y = q.y;
-          v1.x = q.z;
-          v1.y = q.w;
-          fast = true;
+    const int npairs = (int)(((lo[0] + len[0] - 1) >> 1) - eb) + 1 + kHbR; // a few extra: window overrun
+    constexpr int kN1 = (N1 > 0 ? N1 : 1), kN2 = (N2 > 0 ? N2 : 0), kN3 = (N3 > 0 ? N3 : 0);
+    // level-0 samples of a full tile (compile time) -> loads per thread
+    constexpr int kLen0 = (NST == 1)   ? (2 * kHbTile + 4 * kN1 - 3)
+                          : (NST == 2) ? (2 * (2 * kHbTile + 4 * kN2 - 3) + 4 * kN1 - 3)
+                                       : (2 * (2 * (2 * kHbTile + 4 * kN3 - 3) + 4 * kN2 - 3) + 4 * kN1 - 3);
+    constexpr int kMaxPairs = kLen0 / 2 + 2 + kHbR;
+    constexpr int kBatch = (kMaxPairs + kHbThreads - 1) / kHbThreads;
+    bool fast = false;
+    if (LINEAR && sizeof(V) == 8) {
+      const int64_t r0 = 2 * eb - in.start;
+      const float2 *pp = reinterpret_cast<const float2 *>(in.lin) + (size_t)c * in.stride + r0;
+      fast = (r0 >= 0) && (r0 + 2 * (int64_t)npairs <= in.n_new) && ((reinterpret_cast<uintptr_t>(pp) & 15) == 0);
+      if (fast) {
+        // whole tile inside this call's buffer and 16-byte aligned: all 128-bit loads of a
+        // thread are issued back to back (latency overlapped), then scattered to shared memory
+        const float4 *p4 = reinterpret_cast<const float4 *>(pp);
+        float4 q[kBatch];
+#pragma unroll
+        for (int bb = 0; bb < kBatch; bb++) {
+          const int i = threadIdx.x + bb * kHbThreads;
+          q[bb] = (i < npairs) ? p4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int ph0 = (int)((2 * eb) & 3); // Fs/4 phase of pair 0's even sample (0 or 2)
+#pragma unroll
+        for (int bb = 0; bb < kBatch; bb++) {
+          const int i = threadIdx.x + bb * kHbThreads;
+          if (i < npairs && i / kHbR < sl[0]) {
+            float2 v0 = make_float2(q[bb].x, q[bb].y), v1 = make_float2(q[bb].z, q[bb].w);
+            if (fs4) {
+              const int ph = (ph0 + 2 * i) & 3;
+              v0 = fs4_rot(v0, ph);
+              v1 = fs4_rot(v1, ph + 1);
+            }
+            const int pos = hb_pos(i, sl[0]);
+            reinterpret_cast<float2 *>(E[0])[pos] = v0;
+            reinterpret_cast<float2 *>(O[0])[pos] = v1;
+          }
         }
       }
-      if (!fast) {
-        v0 = src_ld<V, LINEAR>(in, c, a0);
-        v1 = src_ld<V, LINEAR>(in, c, a0 + 1);
+    }
+    if (!fast) {
+      for (int i = threadIdx.x; i < npairs; i += kHbThreads) {
+        const int64_t a0 = 2 * (eb + i);
+        V v0 = src_ld<V, LINEAR>(in, c, a0);
+        V v1 = src_ld<V, LINEAR>(in, c, a0 + 1);
+        if (fs4) {
+          v0 = fs4_rot(v0, a0);
+          v1 = fs4_rot(v1, a0 + 1);
+        }
+        if (i / kHbR < sl[0]) {
+          E[0][hb_pos(i, sl[0])] = v0;
+          O[0][hb_pos(i, sl[0])] = v1;
+        }
       }
-      if (fs4) {
-        v0 = fs4_rot(v0, a0);
-        v1 = fs4_rot(v1, a0 + 1);
-      }
-      E[0][i] = v0;
-      O[0][i] = v1;
     }
   }
   __syncthreads();
-#pragma unroll
-  for (int s = 1; s <= NST; s++) {
-    const int n = taps.n[s - 1];
-    const V *Es = E[s - 1];
-    const V *Os = O[s - 1];
-    const int64_t ebp = lo[s - 1] >> 1;        // base of the source level's E/O arrays
-    const int64_t ebn = (s < NST) ? (lo[s] >> 1) : 0;
-    for (int i = threadIdx.x; i < len[s]; i += kHbThreads) {
-      const int64_t m = lo[s] + i;
-      V y;
-      y.x = 0;
-      y.y = 0;
-      if (m >= 0) {
-        const int q = (int)(m - ebp);
-        y = Es[q];
-#pragma unroll 4
-        for (int k = 0; k < n; k++) {
-          const S t = taps.t[s - 1][k];
-          const V u = Os[q + k];
-          const V w = Os[q - k - 1];
-          y.x += t * (u.x + w.x);
-          y.y += t * (u.y + w.y);
-        }
-      }
-      if (s == NST) {
-        out.st(c, m, y);
-      } else {
-        const int idx = (int)((m >> 1) - ebn);
-        if (m & 1) {
-          O[s][idx] = y;
-        } else {
-          E[s][idx] = y;
-        }
-      }
+  if (NST == 1) {
+    hb_stage<S, (N1 > 0 ? N1 : 1), true>(E[0], O[0], sl[0], nullptr, nullptr, 0, 0, taps.t[0], lo[1], len[1], out, c);
+  } else {
+    hb_stage<S, (N1 > 0 ? N1 : 1), false>(E[0], O[0], sl[0], E[1], O[1], sl[1], lo[1] >> 1, taps.t[0], lo[1], len[1],
+                                          out, c);
+    __syncthreads();
+    if (NST == 2) {
+      hb_stage<S, (N2 > 0 ? N2 : 1), true>(E[1], O[1], sl[1], nullptr, nullptr, 0, 0, taps.t[1], lo[2], len[2], out,
+                                           c);
+    } else {
+      hb_stage<S, (N2 > 0 ? N2 : 1), false>(E[1], O[1], sl[1], E[2], O[2], sl[2], lo[2] >> 1, taps.t[1], lo[2],
+                                            len[2], out, c);
+      __syncthreads();
+      hb_stage<S, (N3 > 0 ? N3 : 1), true>(E[2], O[2], sl[2], nullptr, nullptr, 0, 0, taps.t[2], lo[3], len[3], out,
+                                           c);
     }
-    if (s < NST) __syncthreads();
   }
 }
 
@@ -568,11 +643,18 @@ static __global__ void k_fm_agc(Ring<float2> iq_in, Ring<float2> iq_out, FmChanS
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= P.n_channels) return;
   float g = st[c].agc_gain;
+  // register double-buffer: the loads of chunk k+1 are in flight while chunk k runs the recurrence
+  float2 nxt[kCoreChunk];
+#pragma unroll
+  for (int u = 0; u < kCoreChunk; u++) nxt[u] = (u < n_total) ? iq_in.ld(c, t0 + u) : make_float2(0.f, 0.f);
   for (int i0 = 0; i0 < n_total; i0 += kCoreChunk) {
     float2 xin[kCoreChunk];
 #pragma unroll
+    for (int u = 0; u < kCoreChunk; u++) xin[u] = nxt[u];
+#pragma unroll
     for (int u = 0; u < kCoreChunk; u++) {
-      xin[u] = (i0 + u < n_total) ? iq_in.ld(c, t0 + i0 + u) : make_float2(0.f, 0.f);
+      const int i = i0 + kCoreChunk + u;
+      nxt[u] = (i < n_total) ? iq_in.ld(c, t0 + i) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < kCoreChunk; u++) {
@@ -673,28 +755,47 @@ static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanSta
   const double f0 = (19000.0 / 384000.0) * 2.0 * 3.14159265358979323846;
   double sf0, cf0;
   sincos(f0, &sf0, &cf0);
+  const int n_total = n_calls ? (int)call_end[n_calls - 1] : 0;
+  // register double-buffer over the flat sample stream of this launch: `nxt` always holds
+  // the kCoreChunk samples starting at flat index `pos_nxt`
+  float nxt[kCoreChunk];
+#pragma unroll
+  for (int u = 0; u < kCoreChunk; u++) {
+    nxt[u] = (u < n_total) ? mpx.base[(size_t)c * mpx.cap + ((uint32_t)(t0 + u) & (mpx.cap - 1))] : 0.f;
+  }
   uint32_t prev_end = 0;
   for (int b = 0; b < n_calls; b++) {
     const uint32_t end = call_end[b];
     const int n = (int)(end - prev_end);
-    if (n == 0) continue; // main.cpp:933-936: the decoder is not called
-    const int64_t tb = t0 + prev_end;
+    if (n == 0) { // main.cpp:933-936: the decoder is not called
+      flags[(size_t)c * n_calls + b] = (uint8_t)s.stereo_detected;
+      continue;
+    }
+    const uint32_t beg = prev_end;
     prev_end = end;
     s.decoder_calls++;
     const bool was_locked = (s.lock_cnt >= P.lock_delay);
     double last_i = 0.0, last_q = 0.0;
     double psin = 0.0, pcos = 1.0;
-    if (P.stereo) sincos(s.pll_phase, &psin, &pcos);
+    if (P.stereo) sincos(s.pll_phase, &psin, &pcos); // exact re-anchor once per reference call
     for (int i0 = 0; i0 < n; i0 += kCoreChunk) {
+      const int valid = (n - i0 < kCoreChunk) ? (n - i0) : kCoreChunk;
       float din[kCoreChunk];
 #pragma unroll
-      for (int u = 0; u < kCoreChunk; u++) {
-        din[u] = (i0 + u < n) ? mpx.base[(size_t)c * mpx.cap + ((uint32_t)(tb + i0 + u) & (mpx.cap - 1))] : 0.f;
+      for (int u = 0; u < kCoreChunk; u++) din[u] = nxt[u];
+      {
+        const int pos = (int)beg + i0 + valid; // flat index the next chunk (of this or the next call) starts at
+#pragma unroll
+        for (int u = 0; u < kCoreChunk; u++) {
+          nxt[u] = (pos + u < n_total)
+                       ? mpx.base[(size_t)c * mpx.cap + ((uint32_t)(t0 + pos + u) & (mpx.cap - 1))]
+                       : 0.f;
+        }
       }
 #pragma unroll
       for (int u = 0; u < kCoreChunk; u++) {
-        const int i = i0 + u;
-        if (i >= n) break;
+        if (u >= valid) break;
+        const int i = i0 + u; // index within the reference call
         const double xd = (double)din[u];
         double stereo = 0.0;
         if (P.stereo) {
@@ -762,7 +863,7 @@ static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanSta
         double2 o;
         o.x = mono;
         o.y = stereo;
-        out384.st(c, tb + i, o);
+        out384.st(c, t0 + beg + i, o);
       }
     }
     // per-call statistics (FmDecode.cpp:95,146-150)
@@ -815,12 +916,33 @@ static __global__ void k_fm_tail(Ring<double2> in48, double *__restrict__ audio,
   if (c >= P.n_channels) return;
   double m1 = st[c].dc_m_x1, m2 = st[c].dc_m_x2, s1 = st[c].dc_s_x1, s2 = st[c].dc_s_x2;
   double *o = audio + (size_t)c * audio_stride;
-  uint32_t prev_end = 0;
-  for (int b = 0; b < n_calls; b++) {
-    const uint32_t end = call_end48[b];
-    const int det = flags[(size_t)c * n_calls + b];
-    for (uint32_t r = prev_end; r < end; r++) {
-      const double2 x = in48.ld(c, j0 + r);
+  const int n_total = n_calls ? (int)call_end48[n_calls - 1] : 0;
+  int b = 0;
+  while (b < n_calls && call_end48[b] == 0) b++;
+  uint32_t end = (b < n_calls) ? call_end48[b] : 0;
+  int det = (b < n_calls) ? flags[(size_t)c * n_calls + b] : 0;
+  double2 nxt[kCoreChunk];
+#pragma unroll
+  for (int u = 0; u < kCoreChunk; u++) nxt[u] = (u < n_total) ? in48.ld(c, j0 + u) : make_double2(0.0, 0.0);
+  for (int i0 = 0; i0 < n_total; i0 += kCoreChunk) {
+    double2 xin[kCoreChunk];
+#pragma unroll
+    for (int u = 0; u < kCoreChunk; u++) xin[u] = nxt[u];
+#pragma unroll
+    for (int u = 0; u < kCoreChunk; u++) {
+      const int i = i0 + kCoreChunk + u;
+      nxt[u] = (i < n_total) ? in48.ld(c, j0 + i) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < kCoreChunk; u++) {
+      const uint32_t r = (uint32_t)(i0 + u);
+      if ((int)r >= n_total) break;
+      while (r >= end) { // next non-empty call (and its stereo flag)
+        b++;
+        end = call_end48[b];
+        det = flags[(size_t)c * n_calls + b];
+      }
+      const double2 x = xin[u];
       const double m0 = x.x - (P.a1 * m1 + P.a2 * m2);
       const double mono = P.b0 * m0 + P.b1 * m1 + P.b2 * m2;
       m2 = m1;
@@ -855,7 +977,6 @@ static __global__ void k_fm_tail(Ring<double2> in48, double *__restrict__ audio,
       o[2 * (size_t)r] = l;
       o[2 * (size_t)r + 1] = rr;
     }
-    prev_end = end;
   }
   st[c].dc_m_x1 = m1;
   st[c].dc_m_x2 = m2;

@@ -172,8 +172,12 @@ struct MpfDev {
     return FMR_OK;
   }
 
+  // channels [c0, c0+cn) of the handle; in/out/st are already offset to c0 by the caller
   void run(Ring<float2> in, Ring<float2> out, FmChanState *st, const uint32_t *call_end, int n_calls, int64_t t0,
-           cudaStream_t s) {
+           cudaStream_t s, int c0, int cn) {
+    float2 *d_coeff = this->d_coeff + (size_t)c0 * kMpfRing;
+    float2 *d_state = this->d_state + (size_t)c0 * kMpfRing;
+    const int C = cn;
     dim3 grid((C + kMpfWarps - 1) / kMpfWarps);
     dim3 block(32 * kMpfWarps);
 #define FMR_MPF_CASE(j)                                                                                          \

@@ -100,9 +100,10 @@ class FmDecoder(_Base):
 
     def __init__(self, fmfilter=0, stereo=True, deemphasis=50.0, pilot_shift=False, multipath_stages=0, *,
                  input_rate=384000.0, fs4_shift=False, n_channels=1, max_samples_per_call=1 << 20,
-                 max_blocks_per_call=4096, device=0):
-        """fmfilter: 0 none (FilterType Default/Wide), 1 medium, 2 narrow (main.cpp:785-810); the other
-        arguments are FmDecoder's (FmDecode.h:49-64)."""
+                 max_blocks_per_call=4096, device=0, fmfilter_coeff=None):
+        """fmfilter: 0 none (FilterType Default/Wide), 1 medium, 2 narrow (main.cpp:785-810), or pass
+        fmfilter_coeff (the reference's `fmfilter_coeff` vector); the other arguments are FmDecoder's
+        (FmDecode.h:49-64)."""
         L = _capi.lib()
         self._destroy, self._query = L.fmr_fm_destroy, L.fmr_fm_query_output
         self._process_host, self._process_device = L.fmr_fm_process_host, L.fmr_fm_process_device
@@ -110,9 +111,14 @@ class FmDecoder(_Base):
         self.n_channels = int(n_channels)
         self.stereo = bool(stereo)
         self.multipath_stages = int(multipath_stages)
+        coeff = None
+        if fmfilter_coeff is not None:
+            coeff = np.ascontiguousarray(fmfilter_coeff, dtype=np.float32)
+            fmfilter = 3
         cfg = _capi.FmConfig(float(input_rate), int(fs4_shift), int(fmfilter), int(stereo), float(deemphasis),
                              int(pilot_shift), int(multipath_stages), int(n_channels),
-                             int(max_samples_per_call), int(max_blocks_per_call), int(device))
+                             int(max_samples_per_call), int(max_blocks_per_call), int(device),
+                             coeff.ctypes.data if coeff is not None else None, len(coeff) if coeff is not None else 0)
         h = C.c_void_p()
         check(L.fmr_fm_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -177,15 +183,20 @@ class AmDecoder(_Base):
     MODTYPE_AM = 2  # include/SoftFM.h:56
 
     def __init__(self, amfilter=0, mode=2, *, input_rate=48000.0, fs4_shift=False, n_channels=1,
-                 max_samples_per_call=1 << 20, max_blocks_per_call=4096, device=0):
+                 max_samples_per_call=1 << 20, max_blocks_per_call=4096, device=0, amfilter_coeff=None):
         """amfilter: 0 default, 1 medium, 2 narrow, 3 wide (main.cpp:785-810); mode: ModType value."""
         L = _capi.lib()
         self._destroy, self._query = L.fmr_am_destroy, L.fmr_am_query_output
         self._process_host, self._process_device = L.fmr_am_process_host, L.fmr_am_process_device
         self._set_profiling, self._stage_times = L.fmr_am_set_profiling, L.fmr_am_stage_times
         self.n_channels = int(n_channels)
+        coeff = None
+        if amfilter_coeff is not None:
+            coeff = np.ascontiguousarray(amfilter_coeff, dtype=np.float32)
+            amfilter = 4
         cfg = _capi.AmConfig(float(input_rate), int(fs4_shift), int(amfilter), int(mode), int(n_channels),
-                             int(max_samples_per_call), int(max_blocks_per_call), int(device))
+                             int(max_samples_per_call), int(max_blocks_per_call), int(device),
+                             coeff.ctypes.data if coeff is not None else None, len(coeff) if coeff is not None else 0)
         h = C.c_void_p()
         check(L.fmr_am_create(C.byref(cfg), C.byref(h)))
         self._h = h

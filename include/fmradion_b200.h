@@ -60,7 +60,8 @@ typedef struct fmr_fm fmr_fm;
 typedef struct fmr_fm_config {
   double input_rate;          /* IQ sample rate in Hz: 384000, 1e6, 2.5e6, 6e6, 1e7      */
   int fs4_shift;              /* 1: FourthConverterIQ(false) first (zero-IF sources)      */
-  int fmfilter;               /* 0 none (default/wide), 1 medium, 2 narrow (main.cpp:785) */
+  int fmfilter;               /* 0 none (default/wide), 1 medium, 2 narrow (main.cpp:785),
+                                 3 = fmfilter_coeff[fmfilter_ntaps] (FmDecoder ctor `fmfilter_coeff`) */
   int stereo;                 /* FmDecoder ctor `stereo`                                  */
   double deemphasis_us;       /* 50 (EU/JP), 75 (NA), 0 = off                             */
   int pilot_shift;            /* FmDecoder ctor `pilot_shift` (-X)                        */
@@ -69,6 +70,8 @@ typedef struct fmr_fm_config {
   uint32_t max_samples_per_call; /* largest sum(block_len) a process call may carry       */
   uint32_t max_blocks_per_call;  /* largest n_blocks                                       */
   int device;                 /* CUDA device ordinal                                      */
+  const float *fmfilter_coeff;   /* used when fmfilter == 3: symmetric FIR taps (Filter.cpp:27-35) */
+  uint32_t fmfilter_ntaps;
 } fmr_fm_config;
 
 typedef struct fmr_fm_stats_t {
@@ -154,12 +157,15 @@ typedef struct fmr_am fmr_am;
 typedef struct fmr_am_config {
   double input_rate;    /* 48000 or 384000 */
   int fs4_shift;
-  int amfilter;         /* 0 default, 1 medium, 2 narrow, 3 wide (main.cpp:785-810) */
+  int amfilter;         /* 0 default, 1 medium, 2 narrow, 3 wide (main.cpp:785-810),
+                           4 = amfilter_coeff[amfilter_ntaps] (AmDecoder ctor `amfilter_coeff`) */
   int mode;             /* ModType value; only 2 (AM) is implemented */
   uint32_t n_channels;
   uint32_t max_samples_per_call;
   uint32_t max_blocks_per_call;
   int device;
+  const float *amfilter_coeff; /* used when amfilter == 4 */
+  uint32_t amfilter_ntaps;
 } fmr_am_config;
 
 typedef struct fmr_am_stats_t {
