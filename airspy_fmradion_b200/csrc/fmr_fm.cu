@@ -1,8 +1,10 @@
 // fmr_fm.cu — FM broadcast handle: the C ABI of include/fmradion_b200.h for the path
 // FourthConverterIQ -> IfResampler -> FmDecoder::process (main.cpp:912-956,
 // FmDecode.cpp:85-221), many channels per launch.
+#include <algorithm>
 #include <complex>
 #include <cmath>
+#include <cstdlib>
 
 #include "fmr_host.cuh"
 #include "fmr_mpf.cuh"
@@ -13,11 +15,56 @@ thread_local std::string g_err;
 
 using namespace fmr;
 
-constexpr int kMaxGroups = 4;  // channel groups (streams) per process call
+constexpr int kMaxHostChunks = 8;       // time chunks of fmr_fm_process_host's copy/compute pipeline
+constexpr int kHostChunkMinBlocks = 16; // a chunk is at least this many source blocks
+constexpr int kMaxTimeChunks = 8;       // time chunks of the two-stream pipeline inside process_device
+constexpr int kTimeChunkMinBlocks = 32; // a time chunk is at least this many source blocks
+constexpr int kMaxGroups = 4;  // streams owned by the handle
 constexpr int kGroupMin = 1 << 28; // channel groups are disabled: measured slower (all groups hit their serial phase together)
+
+// Debug timeline (FMR_TRACE=1): start/stop events around every launch group of the time-chunk
+// pipeline, printed relative to the fork event after the call has drained.
+struct Trace {
+  struct Item {
+    const char *name;
+    int chunk;
+    cudaEvent_t a, b;
+  };
+  bool on = false;
+  std::vector<Item> items;
+  cudaEvent_t origin = nullptr;
+  void begin(const char *name, int chunk, cudaStream_t st) {
+    if (!on) return;
+    Item it{name, chunk, nullptr, nullptr};
+    cudaEventCreate(&it.a);
+    cudaEventCreate(&it.b);
+    cudaEventRecord(it.a, st);
+    items.push_back(it);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(items.back().b, st);
+  }
+  void dump() {
+    if (!on) return;
+    for (auto &it : items) {
+      float t0 = 0, t1 = 0;
+      cudaEventSynchronize(it.b);
+      cudaEventElapsedTime(&t0, origin, it.a);
+      cudaEventElapsedTime(&t1, origin, it.b);
+      fprintf(stderr, "[fmr trace] chunk %d %-10s %8.3f -> %8.3f ms\n", it.chunk, it.name, t0, t1);
+      cudaEventDestroy(it.a);
+      cudaEventDestroy(it.b);
+    }
+    items.clear();
+  }
+};
 
 struct fmr_fm {
   fmr_fm_config cfg;
+  Trace trace;
+  int max_time_chunks = 8;
+  int chunk_min_blocks = 32;
   int C = 0;
   const ChainDesc *ifc = nullptr; // null when input_rate == 384000 (no IfResampler, main.cpp:778)
   const ChainDesc *auc = nullptr;
@@ -48,7 +95,7 @@ struct fmr_fm {
   float *d_atan = nullptr;
   MpfDev mpf;
   cudaStream_t gstream[kMaxGroups] = {nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {nullptr}, ev_chunk[kMaxTimeChunks] = {nullptr};
   Prof prof;
   int p_hist = -1, p_fmf = -1, p_core = -1, p_agc = -1, p_mpf = -1, p_core2 = -1, p_pcut = -1, p_tail = -1;
   FmCoreParams core;
@@ -56,10 +103,17 @@ struct fmr_fm {
 
   int64_t cum_in = 0, cum384 = 0, cum48 = 0;
   uint32_t last_blocks = 0;
+  // chunked host calls: where the current process_device launch stores its per-block flags,
+  // and the (first block, count) of every launch of the last call, for fmr_fm_block_flags
+  bool in_host_call = false;
+  uint32_t host_b0 = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> last_chunks;
   uint32_t last_launches = 0;
   int64_t last_t0 = 0, last_t1 = 0;
 
   // host staging for the *_host entry point
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in[kMaxHostChunks] = {nullptr}, ev_done[kMaxHostChunks] = {nullptr};
   float *d_iq = nullptr;
   double *d_audio = nullptr;
   size_t audio_cap = 0; // doubles per channel
@@ -105,12 +159,19 @@ static fmr_status fm_build(fmr_fm *h) {
   h->auc = find_chain(384000.0, 48000.0, 1);
   if (!h->auc) return fail(FMR_ERR_UNSUPPORTED, "audio resampler tables missing");
   FMR_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  FMR_CUDA(h->slots.init(2 * sizeof(uint32_t) * (size_t)max_blocks));
+  FMR_CUDA(h->slots.init(4 * sizeof(uint32_t) * (size_t)max_blocks));
+  int prio_least = 0, prio_greatest = 0;
+  FMR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
   for (int g = 0; g < kMaxGroups; g++) {
-    FMR_CUDA(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+    // gstream[1] carries the latency-bound serial kernels of the time-chunk pipeline: it gets the
+    // highest priority so that its few small CTAs are placed as soon as resources free up instead
+    // of queueing behind the tens of thousands of CTAs of the front-end kernels on gstream[0].
+    FMR_CUDA(cudaStreamCreateWithPriority(&h->gstream[g], cudaStreamNonBlocking,
+                                          (g == 1) ? prio_greatest : prio_least));
     FMR_CUDA(cudaEventCreateWithFlags(&h->ev_join[g], cudaEventDisableTiming));
   }
   FMR_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  for (int k = 0; k < kMaxTimeChunks; k++) FMR_CUDA(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
 
   int64_t max384 = max_in + 8;
   if (h->ifc) {
@@ -257,6 +318,9 @@ extern "C" fmr_status fmr_fm_create(const fmr_fm_config *cfg, fmr_fm **out) {
   }
   fmr_fm *h = new fmr_fm();
   h->cfg = *cfg;
+  if (const char *e = getenv("FMR_TRACE")) h->trace.on = atoi(e) != 0;
+  if (const char *e = getenv("FMR_TIME_CHUNKS")) h->max_time_chunks = std::max(1, std::min(atoi(e), kMaxTimeChunks));
+  if (const char *e = getenv("FMR_CHUNK_MIN_BLOCKS")) h->chunk_min_blocks = std::max(1, atoi(e));
   fmr_status s = fm_build(h);
   if (s != FMR_OK) {
     std::string keep = g_err;
@@ -280,6 +344,15 @@ extern "C" void fmr_fm_destroy(fmr_fm *h) {
     if (h->ev_join[g]) cudaEventDestroy(h->ev_join[g]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int k = 0; k < kMaxTimeChunks; k++) {
+    if (h->ev_chunk[k]) cudaEventDestroy(h->ev_chunk[k]);
+  }
+  if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+  if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+  for (int k = 0; k < kMaxHostChunks; k++) {
+    if (h->ev_in[k]) cudaEventDestroy(h->ev_in[k]);
+    if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
+  }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -368,155 +441,198 @@ extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t
   if (audio_len) {
     for (uint32_t b = 0; b < n_blocks; b++) audio_len[b] = (e48[b] - (b ? e48[b - 1] : 0)) * w;
   }
-  FMR_CUDA(cudaMemcpyAsync(h->d_e384, e384, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
-  FMR_CUDA(cudaMemcpyAsync(h->d_e48, e48, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
-  h->slots.commit(slot, st);
-
   int launches = 0;
   Prof &pf = h->prof;
   pf.reset();
   const int64_t t0 = h->cum384, t1 = h->cum384 + n384;
   const int64_t j0 = h->cum48;
-  // Channels are independent, so the handle works through them in groups, each group on its
-  // own stream: the latency-bound serial kernels (AGC, PLL, DC block) of one group overlap the
-  // throughput kernels (half-band cascade, FFT low-pass, audio FIR) of the others.
-  int n_groups = 1;
-  if (!pf.on && C >= 2 * kGroupMin) {
-    n_groups = C / kGroupMin;
-    if (n_groups > kMaxGroups) n_groups = kMaxGroups;
+  // ---- time chunks. The serial recurrences (AGC, PLL, DC block) are latency bound and take the
+  // same time for 1 or 4096 channels; to hide them the call is cut into a few chunks of blocks and
+  // run as a two-stream pipeline: stream A does the front end (half-band cascade, FFT low-pass,
+  // polyphase bank) of chunk k+1 while stream B does the 384 kHz core and the audio tail of chunk k.
+  int n_chunks = 1;
+  if (!pf.on && n_blocks >= 2 * (uint32_t)h->chunk_min_blocks) {
+    n_chunks = (int)(n_blocks / h->chunk_min_blocks);
+    if (n_chunks > h->max_time_chunks) n_chunks = h->max_time_chunks;
+    if (n_chunks < 1) n_chunks = 1;
   }
-  if (n_groups > 1) {
+  Trace &tr = h->trace;
+  std::vector<uint32_t> cb(n_chunks + 1);
+  for (int k = 0; k <= n_chunks; k++) cb[k] = (uint32_t)((uint64_t)n_blocks * k / n_chunks);
+  // chunk-relative call tables (what the kernels walk); e384/e48 themselves stay absolute on the host
+  uint32_t *rel384 = tab + 2 * (size_t)h->cfg.max_blocks_per_call;
+  uint32_t *rel48 = rel384 + h->cfg.max_blocks_per_call;
+  for (int k = 0; k < n_chunks; k++) {
+    const uint32_t base384 = cb[k] ? e384[cb[k] - 1] : 0, base48 = cb[k] ? e48[cb[k] - 1] : 0;
+    for (uint32_t b = cb[k]; b < cb[k + 1]; b++) {
+      rel384[b] = e384[b] - base384;
+      rel48[b] = e48[b] - base48;
+    }
+  }
+  FMR_CUDA(cudaMemcpyAsync(h->d_e384, rel384, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
+  FMR_CUDA(cudaMemcpyAsync(h->d_e48, rel48, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
+  h->slots.commit(slot, st);
+  cudaStream_t sA = st, sB = st;
+  if (n_chunks > 1) {
+    sA = h->gstream[0];
+    sB = h->gstream[1];
     FMR_CUDA(cudaEventRecord(h->ev_fork, st));
-    for (int g = 0; g < n_groups; g++) FMR_CUDA(cudaStreamWaitEvent(h->gstream[g], h->ev_fork, 0));
+    FMR_CUDA(cudaStreamWaitEvent(sA, h->ev_fork, 0));
+    FMR_CUDA(cudaStreamWaitEvent(sB, h->ev_fork, 0));
   }
-  for (int g = 0; g < n_groups; g++) {
-    const int c0 = (int)((int64_t)C * g / n_groups), c1 = (int)((int64_t)C * (g + 1) / n_groups);
-    const int cn = c1 - c0;
-    cudaStream_t gs = (n_groups > 1) ? h->gstream[g] : st;
-    const bool last = (g == n_groups - 1);
-    auto subf2 = [&](Ring<float2> r) { return Ring<float2>{r.base ? r.base + (size_t)c0 * r.cap : nullptr, r.cap}; };
-    auto subd2 = [&](Ring<double2> r) { return Ring<double2>{r.base + (size_t)c0 * r.cap, r.cap}; };
-    const Ring<float2> r_if = subf2(h->r_if), r_iff = subf2(h->r_iff), r_agc = subf2(h->r_agc), r_mpf = subf2(h->r_mpf);
-    const Ring<float> r_mpx{h->r_mpx.base + (size_t)c0 * h->r_mpx.cap, h->r_mpx.cap};
-    const Ring<double2> r_384 = subd2(h->r_384), r_48a = subd2(h->r_48a), r_48b = subd2(h->r_48b);
-    FmChanState *d_state = h->d_state + c0;
-    uint8_t *d_flags = h->d_flags + (size_t)c0 * n_blocks;
-    PpsEventDev *d_pps = h->d_pps + (size_t)c0 * kMaxPps;
-    float *d_stats = h->d_stats + (size_t)c0 * n_blocks * 3;
-    FmCoreParams core = h->core;
-    core.n_channels = cn;
-    FmTailParams tail = h->tail;
-    tail.n_channels = cn;
-    // ---- front end: Fs/4 shift + IF resampler -> r_if[t0, t1)
+  if (tr.on) {
+    if (!tr.origin) cudaEventCreate(&tr.origin);
+    cudaEventRecord(tr.origin, st);
+  }
+  h->ifres.gc0 = 0;
+  h->ifres.gcn = C;
+  h->aures.gc0 = 0;
+  h->aures.gcn = C;
+  const uint32_t flag_b0 = h->in_host_call ? h->host_b0 : 0;
+  if (!h->in_host_call) h->last_chunks.clear();
+  int64_t in_off = 0;
+  for (int k = 0; k < n_chunks; k++) {
+    const uint32_t b0 = cb[k], nb = cb[k + 1] - cb[k];
+    int64_t n_in = 0;
+    for (uint32_t b = b0; b < b0 + nb; b++) n_in += block_len[b];
+    const uint32_t s384 = b0 ? e384[b0 - 1] : 0, s48 = b0 ? e48[b0 - 1] : 0;
+    const uint32_t n384k = e384[b0 + nb - 1] - s384, n48k = e48[b0 + nb - 1] - s48;
+    const int64_t t0k = t0 + s384, j0k = j0 + s48;
+    const uint32_t *d_e384 = h->d_e384 + b0, *d_e48 = h->d_e48 + b0;
+    uint8_t *d_flags = h->d_flags + (size_t)C * (flag_b0 + b0);
+    float *d_stats = h->d_stats + (size_t)C * b0 * 3;
+    h->last_chunks.push_back(std::make_pair(flag_b0 + b0, nb));
+    // ---- stream A: Fs/4 shift + IF resampler -> r_if[t0k, t0k + n384k)
     InSrc<float2> src;
-    src.lin = reinterpret_cast<const float2 *>(d_iq) + (size_t)c0 * iq_stride;
+    src.lin = reinterpret_cast<const float2 *>(d_iq);
     src.stride = iq_stride;
-    src.hist = h->hist[h->hist_cur] + (size_t)c0 * kHist;
+    src.hist = h->hist[h->hist_cur];
     src.start = h->cum_in;
-    src.n_new = (int64_t)total_in;
+    src.n_new = in_off + n_in; // samples of this call readable so far
     src.ring = Ring<float2>{nullptr, 0};
     if (h->ifc) {
       int64_t o0, o1;
-      h->ifres.gc0 = c0;
-      h->ifres.gcn = cn;
-      s = h->ifres.run(src, (int64_t)total_in, r_if, h->cfg.fs4_shift, gs, &o0, &o1, &launches, last);
+      tr.begin("frontend", k, sA);
+      s = h->ifres.run(src, n_in, h->r_if, h->cfg.fs4_shift, sA, &o0, &o1, &launches, true);
+      tr.end(sA);
       if (s != FMR_OK) return s;
-      if (o0 != t0 || o1 != t1) return fail(FMR_ERR_INVALID, "internal: IF schedule mismatch");
-    } else if (total_in > 0) {
+      if (o0 != t0k || o1 != t0k + n384k) return fail(FMR_ERR_INVALID, "internal: IF schedule mismatch");
+    } else if (n_in > 0) {
       HbTaps<float> t;
       memset(&t, 0, sizeof(t));
-      dim3 grid((unsigned)((total_in + kHbTile - 1) / kHbTile), cn);
-      pf.begin(h->ifres.p_hb, gs);
-      k_hb_cascade<float, 0, true, 0, 0, 0><<<grid, kHbThreads, Resampler<float>::hb_smem(t, 0), gs>>>(
-          src, r_if, t, t0, (int)total_in, h->cfg.fs4_shift);
-      pf.end(h->ifres.p_hb, gs);
+      InSrc<float2> s2 = src;
+      dim3 grid((unsigned)((n_in + kHbTile - 1) / kHbTile), C);
+      pf.begin(h->ifres.p_hb, sA);
+      k_hb_cascade<float, 0, true, 0, 0, 0><<<grid, kHbThreads, Resampler<float>::hb_smem(t, 0), sA>>>(
+          s2, h->r_if, t, t0k, (int)n_in, h->cfg.fs4_shift);
+      pf.end(h->ifres.p_hb, sA);
       launches++;
     }
-    if (h->ifc && total_in > 0) {
-      pf.begin(h->p_hist, gs);
-      k_save_hist<float2><<<cn, 128, 0, gs>>>(src.lin, iq_stride, (int64_t)total_in, src.hist,
-                                              h->hist[h->hist_cur ^ 1] + (size_t)c0 * kHist);
-      pf.end(h->p_hist, gs);
+    in_off += n_in;
+    if (k == n_chunks - 1 && h->ifc && total_in > 0) {
+      pf.begin(h->p_hist, sA);
+      k_save_hist<float2><<<C, 128, 0, sA>>>(src.lin, iq_stride, (int64_t)total_in, h->hist[h->hist_cur],
+                                             h->hist[h->hist_cur ^ 1]);
+      pf.end(h->p_hist, sA);
       launches++;
     }
-    if (n384 > 0) {
-      // ---- optional IF filter (FmDecode.cpp:98-102)
-      if (h->cfg.fmfilter) {
-        dim3 grid((n384 + 127) / 128, cn);
-        pf.begin(h->p_fmf, gs);
-        k_fir_quirk<float><<<grid, 128, 0, gs>>>(r_if, r_iff, h->d_fmfilter, h->fmfilter_taps, t0, (int)n384,
-                                                 h->d_e384, (int)n_blocks);
-        pf.end(h->p_fmf, gs);
-        launches++;
-      }
-      // ---- 384 kHz core: AGC (serial) -> [multipath] -> discriminator + statistics (parallel) -> PLL (serial)
-      dim3 cgrid((cn + 31) / 32);
-      pf.begin(h->p_agc, gs);
-      k_fm_agc<<<cgrid, 32, 0, gs>>>(r_iff, r_agc, d_state, (int)n384, t0, core);
-      pf.end(h->p_agc, gs);
-      launches++;
-      Ring<float2> disc_in = r_agc;
-      if (h->cfg.multipath_stages > 0) {
-        pf.begin(h->p_mpf, gs);
-        h->mpf.run(r_agc, r_mpf, d_state, h->d_e384, (int)n_blocks, t0, gs, c0, cn);
-        pf.end(h->p_mpf, gs);
-        launches++;
-        disc_in = r_mpf;
-      }
-      pf.begin(h->p_core, gs);
-      {
-        dim3 g1((n384 + 255) / 256, cn);
-        k_fm_disc<<<g1, 256, 0, gs>>>(disc_in, r_mpx, (int)n384, t0, core);
-        dim3 g2((n_blocks + 3) / 4, cn);
-        k_fm_call_stats<<<g2, 128, 0, gs>>>(r_if, r_mpx, d_stats, h->d_e384, (int)n_blocks, t0);
-      }
-      pf.end(h->p_core, gs);
-      pf.begin(h->p_core2, gs);
-      k_fm_pll<<<cgrid, 32, 0, gs>>>(r_mpx, r_384, d_state, d_flags, d_pps, d_stats, h->d_e384, (int)n_blocks, t0,
-                                     core, h->d_atan);
-      pf.end(h->p_core2, gs);
-      launches += 3;
-      // ---- audio resamplers (mono and L-R in lock step, FmDecode.cpp:172-183)
-      InSrc<double2> asrc;
-      memset(&asrc, 0, sizeof(asrc));
-      asrc.ring = r_384;
-      int64_t a0, a1;
-      h->aures.gc0 = c0;
-      h->aures.gcn = cn;
-      s = h->aures.run(asrc, (int64_t)n384, r_48a, 0, gs, &a0, &a1, &launches, last);
-      if (s != FMR_OK) return s;
-      if (a0 != j0 || a1 != j0 + n48) return fail(FMR_ERR_INVALID, "internal: audio schedule mismatch");
-      if (n48 > 0) {
-        // ---- pilot-cut FIR (FmDecode.cpp:190,196) then DC block + matrix
-        dim3 grid((n48 + 127) / 128, cn);
-        pf.begin(h->p_pcut, gs);
-        k_fir_quirk<double><<<grid, 128, 0, gs>>>(r_48a, r_48b, h->d_pilotcut, 127, j0, (int)n48, h->d_e48,
-                                                  (int)n_blocks);
-        pf.end(h->p_pcut, gs);
-        pf.begin(h->p_tail, gs);
-        k_fm_tail<<<cgrid, 32, 0, gs>>>(r_48b, d_audio + (size_t)c0 * audio_stride, audio_stride, d_state, d_flags,
-                                        h->d_e48, (int)n_blocks, j0, tail);
-        pf.end(h->p_tail, gs);
-        launches += 2;
-      }
+    if (n_chunks > 1) {
+      FMR_CUDA(cudaEventRecord(h->ev_chunk[k], sA));
+      FMR_CUDA(cudaStreamWaitEvent(sB, h->ev_chunk[k], 0));
     }
-    if (n_groups > 1) {
-      FMR_CUDA(cudaEventRecord(h->ev_join[g], gs));
-      FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[g], 0));
+    if (n384k == 0) continue;
+    // ---- stream B: optional IF filter (FmDecode.cpp:98-102)
+    if (h->cfg.fmfilter) {
+      dim3 grid((n384k + 127) / 128, C);
+      pf.begin(h->p_fmf, sB);
+      k_fir_quirk<float><<<grid, 128, 0, sB>>>(h->r_if, h->r_iff, h->d_fmfilter, h->fmfilter_taps, t0k, (int)n384k,
+                                               d_e384, (int)nb);
+      pf.end(h->p_fmf, sB);
+      launches++;
+    }
+    // ---- 384 kHz core: AGC (serial) -> [multipath] -> discriminator + statistics (parallel) -> PLL (serial)
+    dim3 cgrid((C + 31) / 32);
+    pf.begin(h->p_agc, sB);
+    tr.begin("agc", k, sB);
+    k_fm_agc<<<cgrid, 32, 0, sB>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
+    tr.end(sB);
+    pf.end(h->p_agc, sB);
+    launches++;
+    Ring<float2> disc_in = h->r_agc;
+    if (h->cfg.multipath_stages > 0) {
+      pf.begin(h->p_mpf, sB);
+      h->mpf.run(h->r_agc, h->r_mpf, h->d_state, d_e384, (int)nb, t0k, sB, 0, C);
+      pf.end(h->p_mpf, sB);
+      launches++;
+      disc_in = h->r_mpf;
+    }
+    pf.begin(h->p_core, sB);
+    {
+      dim3 g1((n384k + 255) / 256, C);
+      k_fm_disc<<<g1, 256, 0, sB>>>(disc_in, h->r_mpx, (int)n384k, t0k, h->core);
+      dim3 g2((nb + 3) / 4, C);
+      k_fm_call_stats<<<g2, 128, 0, sB>>>(h->r_if, h->r_mpx, d_stats, d_e384, (int)nb, t0k);
+    }
+    pf.end(h->p_core, sB);
+    pf.begin(h->p_core2, sB);
+    tr.begin("pll", k, sB);
+    k_fm_pll<<<cgrid, 32, 0, sB>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
+                                   h->core, h->d_atan, (int)(flag_b0 + b0), (k == 0 && flag_b0 == 0) ? 1 : 0);
+    tr.end(sB);
+    pf.end(h->p_core2, sB);
+    launches += 3;
+    // ---- audio resamplers (mono and L-R in lock step, FmDecode.cpp:172-183)
+    InSrc<double2> asrc;
+    memset(&asrc, 0, sizeof(asrc));
+    asrc.ring = h->r_384;
+    int64_t a0, a1;
+    tr.begin("audio", k, sB);
+    s = h->aures.run(asrc, (int64_t)n384k, h->r_48a, 0, sB, &a0, &a1, &launches, true);
+    tr.end(sB);
+    if (s != FMR_OK) return s;
+    if (a0 != j0k || a1 != j0k + n48k) return fail(FMR_ERR_INVALID, "internal: audio schedule mismatch");
+    if (n48k > 0) {
+      // ---- pilot-cut FIR (FmDecode.cpp:190,196) then DC block + matrix
+      dim3 grid((n48k + 127) / 128, C);
+      pf.begin(h->p_pcut, sB);
+      k_fir_quirk<double><<<grid, 128, 0, sB>>>(h->r_48a, h->r_48b, h->d_pilotcut, 127, j0k, (int)n48k, d_e48, (int)nb);
+      pf.end(h->p_pcut, sB);
+      pf.begin(h->p_tail, sB);
+      k_fm_tail<<<cgrid, 32, 0, sB>>>(h->r_48b, d_audio + (size_t)s48 * w, audio_stride, h->d_state, d_flags, d_e48,
+                                      (int)nb, j0k, h->tail);
+      pf.end(h->p_tail, sB);
+      launches += 2;
     }
   }
+  if (n_chunks > 1) {
+    FMR_CUDA(cudaEventRecord(h->ev_join[0], sA));
+    FMR_CUDA(cudaEventRecord(h->ev_join[1], sB));
+    FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[0], 0));
+    FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[1], 0));
+  }
   if (h->ifc && total_in > 0) h->hist_cur ^= 1;
+  if (tr.on) {
+    cudaStreamSynchronize(st);
+    tr.dump();
+  }
   FMR_CUDA(cudaGetLastError());
   h->cum_in += (int64_t)total_in;
   h->cum384 += n384;
   h->cum48 += n48;
-  h->last_blocks = n_blocks;
-  h->last_launches = (uint32_t)launches;
-  h->last_t0 = t0;
+  if (!h->in_host_call) {
+    h->last_blocks = n_blocks;
+    h->last_launches = (uint32_t)launches;
+    h->last_t0 = t0;
+  } else {
+    h->last_launches += (uint32_t)launches;
+  }
   h->last_t1 = t1;
   return FMR_OK;
 }
 
+// Host-buffer entry point. The super-block is cut into a few time chunks so that the H2D copy
+// of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap (three streams,
+// events); with pinned host memory the call is PCIe-bound instead of copy + compute + copy.
 extern "C" fmr_status fmr_fm_process_host(fmr_fm *h, const float *iq, size_t iq_stride, const uint32_t *block_len,
                                           uint32_t n_blocks, double *audio, size_t audio_stride,
                                           uint32_t *audio_len) {
@@ -526,28 +642,65 @@ extern "C" fmr_status fmr_fm_process_host(fmr_fm *h, const float *iq, size_t iq_
   for (uint32_t b = 0; b < n_blocks; b++) total += block_len[b];
   if (total > h->cfg.max_samples_per_call) return fail(FMR_ERR_CAPACITY, "sum(block_len) > max_samples_per_call");
   if (total > iq_stride) return fail(FMR_ERR_INVALID, "iq_stride < sum(block_len)");
+  if (n_blocks > h->cfg.max_blocks_per_call) return fail(FMR_ERR_CAPACITY, "n_blocks > max_blocks_per_call");
   const int C = h->C;
   if (!h->d_iq) {
     FMR_CUDA(h->mem.alloc(&h->d_iq, (size_t)C * h->cfg.max_samples_per_call * 2, false));
     FMR_CUDA(h->mem.alloc(&h->d_audio, (size_t)C * h->audio_cap, false));
-  }
-  cudaStream_t st = h->own_stream;
-  if (total > 0) {
-    FMR_CUDA(cudaMemcpy2DAsync(h->d_iq, (size_t)total * 8, iq, iq_stride * 8, (size_t)total * 8, C,
-                               cudaMemcpyHostToDevice, st));
+    FMR_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    FMR_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < kMaxHostChunks; k++) {
+      FMR_CUDA(cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming));
+      FMR_CUDA(cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
+    }
   }
   uint64_t out_total = 0;
   fmr_status s = fmr_fm_query_output(h, block_len, n_blocks, &out_total, nullptr);
   if (s != FMR_OK) return s;
   if (out_total > audio_stride) return fail(FMR_ERR_CAPACITY, "audio_stride too small for this call");
-  s = fmr_fm_process_device(h, h->d_iq, (size_t)total, block_len, n_blocks, h->d_audio, h->audio_cap, audio_len,
-                            (void *)st);
-  if (s != FMR_OK) return s;
-  if (out_total > 0) {
-    FMR_CUDA(cudaMemcpy2DAsync(audio, audio_stride * 8, h->d_audio, h->audio_cap * 8, (size_t)out_total * 8, C,
-                               cudaMemcpyDeviceToHost, st));
+  if (n_blocks == 0) return FMR_OK;
+  int n_chunks = (int)(n_blocks / kHostChunkMinBlocks);
+  if (n_chunks > kMaxHostChunks) n_chunks = kMaxHostChunks;
+  if (n_chunks < 1) n_chunks = 1;
+  cudaStream_t st = h->own_stream;
+  size_t in_off = 0, out_off = 0;
+  h->in_host_call = true;
+  h->last_chunks.clear();
+  h->last_launches = 0;
+  h->last_t0 = h->cum384;
+  h->last_blocks = n_blocks;
+  struct Guard {
+    fmr_fm *h;
+    ~Guard() { h->in_host_call = false; }
+  } guard{h};
+  for (int k = 0; k < n_chunks; k++) {
+    const uint32_t b0 = (uint32_t)((uint64_t)n_blocks * k / n_chunks), b1 = (uint32_t)((uint64_t)n_blocks * (k + 1) / n_chunks);
+    uint64_t n_in = 0;
+    for (uint32_t b = b0; b < b1; b++) n_in += block_len[b];
+    if (n_in > 0) {
+      FMR_CUDA(cudaMemcpy2DAsync(h->d_iq + 2 * in_off, (size_t)total * 8, iq + 2 * in_off, iq_stride * 8,
+                                 (size_t)n_in * 8, C, cudaMemcpyHostToDevice, h->s_h2d));
+    }
+    FMR_CUDA(cudaEventRecord(h->ev_in[k], h->s_h2d));
+    FMR_CUDA(cudaStreamWaitEvent(st, h->ev_in[k], 0));
+    uint64_t n_out = 0;
+    s = fmr_fm_query_output(h, block_len + b0, b1 - b0, &n_out, nullptr);
+    if (s != FMR_OK) return s;
+    h->host_b0 = b0;
+    s = fmr_fm_process_device(h, h->d_iq + 2 * in_off, (size_t)total, block_len + b0, b1 - b0, h->d_audio + out_off,
+                              h->audio_cap, audio_len ? audio_len + b0 : nullptr, (void *)st);
+    if (s != FMR_OK) return s;
+    FMR_CUDA(cudaEventRecord(h->ev_done[k], st));
+    if (n_out > 0) {
+      FMR_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_done[k], 0));
+      FMR_CUDA(cudaMemcpy2DAsync(audio + out_off, audio_stride * 8, h->d_audio + out_off, h->audio_cap * 8,
+                                 (size_t)n_out * 8, C, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    in_off += (size_t)n_in;
+    out_off += (size_t)n_out;
   }
   FMR_CUDA(cudaStreamSynchronize(st));
+  FMR_CUDA(cudaStreamSynchronize(h->s_d2h));
   return FMR_OK;
 }
 
@@ -606,7 +759,12 @@ extern "C" fmr_status fmr_fm_block_flags(fmr_fm *h, uint32_t channel, uint8_t *s
   }
   FMR_CUDA(cudaSetDevice(h->cfg.device));
   FMR_CUDA(cudaDeviceSynchronize());
-  FMR_CUDA(cudaMemcpy(stereo, h->d_flags + (size_t)channel * n_blocks, n_blocks, cudaMemcpyDeviceToHost));
+  for (const auto &ch : h->last_chunks) {
+    const uint32_t b0 = ch.first, nb = ch.second;
+    if (nb == 0) continue;
+    FMR_CUDA(cudaMemcpy(stereo + b0, h->d_flags + (size_t)h->C * b0 + (size_t)channel * nb, nb,
+                        cudaMemcpyDeviceToHost));
+  }
   return FMR_OK;
 }
 

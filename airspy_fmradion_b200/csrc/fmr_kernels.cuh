@@ -747,11 +747,14 @@ static __global__ void k_fm_call_stats(Ring<float2> if_raw, Ring<float> mpx, flo
 static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanState *__restrict__ st,
                          uint8_t *__restrict__ flags, PpsEventDev *__restrict__ pps,
                          const float *__restrict__ stats, const uint32_t *__restrict__ call_end, int n_calls,
-                         int64_t t0, FmCoreParams P, const float *__restrict__ atan_tbl) {
+                         int64_t t0, FmCoreParams P, const float *__restrict__ atan_tbl, int block_off,
+                         int reset_pps) {
+  // block_off / reset_pps: a process call may be cut into several launches (time chunks); PPS
+  // events are numbered by the block index within the whole call and accumulate across them.
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= P.n_channels) return;
   FmChanState s = st[c];
-  s.n_pps = 0;
+  if (reset_pps) s.n_pps = 0;
   const double f0 = (19000.0 / 384000.0) * 2.0 * 3.14159265358979323846;
   double sf0, cf0;
   sincos(f0, &sf0, &cf0);
@@ -841,7 +844,7 @@ static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanSta
                   ev.pps_index = s.pps_cnt;
                   ev.sample_index = s.sample_cnt + (unsigned long long)i;
                   ev.block_position = (double)i / (double)n;
-                  ev.block = (uint32_t)b;
+                  ev.block = (uint32_t)(b + block_off);
                   ev.pad = 0;
                   pps[(size_t)c * kMaxPps + s.n_pps] = ev;
                 }
@@ -887,7 +890,7 @@ static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanSta
         s.pps_cnt = 0;
         // events of THIS call are dropped
         while (s.n_pps > 0 && s.n_pps <= (uint32_t)kMaxPps &&
-               pps[(size_t)c * kMaxPps + s.n_pps - 1].block == (uint32_t)b) {
+               pps[(size_t)c * kMaxPps + s.n_pps - 1].block == (uint32_t)(b + block_off)) {
           s.n_pps--;
         }
       }

@@ -278,7 +278,7 @@ def main():
     # end to end through the host-buffer entry point (pinned host memory, H2D + D2H inside)
     e2e = None
     if not args.no_e2e:
-        Ce = min(C, 256)
+        Ce = min(C, 1024)
         dec2 = make_decoder(wl, Ce, T, nblk, dev_index)
         h_iq = torch.empty((Ce, T), dtype=torch.complex64, pin_memory=True)
         h_iq.copy_(iq[:Ce])
