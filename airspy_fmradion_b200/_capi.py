@@ -58,6 +58,7 @@ class AmStats(C.Structure):
 EXPORTS = [
     "fmr_last_error", "fmr_version", "fmr_device_sm_count",
     "fmr_fm_create", "fmr_fm_destroy", "fmr_fm_process_host", "fmr_fm_process_device",
+    "fmr_fm_process_host_i16", "fmr_fm_process_device_i16",
     "fmr_fm_query_output", "fmr_fm_schedule", "fmr_am_schedule", "fmr_fm_stats", "fmr_fm_pps_events", "fmr_fm_coeffs",
     "fmr_fm_block_flags", "fmr_fm_tap_if", "fmr_fm_last_launches", "fmr_fm_set_profiling",
     "fmr_fm_stage_times",
@@ -88,6 +89,8 @@ def lib():
     proc_host = [vp, vp, C.c_size_t, vp, C.c_uint32, vp, C.c_size_t, vp]
     L.fmr_fm_process_host.argtypes = proc_host
     L.fmr_fm_process_device.argtypes = proc_host + [vp]
+    L.fmr_fm_process_host_i16.argtypes = proc_host
+    L.fmr_fm_process_device_i16.argtypes = proc_host + [vp]
     L.fmr_fm_query_output.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint64), vp]
     L.fmr_fm_stats.argtypes = [vp, C.c_uint32, C.POINTER(FmStats)]
     L.fmr_fm_pps_events.argtypes = [vp, C.c_uint32, vp, C.c_uint32, u32p]

@@ -329,6 +329,7 @@ extern "C" fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t
   InSrc<float2> src;
   src.lin = reinterpret_cast<const float2 *>(d_iq);
   src.stride = iq_stride;
+  src.fmt = 0;
   src.hist = h->hist[h->hist_cur];
   src.start = h->cum_in;
   src.n_new = (int64_t)total_in;
@@ -342,7 +343,7 @@ extern "C" fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t
     if (total_in > 0) {
       pf.begin(h->p_hist, st);
       k_save_hist<float2><<<C, 128, 0, st>>>(src.lin, iq_stride, (int64_t)total_in, h->hist[h->hist_cur],
-                                             h->hist[h->hist_cur ^ 1]);
+                                             h->hist[h->hist_cur ^ 1], 0);
       pf.end(h->p_hist, st);
       h->hist_cur ^= 1;
       launches++;

@@ -63,7 +63,7 @@ struct Trace {
 struct fmr_fm {
   fmr_fm_config cfg;
   Trace trace;
-  int max_time_chunks = 8;
+  int max_time_chunks = 1; // FMR_TIME_CHUNKS: the two-stream pipeline is off by default
   int chunk_min_blocks = 32;
   int C = 0;
   const ChainDesc *ifc = nullptr; // null when input_rate == 384000 (no IfResampler, main.cpp:778)
@@ -105,6 +105,7 @@ struct fmr_fm {
   uint32_t last_blocks = 0;
   // chunked host calls: where the current process_device launch stores its per-block flags,
   // and the (first block, count) of every launch of the last call, for fmr_fm_block_flags
+  int iq_fmt = 0; // sample format of the d_iq pointer of the call in progress (0 cf32, 1 int16 pairs)
   bool in_host_call = false;
   uint32_t host_b0 = 0;
   std::vector<std::pair<uint32_t, uint32_t>> last_chunks;
@@ -418,9 +419,33 @@ extern "C" fmr_status fmr_fm_query_output(fmr_fm *h, const uint32_t *block_len, 
   return FMR_OK;
 }
 
+static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq_stride, const uint32_t *block_len,
+                                         uint32_t n_blocks, double *d_audio, size_t audio_stride,
+                                         uint32_t *audio_len, void *stream);
+
 extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t iq_stride,
                                             const uint32_t *block_len, uint32_t n_blocks, double *d_audio,
                                             size_t audio_stride, uint32_t *audio_len, void *stream) {
+  if (!h) return fail(FMR_ERR_INVALID, "null argument");
+  if (!h->in_host_call) h->iq_fmt = 0;
+  return fm_process_device_impl(h, d_iq, iq_stride, block_len, n_blocks, d_audio, audio_stride, audio_len, stream);
+}
+
+extern "C" fmr_status fmr_fm_process_device_i16(fmr_fm *h, const int16_t *d_iq, size_t iq_stride,
+                                                const uint32_t *block_len, uint32_t n_blocks, double *d_audio,
+                                                size_t audio_stride, uint32_t *audio_len, void *stream) {
+  if (!h) return fail(FMR_ERR_INVALID, "null argument");
+  if (h->cfg.input_rate == 384000.0) return fail(FMR_ERR_UNSUPPORTED, "int16 ingest needs an IF resampler stage");
+  h->iq_fmt = 1;
+  fmr_status s = fm_process_device_impl(h, reinterpret_cast<const float *>(d_iq), iq_stride, block_len, n_blocks,
+                                        d_audio, audio_stride, audio_len, stream);
+  if (!h->in_host_call) h->iq_fmt = 0;
+  return s;
+}
+
+static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq_stride, const uint32_t *block_len,
+                                         uint32_t n_blocks, double *d_audio, size_t audio_stride,
+                                         uint32_t *audio_len, void *stream) {
   if (!h || !d_iq || !block_len || !d_audio) return fail(FMR_ERR_INVALID, "null argument");
   if (n_blocks == 0) return FMR_OK;
   if (n_blocks > h->cfg.max_blocks_per_call) return fail(FMR_ERR_CAPACITY, "n_blocks > max_blocks_per_call");
@@ -506,6 +531,7 @@ extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t
     InSrc<float2> src;
     src.lin = reinterpret_cast<const float2 *>(d_iq);
     src.stride = iq_stride;
+    src.fmt = h->iq_fmt;
     src.hist = h->hist[h->hist_cur];
     src.start = h->cum_in;
     src.n_new = in_off + n_in; // samples of this call readable so far
@@ -532,7 +558,7 @@ extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t
     if (k == n_chunks - 1 && h->ifc && total_in > 0) {
       pf.begin(h->p_hist, sA);
       k_save_hist<float2><<<C, 128, 0, sA>>>(src.lin, iq_stride, (int64_t)total_in, h->hist[h->hist_cur],
-                                             h->hist[h->hist_cur ^ 1]);
+                                             h->hist[h->hist_cur ^ 1], h->iq_fmt);
       pf.end(h->p_hist, sA);
       launches++;
     }
@@ -633,10 +659,30 @@ extern "C" fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t
 // Host-buffer entry point. The super-block is cut into a few time chunks so that the H2D copy
 // of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap (three streams,
 // events); with pinned host memory the call is PCIe-bound instead of copy + compute + copy.
+static fmr_status fm_process_host_impl(fmr_fm *h, const float *iq, size_t iq_stride, const uint32_t *block_len,
+                                       uint32_t n_blocks, double *audio, size_t audio_stride, uint32_t *audio_len,
+                                       int fmt);
+
 extern "C" fmr_status fmr_fm_process_host(fmr_fm *h, const float *iq, size_t iq_stride, const uint32_t *block_len,
                                           uint32_t n_blocks, double *audio, size_t audio_stride,
                                           uint32_t *audio_len) {
+  return fm_process_host_impl(h, iq, iq_stride, block_len, n_blocks, audio, audio_stride, audio_len, 0);
+}
+
+extern "C" fmr_status fmr_fm_process_host_i16(fmr_fm *h, const int16_t *iq, size_t iq_stride,
+                                              const uint32_t *block_len, uint32_t n_blocks, double *audio,
+                                              size_t audio_stride, uint32_t *audio_len) {
+  if (h && h->cfg.input_rate == 384000.0) return fail(FMR_ERR_UNSUPPORTED, "int16 ingest needs an IF resampler stage");
+  return fm_process_host_impl(h, reinterpret_cast<const float *>(iq), iq_stride, block_len, n_blocks, audio,
+                              audio_stride, audio_len, 1);
+}
+
+static fmr_status fm_process_host_impl(fmr_fm *h, const float *iq, size_t iq_stride, const uint32_t *block_len,
+                                       uint32_t n_blocks, double *audio, size_t audio_stride, uint32_t *audio_len,
+                                       int fmt) {
   if (!h || !iq || !block_len || !audio) return fail(FMR_ERR_INVALID, "null argument");
+  const size_t esz = fmt ? 4 : 8;               // bytes per complex sample
+  const size_t fstep = fmt ? 1 : 2;             // float-pointer units per complex sample
   FMR_CUDA(cudaSetDevice(h->cfg.device));
   uint64_t total = 0;
   for (uint32_t b = 0; b < n_blocks; b++) total += block_len[b];
@@ -671,15 +717,18 @@ extern "C" fmr_status fmr_fm_process_host(fmr_fm *h, const float *iq, size_t iq_
   h->last_blocks = n_blocks;
   struct Guard {
     fmr_fm *h;
-    ~Guard() { h->in_host_call = false; }
+    ~Guard() {
+      h->in_host_call = false;
+      h->iq_fmt = 0;
+    }
   } guard{h};
   for (int k = 0; k < n_chunks; k++) {
     const uint32_t b0 = (uint32_t)((uint64_t)n_blocks * k / n_chunks), b1 = (uint32_t)((uint64_t)n_blocks * (k + 1) / n_chunks);
     uint64_t n_in = 0;
     for (uint32_t b = b0; b < b1; b++) n_in += block_len[b];
     if (n_in > 0) {
-      FMR_CUDA(cudaMemcpy2DAsync(h->d_iq + 2 * in_off, (size_t)total * 8, iq + 2 * in_off, iq_stride * 8,
-                                 (size_t)n_in * 8, C, cudaMemcpyHostToDevice, h->s_h2d));
+      FMR_CUDA(cudaMemcpy2DAsync(h->d_iq + fstep * in_off, (size_t)total * esz, iq + fstep * in_off, iq_stride * esz,
+                                 (size_t)n_in * esz, C, cudaMemcpyHostToDevice, h->s_h2d));
     }
     FMR_CUDA(cudaEventRecord(h->ev_in[k], h->s_h2d));
     FMR_CUDA(cudaStreamWaitEvent(st, h->ev_in[k], 0));
@@ -687,8 +736,9 @@ extern "C" fmr_status fmr_fm_process_host(fmr_fm *h, const float *iq, size_t iq_
     s = fmr_fm_query_output(h, block_len + b0, b1 - b0, &n_out, nullptr);
     if (s != FMR_OK) return s;
     h->host_b0 = b0;
-    s = fmr_fm_process_device(h, h->d_iq + 2 * in_off, (size_t)total, block_len + b0, b1 - b0, h->d_audio + out_off,
-                              h->audio_cap, audio_len ? audio_len + b0 : nullptr, (void *)st);
+    h->iq_fmt = fmt;
+    s = fm_process_device_impl(h, h->d_iq + fstep * in_off, (size_t)total, block_len + b0, b1 - b0,
+                               h->d_audio + out_off, h->audio_cap, audio_len ? audio_len + b0 : nullptr, (void *)st);
     if (s != FMR_OK) return s;
     FMR_CUDA(cudaEventRecord(h->ev_done[k], st));
     if (n_out > 0) {

@@ -43,6 +43,8 @@ template <typename V> struct Ring {
 // history of the previous call's tail, or a ring.
 template <typename V> struct InSrc {
   const V *lin;      // [C][stride], sample 0 has absolute index `start`
+  int fmt;           // 0: lin holds elements of V; 1: lin holds int16 (re,im) pairs, value/32768
+                     // (what FileSource's sf_read_float yields for 16-bit PCM, FileSource.cpp:491-531)
   size_t stride;
   const V *hist;     // [C][HIST], absolute indices start-HIST .. start-1
   int64_t start;
@@ -62,7 +64,15 @@ __device__ __forceinline__ V src_ld(const InSrc<V> &s, uint32_t c, int64_t i) {
     if (r < 0) {
       return (r >= -kHist) ? s.hist[(size_t)c * kHist + (kHist + r)] : z;
     }
-    return (r < s.n_new) ? s.lin[(size_t)c * s.stride + r] : z;
+    if (r >= s.n_new) return z;
+    if (s.fmt == 1) {
+      const short2 q = reinterpret_cast<const short2 *>(s.lin)[(size_t)c * s.stride + r];
+      V v;
+      v.x = (float)q.x * (1.0f / 32768.0f);
+      v.y = (float)q.y * (1.0f / 32768.0f);
+      return v;
+    }
+    return s.lin[(size_t)c * s.stride + r];
   } else {
     return s.ring.ld(c, i);
   }
@@ -239,8 +249,41 @@ __global__ void __launch_bounds__(kHbThreads)
     if (LINEAR && sizeof(V) == 8) {
       const int64_t r0 = 2 * eb - in.start;
       const float2 *pp = reinterpret_cast<const float2 *>(in.lin) + (size_t)c * in.stride + r0;
-      fast = (r0 >= 0) && (r0 + 2 * (int64_t)npairs <= in.n_new) && ((reinterpret_cast<uintptr_t>(pp) & 15) == 0);
-      if (fast) {
+      const short2 *ps = reinterpret_cast<const short2 *>(in.lin) + (size_t)c * in.stride + r0;
+      const bool inside = (r0 >= 0) && (r0 + 2 * (int64_t)npairs <= in.n_new);
+      if (in.fmt == 1 && inside && ((reinterpret_cast<uintptr_t>(ps) & 7) == 0)) {
+        // int16 IQ: one 64-bit load per pair of samples, converted on the fly
+        fast = true;
+        const uint2 *p2 = reinterpret_cast<const uint2 *>(ps);
+        uint2 q[kBatch];
+#pragma unroll
+        for (int bb = 0; bb < kBatch; bb++) {
+          const int i = threadIdx.x + bb * kHbThreads;
+          q[bb] = (i < npairs) ? p2[i] : make_uint2(0u, 0u);
+        }
+        const int ph0 = (int)((2 * eb) & 3);
+#pragma unroll
+        for (int bb = 0; bb < kBatch; bb++) {
+          const int i = threadIdx.x + bb * kHbThreads;
+          if (i < npairs && i / kHbR < sl[0]) {
+            const float k = 1.0f / 32768.0f;
+            float2 v0 = make_float2((float)(short)(q[bb].x & 0xffff) * k, (float)(short)(q[bb].x >> 16) * k);
+            float2 v1 = make_float2((float)(short)(q[bb].y & 0xffff) * k, (float)(short)(q[bb].y >> 16) * k);
+            if (fs4) {
+              const int ph = (ph0 + 2 * i) & 3;
+              v0 = fs4_rot(v0, ph);
+              v1 = fs4_rot(v1, ph + 1);
+            }
+            const int pos = hb_pos(i, sl[0]);
+            reinterpret_cast<float2 *>(E[0])[pos] = v0;
+            reinterpret_cast<float2 *>(O[0])[pos] = v1;
+          }
+        }
+      }
+      if (!fast && in.fmt == 0) {
+        fast = inside && ((reinterpret_cast<uintptr_t>(pp) & 15) == 0);
+      }
+      if (fast && in.fmt == 0) {
         // whole tile inside this call's buffer and 16-byte aligned: all 128-bit loads of a
         // thread are issued back to back (latency overlapped), then scattered to shared memory
         const float4 *p4 = reinterpret_cast<const float4 *>(pp);
@@ -990,13 +1033,19 @@ static __global__ void k_fm_tail(Ring<double2> in48, double *__restrict__ audio,
 // Keep the last kHist input samples of every channel for the next call's halo.
 template <typename V>
 __global__ void k_save_hist(const V *__restrict__ lin, size_t stride, int64_t n_new, const V *__restrict__ hist_old,
-                            V *__restrict__ hist_new) {
+                            V *__restrict__ hist_new, int fmt) {
   const uint32_t c = blockIdx.x;
   for (int i = threadIdx.x; i < kHist; i += blockDim.x) {
     const int64_t r = n_new - kHist + i; // index into this call's samples
     V v;
     if (r >= 0) {
-      v = lin[(size_t)c * stride + r];
+      if (fmt == 1) {
+        const short2 q = reinterpret_cast<const short2 *>(lin)[(size_t)c * stride + r];
+        v.x = (float)q.x * (1.0f / 32768.0f);
+        v.y = (float)q.y * (1.0f / 32768.0f);
+      } else {
+        v = lin[(size_t)c * stride + r];
+      }
     } else {
       const int64_t h = kHist + r; // = i + n_new, < kHist
       v = hist_old[(size_t)c * kHist + h];

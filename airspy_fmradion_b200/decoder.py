@@ -45,8 +45,16 @@ class _Base:
         check(self._query(self._h, bl.ctypes.data, len(bl), C.byref(tot), lens.ctypes.data))
         return int(tot.value), lens
 
-    def process_blocks(self, iq, block_len):
-        """iq: complex64 [C, T] (or [T] for one channel); returns (audio [C, n], audio_len[n_blocks])."""
+    def _out_buffer(self, out, out_total):
+        if out is None:
+            return np.zeros((self.n_channels, max(out_total, 1)), dtype=np.float64)
+        assert out.dtype == np.float64 and out.ndim == 2 and out.shape[0] == self.n_channels
+        assert out.shape[1] >= out_total and out.flags["C_CONTIGUOUS"]
+        return out
+
+    def process_blocks(self, iq, block_len, out=None):
+        """iq: complex64 [C, T] (or [T] for one channel); returns (audio [C, n], audio_len[n_blocks]).
+        `out`: optional caller-owned float64 [C, >=n] buffer (e.g. pinned memory) to write into."""
         iq = np.ascontiguousarray(iq, dtype=np.complex64)
         if iq.ndim == 1:
             iq = iq[None, :]
@@ -54,7 +62,7 @@ class _Base:
         bl, total = self._blocks(block_len)
         assert total <= iq.shape[1]
         out_total, _ = self.query_output(bl)
-        audio = np.zeros((self.n_channels, max(out_total, 1)), dtype=np.float64)
+        audio = self._out_buffer(out, out_total)
         lens = np.zeros(len(bl), dtype=np.uint32)
         check(self._process_host(self._h, iq.ctypes.data, iq.shape[1], bl.ctypes.data, len(bl),
                                  audio.ctypes.data, audio.shape[1], lens.ctypes.data))
@@ -122,6 +130,19 @@ class FmDecoder(_Base):
         h = C.c_void_p()
         check(L.fmr_fm_create(C.byref(cfg), C.byref(h)))
         self._h = h
+
+    def process_blocks_i16(self, iq_i16, block_len, out=None):
+        """iq_i16: int16 [C, T, 2] (re,im) pairs as FileSource reads them from a 16-bit WAV."""
+        iq = np.ascontiguousarray(iq_i16, dtype=np.int16)
+        assert iq.ndim == 3 and iq.shape[0] == self.n_channels and iq.shape[2] == 2
+        bl, total = self._blocks(block_len)
+        assert total <= iq.shape[1]
+        out_total, _ = self.query_output(bl)
+        audio = self._out_buffer(out, out_total)
+        lens = np.zeros(len(bl), dtype=np.uint32)
+        check(_capi.lib().fmr_fm_process_host_i16(self._h, iq.ctypes.data, iq.shape[1], bl.ctypes.data, len(bl),
+                                                  audio.ctypes.data, audio.shape[1], lens.ctypes.data))
+        return audio[:, :out_total], lens
 
     def stats(self, channel=0):
         s = _capi.FmStats()

@@ -121,6 +121,18 @@ fmr_status fmr_fm_process_device(fmr_fm *h, const float *d_iq, size_t iq_stride,
                                  double *d_audio, size_t audio_stride, uint32_t *audio_len,
                                  void *stream);
 
+/* Same, for IQ delivered as interleaved int16 (re,im) pairs, value/32768 — what FileSource's
+ * sf_read_float yields for 16-bit PCM files (sfmbase/FileSource.cpp:491-531). The conversion is
+ * fused into the first kernel's load, so only half the bytes cross PCIe/HBM. iq_stride in complex
+ * samples. Needs input_rate != 384000 (the conversion lives in the IF resampler's first stage). */
+fmr_status fmr_fm_process_host_i16(fmr_fm *h, const int16_t *iq, size_t iq_stride,
+                                   const uint32_t *block_len, uint32_t n_blocks,
+                                   double *audio, size_t audio_stride, uint32_t *audio_len);
+fmr_status fmr_fm_process_device_i16(fmr_fm *h, const int16_t *d_iq, size_t iq_stride,
+                                     const uint32_t *block_len, uint32_t n_blocks,
+                                     double *d_audio, size_t audio_stride, uint32_t *audio_len,
+                                     void *stream);
+
 /* Audio doubles per channel the next process call with these block lengths will produce
  * (lets the caller size `audio`); does not advance the stream. */
 fmr_status fmr_fm_query_output(fmr_fm *h, const uint32_t *block_len, uint32_t n_blocks,

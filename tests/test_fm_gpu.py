@@ -138,3 +138,27 @@ def test_cfg3_multipath_E200():
     assert rel <= 1e-3
     # the filter really adapted (it is not the identity any more)
     assert np.abs(ref_coef).sum() > 1.05
+
+
+def test_int16_ingest():
+    """IQ delivered as int16 pairs (what FileSource hands over for 16-bit WAV files after
+    sf_read_float: value/32768, FileSource.cpp:491-531); conversion fused into the first kernel."""
+    from airspy_fmradion_b200 import FmDecoder
+    fs, blk, nblk = 1.0e7, 2048, 600
+    iq = siggen.fm_stereo_iq(fs, blk * nblk, 4)
+    q = np.empty((1, len(iq), 2), dtype=np.int16)
+    q[0, :, 0] = np.clip(np.round(iq.real * 32768.0), -32768, 32767)
+    q[0, :, 1] = np.clip(np.round(iq.imag * 32768.0), -32768, 32767)
+    as_float = (q[0, :, 0].astype(np.float32) / np.float32(32768.0)) + 1j * (q[0, :, 1].astype(np.float32) / np.float32(32768.0))
+    dec = FmDecoder(stereo=True, input_rate=fs, fs4_shift=True, n_channels=1, max_samples_per_call=blk * 300)
+    outs, lens = [], []
+    for o in range(0, nblk, 300):
+        a, l = dec.process_blocks_i16(q[:, o * blk:(o + 300) * blk], [blk] * 300)
+        outs.append(a)
+        lens.append(l)
+    audio, lens = np.concatenate(outs, axis=1), np.concatenate(lens)
+    ref_audio, ref_lens = oracle_fm_run(as_float.astype(np.complex64), fs, blk, stereo=True, fs4=True)
+    assert list(lens) == list(ref_lens)
+    d = audio[0] - ref_audio
+    print("int16 ingest: n=%d max %.3e" % (len(d), np.abs(d).max()))
+    assert len(d) > 1000 and np.abs(d).max() <= TOL_MAX
