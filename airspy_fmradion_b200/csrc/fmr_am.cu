@@ -197,6 +197,8 @@ static fmr_status am_build(fmr_am *h) {
     FMR_CUDA(h->mem.alloc(&h->d_amfilter, (size_t)h->amfilter_taps, false));
     FMR_CUDA(cudaMemcpy(h->d_amfilter, tbl, h->amfilter_taps * sizeof(float), cudaMemcpyHostToDevice));
   }
+  FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)fq_smem(h->amfilter_taps, sizeof(float2), sizeof(float))));
   FMR_CUDA(h->mem.alloc(&h->d_state, (size_t)C));
   FMR_CUDA(h->mem.alloc(&h->d_e48, (size_t)max_blocks));
   {
@@ -359,9 +361,9 @@ extern "C" fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t
     launches++;
   }
   if (n48 > 0) {
-    dim3 grid((n48 + 127) / 128, C);
+    dim3 grid((n48 + kQTile - 1) / kQTile, C);
     pf.begin(h->p_flt, st);
-    k_fir_quirk<float><<<grid, 128, 0, st>>>(h->r_if, h->r_flt, h->d_amfilter, h->amfilter_taps, t0, (int)n48,
+    k_fir_quirk<float><<<grid, kQThreads, fq_smem(h->amfilter_taps, sizeof(float2), sizeof(float)), st>>>(h->r_if, h->r_flt, h->d_amfilter, h->amfilter_taps, t0, (int)n48,
                                              h->d_e48, (int)n_blocks);
     pf.end(h->p_flt, st);
     pf.begin(h->p_core, st);

@@ -239,6 +239,10 @@ static fmr_status fm_build(fmr_fm *h) {
   FMR_CUDA(h->mem.alloc(&h->d_atan, 257, false));
   FMR_CUDA(cudaMemcpy(h->d_atan, k_fast_atan_table, 257 * sizeof(float), cudaMemcpyHostToDevice));
 
+  FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)fq_smem(h->fmfilter_taps > 0 ? h->fmfilter_taps : 127, sizeof(float2), sizeof(float))));
+  FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)fq_smem(127, sizeof(double2), sizeof(double))));
   // initial state (constructors: FmDecode.cpp:25-83, PilotPhaseLock.cpp:35-54, IfSimpleAgc.cpp:22-32)
   {
     std::vector<FmChanState> st(C);
@@ -569,9 +573,9 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
     if (n384k == 0) continue;
     // ---- stream B: optional IF filter (FmDecode.cpp:98-102)
     if (h->cfg.fmfilter) {
-      dim3 grid((n384k + 127) / 128, C);
+      dim3 grid((n384k + kQTile - 1) / kQTile, C);
       pf.begin(h->p_fmf, sB);
-      k_fir_quirk<float><<<grid, 128, 0, sB>>>(h->r_if, h->r_iff, h->d_fmfilter, h->fmfilter_taps, t0k, (int)n384k,
+      k_fir_quirk<float><<<grid, kQThreads, fq_smem(h->fmfilter_taps, sizeof(float2), sizeof(float)), sB>>>(h->r_if, h->r_iff, h->d_fmfilter, h->fmfilter_taps, t0k, (int)n384k,
                                                d_e384, (int)nb);
       pf.end(h->p_fmf, sB);
       launches++;
@@ -619,9 +623,9 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
     if (a0 != j0k || a1 != j0k + n48k) return fail(FMR_ERR_INVALID, "internal: audio schedule mismatch");
     if (n48k > 0) {
       // ---- pilot-cut FIR (FmDecode.cpp:190,196) then DC block + matrix
-      dim3 grid((n48k + 127) / 128, C);
+      dim3 grid((n48k + kQTile - 1) / kQTile, C);
       pf.begin(h->p_pcut, sB);
-      k_fir_quirk<double><<<grid, 128, 0, sB>>>(h->r_48a, h->r_48b, h->d_pilotcut, 127, j0k, (int)n48k, d_e48, (int)nb);
+      k_fir_quirk<double><<<grid, kQThreads, fq_smem(127, sizeof(double2), sizeof(double)), sB>>>(h->r_48a, h->r_48b, h->d_pilotcut, 127, j0k, (int)n48k, d_e48, (int)nb);
       pf.end(h->p_pcut, sB);
       pf.begin(h->p_tail, sB);
       k_fm_tail<<<cgrid, 32, 0, sB>>>(h->r_48b, d_audio + (size_t)s48 * w, audio_stride, h->d_state, d_flags, d_e48,

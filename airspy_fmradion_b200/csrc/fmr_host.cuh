@@ -199,7 +199,7 @@ template <typename S> struct Resampler {
   S *d_bc = nullptr, *d_fi = nullptr;
   HbTaps<S> hbt;
   int64_t cum_in = 0;
-  size_t smem_hb = 0, smem_fir = 0;
+  size_t smem_hb = 0, smem_fir = 0, smem_fi = 0;
   Prof *prof = nullptr;
   int p_hb = -1, p_bc = -1, p_fi = -1;
   float2 *d_H = nullptr; // filter spectrum for k_fir_fft (float chains only)
@@ -299,6 +299,8 @@ template <typename S> struct Resampler {
       for (size_t i = 0; i < nt; i++) h[i] = (S)d->fi.taps[i];
       FMR_CUDA(mem.alloc(&d_fi, nt, false));
       FMR_CUDA(cudaMemcpy(d_fi, h.data(), nt * sizeof(S), cudaMemcpyHostToDevice));
+      smem_fi = fi_smem(d->fi.instep, d->fi.outstep, d->fi.flen, sizeof(V), sizeof(S));
+      FMR_CUDA(cudaFuncSetAttribute(k_frac_interp<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fi));
     }
     return FMR_OK;
   }
@@ -365,9 +367,10 @@ template <typename S> struct Resampler {
     if (d->has_fi) {
       const int n = (int)(f1 - f0);
       if (n > 0) {
-        dim3 grid((n + 127) / 128, gcn);
+        dim3 grid((n + kFiTile - 1) / kFiTile, gcn);
         if (prof) prof->begin(p_fi, st);
-        k_frac_interp<S><<<grid, 128, 0, st>>>(sub(r_bc), out, d_fi, d->fi.instep, d->fi.outstep, d->fi.flen, f0, n);
+        k_frac_interp<S><<<grid, kFiThreads, smem_fi, st>>>(sub(r_bc), out, d_fi, d->fi.instep, d->fi.outstep,
+                                                            d->fi.flen, f0, n);
         if (prof) prof->end(p_fi, st);
         (*launches)++;
       }

@@ -91,8 +91,14 @@ template <typename S> struct HbTaps {
   int sl[3]; // shared-memory sub-array length per level (host-computed, hb_sub_len)
   S t[3][14];
 };
-constexpr int kHbTile = 512;
-constexpr int kHbThreads = 256;
+#ifndef FMR_HB_TILE
+#define FMR_HB_TILE 256
+#endif
+#ifndef FMR_HB_THREADS
+#define FMR_HB_THREADS 128
+#endif
+constexpr int kHbTile = FMR_HB_TILE;
+constexpr int kHbThreads = FMR_HB_THREADS;
 constexpr int kHbR = 4; // consecutive outputs per thread (register blocking)
 
 // Shared-memory layout of one level: even- and odd-indexed samples in two separate arrays
@@ -135,6 +141,17 @@ template <typename V> __device__ __forceinline__ V fs4_rot(V v, int64_t ai) {
   return w;
 }
 
+// y += t * (u + v) on an (re, im) pair. For float2 this is one FADD2 + one FFMA2 (Blackwell's
+// packed FP32 pipe: both lanes of the pair in one issue slot, the tap as a broadcast scalar).
+__device__ __forceinline__ float2 hb_acc(float2 y, float t, float2 u, float2 v) {
+  return __ffma2_rn(make_float2(t, t), __fadd2_rn(u, v), y);
+}
+__device__ __forceinline__ double2 hb_acc(double2 y, double t, double2 u, double2 v) {
+  y.x += t * (u.x + v.x);
+  y.y += t * (u.y + v.y);
+  return y;
+}
+
 // One half-band stage with N taps: outputs [lo_out, lo_out+len_out) from the source level's
 // E/O arrays (base index ebp = lo_out - N), written to the next level's arrays or to `out`.
 template <typename S, int N, bool LAST>
@@ -158,10 +175,7 @@ __device__ __forceinline__ void hb_stage(const typename V2<S>::type *__restrict_
       V y = e[r];
 #pragma unroll
       for (int k = 0; k < N; k++) {
-        const V u = w[r + N + k];
-        const V v = w[r + N - k - 1];
-        y.x += t[k] * (u.x + v.x);
-        y.y += t[k] * (u.y + v.y);
+        y = hb_acc(y, t[k], w[r + N + k], w[r + N - k - 1]);
       }
       const int i = kHbR * g + r;
       if (i < len_out) {
@@ -491,30 +505,61 @@ static __global__ void __launch_bounds__(kDecThreads)
 // Whole-step polyphase interpolator (reference: r8b::CDSPFracInterpolator::convolve0,
 // CDSPFracInterpolator.h:992-1060): output m reads flen inputs starting at
 // floor(m*instep/outstep) - (flen/2 - 1) with the bank row (m*instep) mod outstep.
+constexpr int kFiThreads = 128;
+constexpr int kFiPer = 4; // outputs per thread (strided), so one copy of the bank serves 512 outputs
+constexpr int kFiTile = kFiThreads * kFiPer;
+
+// smem: input window of the tile + the whole bank, rows padded to an odd length
+__host__ __device__ inline int fi_row(int flen) { return flen | 1; }
+__host__ inline size_t fi_smem(int instep, int outstep, int flen, size_t vbytes, size_t sbytes) {
+  const int span = (int)(((int64_t)kFiTile * instep) / outstep) + flen + 4;
+  return (size_t)span * vbytes + (size_t)outstep * fi_row(flen) * sbytes + 16;
+}
+
 template <typename S>
-__global__ void k_frac_interp(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out,
-                              const S *__restrict__ bank, int instep, int outstep, int flen, int64_t m0,
-                              int n_out) {
+__global__ void __launch_bounds__(kFiThreads)
+    k_frac_interp(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out, const S *__restrict__ bank, int instep,
+                  int outstep, int flen, int64_t m0, int n_out) {
   using V = typename V2<S>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t c = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_out) return;
-  const int64_t m = m0 + i;
-  const int64_t pos = m * instep;
-  const int64_t ip = pos / outstep;
-  const int ph = (int)(pos - ip * outstep);
-  const S *row = bank + (size_t)ph * flen;
-  const int64_t x0 = ip - (flen / 2 - 1);
-  V acc;
-  acc.x = 0;
-  acc.y = 0;
-  for (int k = 0; k < flen; k++) {
-    const V x = in.ld(c, x0 + k);
-    const S h = row[k];
-    acc.x += h * x.x;
-    acc.y += h * x.y;
+  const int tile0 = blockIdx.x * kFiTile;
+  int cnt = n_out - tile0;
+  if (cnt > kFiTile) cnt = kFiTile;
+  if (cnt <= 0) return;
+  const int span = (int)(((int64_t)kFiTile * instep) / outstep) + flen + 4;
+  V *xs = reinterpret_cast<V *>(smem_raw);
+  S *bs = reinterpret_cast<S *>(xs + span);
+  const int rowp = fi_row(flen);
+  const int64_t mt = m0 + tile0;
+  const int64_t xbase = (mt * instep) / outstep - (flen / 2 - 1); // first input the tile reads
+  for (int i = threadIdx.x; i < span; i += kFiThreads) xs[i] = in.ld(c, xbase + i);
+  for (int i = threadIdx.x; i < outstep * flen; i += kFiThreads) {
+    const int ph = i / flen, k = i - ph * flen;
+    bs[ph * rowp + k] = bank[i];
   }
-  out.st(c, m, acc);
+  __syncthreads();
+#pragma unroll
+  for (int rr = 0; rr < kFiPer; rr++) {
+    const int i = threadIdx.x + rr * kFiThreads;
+    if (i >= cnt) break;
+    const int64_t m = mt + i;
+    const int64_t pos = m * instep;
+    const int64_t ip = pos / outstep;
+    const int ph = (int)(pos - ip * outstep);
+    const S *row = bs + ph * rowp;
+    const int x0 = (int)(ip - (flen / 2 - 1) - xbase);
+    V acc;
+    acc.x = 0;
+    acc.y = 0;
+    for (int k = 0; k < flen; k++) {
+      const V x = xs[x0 + k];
+      const S h = row[k];
+      acc.x += h * x.x;
+      acc.y += h * x.y;
+    }
+    out.st(c, m, acc);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -537,30 +582,96 @@ __device__ __forceinline__ int find_call(const uint32_t *__restrict__ call_end, 
   return lo;
 }
 
+constexpr int kQR = 4;        // consecutive outputs per thread
+constexpr int kQThreads = 64; // tile = 256 outputs
+constexpr int kQTile = kQR * kQThreads;
+
+__host__ __device__ inline int fq_len(int ntp) { return kQThreads + ntp / kQR + 3; }
+__host__ inline size_t fq_smem(int ntaps, size_t vbytes, size_t sbytes) {
+  const int ntp = (ntaps + kQR - 1) / kQR * kQR;
+  return (size_t)kQR * fq_len(ntp) * vbytes + (size_t)ntp * sbytes + 16;
+}
+
+// Register-blocked form: every thread owns kQR consecutive outputs and slides a window of
+// inputs through registers (one shared-memory load per tap for 2*kQR FMAs); inputs are stored
+// kQR-way interleaved so the window loads of a warp are contiguous. All taps are accumulated;
+// the coeff[0]*x[p] term is then taken out again for the outputs that fall into the head region
+// of their reference call (same value as never adding it, up to one float rounding).
 template <typename S>
-__global__ void k_fir_quirk(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out,
-                            const S *__restrict__ coeff, int ntaps, int64_t j0, int n_out,
-                            const uint32_t *__restrict__ call_end, int n_calls) {
+__global__ void __launch_bounds__(kQThreads)
+    k_fir_quirk(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out, const S *__restrict__ coeff,
+                int ntaps, int64_t j0, int n_out, const uint32_t *__restrict__ call_end, int n_calls) {
   using V = typename V2<S>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t c = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_out) return;
+  const int tile0 = blockIdx.x * kQTile;
+  int cnt = n_out - tile0;
+  if (cnt > kQTile) cnt = kQTile;
+  if (cnt <= 0) return;
   const int order = ntaps - 1;
-  const int b = find_call(call_end, n_calls, (uint32_t)i);
-  const uint32_t cstart = (b == 0) ? 0u : call_end[b - 1];
-  const int p = i - (int)cstart; // index within the reference's process() call
-  const int k0 = (p < order) ? 1 : 0;
-  const int64_t j = j0 + i;
-  V acc;
-  acc.x = 0;
-  acc.y = 0;
-  for (int k = k0; k <= order; k++) {
-    const V x = in.ld(c, j - k);
-    const S h = coeff[k];
-    acc.x += h * x.x;
-    acc.y += h * x.y;
+  const int ntp = (ntaps + kQR - 1) / kQR * kQR;
+  const int LEN = fq_len(ntp);
+  // The tile is stored REVERSED in time and shifted by one: Z[i] = x[E - 1 - i] with E the last
+  // output index of a full tile; thread outputs are v = kQTile-1-u, so y_v = sum_{k>=1} coeff[k] *
+  // Z[v + k - 1] walks the taps in increasing k — the order of the reference's head loop
+  // (Filter.cpp:59-68). Tap 0 is NOT part of the loop: like the reference it is added only for
+  // outputs outside the head region, so a head output never sees x[p] at all (exact zeros at
+  // stream start stay exact zeros, which the discriminator's atan2(0,0) depends on).
+  V *xs = reinterpret_cast<V *>(smem_raw); // [kQR][LEN]
+  S *hs = reinterpret_cast<S *>(xs + kQR * LEN); // hs[k'] = coeff[k' + 1]
+  const int64_t E = j0 + tile0 + kQTile - 2;
+  const int span = kQTile + ntp + kQR;
+  const int64_t last = j0 + tile0 + cnt - 1; // newest sample this tile may read
+  for (int i = threadIdx.x; i < span; i += kQThreads) {
+    V v;
+    v.x = 0;
+    v.y = 0;
+    const int64_t xi = E - i;
+    if (xi <= last && i < kQTile + order) v = in.ld(c, xi);
+    if (i / kQR < LEN) xs[(i % kQR) * LEN + i / kQR] = v;
   }
-  out.st(c, j, acc);
+  for (int i = threadIdx.x; i < ntp; i += kQThreads) hs[i] = (i < order) ? coeff[i + 1] : (S)0;
+  __syncthreads();
+  const int tid = threadIdx.x;
+  V acc[kQR], w[kQR];
+#pragma unroll
+  for (int r = 0; r < kQR; r++) {
+    acc[r].x = 0;
+    acc[r].y = 0;
+    w[r] = xs[r * LEN + tid];
+  }
+  // y[v] = sum_k' hs[k'] * Z[v + k'], v = kQR*tid + r
+  for (int q0 = 0; q0 < ntp; q0 += kQR) {
+#pragma unroll
+    for (int qq = 0; qq < kQR; qq++) {
+      const S h = hs[q0 + qq];
+#pragma unroll
+      for (int r = 0; r < kQR; r++) {
+        const V x = w[(r + qq) % kQR];
+        acc[r].x += h * x.x;
+        acc[r].y += h * x.y;
+      }
+      w[qq] = xs[qq * LEN + tid + q0 / kQR + 1];
+    }
+  }
+  const S c0 = coeff[0];
+#pragma unroll
+  for (int r = 0; r < kQR; r++) {
+    const int v = kQR * tid + r;
+    const int u = kQTile - 1 - v;
+    const int i = tile0 + u; // index within this launch
+    if (u < cnt) {
+      const int b = find_call(call_end, n_calls, (uint32_t)i);
+      const uint32_t cstart = (b == 0) ? 0u : call_end[b - 1];
+      V y = acc[r];
+      if (i - (int)cstart >= order) { // outside the head loop of the reference: coeff[0]*x[p] is added
+        const V x = in.ld(c, j0 + i);
+        y.x += c0 * x.x;
+        y.y += c0 * x.y;
+      }
+      out.st(c, j0 + i, y);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------

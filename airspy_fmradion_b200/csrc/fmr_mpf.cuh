@@ -61,8 +61,17 @@ __global__ void __launch_bounds__(32 * kMpfWarps)
       continue;
     }
     bool ok = true;
+    float2 xbuf[8]; // samples are fetched 8 at a time so their latency is not paid per sample
     for (int i = 0; i < n; i++) {
-      const float2 x = in.ld(c, tb + i);
+      if ((i & 7) == 0) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) xbuf[u] = (i + u < n) ? in.ld(c, tb + i + u) : make_float2(0.f, 0.f);
+      }
+      float2 x = xbuf[0];
+#pragma unroll
+      for (int u = 1; u < 8; u++) {
+        if ((i & 7) == u) x = xbuf[u];
+      }
       cnt++;
       if (lane == 0) ring[cnt & (kMpfRing - 1)] = x;
       __syncwarp();
