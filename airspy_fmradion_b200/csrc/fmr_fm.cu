@@ -8,6 +8,7 @@
 
 #include "fmr_host.cuh"
 #include "fmr_mpf.cuh"
+#include "fmr_partition.cuh"
 
 namespace fmr {
 thread_local std::string g_err;
@@ -17,7 +18,7 @@ using namespace fmr;
 
 constexpr int kMaxHostChunks = 8;       // time chunks of fmr_fm_process_host's copy/compute pipeline
 constexpr int kHostChunkMinBlocks = 16; // a chunk is at least this many source blocks
-constexpr int kMaxTimeChunks = 8;       // time chunks of the two-stream pipeline inside process_device
+#define kMaxTimeChunks 8                // time chunks of the pipeline inside process_device
 constexpr int kTimeChunkMinBlocks = 32; // a time chunk is at least this many source blocks
 constexpr int kMaxGroups = 4;  // streams owned by the handle
 constexpr int kGroupMin = 1 << 28; // channel groups are disabled: measured slower (all groups hit their serial phase together)
@@ -63,8 +64,11 @@ struct Trace {
 struct fmr_fm {
   fmr_fm_config cfg;
   Trace trace;
+  SmPartition part;       // FMR_SERIAL_SMS > 0: private SMs for the serial kernels (green contexts)
+  cudaEvent_t ev_p[kMaxTimeChunks][5] = {{nullptr}};
   int max_time_chunks = 1; // FMR_TIME_CHUNKS: the two-stream pipeline is off by default
   int chunk_min_blocks = 32;
+  int want_serial_sms = 0;
   int C = 0;
   const ChainDesc *ifc = nullptr; // null when input_rate == 384000 (no IfResampler, main.cpp:778)
   const ChainDesc *auc = nullptr;
@@ -95,7 +99,7 @@ struct fmr_fm {
   float *d_atan = nullptr;
   MpfDev mpf;
   cudaStream_t gstream[kMaxGroups] = {nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {nullptr}, ev_chunk[kMaxTimeChunks] = {nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[kMaxGroups] = {nullptr}, ev_chunk[kMaxTimeChunks] = {nullptr};
   Prof prof;
   int p_hist = -1, p_fmf = -1, p_core = -1, p_agc = -1, p_mpf = -1, p_core2 = -1, p_pcut = -1, p_tail = -1;
   FmCoreParams core;
@@ -172,7 +176,15 @@ static fmr_status fm_build(fmr_fm *h) {
     FMR_CUDA(cudaEventCreateWithFlags(&h->ev_join[g], cudaEventDisableTiming));
   }
   FMR_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-  for (int k = 0; k < kMaxTimeChunks; k++) FMR_CUDA(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
+  FMR_CUDA(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
+  for (int k = 0; k < kMaxTimeChunks; k++) {
+    FMR_CUDA(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
+    for (int q = 0; q < 5; q++) FMR_CUDA(cudaEventCreateWithFlags(&h->ev_p[k][q], cudaEventDisableTiming));
+  }
+  if (h->want_serial_sms > 0 && h->max_time_chunks > 1) {
+    FMR_CUDA(cudaFree(0));
+    h->part.init(cfg.device, h->want_serial_sms, h->trace.on);
+  }
 
   int64_t max384 = max_in + 8;
   if (h->ifc) {
@@ -326,6 +338,8 @@ extern "C" fmr_status fmr_fm_create(const fmr_fm_config *cfg, fmr_fm **out) {
   if (const char *e = getenv("FMR_TRACE")) h->trace.on = atoi(e) != 0;
   if (const char *e = getenv("FMR_TIME_CHUNKS")) h->max_time_chunks = std::max(1, std::min(atoi(e), kMaxTimeChunks));
   if (const char *e = getenv("FMR_CHUNK_MIN_BLOCKS")) h->chunk_min_blocks = std::max(1, atoi(e));
+  h->want_serial_sms = 0;
+  if (const char *e = getenv("FMR_SERIAL_SMS")) h->want_serial_sms = std::max(0, atoi(e));
   fmr_status s = fm_build(h);
   if (s != FMR_OK) {
     std::string keep = g_err;
@@ -501,14 +515,36 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
   FMR_CUDA(cudaMemcpyAsync(h->d_e384, rel384, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
   FMR_CUDA(cudaMemcpyAsync(h->d_e48, rel48, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
   h->slots.commit(slot, st);
-  cudaStream_t sA = st, sB = st;
+  // sA: front end; sB: parallel kernels after it; sS: the serial recurrences. Without an SM
+  // partition sS == sB (one in-order stream, no extra events needed).
+  // sG / sL / sT: AGC, PLL and tail each get their own in-order stream on the serial partition, so
+  // that AGC of chunk k+1, PLL of chunk k and the tail of chunk k-1 form a pipeline.
+  cudaStream_t sA = st, sB = st, sU = st, sG = st, sL = st, sT = st;
+  const bool parted = (n_chunks > 1 && h->part.ok);
   if (n_chunks > 1) {
-    sA = h->gstream[0];
-    sB = h->gstream[1];
+    sA = parted ? h->part.s_front : h->gstream[0];
+    sB = parted ? h->part.s_post : h->gstream[1];
+    sU = parted ? h->part.s_post2 : sB;
+    sG = parted ? h->part.s_serial : sB;
+    sL = parted ? h->part.s_serial2 : sB;
+    sT = parted ? h->part.s_serial3 : sB;
     FMR_CUDA(cudaEventRecord(h->ev_fork, st));
     FMR_CUDA(cudaStreamWaitEvent(sA, h->ev_fork, 0));
     FMR_CUDA(cudaStreamWaitEvent(sB, h->ev_fork, 0));
+    if (parted) {
+      FMR_CUDA(cudaStreamWaitEvent(sU, h->ev_fork, 0));
+      FMR_CUDA(cudaStreamWaitEvent(sG, h->ev_fork, 0));
+      FMR_CUDA(cudaStreamWaitEvent(sL, h->ev_fork, 0));
+      FMR_CUDA(cudaStreamWaitEvent(sT, h->ev_fork, 0));
+    }
   }
+  // hand-over between sB and sS (only when they differ)
+  auto hop = [&](cudaStream_t from, cudaStream_t to, cudaEvent_t ev) -> cudaError_t {
+    if (from == to) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(ev, from);
+    if (e != cudaSuccess) return e;
+    return cudaStreamWaitEvent(to, ev, 0);
+  };
   if (tr.on) {
     if (!tr.origin) cudaEventCreate(&tr.origin);
     cudaEventRecord(tr.origin, st);
@@ -569,6 +605,7 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
     if (n_chunks > 1) {
       FMR_CUDA(cudaEventRecord(h->ev_chunk[k], sA));
       FMR_CUDA(cudaStreamWaitEvent(sB, h->ev_chunk[k], 0));
+      if (parted) FMR_CUDA(cudaStreamWaitEvent(sG, h->ev_chunk[k], 0));
     }
     if (n384k == 0) continue;
     // ---- stream B: optional IF filter (FmDecode.cpp:98-102)
@@ -582,12 +619,14 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
     }
     // ---- 384 kHz core: AGC (serial) -> [multipath] -> discriminator + statistics (parallel) -> PLL (serial)
     dim3 cgrid((C + 31) / 32);
-    pf.begin(h->p_agc, sB);
-    tr.begin("agc", k, sB);
-    k_fm_agc<<<cgrid, 32, 0, sB>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
-    tr.end(sB);
-    pf.end(h->p_agc, sB);
+    if (h->cfg.fmfilter) FMR_CUDA(hop(sB, sG, h->ev_p[k][0]));
+    pf.begin(h->p_agc, sG);
+    tr.begin("agc", k, sG);
+    k_fm_agc<<<cgrid, 32, 0, sG>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
+    tr.end(sG);
+    pf.end(h->p_agc, sG);
     launches++;
+    FMR_CUDA(hop(sG, sB, h->ev_p[k][1]));
     Ring<float2> disc_in = h->r_agc;
     if (h->cfg.multipath_stages > 0) {
       pf.begin(h->p_mpf, sB);
@@ -604,33 +643,36 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
       k_fm_call_stats<<<g2, 128, 0, sB>>>(h->r_if, h->r_mpx, d_stats, d_e384, (int)nb, t0k);
     }
     pf.end(h->p_core, sB);
-    pf.begin(h->p_core2, sB);
-    tr.begin("pll", k, sB);
-    k_fm_pll<<<cgrid, 32, 0, sB>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
+    FMR_CUDA(hop(sB, sL, h->ev_p[k][2]));
+    pf.begin(h->p_core2, sL);
+    tr.begin("pll", k, sL);
+    k_fm_pll<<<cgrid, 32, 0, sL>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
                                    h->core, h->d_atan, (int)(flag_b0 + b0), (k == 0 && flag_b0 == 0) ? 1 : 0);
-    tr.end(sB);
-    pf.end(h->p_core2, sB);
+    tr.end(sL);
+    pf.end(h->p_core2, sL);
+    FMR_CUDA(hop(sL, sU, h->ev_p[k][3]));
     launches += 3;
     // ---- audio resamplers (mono and L-R in lock step, FmDecode.cpp:172-183)
     InSrc<double2> asrc;
     memset(&asrc, 0, sizeof(asrc));
     asrc.ring = h->r_384;
     int64_t a0, a1;
-    tr.begin("audio", k, sB);
-    s = h->aures.run(asrc, (int64_t)n384k, h->r_48a, 0, sB, &a0, &a1, &launches, true);
-    tr.end(sB);
+    tr.begin("audio", k, sU);
+    s = h->aures.run(asrc, (int64_t)n384k, h->r_48a, 0, sU, &a0, &a1, &launches, true);
+    tr.end(sU);
     if (s != FMR_OK) return s;
     if (a0 != j0k || a1 != j0k + n48k) return fail(FMR_ERR_INVALID, "internal: audio schedule mismatch");
     if (n48k > 0) {
       // ---- pilot-cut FIR (FmDecode.cpp:190,196) then DC block + matrix
       dim3 grid((n48k + kQTile - 1) / kQTile, C);
-      pf.begin(h->p_pcut, sB);
-      k_fir_quirk<double><<<grid, kQThreads, fq_smem(127, sizeof(double2), sizeof(double)), sB>>>(h->r_48a, h->r_48b, h->d_pilotcut, 127, j0k, (int)n48k, d_e48, (int)nb);
-      pf.end(h->p_pcut, sB);
-      pf.begin(h->p_tail, sB);
-      k_fm_tail<<<cgrid, 32, 0, sB>>>(h->r_48b, d_audio + (size_t)s48 * w, audio_stride, h->d_state, d_flags, d_e48,
+      pf.begin(h->p_pcut, sU);
+      k_fir_quirk<double><<<grid, kQThreads, fq_smem(127, sizeof(double2), sizeof(double)), sU>>>(h->r_48a, h->r_48b, h->d_pilotcut, 127, j0k, (int)n48k, d_e48, (int)nb);
+      pf.end(h->p_pcut, sU);
+      FMR_CUDA(hop(sU, sT, h->ev_p[k][4]));
+      pf.begin(h->p_tail, sT);
+      k_fm_tail<<<cgrid, 32, 0, sT>>>(h->r_48b, d_audio + (size_t)s48 * w, audio_stride, h->d_state, d_flags, d_e48,
                                       (int)nb, j0k, h->tail);
-      pf.end(h->p_tail, sB);
+      pf.end(h->p_tail, sT);
       launches += 2;
     }
   }
@@ -639,6 +681,16 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
     FMR_CUDA(cudaEventRecord(h->ev_join[1], sB));
     FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[0], 0));
     FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[1], 0));
+    if (parted) {
+      FMR_CUDA(cudaEventRecord(h->ev_chunk[0], sU));
+      FMR_CUDA(cudaStreamWaitEvent(st, h->ev_chunk[0], 0));
+      FMR_CUDA(cudaEventRecord(h->ev_join[2], sG));
+      FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[2], 0));
+      FMR_CUDA(cudaEventRecord(h->ev_join[3], sL));
+      FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[3], 0));
+      FMR_CUDA(cudaEventRecord(h->ev_fork2, sT));
+      FMR_CUDA(cudaStreamWaitEvent(st, h->ev_fork2, 0));
+    }
   }
   if (h->ifc && total_in > 0) h->hist_cur ^= 1;
   if (tr.on) {

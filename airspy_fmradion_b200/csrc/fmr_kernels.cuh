@@ -688,7 +688,10 @@ __device__ __forceinline__ float fast_atan2f_dev(float y, float x, const float *
     z = x_abs / y_abs;
   }
   float base_angle;
-  if ((double)z < 0.003921569) {
+  // reference: `z < TAN_MAP_RES` with the double literal 0.003921569, i.e. (double)z < T. For a float
+  // z that is equivalent to z < Tf with Tf the smallest float >= T (0x3b808082 = 0.00392156932...),
+  // which avoids a float->double conversion on the PLL's critical path.
+  if (z < __int_as_float(0x3b808082)) {
     base_angle = z;
   } else {
     float alpha = z * 255.0f;
@@ -913,13 +916,14 @@ static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanSta
   double sf0, cf0;
   sincos(f0, &sf0, &cf0);
   const int n_total = n_calls ? (int)call_end[n_calls - 1] : 0;
+  const float *__restrict__ mrow = mpx.base + (size_t)c * mpx.cap;
+  double2 *__restrict__ orow = out384.base + (size_t)c * out384.cap;
+  const uint32_t mmask = mpx.cap - 1, omask = out384.cap - 1, t0lo = (uint32_t)t0;
   // register double-buffer over the flat sample stream of this launch: `nxt` always holds
   // the kCoreChunk samples starting at flat index `pos_nxt`
   float nxt[kCoreChunk];
 #pragma unroll
-  for (int u = 0; u < kCoreChunk; u++) {
-    nxt[u] = (u < n_total) ? mpx.base[(size_t)c * mpx.cap + ((uint32_t)(t0 + u) & (mpx.cap - 1))] : 0.f;
-  }
+  for (int u = 0; u < kCoreChunk; u++) nxt[u] = (u < n_total) ? mrow[(t0lo + (uint32_t)u) & mmask] : 0.f;
   uint32_t prev_end = 0;
   for (int b = 0; b < n_calls; b++) {
     const uint32_t end = call_end[b];
@@ -944,9 +948,7 @@ static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanSta
         const int pos = (int)beg + i0 + valid; // flat index the next chunk (of this or the next call) starts at
 #pragma unroll
         for (int u = 0; u < kCoreChunk; u++) {
-          nxt[u] = (pos + u < n_total)
-                       ? mpx.base[(size_t)c * mpx.cap + ((uint32_t)(t0 + pos + u) & (mpx.cap - 1))]
-                       : 0.f;
+          nxt[u] = (pos + u < n_total) ? mrow[(t0lo + (uint32_t)(pos + u)) & mmask] : 0.f;
         }
       }
 #pragma unroll
@@ -972,7 +974,12 @@ static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanSta
           s.lf_x1 = perr;
           s.freq_err = ferr;
           s.pll_freq += ferr;
-          s.pll_freq = fmax(P.pll_minfreq, fmin(P.pll_maxfreq, s.pll_freq));
+          // std::max(m_minfreq, std::min(m_maxfreq, m_freq)) with std::min/max's own comparisons
+        // (PilotPhaseLock.cpp:119); plain selects are far cheaper than IEEE fmin/fmax on FP64
+        {
+          const double fq = (s.pll_freq < P.pll_maxfreq) ? s.pll_freq : P.pll_maxfreq;
+          s.pll_freq = (P.pll_minfreq < fq) ? fq : P.pll_minfreq;
+        }
           s.pll_phase += s.pll_freq;
           // advance the phasor by m_freq = f0 + dl
           {
@@ -1020,7 +1027,7 @@ static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanSta
         double2 o;
         o.x = mono;
         o.y = stereo;
-        out384.st(c, t0 + beg + i, o);
+        orow[(t0lo + beg + (uint32_t)i) & omask] = o;
       }
     }
     // per-call statistics (FmDecode.cpp:95,146-150)
@@ -1053,7 +1060,33 @@ static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanSta
     }
     flags[(size_t)c * n_calls + b] = (uint8_t)s.stereo_detected;
   }
-  st[c] = s;
+  // Field-wise write-back of what this kernel owns: with the pipelined schedule the AGC kernel of
+  // the next time chunk (agc_gain) and the tail kernel of the previous one (dc_*) may be updating
+  // their own fields of the same struct concurrently.
+  {
+    FmChanState *o = st + c;
+    o->baseband_mean = s.baseband_mean;
+    o->baseband_level = s.baseband_level;
+    o->if_rms = s.if_rms;
+    o->stereo_detected = s.stereo_detected;
+    o->lock_cnt = s.lock_cnt;
+    o->pilot_periods = s.pilot_periods;
+    o->n_pps = s.n_pps;
+    o->pll_phase = s.pll_phase;
+    o->pll_freq = s.pll_freq;
+    o->bi_x1 = s.bi_x1;
+    o->bi_x2 = s.bi_x2;
+    o->bq_x1 = s.bq_x1;
+    o->bq_x2 = s.bq_x2;
+    o->lf_x1 = s.lf_x1;
+    o->pilot_level = s.pilot_level;
+    o->freq_err = s.freq_err;
+    o->pps_cnt = s.pps_cnt;
+    o->sample_cnt = s.sample_cnt;
+    o->de_m_x1 = s.de_m_x1;
+    o->de_s_x1 = s.de_s_x1;
+    o->decoder_calls = s.decoder_calls;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
