@@ -212,9 +212,9 @@ def main():
 
     nblk = args.blocks
     T = nblk * BLK
-    C = args.channels or {"fm": 4096 if fs >= 5e6 else 8192, "am": 8192}[mode]
+    C = args.channels or {"fm": 8192, "am": 8192}[mode]
     if mpf:
-        C = args.channels or 512
+        C = args.channels or 1776  # 444 CTAs of 4 channels = one wave of the multipath kernel (3 CTAs/SM)
     dec = make_decoder(wl, C, T, nblk, dev_index)
     iq = gen_iq_device(torch, dev, fs, C, T, mode)
     width = 2 if (mode == "fm" and stereo) else 1
@@ -268,10 +268,17 @@ def main():
     peak, peak_src = peaks()
     alg_bytes = C * T * 8 + C * int(lens.sum()) * 8  # IQ read + audio written, per launch/step
     roof = None
+    traffic = None
+    try:  # DRAM bytes per input sample of the dominant kernel from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+        if dom in tj:
+            traffic = tj[dom]["bytes_per_input_sample"] * C * T
+    except Exception:
+        traffic = None
     if dom:
         ach = alg_bytes / (stage[dom] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": stage[dom],
+                "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "kernel_ms": stage[dom],
                 "whole_step_frac": (alg_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
                 "stage_ms": {k: round(v, 4) for k, v in stage.items()}}
 
