@@ -1,19 +1,28 @@
 // fmr_fft.cuh — the long zero-phase low-pass as overlap-save fast convolution, entirely in
 // shared memory (reference: r8b::CDSPBlockConvolver::process, CDSPBlockConvolver.h:252-353,
-// which does the same linear convolution with a 16384-point double-precision FFT).
+// which does the same linear convolution with a double-precision FFT of 8192/16384 points).
 //
-// One CTA filters one block of one channel: 16384 complex FP32 points live in 136 KB of
-// shared memory; forward FFT, multiply by the filter spectrum H (precomputed on the host
-// in double, 1/N folded in), inverse FFT via the conjugation identity, and only the
-// 16384-(klen-1) alias-free outputs are written. The complex IQ stream rides through one
-// complex FFT (the filter is real, so I and Q need no separate transforms).
+// One CTA filters one block of one channel: N complex points live in shared memory
+// (N = 16384 FP32: 136 KB; N = 8192 FP32: 68 KB; N = 8192 FP64: 139 KB); forward FFT, multiply
+// by the filter spectrum H (precomputed on the host in double, 1/N folded in), inverse FFT via
+// the conjugation identity, and only the N-(klen-1) alias-free outputs are used. A complex
+// stream rides through one complex FFT (the filter is real): I/Q for the IF chain, (mono, L-R)
+// for the two audio resamplers that the reference runs in lock step (FmDecode.cpp:172-183).
 //
-// FFT: in-place Stockham autosort, radix 16,16,16,4 (DIT twiddles on the inputs), every
-// thread keeps its butterfly inputs in registers across the barrier so one buffer
-// suffices. The first forward pass reads straight from the global ring, the last forward
-// pass applies H and the conjugation, the last inverse pass writes straight to global:
-// 7 shared-memory round trips per block. Shared-memory layout is skewed (one pad slot per
-// 16) so both the stride-1024 reads and the stride-16 writes are bank-conflict free.
+// FFT: in-place Stockham autosort, radix 16,16,16,R (R = N/4096 = 4 or 2; DIT twiddles on the
+// inputs), every thread keeps its butterfly inputs in registers across the barrier so one buffer
+// suffices. The first forward pass reads straight from the global ring, the last forward pass
+// applies H and the conjugation: 7 shared-memory round trips per block. Shared-memory layout
+// is skewed (one pad slot per 16) so both the strided reads and the stride-16 writes are
+// bank-conflict free.
+//
+// Epilogue, two forms:
+//   plain : the last inverse pass writes the alias-free outputs (every `down`-th) to the ring;
+//   fused : (IF chain) the filtered block stays in shared memory and the whole-step polyphase
+//           interpolator (r8b::CDSPFracInterpolator::convolve0, CDSPFracInterpolator.h:992-1060)
+//           is applied from there, so the 1.25 MHz intermediate stream never touches HBM.
+//           Blocks are placed so that every interpolator window lies inside one block's
+//           alias-free region (consecutive blocks overlap by flen extra samples).
 #ifndef FMR_FFT_CUH
 #define FMR_FFT_CUH
 
@@ -21,215 +30,327 @@
 
 namespace fmr {
 
-constexpr int kFftN = 16384;
 constexpr int kFftThreads = 512;
-constexpr int kFftSmemBytes = (kFftN + kFftN / 16) * 8 + 256 * 8;
+
+template <typename S, int N> struct FftCfg {
+  using V = typename V2<S>::type;
+  static constexpr int kN = N;
+  static constexpr int kQ = N / 16;             // stride of the radix-16 passes
+  static constexpr int kSets = N / 16 / kFftThreads; // butterflies of 16 per thread per pass
+  static constexpr int kR4 = N / 4096;          // radix of the last pass
+  static constexpr int kSmemBytes = (N + N / 16) * (int)sizeof(V) + 256 * (int)sizeof(V);
+  static_assert(kSets >= 1 && (kR4 == 2 || kR4 == 4), "unsupported FFT size");
+};
 
 __device__ __forceinline__ int fpad(int n) { return n + (n >> 4); }
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
-__device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
-  const float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y);
-  const float2 d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
-  const float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y);
-  const float2 d13 = make_float2(a1.x - a3.x, a1.y - a3.y);
-  a0 = make_float2(s02.x + s13.x, s02.y + s13.y);
-  a2 = make_float2(s02.x - s13.x, s02.y - s13.y);
-  a1 = make_float2(d02.x + d13.y, d02.y - d13.x); // d02 - j d13
-  a3 = make_float2(d02.x - d13.y, d02.y + d13.x); // d02 + j d13
+template <typename V> __device__ __forceinline__ V cmk(decltype(V().x) a, decltype(V().x) b) {
+  V v;
+  v.x = a;
+  v.y = b;
+  return v;
+}
+template <typename V> __device__ __forceinline__ V cmulv(V a, V b) {
+  return cmk<V>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+template <typename V> __device__ __forceinline__ V cconjv(V a) { return cmk<V>(a.x, -a.y); }
+
+template <typename V> __device__ __forceinline__ void fft4(V &a0, V &a1, V &a2, V &a3) {
+  const V s02 = cmk<V>(a0.x + a2.x, a0.y + a2.y);
+  const V d02 = cmk<V>(a0.x - a2.x, a0.y - a2.y);
+  const V s13 = cmk<V>(a1.x + a3.x, a1.y + a3.y);
+  const V d13 = cmk<V>(a1.x - a3.x, a1.y - a3.y);
+  a0 = cmk<V>(s02.x + s13.x, s02.y + s13.y);
+  a2 = cmk<V>(s02.x - s13.x, s02.y - s13.y);
+  a1 = cmk<V>(d02.x + d13.y, d02.y - d13.x); // d02 - j d13
+  a3 = cmk<V>(d02.x - d13.y, d02.y + d13.x); // d02 + j d13
 }
 
 // 16-point forward DFT in registers; result X[m] is left in v[4*(m&3) + (m>>2)].
-__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+template <typename V> __device__ __forceinline__ void fft16(V (&v)[16]) {
+  using S = decltype(V().x);
 #pragma unroll
   for (int n2 = 0; n2 < 4; n2++) fft4(v[n2], v[n2 + 4], v[n2 + 8], v[n2 + 12]);
   // twiddles W16^(n2*k1), element v[n2 + 4*k1]
-  const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+  const S c1 = (S)0.92387953251128675613, s1 = (S)0.38268343236508977173, r2 = (S)0.70710678118654752440;
   // k1 = 1: W^n2
-  v[1 + 4] = cmulf(v[1 + 4], make_float2(c1, -s1));
-  v[2 + 4] = cmulf(v[2 + 4], make_float2(r2, -r2));
-  v[3 + 4] = cmulf(v[3 + 4], make_float2(s1, -c1));
+  v[1 + 4] = cmulv(v[1 + 4], cmk<V>(c1, -s1));
+  v[2 + 4] = cmulv(v[2 + 4], cmk<V>(r2, -r2));
+  v[3 + 4] = cmulv(v[3 + 4], cmk<V>(s1, -c1));
   // k1 = 2: W^(2 n2)
-  v[1 + 8] = cmulf(v[1 + 8], make_float2(r2, -r2));
-  v[2 + 8] = make_float2(v[2 + 8].y, -v[2 + 8].x); // W^4 = -j
-  v[3 + 8] = cmulf(v[3 + 8], make_float2(-r2, -r2));
+  v[1 + 8] = cmulv(v[1 + 8], cmk<V>(r2, -r2));
+  v[2 + 8] = cmk<V>(v[2 + 8].y, -v[2 + 8].x); // W^4 = -j
+  v[3 + 8] = cmulv(v[3 + 8], cmk<V>(-r2, -r2));
   // k1 = 3: W^(3 n2)
-  v[1 + 12] = cmulf(v[1 + 12], make_float2(s1, -c1));
-  v[2 + 12] = cmulf(v[2 + 12], make_float2(-r2, -r2));
-  v[3 + 12] = cmulf(v[3 + 12], make_float2(-c1, s1)); // W^9
+  v[1 + 12] = cmulv(v[1 + 12], cmk<V>(s1, -c1));
+  v[2 + 12] = cmulv(v[2 + 12], cmk<V>(-r2, -r2));
+  v[3 + 12] = cmulv(v[3 + 12], cmk<V>(-c1, s1)); // W^9
 #pragma unroll
   for (int k1 = 0; k1 < 4; k1++) fft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
 }
 
-// W_16384^m from the two-level table: tw[0..127] = W^(128 q), tw[128..255] = W^l.
-__device__ __forceinline__ float2 tw_lookup(const float2 *tw, int m) {
-  return cmulf(tw[m >> 7], tw[128 + (m & 127)]);
+// W_N^m from the two-level table: tw[0..127] = W^(128 q), tw[128..255] = W^l.
+template <typename V> __device__ __forceinline__ V tw_lookup(const V *tw, int m) {
+  return cmulv(tw[m >> 7], tw[128 + (m & 127)]);
 }
 
 // apply w^r (r = 1..15) to v[r]
-__device__ __forceinline__ void twiddle16(float2 (&v)[16], float2 w1) {
-  const float2 w2 = cmulf(w1, w1);
-  const float2 w3 = cmulf(w2, w1);
-  const float2 w4 = cmulf(w2, w2);
-  const float2 w5 = cmulf(w4, w1);
-  const float2 w6 = cmulf(w3, w3);
-  const float2 w7 = cmulf(w4, w3);
-  const float2 w8 = cmulf(w4, w4);
-  v[1] = cmulf(v[1], w1);
-  v[2] = cmulf(v[2], w2);
-  v[3] = cmulf(v[3], w3);
-  v[4] = cmulf(v[4], w4);
-  v[5] = cmulf(v[5], w5);
-  v[6] = cmulf(v[6], w6);
-  v[7] = cmulf(v[7], w7);
-  v[8] = cmulf(v[8], w8);
-  v[9] = cmulf(v[9], cmulf(w8, w1));
-  v[10] = cmulf(v[10], cmulf(w8, w2));
-  v[11] = cmulf(v[11], cmulf(w8, w3));
-  v[12] = cmulf(v[12], cmulf(w8, w4));
-  v[13] = cmulf(v[13], cmulf(w8, w5));
-  v[14] = cmulf(v[14], cmulf(w8, w6));
-  v[15] = cmulf(v[15], cmulf(w8, w7));
+template <typename V> __device__ __forceinline__ void twiddle16(V (&v)[16], V w1) {
+  const V w2 = cmulv(w1, w1);
+  const V w3 = cmulv(w2, w1);
+  const V w4 = cmulv(w2, w2);
+  const V w5 = cmulv(w4, w1);
+  const V w6 = cmulv(w3, w3);
+  const V w7 = cmulv(w4, w3);
+  const V w8 = cmulv(w4, w4);
+  v[1] = cmulv(v[1], w1);
+  v[2] = cmulv(v[2], w2);
+  v[3] = cmulv(v[3], w3);
+  v[4] = cmulv(v[4], w4);
+  v[5] = cmulv(v[5], w5);
+  v[6] = cmulv(v[6], w6);
+  v[7] = cmulv(v[7], w7);
+  v[8] = cmulv(v[8], w8);
+  v[9] = cmulv(v[9], cmulv(w8, w1));
+  v[10] = cmulv(v[10], cmulv(w8, w2));
+  v[11] = cmulv(v[11], cmulv(w8, w3));
+  v[12] = cmulv(v[12], cmulv(w8, w4));
+  v[13] = cmulv(v[13], cmulv(w8, w5));
+  v[14] = cmulv(v[14], cmulv(w8, w6));
+  v[15] = cmulv(v[15], cmulv(w8, w7));
+}
+
+// First pass of a transform whose input already sits in the buffer (p = 1, no twiddles).
+template <typename CFG> __device__ __forceinline__ void pass16_first_smem(typename CFG::V *buf) {
+  using V = typename CFG::V;
+  V v[CFG::kSets][16];
+#pragma unroll
+  for (int s = 0; s < CFG::kSets; s++) {
+    const int i = threadIdx.x + s * kFftThreads;
+#pragma unroll
+    for (int r = 0; r < 16; r++) v[s][r] = buf[fpad(i + r * CFG::kQ)];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < CFG::kSets; s++) {
+    const int i = threadIdx.x + s * kFftThreads;
+    fft16(v[s]);
+#pragma unroll
+    for (int r = 0; r < 16; r++) buf[fpad(i * 16 + r)] = v[s][4 * (r & 3) + (r >> 2)];
+  }
+  __syncthreads();
 }
 
 // One radix-16 Stockham pass over the whole buffer, in place: p = 16 or 256.
-__device__ __forceinline__ void pass16_smem(float2 *buf, const float2 *tw, int p, int scale) {
-  float2 va[16], vb[16];
-  const int ia = threadIdx.x, ib = threadIdx.x + kFftThreads;
+template <typename CFG>
+__device__ __forceinline__ void pass16_smem(typename CFG::V *buf, const typename CFG::V *tw, int p) {
+  using V = typename CFG::V;
+  const int scale = CFG::kN / (16 * p);
+  V v[CFG::kSets][16];
 #pragma unroll
-  for (int r = 0; r < 16; r++) {
-    va[r] = buf[fpad(ia + r * 1024)];
-    vb[r] = buf[fpad(ib + r * 1024)];
+  for (int s = 0; s < CFG::kSets; s++) {
+    const int i = threadIdx.x + s * kFftThreads;
+#pragma unroll
+    for (int r = 0; r < 16; r++) v[s][r] = buf[fpad(i + r * CFG::kQ)];
   }
   __syncthreads();
-  {
-    const int k = ia & (p - 1);
-    twiddle16(va, tw_lookup(tw, k * scale));
-    fft16(va);
-    const int j = (ia - k) * 16 + k;
 #pragma unroll
-    for (int r = 0; r < 16; r++) buf[fpad(j + r * p)] = va[4 * (r & 3) + (r >> 2)];
-  }
-  {
-    const int k = ib & (p - 1);
-    twiddle16(vb, tw_lookup(tw, k * scale));
-    fft16(vb);
-    const int j = (ib - k) * 16 + k;
+  for (int s = 0; s < CFG::kSets; s++) {
+    const int i = threadIdx.x + s * kFftThreads;
+    const int k = i & (p - 1);
+    twiddle16(v[s], tw_lookup(tw, k * scale));
+    fft16(v[s]);
+    const int j = (i - k) * 16 + k;
 #pragma unroll
-    for (int r = 0; r < 16; r++) buf[fpad(j + r * p)] = vb[4 * (r & 3) + (r >> 2)];
+    for (int r = 0; r < 16; r++) buf[fpad(j + r * p)] = v[s][4 * (r & 3) + (r >> 2)];
   }
   __syncthreads();
 }
 
-// k_fir_fft: y[q] = sum_j h[j] x[q*down - fl2 + j] for q in [q0, q0+n_out), block-wise.
-//   n_in_avail : number of valid input samples in the ring (indices >= it read as zero)
-//   lq         : outputs per block = (16384 - klen + 1) / down
-static __global__ void __launch_bounds__(kFftThreads, 1)
-    k_fir_fft(Ring<float2> in, Ring<float2> out, const float2 *__restrict__ H, int klen, int down, int64_t q0,
-              int n_out, int64_t n_in_avail, int lq) {
+// Last pass (radix 4 or 2, p = 4096) on the elements {i + r*4096}; in place: a[r] <- X[i + r*4096].
+template <typename CFG>
+__device__ __forceinline__ void last_pass_load(const typename CFG::V *buf, const typename CFG::V *tw, int i,
+                                               typename CFG::V (&a)[4]) {
+  using V = typename CFG::V;
+  const V w1 = tw_lookup(tw, i);
+  if (CFG::kR4 == 4) {
+    a[0] = buf[fpad(i)];
+    a[1] = buf[fpad(i + 4096)];
+    a[2] = buf[fpad(i + 8192)];
+    a[3] = buf[fpad(i + 12288)];
+    const V w2 = cmulv(w1, w1);
+    a[1] = cmulv(a[1], w1);
+    a[2] = cmulv(a[2], w2);
+    a[3] = cmulv(a[3], cmulv(w2, w1));
+    fft4(a[0], a[1], a[2], a[3]);
+  } else {
+    const V x0 = buf[fpad(i)];
+    const V x1 = cmulv(buf[fpad(i + 4096)], w1);
+    a[0] = cmk<V>(x0.x + x1.x, x0.y + x1.y);
+    a[1] = cmk<V>(x0.x - x1.x, x0.y - x1.y);
+    a[2] = a[0];
+    a[3] = a[0];
+  }
+}
+
+struct FftFuse {
+  const void *bank; // [outstep][flen] interpolator bank, scalar type of the chain
+  int instep, outstep, flen;
+  int64_t m0;       // first interpolator output of this launch
+  int n_m;          // interpolator outputs of this launch
+  int mo;           // interpolator outputs per block
+  // The last block of a call also leaves the newest filtered samples [tail_lo, tail_hi) in the
+  // intermediate ring (`tail_base`, capacity `tail_cap`), where the unfused kernels of a later,
+  // smaller call expect the interpolator's history. tail_hi <= tail_lo disables it.
+  void *tail_base;
+  uint32_t tail_cap;
+  int64_t tail_lo, tail_hi;
+};
+
+// k_fir_fft: y[q] = sum_j h[j] x[q*down - fl2 + j].
+//   plain: q in [q0, q0+n_out), lq = (N - klen + 1) / down outputs per block.
+//   fused: block b produces interpolator outputs m in [m0 + b*mo, ...) from the filtered samples
+//          it holds (down must be 1); samples with negative index read as zero like the ring does.
+//   n_in_avail: number of valid input samples in the ring (indices >= it read as zero)
+template <typename S, int N, bool FUSE>
+__global__ void __launch_bounds__(kFftThreads, 1)
+    k_fir_fft(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out, const typename V2<S>::type *__restrict__ H,
+              int klen, int down, int64_t q0, int n_out, int64_t n_in_avail, int lq, FftFuse fz) {
+  using CFG = FftCfg<S, N>;
+  using V = typename CFG::V;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *buf = reinterpret_cast<float2 *>(smem_raw);
-  float2 *tw = buf + (kFftN + kFftN / 16);
+  V *buf = reinterpret_cast<V *>(smem_raw);
+  V *tw = buf + (N + N / 16);
   const uint32_t c = blockIdx.y;
   const int blk = blockIdx.x;
-  int cnt = n_out - blk * lq;
-  if (cnt > lq) cnt = lq;
-  if (cnt <= 0) return;
+  int cnt;        // plain: filter outputs of this block; fused: interpolator outputs of this block
+  int64_t qb;     // filter output index held by buffer slot klen-1
+  int64_t mb = 0; // fused: first interpolator output of this block
+  if (FUSE) {
+    cnt = fz.n_m - blk * fz.mo;
+    if (cnt > fz.mo) cnt = fz.mo;
+    if (cnt <= 0) return;
+    mb = fz.m0 + (int64_t)blk * fz.mo;
+    qb = (mb * fz.instep) / fz.outstep - (fz.flen / 2 - 1);
+  } else {
+    cnt = n_out - blk * lq;
+    if (cnt > lq) cnt = lq;
+    if (cnt <= 0) return;
+    qb = q0 + (int64_t)blk * lq;
+  }
   const int fl2 = (klen - 1) / 2;
-  const int64_t t_first = (q0 + (int64_t)blk * lq) * down;
-  const int64_t base = t_first - fl2; // input sample index held by buffer slot 0
+  const int64_t base = qb * down - fl2; // input sample index held by buffer slot 0
   // twiddle tables
   if (threadIdx.x < 256) {
     const int q = threadIdx.x;
     const int m = (q < 128) ? (q * 128) : (q - 128);
-    float s, co;
-    sincospif(-2.0f * (float)m / 16384.0f, &s, &co);
-    tw[q] = make_float2(co, s);
+    S s, co;
+    if (sizeof(S) == 4) {
+      float fs, fc;
+      sincospif(-2.0f * (float)m / (float)N, &fs, &fc);
+      s = (S)fs;
+      co = (S)fc;
+    } else {
+      double ds, dc;
+      sincospi(-2.0 * (double)m / (double)N, &ds, &dc);
+      s = (S)ds;
+      co = (S)dc;
+    }
+    tw[q] = cmk<V>(co, s);
   }
   // ---- forward pass 1 (p = 1, no twiddles), inputs straight from the global ring
   {
-    float2 va[16], vb[16];
-    const int ia = threadIdx.x, ib = threadIdx.x + kFftThreads;
+    V v[CFG::kSets][16];
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-      const int64_t ta = base + ia + r * 1024;
-      const int64_t tb = base + ib + r * 1024;
-      va[r] = (ta < n_in_avail) ? in.ld(c, ta) : make_float2(0.f, 0.f);
-      vb[r] = (tb < n_in_avail) ? in.ld(c, tb) : make_float2(0.f, 0.f);
+    for (int s = 0; s < CFG::kSets; s++) {
+      const int i = threadIdx.x + s * kFftThreads;
+#pragma unroll
+      for (int r = 0; r < 16; r++) {
+        const int64_t t = base + i + r * CFG::kQ;
+        v[s][r] = (t < n_in_avail) ? in.ld(c, t) : cmk<V>(0, 0);
+      }
     }
-    fft16(va);
-    fft16(vb);
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-      buf[fpad(ia * 16 + r)] = va[4 * (r & 3) + (r >> 2)];
-      buf[fpad(ib * 16 + r)] = vb[4 * (r & 3) + (r >> 2)];
+    for (int s = 0; s < CFG::kSets; s++) {
+      const int i = threadIdx.x + s * kFftThreads;
+      fft16(v[s]);
+#pragma unroll
+      for (int r = 0; r < 16; r++) buf[fpad(i * 16 + r)] = v[s][4 * (r & 3) + (r >> 2)];
     }
     __syncthreads();
   }
-  pass16_smem(buf, tw, 16, 64);
-  pass16_smem(buf, tw, 256, 4);
-  // ---- forward pass 4 (radix 4, p = 4096) fused with Y = conj(X * H)
+  pass16_smem<CFG>(buf, tw, 16);
+  pass16_smem<CFG>(buf, tw, 256);
+  // ---- forward last pass fused with Y = conj(X * H)
 #pragma unroll 2
-  for (int b = 0; b < 8; b++) {
+  for (int b = 0; b < 4096 / kFftThreads; b++) {
     const int i = threadIdx.x + b * kFftThreads;
-    float2 a0 = buf[fpad(i)], a1 = buf[fpad(i + 4096)], a2 = buf[fpad(i + 8192)], a3 = buf[fpad(i + 12288)];
-    const float2 w1 = tw_lookup(tw, i);
-    const float2 w2 = cmulf(w1, w1);
-    a1 = cmulf(a1, w1);
-    a2 = cmulf(a2, w2);
-    a3 = cmulf(a3, cmulf(w2, w1));
-    fft4(a0, a1, a2, a3);
-    buf[fpad(i)] = cconj(cmulf(a0, H[i]));
-    buf[fpad(i + 4096)] = cconj(cmulf(a1, H[i + 4096]));
-    buf[fpad(i + 8192)] = cconj(cmulf(a2, H[i + 8192]));
-    buf[fpad(i + 12288)] = cconj(cmulf(a3, H[i + 12288]));
+    V a[4];
+    last_pass_load<CFG>(buf, tw, i, a);
+#pragma unroll
+    for (int r = 0; r < CFG::kR4; r++) buf[fpad(i + r * 4096)] = cconjv(cmulv(a[r], H[i + r * 4096]));
   }
   __syncthreads();
-  // ---- inverse = conj(FFT(conj(.))): pass 1 from shared memory
-  {
-    float2 va[16], vb[16];
-    const int ia = threadIdx.x, ib = threadIdx.x + kFftThreads;
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-      va[r] = buf[fpad(ia + r * 1024)];
-      vb[r] = buf[fpad(ib + r * 1024)];
-    }
-    __syncthreads();
-    fft16(va);
-    fft16(vb);
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-      buf[fpad(ia * 16 + r)] = va[4 * (r & 3) + (r >> 2)];
-      buf[fpad(ib * 16 + r)] = vb[4 * (r & 3) + (r >> 2)];
-    }
-    __syncthreads();
-  }
-  pass16_smem(buf, tw, 16, 64);
-  pass16_smem(buf, tw, 256, 4);
-  // ---- inverse pass 4, outputs straight to the global ring (only the alias-free part)
-  const int64_t qb = q0 + (int64_t)blk * lq;
+  // ---- inverse = conj(FFT(conj(.)))
+  pass16_first_smem<CFG>(buf);
+  pass16_smem<CFG>(buf, tw, 16);
+  pass16_smem<CFG>(buf, tw, 256);
+  if (!FUSE) {
+    // ---- inverse last pass, outputs straight to the global ring (only the alias-free part)
 #pragma unroll 2
-  for (int b = 0; b < 8; b++) {
-    const int i = threadIdx.x + b * kFftThreads;
-    float2 a0 = buf[fpad(i)], a1 = buf[fpad(i + 4096)], a2 = buf[fpad(i + 8192)], a3 = buf[fpad(i + 12288)];
-    const float2 w1 = tw_lookup(tw, i);
-    const float2 w2 = cmulf(w1, w1);
-    a1 = cmulf(a1, w1);
-    a2 = cmulf(a2, w2);
-    a3 = cmulf(a3, cmulf(w2, w1));
-    fft4(a0, a1, a2, a3);
-    const float2 y[4] = {a0, a1, a2, a3};
+    for (int b = 0; b < 4096 / kFftThreads; b++) {
+      const int i = threadIdx.x + b * kFftThreads;
+      V a[4];
+      last_pass_load<CFG>(buf, tw, i, a);
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const int n = i + r * 4096;        // buffer slot; output u sits at slot u*down + klen - 1
-      const int rel = n - (klen - 1);
-      if (rel >= 0) {
-        const int u = rel / down;
-        if (u * down == rel && u < cnt) out.st(c, qb + u, cconj(y[r]));
+      for (int r = 0; r < CFG::kR4; r++) {
+        const int n = i + r * 4096; // buffer slot; output u sits at slot u*down + klen - 1
+        const int rel = n - (klen - 1);
+        if (rel >= 0) {
+          const int u = rel / down;
+          if (u * down == rel && u < cnt) out.st(c, qb + u, cconjv(a[r]));
+        }
       }
+    }
+  } else {
+    // ---- inverse last pass in place (slot n holds filter output qb + n - (klen-1)), then the
+    // polyphase interpolator straight from shared memory
+#pragma unroll 2
+    for (int b = 0; b < 4096 / kFftThreads; b++) {
+      const int i = threadIdx.x + b * kFftThreads;
+      V a[4];
+      last_pass_load<CFG>(buf, tw, i, a);
+#pragma unroll
+      for (int r = 0; r < CFG::kR4; r++) {
+        const int n = i + r * 4096;
+        const int64_t t = qb + (n - (klen - 1));
+        const V y = (t >= 0) ? cconjv(a[r]) : cmk<V>(0, 0);
+        buf[fpad(n)] = y;
+        if (t >= fz.tail_lo && t < fz.tail_hi && n >= klen - 1 && blk == (int)gridDim.x - 1) {
+          Ring<V>{reinterpret_cast<V *>(fz.tail_base), fz.tail_cap}.st(c, t, y);
+        }
+      }
+    }
+    __syncthreads();
+    const S *__restrict__ bank = reinterpret_cast<const S *>(fz.bank);
+    const int64_t pos_b = mb * fz.instep;
+    const int64_t ip_b = pos_b / fz.outstep;
+    const int rem_b = (int)(pos_b - ip_b * fz.outstep);
+    // slot of the first tap of output mb: ip_b - (flen/2-1) - qb + klen-1 = klen-1
+    for (int i = threadIdx.x; i < cnt; i += kFftThreads) {
+      const int prel = i * fz.instep + rem_b;
+      const int dip = prel / fz.outstep;
+      const int ph = prel - dip * fz.outstep;
+      const S *__restrict__ row = bank + (size_t)ph * fz.flen;
+      const int n0 = (klen - 1) + dip;
+      V acc = cmk<V>(0, 0);
+      for (int k = 0; k < fz.flen; k++) {
+        const V x = buf[fpad(n0 + k)];
+        const S h = __ldg(row + k);
+        acc.x += h * x.x;
+        acc.y += h * x.y;
+      }
+      out.st(c, mb + i, acc);
     }
   }
 }

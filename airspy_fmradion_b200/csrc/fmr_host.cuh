@@ -7,7 +7,9 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,6 +19,7 @@
 #include <complex>
 
 #include "fmr_fft.cuh"
+#include "fmr_hbstream.cuh"
 #include "fmr_kernels.cuh"
 #include "fmr_tables.h"
 
@@ -184,8 +187,10 @@ inline void host_fft(std::vector<std::complex<double>> &a) {
   }
 }
 
-// Outputs per launch below which the direct-form kernel is used instead of the FFT one.
-constexpr int kFftMinOut = 3000;
+// Filter outputs per launch below which the direct-form kernels are used instead of the FFT one
+// (a partial 8192-point block still beats klen multiply-adds per output well below one block).
+constexpr int kFftMinOutF32 = 1500;
+constexpr int kFftMinOutF64 = 500;
 
 template <typename S> struct Resampler {
   using V = typename V2<S>::type;
@@ -202,9 +207,14 @@ template <typename S> struct Resampler {
   size_t smem_hb = 0, smem_fir = 0, smem_fi = 0;
   Prof *prof = nullptr;
   int p_hb = -1, p_bc = -1, p_fi = -1;
-  float2 *d_H = nullptr; // filter spectrum for k_fir_fft (float chains only)
+  V *d_H16 = nullptr, *d_H8 = nullptr; // filter spectra for k_fir_fft (16384: float chains only)
   bool use_fft = false;
   bool use_dec2 = false; // double chains with a decimate-by-2 low-pass (audio resampler)
+  bool fuse_fi = true;   // FMR_FUSE_FI=0: keep the polyphase bank as its own launch
+  bool hb_stream = false; // streaming register-resident half-band cascade (10 MHz chain, cf32 input)
+  int hbs_tile = 0;       // FMR_HBS_TILE: outputs per stream tile (0 = choose by problem size)
+  int sm_count = 148;
+  int fft_min_out = 0;
 
   static size_t hb_smem(const HbTaps<S> &t, int nst) {
     size_t total = 0;
@@ -259,6 +269,17 @@ template <typename S> struct Resampler {
       return fail(FMR_ERR_UNSUPPORTED, "half-band tap combination not instantiated");
     }
     FMR_CUDA(e);
+    if constexpr (sizeof(S) == sizeof(float)) {
+      if (lin && d->n_hb == 3 && hbt.n[0] == 4 && hbt.n[1] == 5 && hbt.n[2] == 8 && !env_off("FMR_HB_STREAM")) {
+        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream<4, 5, 8, kHbsU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kHbsSmemBytes)));
+        hb_stream = true;
+        if (const char *ev = getenv("FMR_HBS_TILE")) hbs_tile = atoi(ev);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+      }
+    }
     const int64_t max_hb = (max_in >> d->n_hb) + 4;
     if (d->n_hb > 0 || lin) {
       r_hb.cap = pow2ceil((uint64_t)(max_hb + d->bc.latency + d->bc.klen + 64));
@@ -270,18 +291,37 @@ template <typename S> struct Resampler {
       FMR_CUDA(mem.alloc(&d_bc, h.size(), false));
       FMR_CUDA(cudaMemcpy(d_bc, h.data(), h.size() * sizeof(S), cudaMemcpyHostToDevice));
     }
-    if (sizeof(S) == sizeof(float) && d->bc.klen < kFftN / 2) {
-      std::vector<std::complex<double>> hc(kFftN, std::complex<double>(0.0, 0.0));
-      for (int i = 0; i < d->bc.klen; i++) hc[i] = d->bc.taps[i];
-      host_fft(hc);
-      std::vector<float2> hf(kFftN);
-      for (int i = 0; i < kFftN; i++) {
-        hf[i] = make_float2((float)(hc[i].real() / kFftN), (float)(hc[i].imag() / kFftN));
+    if (d->bc.klen < 8192 / 2 && !env_off("FMR_FFT") && !(sizeof(S) == sizeof(double) && env_off("FMR_FFT_F64"))) {
+      // filter spectra, computed in double, 1/N folded in
+      auto make_H = [&](int n, V **dst) -> cudaError_t {
+        std::vector<std::complex<double>> hc(n, std::complex<double>(0.0, 0.0));
+        for (int i = 0; i < d->bc.klen; i++) hc[i] = d->bc.taps[i];
+        host_fft(hc);
+        std::vector<V> hf(n);
+        for (int i = 0; i < n; i++) {
+          hf[i].x = (S)(hc[i].real() / n);
+          hf[i].y = (S)(hc[i].imag() / n);
+        }
+        cudaError_t e2 = mem.alloc(dst, (size_t)n, false);
+        if (e2 != cudaSuccess) return e2;
+        return cudaMemcpy(*dst, hf.data(), sizeof(V) * n, cudaMemcpyHostToDevice);
+      };
+      FMR_CUDA(make_H(8192, &d_H8));
+      FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<S, 8192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     FftCfg<S, 8192>::kSmemBytes)));
+      FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<S, 8192, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     FftCfg<S, 8192>::kSmemBytes)));
+      if constexpr (sizeof(S) == sizeof(float)) {
+        FMR_CUDA(make_H(16384, &d_H16));
+        FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<S, 16384, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       FftCfg<S, 16384>::kSmemBytes)));
+        FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<S, 16384, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       FftCfg<S, 16384>::kSmemBytes)));
       }
-      FMR_CUDA(mem.alloc(&d_H, (size_t)kFftN, false));
-      FMR_CUDA(cudaMemcpy(d_H, hf.data(), sizeof(float2) * kFftN, cudaMemcpyHostToDevice));
-      FMR_CUDA(cudaFuncSetAttribute(k_fir_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemBytes));
       use_fft = true;
+      fft_min_out = (sizeof(S) == sizeof(float)) ? kFftMinOutF32 : kFftMinOutF64;
+      if (const char *e = getenv("FMR_FFT_MIN_OUT")) fft_min_out = atoi(e);
+      fuse_fi = !env_off("FMR_FUSE_FI");
     }
     if (sizeof(S) == sizeof(double) && d->bc.down == 2 && (d->bc.klen + 1) / 2 <= kDecMaxTaps) {
       FMR_CUDA(cudaFuncSetAttribute(k_fir_dec2_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -307,17 +347,161 @@ template <typename S> struct Resampler {
 
   int64_t max_out(int64_t max_in) const { return chain_out(d, max_in + (int64_t)1) + 8; }
 
-  void launch_fft(Ring<float2> in, Ring<float2> o, int64_t q0, int n, int64_t avail, cudaStream_t st) {
-    const int lq = (kFftN - d->bc.klen + 1) / d->bc.down;
-    dim3 grid((n + lq - 1) / lq, gcn);
-    k_fir_fft<<<grid, kFftThreads, kFftSmemBytes, st>>>(in, o, d_H, d->bc.klen, d->bc.down, q0, n, avail, lq);
+  static bool env_off(const char *name) {
+    const char *e = getenv(name);
+    return e && atoi(e) == 0;
   }
-  void launch_fft(Ring<double2>, Ring<double2>, int64_t, int, int64_t, cudaStream_t) {}
+  // Block plan of one FFT launch group: `per16` / `per8` results per 16384- / 8192-point block;
+  // full 16384 blocks first, the remainder in one more 16384 block or in 8192 blocks, whichever
+  // is less work. Double chains only have the 8192-point kernel.
+  static void fft_plan(int n, int per16, int per8, bool have16, int *nb16, int *nb8) {
+    *nb16 = 0;
+    *nb8 = 0;
+    if (!have16 || per16 <= 0) {
+      *nb8 = (n + per8 - 1) / per8;
+      return;
+    }
+    *nb16 = n / per16;
+    const int rem = n - *nb16 * per16;
+    if (rem > per8) {
+      (*nb16)++;
+    } else if (rem > 0) {
+      *nb8 = 1;
+    }
+  }
+  // plain form: filter outputs [q0, q0+n) -> o
+  int launch_fft(Ring<V> in, Ring<V> o, int64_t q0, int n, int64_t avail, cudaStream_t st) {
+    const int klen = d->bc.klen, down = d->bc.down;
+    const int lq16 = (16384 - klen + 1) / down, lq8 = (8192 - klen + 1) / down;
+    int nb16, nb8;
+    fft_plan(n, lq16, lq8, sizeof(S) == sizeof(float), &nb16, &nb8);
+    FftFuse fz;
+    memset(&fz, 0, sizeof(fz));
+    int launched = 0;
+    int done = 0;
+    if constexpr (sizeof(S) == sizeof(float)) {
+      if (nb16 > 0) {
+        const int cnt = std::min(n, nb16 * lq16);
+        dim3 grid(nb16, gcn);
+        k_fir_fft<S, 16384, false><<<grid, kFftThreads, FftCfg<S, 16384>::kSmemBytes, st>>>(in, o, d_H16, klen, down, q0,
+                                                                                          cnt, avail, lq16, fz);
+        done = cnt;
+        launched++;
+      }
+    }
+    if (nb8 > 0 && done < n) {
+      dim3 grid(nb8, gcn);
+      k_fir_fft<S, 8192, false><<<grid, kFftThreads, FftCfg<S, 8192>::kSmemBytes, st>>>(in, o, d_H8, klen, down, q0 + done,
+                                                                                      n - done, avail, lq8, fz);
+      launched++;
+    }
+    return launched;
+  }
+  // fused form: interpolator outputs [m0, m0+n_m) -> o straight from the filtered blocks; the
+  // newest filtered samples before `b1` also go to the intermediate ring (see FftFuse).
+  int launch_fft_fused(Ring<V> in, Ring<V> o, int64_t m0, int n_m, int64_t avail, int64_t b1, cudaStream_t st) {
+    const int klen = d->bc.klen;
+    const int lq16 = 16384 - klen + 1, lq8 = 8192 - klen + 1;
+    auto per = [&](int lq) { return (int)(((int64_t)(lq - d->fi.flen - 8) * d->fi.outstep) / d->fi.instep); };
+    const int mo16 = per(lq16), mo8 = per(lq8);
+    int nb16, nb8;
+    fft_plan(n_m, mo16, mo8, sizeof(S) == sizeof(float), &nb16, &nb8);
+    FftFuse fz;
+    memset(&fz, 0, sizeof(fz));
+    fz.bank = d_fi;
+    fz.instep = d->fi.instep;
+    fz.outstep = d->fi.outstep;
+    fz.flen = d->fi.flen;
+    const Ring<V> tail = sub(r_bc);
+    fz.tail_base = tail.base;
+    fz.tail_cap = tail.cap;
+    int launched = 0, done = 0;
+    if constexpr (sizeof(S) == sizeof(float)) {
+      if (nb16 > 0) {
+        const int cnt = std::min(n_m, nb16 * mo16);
+        fz.m0 = m0;
+        fz.n_m = cnt;
+        fz.mo = mo16;
+        const bool last = (cnt == n_m);
+        fz.tail_hi = last ? b1 : 0;
+        fz.tail_lo = last ? b1 - (2 * d->fi.flen + 16) : 0;
+        dim3 grid(nb16, gcn);
+        k_fir_fft<S, 16384, true><<<grid, kFftThreads, FftCfg<S, 16384>::kSmemBytes, st>>>(in, o, d_H16, klen, 1, 0, 0,
+                                                                                         avail, lq16, fz);
+        done = cnt;
+        launched++;
+      }
+    }
+    if (nb8 > 0 && done < n_m) {
+      fz.m0 = m0 + done;
+      fz.n_m = n_m - done;
+      fz.mo = mo8;
+      fz.tail_hi = b1;
+      fz.tail_lo = b1 - (2 * d->fi.flen + 16);
+      dim3 grid(nb8, gcn);
+      k_fir_fft<S, 8192, true><<<grid, kFftThreads, FftCfg<S, 8192>::kSmemBytes, st>>>(in, o, d_H8, klen, 1, 0, 0, avail,
+                                                                                     lq8, fz);
+      launched++;
+    }
+    return launched;
+  }
   void launch_dec2(Ring<double2> in, Ring<double2> o, int64_t q0, int n, cudaStream_t st) {
     dim3 grid((n + kDecTile - 1) / kDecTile, gcn);
     k_fir_dec2_f64<<<grid, kDecThreads, dec2_smem(d->bc.klen), st>>>(in, o, d_bc, d->bc.klen, q0, n);
   }
   void launch_dec2(Ring<float2>, Ring<float2>, int64_t, int, cudaStream_t) {}
+
+  // Streaming half-band cascade over the part [*sa, return) of [h0, h1) whose input lies entirely in
+  // the caller's buffer of this call (the tiled kernel does the few outputs before and after it,
+  // which need the history buffer or are not a whole stream tile). Returns *sa when not applicable.
+  int64_t hbs_launch(const InSrc<float2> &src, Ring<float2> o, int64_t h0, int64_t h1, int64_t *sa, cudaStream_t st,
+                     int *launches) {
+    using D = HbsDelays<4, 5, 8>;
+    *sa = h0;
+    if ((src.start & 1) || (src.stride & 1) || (reinterpret_cast<uintptr_t>(src.lin) & 15)) return h0;
+    // first even output whose warm-up chunks start inside the buffer
+    const int64_t c0 = (src.start + 15) / 16; // first whole 16-sample chunk of the buffer
+    int64_t a = 2 * (c0 + D::kWarm) - D::A3;
+    if (a < h0) a = h0;
+    a += (a & 1);
+    const int64_t avail = h1 - a;
+    if (avail < 64) return h0;
+    int tile = hbs_tile;
+    if (tile <= 0) {
+      // largest tile that still fills every SM three CTAs deep; warm-up costs 2*kWarm outputs per tile
+      tile = 512;
+      while (tile > 128 && (int64_t)gcn * (avail / tile) < (int64_t)sm_count * 3 * kHbsThreads) tile >>= 1;
+    }
+    tile = std::max(2 * kHbsU, tile / (2 * kHbsU) * (2 * kHbsU));
+    const int nbs = (D::kWarm + tile / 2 + kHbsU - 1) / kHbsU;
+    // last chunk (exclusive) a tile starting at output m touches: (m + A3)/2 - kWarm + nbs*U
+    const int64_t c_end = (src.start + src.n_new) / 16; // chunks [.., c_end) are complete
+    // m_last + A3 <= 2 * (c_end - nbs*U + kWarm)
+    const int64_t m_last_max = 2 * (c_end - (int64_t)nbs * kHbsU + D::kWarm) - D::A3;
+    if (m_last_max < a) return h0;
+    int64_t tiles = (m_last_max - a) / tile + 1;
+    if (tiles > avail / tile) tiles = avail / tile;
+    if (tiles <= 0) return h0;
+    HbsParams P;
+    P.lin = src.lin;
+    P.stride = src.stride;
+    P.start = src.start;
+    P.a_out = a;
+    P.tile = tile;
+    P.tiles_per_ch = (int)tiles;
+    P.n_streams = (int)(tiles * gcn);
+    P.n_block_steps = nbs;
+    for (int k = 0; k < 8; k++) {
+      P.t1[k] = hbt.t[0][k];
+      P.t2[k] = hbt.t[1][k];
+      P.t3[k] = hbt.t[2][k];
+    }
+    const int grid = (P.n_streams + kHbsThreads - 1) / kHbsThreads;
+    k_hb_stream<4, 5, 8, kHbsU><<<grid, kHbsThreads, kHbsSmemBytes, st>>>(P, o);
+    (*launches)++;
+    *sa = a;
+    return a + tiles * tile;
+  }
 
   // Consume n_new more input samples; produce the reference's output index range into `out`.
   fmr_status run(InSrc<V> src, int64_t n_new, Ring<V> out, int fs4, cudaStream_t st, int64_t *o0,
@@ -335,42 +519,52 @@ template <typename S> struct Resampler {
       const int n = (int)(h1 - h0);
       if (n > 0) {
         if (prof) prof->begin(p_hb, st);
-        {
-          dim3 grid((n + kHbTile - 1) / kHbTile, gcn);
-          const Ring<V> hb_out_ring = sub(r_hb);
-          const HbTaps<S> tp = hbt;
-          const size_t sm = smem_hb;
-          hb_dispatch([&](auto kern) { kern<<<grid, kHbThreads, sm, st>>>(src, hb_out_ring, tp, h0, n, fs4); });
+        const Ring<V> hb_out_ring = sub(r_hb);
+        const HbTaps<S> tp = hbt;
+        const size_t sm = smem_hb;
+        auto tiled = [&](int64_t o0, int cnt) {
+          if (cnt <= 0) return;
+          dim3 grid((cnt + kHbTile - 1) / kHbTile, gcn);
+          hb_dispatch([&](auto kern) { kern<<<grid, kHbThreads, sm, st>>>(src, hb_out_ring, tp, o0, cnt, fs4); });
+          (*launches)++;
+        };
+        int64_t sa = h0, sb = h0; // [sa, sb): outputs the streaming kernel produces
+        if constexpr (sizeof(S) == sizeof(float)) {
+          if (hb_stream && src.fmt == 0 && !fs4) sb = hbs_launch(src, hb_out_ring, h0, h1, &sa, st, launches);
         }
-        (*launches)++;
+        tiled(h0, (int)(sa - h0));
+        tiled(sb, (int)(h1 - sb));
         if (prof) prof->end(p_hb, st);
       }
       bc_in = sub(r_hb);
     }
-    {
-      const int n = (int)(b1 - b0);
-      if (n > 0) {
+    const int n_bc = (int)(b1 - b0), n_fi = (int)(f1 - f0);
+    // fused low-pass + polyphase bank: the intermediate stream stays in shared memory
+    if (d->has_fi && use_fft && fuse_fi && d->bc.down == 1 && n_bc >= fft_min_out && n_fi > 0) {
+      if (prof) prof->begin(p_bc, st);
+      (*launches) += launch_fft_fused(bc_in, out, f0, n_fi, h1, b1, st);
+      if (prof) prof->end(p_bc, st);
+    } else {
+      if (n_bc > 0) {
         if (prof) prof->begin(p_bc, st);
-        if (use_fft && n >= kFftMinOut) {
-          launch_fft(bc_in, d->has_fi ? sub(r_bc) : out, b0, n, h1, st);
+        if (use_fft && n_bc >= fft_min_out) {
+          (*launches) += launch_fft(bc_in, d->has_fi ? sub(r_bc) : out, b0, n_bc, h1, st);
         } else if (use_dec2) {
-          launch_dec2(bc_in, d->has_fi ? sub(r_bc) : out, b0, n, st);
+          launch_dec2(bc_in, d->has_fi ? sub(r_bc) : out, b0, n_bc, st);
+          (*launches)++;
         } else {
-          dim3 grid((n + kFirTile - 1) / kFirTile, gcn);
+          dim3 grid((n_bc + kFirTile - 1) / kFirTile, gcn);
           k_fir_long<S><<<grid, kFirThreads, smem_fir, st>>>(bc_in, d->has_fi ? sub(r_bc) : out, d_bc, d->bc.klen,
-                                                              d->bc.down, b0, n);
+                                                              d->bc.down, b0, n_bc);
+          (*launches)++;
         }
         if (prof) prof->end(p_bc, st);
-        (*launches)++;
       }
-    }
-    if (d->has_fi) {
-      const int n = (int)(f1 - f0);
-      if (n > 0) {
-        dim3 grid((n + kFiTile - 1) / kFiTile, gcn);
+      if (d->has_fi && n_fi > 0) {
+        dim3 grid((n_fi + kFiTile - 1) / kFiTile, gcn);
         if (prof) prof->begin(p_fi, st);
         k_frac_interp<S><<<grid, kFiThreads, smem_fi, st>>>(sub(r_bc), out, d_fi, d->fi.instep, d->fi.outstep,
-                                                            d->fi.flen, f0, n);
+                                                            d->fi.flen, f0, n_fi);
         if (prof) prof->end(p_fi, st);
         (*launches)++;
       }

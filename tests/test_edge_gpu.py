@@ -215,3 +215,59 @@ def test_block_flags_and_chunked_calls():
     assert a2.shape[1] == len(ref_audio)
     assert np.abs(a2[0] - ref_audio).max() <= 2e-5 and np.array_equal(a2[0], a2[1])
     assert dec2.stats(0).pll_lock_cnt == c.stats().pll_lock_cnt
+
+
+def test_mixed_call_sizes_10msps():
+    """Super-blocks of very different sizes in one stream: big calls take the streaming half-band
+    cascade and the fused FFT low-pass + polyphase bank (the 1.25 MHz stream stays on chip), small
+    calls take the tiled / direct-form kernels that read the intermediate rings. The hand-over in
+    both directions must be seamless: audio, per-call sizes and the IF stream match the oracle."""
+    from airspy_fmradion_b200 import FmDecoder
+    fs, blk = 1.0e7, 2048
+    calls = [150, 3, 1, 40, 2, 2, 200, 1, 1, 1, 90, 5, 120]
+    nblk = sum(calls)
+    iq = siggen.fm_stereo_iq(fs, blk * nblk, 6)[None, :]
+    dec = FmDecoder(stereo=True, input_rate=fs, n_channels=1, max_samples_per_call=blk * max(calls),
+                    max_blocks_per_call=max(calls))
+    outs, lens, ifs, o = [], [], [], 0
+    for k in calls:
+        a, l = dec.process_blocks(iq[:, o * blk:(o + k) * blk], [blk] * k)
+        outs.append(a)
+        lens.append(l)
+        ifs.append(dec.tap_if(0))
+        o += k
+    audio, lens = np.concatenate(outs, axis=1), np.concatenate(lens)
+    ref_audio, ref_lens, td, _ = oracle_fm_run(iq[0], fs, blk, stereo=True, taps=("if",))
+    assert list(lens) == list(ref_lens)
+    got_if, want_if = np.concatenate(ifs), np.concatenate(td["if"])
+    assert len(got_if) == len(want_if)
+    e_if = np.abs(got_if - want_if).max()
+    d = audio[0] - ref_audio
+    print("mixed calls: IF max %.3e, audio max %.3e (n=%d)" % (e_if, np.abs(d).max(), len(d)))
+    assert e_if < 2e-6
+    assert np.abs(d).max() <= 2e-5
+
+
+def test_streaming_halfband_equals_tiled(monkeypatch):
+    """The streaming register-resident half-band cascade evaluates the same expression in the same
+    order as the tiled kernel: the decoder's IF stream must not change by a single bit when it is
+    switched off (FMR_HB_STREAM=0), for one big call and for a chunked stream."""
+    from airspy_fmradion_b200 import FmDecoder
+    fs, blk, nblk, C = 1.0e7, 2048, 96, 5
+    iq = np.stack([siggen.fm_stereo_iq(fs, blk * nblk, 10 + c) for c in range(C)])
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("FMR_HB_STREAM", mode)
+        for per_call in (96, 32):
+            dec = FmDecoder(stereo=True, input_rate=fs, n_channels=C, max_samples_per_call=blk * per_call,
+                            max_blocks_per_call=per_call)
+            taps = []
+            for o in range(0, nblk, per_call):
+                dec.process_blocks(iq[:, o * blk:(o + per_call) * blk], [blk] * per_call)
+                taps.append(np.stack([dec.tap_if(c) for c in range(C)]))
+            res[(mode, per_call)] = np.concatenate(taps, axis=1)
+            dec.close()
+    for per_call in (96, 32):
+        a, b = res[("1", per_call)], res[("0", per_call)]
+        assert a.shape == b.shape and a.shape[1] > 3000
+        assert np.array_equal(a.view(np.float32), b.view(np.float32)), np.abs(a - b).max()
