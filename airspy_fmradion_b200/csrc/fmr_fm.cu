@@ -69,6 +69,7 @@ struct fmr_fm {
   int max_time_chunks = 1; // FMR_TIME_CHUNKS: the two-stream pipeline is off by default
   int chunk_min_blocks = 32;
   int want_serial_sms = 0;
+  bool serial_v2 = true;  // FMR_SERIAL_V2=0: the first-generation AGC / PLL kernels
   int C = 0;
   const ChainDesc *ifc = nullptr; // null when input_rate == 384000 (no IfResampler, main.cpp:778)
   const ChainDesc *auc = nullptr;
@@ -340,6 +341,7 @@ extern "C" fmr_status fmr_fm_create(const fmr_fm_config *cfg, fmr_fm **out) {
   if (const char *e = getenv("FMR_CHUNK_MIN_BLOCKS")) h->chunk_min_blocks = std::max(1, atoi(e));
   h->want_serial_sms = 0;
   if (const char *e = getenv("FMR_SERIAL_SMS")) h->want_serial_sms = std::max(0, atoi(e));
+  if (const char *e = getenv("FMR_SERIAL_V2")) h->serial_v2 = atoi(e) != 0;
   fmr_status s = fm_build(h);
   if (s != FMR_OK) {
     std::string keep = g_err;
@@ -622,7 +624,11 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
     if (h->cfg.fmfilter) FMR_CUDA(hop(sB, sG, h->ev_p[k][0]));
     pf.begin(h->p_agc, sG);
     tr.begin("agc", k, sG);
-    k_fm_agc<<<cgrid, 32, 0, sG>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
+    if (h->serial_v2) {
+      k_fm_agc2<<<cgrid, 32, 0, sG>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
+    } else {
+      k_fm_agc<<<cgrid, 32, 0, sG>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
+    }
     tr.end(sG);
     pf.end(h->p_agc, sG);
     launches++;
@@ -646,8 +652,13 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
     FMR_CUDA(hop(sB, sL, h->ev_p[k][2]));
     pf.begin(h->p_core2, sL);
     tr.begin("pll", k, sL);
-    k_fm_pll<<<cgrid, 32, 0, sL>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
-                                   h->core, h->d_atan, (int)(flag_b0 + b0), (k == 0 && flag_b0 == 0) ? 1 : 0);
+    if (h->serial_v2) {
+      k_fm_pll2<<<cgrid, 32, 0, sL>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
+                                      h->core, h->d_atan, (int)(flag_b0 + b0), (k == 0 && flag_b0 == 0) ? 1 : 0);
+    } else {
+      k_fm_pll<<<cgrid, 32, 0, sL>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
+                                     h->core, h->d_atan, (int)(flag_b0 + b0), (k == 0 && flag_b0 == 0) ? 1 : 0);
+    }
     tr.end(sL);
     pf.end(h->p_core2, sL);
     FMR_CUDA(hop(sL, sU, h->ev_p[k][3]));

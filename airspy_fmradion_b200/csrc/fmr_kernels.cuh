@@ -834,6 +834,62 @@ static __global__ void k_fm_agc(Ring<float2> iq_in, Ring<float2> iq_out, FmChanS
   st[c].agc_gain = g;
 }
 
+// k_fm_agc2 — the same recurrence as k_fm_agc with the bookkeeping taken out of the loop (row
+// pointers and ring masks hoisted, no sign checks on the absolute index): the kernel is bound by
+// dependent-issue latency of ONE warp per SM sub-partition, so every instruction that is not the
+// recurrence costs as much as one that is.
+static __global__ void __launch_bounds__(32)
+    k_fm_agc2(Ring<float2> iq_in, Ring<float2> iq_out, FmChanState *__restrict__ st, int n_total, int64_t t0,
+              FmCoreParams P) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.n_channels) return;
+  float g = st[c].agc_gain;
+  const float2 *__restrict__ irow = iq_in.base + (size_t)c * iq_in.cap;
+  float2 *__restrict__ orow = iq_out.base + (size_t)c * iq_out.cap;
+  const uint32_t imask = iq_in.cap - 1, omask = iq_out.cap - 1, t0lo = (uint32_t)t0;
+  const double rate = (double)P.agc_rate;
+  const float gmax = P.agc_max;
+  float2 nxt[kCoreChunk];
+#pragma unroll
+  for (int u = 0; u < kCoreChunk; u++) nxt[u] = (u < n_total) ? irow[(t0lo + (uint32_t)u) & imask] : make_float2(0.f, 0.f);
+  for (int i0 = 0; i0 < n_total; i0 += kCoreChunk) {
+    float2 xin[kCoreChunk];
+#pragma unroll
+    for (int u = 0; u < kCoreChunk; u++) xin[u] = nxt[u];
+#pragma unroll
+    for (int u = 0; u < kCoreChunk; u++) {
+      const int i = i0 + kCoreChunk + u;
+      nxt[u] = (i < n_total) ? irow[(t0lo + (uint32_t)i) & imask] : make_float2(0.f, 0.f);
+    }
+    if (i0 + kCoreChunk <= n_total) {
+#pragma unroll
+      for (int u = 0; u < kCoreChunk; u++) {
+        // IfSimpleAgc::process (IfSimpleAgc.cpp:37-57)
+        float2 x2;
+        x2.x = xin[u].x * g;
+        x2.y = xin[u].y * g;
+        const float nrm = x2.x * x2.x + x2.y * x2.y;
+        const float z = (float)(1.0 + (rate * (1.0 - (double)nrm)));
+        g *= z;
+        g = isfinite(g) ? ((g > gmax) ? gmax : g) : 1.0f;
+        orow[(t0lo + (uint32_t)(i0 + u)) & omask] = x2;
+      }
+    } else {
+      for (int u = 0; u < kCoreChunk && i0 + u < n_total; u++) {
+        float2 x2;
+        x2.x = xin[u].x * g;
+        x2.y = xin[u].y * g;
+        const float nrm = x2.x * x2.x + x2.y * x2.y;
+        const float z = (float)(1.0 + (rate * (1.0 - (double)nrm)));
+        g *= z;
+        g = isfinite(g) ? ((g > gmax) ? gmax : g) : 1.0f;
+        orow[(t0lo + (uint32_t)(i0 + u)) & omask] = x2;
+      }
+    }
+  }
+  st[c].agc_gain = g;
+}
+
 // One thread per 384 kHz sample: PhaseDiscriminator::process (PhaseDiscriminator.cpp:33-46).
 // The previous sample's phase is recomputed from the ring (bit-identical to the value the
 // serial loop would have carried); before the very first sample m_save_value is 0.
@@ -1085,6 +1141,248 @@ static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanSta
     o->sample_cnt = s.sample_cnt;
     o->de_m_x1 = s.de_m_x1;
     o->de_s_x1 = s.de_s_x1;
+    o->decoder_calls = s.decoder_calls;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_fm_pll2 — same block as k_fm_pll (PilotPhaseLock::process + demod_stereo + deemphasis), with
+// the per-sample recurrence written for the shortest dependent chain. The loop
+//   phase -> (sin, cos) -> x*sin, x*cos -> biquads -> fast_atan2f -> loop filter -> freq -> phase
+// is strictly serial and one warp per SM sub-partition runs it, so its time is the latency of
+// the chain times the number of 384 kHz samples, whatever the channel count. Changes against
+// k_fm_pll, none of which alters a rounding that the reference performs in float:
+//   * fast_atan2f without branches: min/max instead of the if/else quotient, the octant logic
+//     folded into one fused multiply-add  angle = K + sg*base  with K in {0, pi/2, pi} and
+//     sg = +-1 chosen from the signs while the division is still in flight (K + sg*base rounds
+//     exactly like the reference's single add/subtract), table entries stored as
+//     (tbl[i], tbl[i+1]-tbl[i]) pairs in shared memory (one LDS.64 instead of two dependent loads
+//     and a subtract; the float difference is the same IEEE operation done once on the host);
+//   * the phasor is first rotated by the constant centre frequency (off the critical path) and
+//     only the small correction through dl = freq - f0 sits behind the loop filter;
+//   * biquad and loop-filter feedback terms are formed before the sample's own product arrives;
+//   * phase wrap, period counting and the PPS test are selects plus one rarely taken branch.
+struct PllTab {
+  float2 e[256]; // (tbl[i], tbl[i+1] - tbl[i])
+};
+
+__device__ __forceinline__ float fast_atan2f_bf(float y, float x, const float2 *__restrict__ tab) {
+  const float ya = fabsf(y), xa = fabsf(x);
+  const float num = fminf(ya, xa), den = fmaxf(ya, xa);
+  const bool xbig = xa > ya, xpos = x >= 0.0f, ypos = y >= 0.0f;
+  float K = xbig ? (xpos ? 0.0f : 3.14159265358979323846f) : 1.57079632679489661923f;
+  float sg = (xbig == xpos) ? 1.0f : -1.0f;
+  K = ypos ? K : -K;
+  sg = ypos ? sg : -sg;
+  // z = num / den: reciprocal estimate, quotient, one exact-residual correction. For the operand
+  // range of the loop (den is a pilot amplitude, never denormal) this is the correctly rounded
+  // quotient in all but a vanishing fraction of cases and within 1 ulp otherwise; it drops the
+  // denormal check and its branch from the recurrence.
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+  float z = num * r;
+  z = fmaf(fmaf(-den, z, num), r, z);
+  float alpha = z * 255.0f;
+  const int index = (int)alpha; // 0..255 because num <= den
+  alpha -= (float)index;
+  const float2 te = tab[index & 0xff];
+  float base = fmaf(te.y, alpha, te.x);
+  base = (z < __int_as_float(0x3b808082)) ? z : base; // (double)z < 0.003921569, see fast_atan2f_dev
+  const float angle = fmaf(sg, base, K);
+  return (den > 0.0f) ? angle : 0.0f; // both inputs zero (Utility.h:245-247)
+}
+
+static __global__ void __launch_bounds__(32)
+    k_fm_pll2(Ring<float> mpx, Ring<double2> out384, FmChanState *__restrict__ st, uint8_t *__restrict__ flags,
+              PpsEventDev *__restrict__ pps, const float *__restrict__ stats, const uint32_t *__restrict__ call_end,
+              int n_calls, int64_t t0, FmCoreParams P, const float *__restrict__ atan_tbl, int block_off,
+              int reset_pps) {
+  __shared__ float2 tab[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = make_float2(atan_tbl[i], atan_tbl[i + 1] - atan_tbl[i]);
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.n_channels) return;
+  FmChanState s = st[c];
+  if (reset_pps) s.n_pps = 0;
+  const double kTwoPi = 2.0 * 3.14159265358979323846;
+  const double f0 = (19000.0 / 384000.0) * kTwoPi;
+  double sf0, cf0;
+  sincos(f0, &sf0, &cf0);
+  const int n_total = n_calls ? (int)call_end[n_calls - 1] : 0;
+  const float *__restrict__ mrow = mpx.base + (size_t)c * mpx.cap;
+  double2 *__restrict__ orow = out384.base + (size_t)c * out384.cap;
+  const uint32_t mmask = mpx.cap - 1, omask = out384.cap - 1, t0lo = (uint32_t)t0;
+  const bool stereo = P.stereo != 0, shift = P.pilot_shift != 0, de_st = P.deemph_on_stereo != 0;
+  // loop constants pinned in registers (an operand fetched from the constant bank on the critical
+  // path costs a load latency every sample)
+  double minf = P.pll_minfreq, maxf = P.pll_maxfreq, lf_b0 = P.lf_b0, lf_b1 = P.lf_b1, bq_b0 = P.bq_b0;
+  double dlmin = minf - f0, dlmax = maxf - f0;
+  asm volatile("" : "+d"(minf), "+d"(maxf), "+d"(lf_b0), "+d"(lf_b1), "+d"(bq_b0), "+d"(dlmin), "+d"(dlmax));
+  float nxt[kCoreChunk];
+#pragma unroll
+  for (int u = 0; u < kCoreChunk; u++) nxt[u] = (u < n_total) ? mrow[(t0lo + (uint32_t)u) & mmask] : 0.f;
+  // working registers of the recurrences
+  double bi1 = s.bi_x1, bi2 = s.bi_x2, bq1 = s.bq_x1, bq2 = s.bq_x2, lf1 = s.lf_x1;
+  double freq = s.pll_freq, phase = s.pll_phase, ferr = s.freq_err;
+  double dem = s.de_m_x1, des = s.de_s_x1;
+  int periods = s.pilot_periods;
+  uint32_t prev_end = 0;
+  for (int b = 0; b < n_calls; b++) {
+    const uint32_t end = call_end[b];
+    const int n = (int)(end - prev_end);
+    if (n == 0) { // main.cpp:933-936: the decoder is not called
+      flags[(size_t)c * n_calls + b] = (uint8_t)s.stereo_detected;
+      continue;
+    }
+    const uint32_t beg = prev_end;
+    prev_end = end;
+    s.decoder_calls++;
+    const bool was_locked = (s.lock_cnt >= P.lock_delay);
+    double last_i = 0.0, last_q = 0.0;
+    double psin = 0.0, pcos = 1.0;
+    if (stereo) sincos(phase, &psin, &pcos); // exact re-anchor once per reference call
+    for (int i0 = 0; i0 < n; i0 += kCoreChunk) {
+      const int valid = (n - i0 < kCoreChunk) ? (n - i0) : kCoreChunk;
+      float din[kCoreChunk];
+#pragma unroll
+      for (int u = 0; u < kCoreChunk; u++) din[u] = nxt[u];
+      {
+        const int pos = (int)beg + i0 + valid;
+#pragma unroll
+        for (int u = 0; u < kCoreChunk; u++) {
+          nxt[u] = (pos + u < n_total) ? mrow[(t0lo + (uint32_t)(pos + u)) & mmask] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kCoreChunk; u++) {
+        if (u >= valid) break;
+        const int i = i0 + u;
+        const double xd = (double)din[u];
+        double ster = 0.0;
+        if (stereo) {
+          // ---- off the critical path: feedback terms, centre-frequency rotation, tone
+          const double fb_i = P.bq_a1 * bi1 + P.bq_a2 * bi2;
+          const double fb_q = P.bq_a1 * bq1 + P.bq_a2 * bq2;
+          const double fb_l = __dmul_rn(lf_b1, lf1);
+          const double as = psin * cf0 + pcos * sf0; // sin(phase + f0)
+          const double ac = pcos * cf0 - psin * sf0; // cos(phase + f0)
+          const double tone = shift ? (2 * pcos * pcos - 1) : (2 * psin * pcos);
+          // ---- critical path
+          const double i0v = psin * xd - fb_i;
+          const double q0v = pcos * xd - fb_q;
+          const double new_i = bq_b0 * i0v;
+          const double new_q = bq_b0 * q0v;
+          bi2 = bi1;
+          bi1 = i0v;
+          bq2 = bq1;
+          bq1 = q0v;
+          const double perr = (double)fast_atan2f_bf((float)new_q, (float)new_i, tab);
+          last_i = new_i;
+          last_q = new_q;
+          ferr = fma(lf_b0, perr, fb_l);
+          lf1 = perr;
+          const double fraw = freq + ferr;
+          // std::max(m_minfreq, std::min(m_maxfreq, m_freq)) (PilotPhaseLock.cpp:119) with both
+          // comparisons taken on the raw value, and the same clamp applied to dl = freq - f0
+          // directly (maxf - f0 and minf - f0 are the values the subtraction would give)
+          const bool below_max = fraw < maxf, above_min = minf < fraw;
+          const double dlr = fraw - f0;
+          freq = below_max ? (above_min ? fraw : minf) : maxf;
+          const double dl = below_max ? (above_min ? dlr : dlmin) : dlmax;
+          {
+            // sin(dl) = dl - dl^3/6, cos(dl) - 1 = -dl^2/2: |dl| < 4.91e-4 (the +-30 Hz clamp), so the
+            // dropped terms are below 2.5e-15 per sample and the phasor is re-anchored every call
+            const double d2 = dl * dl;
+            const double sd = fma(dl * d2, -1.0 / 6.0, dl);
+            psin = fma(ac, sd, fma(-0.5 * as, d2, as));
+            pcos = fma(-as, sd, fma(-0.5 * ac, d2, ac));
+          }
+          // ---- phase accumulator (its own short recurrence), wrap and PPS
+          phase += freq;
+          const bool wrap = phase > kTwoPi;
+          phase = wrap ? phase - kTwoPi : phase;
+          periods += wrap ? 1 : 0;
+          if (wrap && periods == 19000) {
+            periods = 0;
+            if (was_locked) {
+              if (s.n_pps < (uint32_t)kMaxPps) {
+                PpsEventDev ev;
+                ev.pps_index = s.pps_cnt;
+                ev.sample_index = s.sample_cnt + (unsigned long long)i;
+                ev.block_position = (double)i / (double)n;
+                ev.block = (uint32_t)(b + block_off);
+                ev.pad = 0;
+                pps[(size_t)c * kMaxPps + s.n_pps] = ev;
+              }
+              s.n_pps++;
+              s.pps_cnt++;
+            }
+          }
+          ster = (tone * xd) * 2.0;
+          if (de_st) {
+            const double x0 = ster - P.de_a1 * des;
+            ster = P.de_b0 * x0;
+            des = x0;
+          }
+        }
+        const double m0 = xd - P.de_a1 * dem;
+        const double mono = P.de_b0 * m0;
+        dem = m0;
+        double2 o;
+        o.x = mono;
+        o.y = ster;
+        orow[(t0lo + beg + (uint32_t)i) & omask] = o;
+      }
+    }
+    // per-call statistics (FmDecode.cpp:95,146-150)
+    {
+      const float *sv = stats + ((size_t)c * n_calls + b) * 3;
+      s.if_rms = sv[0];
+      s.baseband_mean = (float)(0.95 * (double)s.baseband_mean + 0.05 * (double)sv[1]);
+      s.baseband_level = (float)(0.95 * (double)s.baseband_level + 0.05 * (double)sv[2]);
+    }
+    if (stereo) {
+      s.pilot_level = sqrt(last_i * last_i + last_q * last_q); // PilotPhaseLock.cpp:106, last sample
+      if (2 * s.pilot_level > P.minsignal) {                     // PilotPhaseLock.cpp:153-170
+        if (s.lock_cnt < P.lock_delay) s.lock_cnt += n;
+      } else {
+        s.lock_cnt = 0;
+      }
+      if (s.lock_cnt < P.lock_delay) {
+        periods = 0;
+        s.pps_cnt = 0;
+        while (s.n_pps > 0 && s.n_pps <= (uint32_t)kMaxPps &&
+               pps[(size_t)c * kMaxPps + s.n_pps - 1].block == (uint32_t)(b + block_off)) {
+          s.n_pps--;
+        }
+      }
+      s.sample_cnt += (unsigned long long)n;
+      s.stereo_detected = (s.lock_cnt >= P.lock_delay) ? 1 : 0;
+    }
+    flags[(size_t)c * n_calls + b] = (uint8_t)s.stereo_detected;
+  }
+  {
+    FmChanState *o = st + c;
+    o->baseband_mean = s.baseband_mean;
+    o->baseband_level = s.baseband_level;
+    o->if_rms = s.if_rms;
+    o->stereo_detected = s.stereo_detected;
+    o->lock_cnt = s.lock_cnt;
+    o->pilot_periods = periods;
+    o->n_pps = s.n_pps;
+    o->pll_phase = phase;
+    o->pll_freq = freq;
+    o->bi_x1 = bi1;
+    o->bi_x2 = bi2;
+    o->bq_x1 = bq1;
+    o->bq_x2 = bq2;
+    o->lf_x1 = lf1;
+    o->pilot_level = s.pilot_level;
+    o->freq_err = ferr;
+    o->pps_cnt = s.pps_cnt;
+    o->sample_cnt = s.sample_cnt;
+    o->de_m_x1 = dem;
+    o->de_s_x1 = des;
     o->decoder_calls = s.decoder_calls;
   }
 }
