@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 
+#include "fmr_core.cuh"
 #include "fmr_host.cuh"
 #include "fmr_mpf.cuh"
 #include "fmr_partition.cuh"
@@ -70,6 +71,7 @@ struct fmr_fm {
   int chunk_min_blocks = 32;
   int want_serial_sms = 0;
   bool serial_v2 = true;  // FMR_SERIAL_V2=0: the first-generation AGC / PLL kernels
+  bool core_fused = true; // FMR_CORE_FUSED=0: AGC / discriminator / PLL as separate launches
   int C = 0;
   const ChainDesc *ifc = nullptr; // null when input_rate == 384000 (no IfResampler, main.cpp:778)
   const ChainDesc *auc = nullptr;
@@ -102,7 +104,7 @@ struct fmr_fm {
   cudaStream_t gstream[kMaxGroups] = {nullptr};
   cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[kMaxGroups] = {nullptr}, ev_chunk[kMaxTimeChunks] = {nullptr};
   Prof prof;
-  int p_hist = -1, p_fmf = -1, p_core = -1, p_agc = -1, p_mpf = -1, p_core2 = -1, p_pcut = -1, p_tail = -1;
+  int p_hist = -1, p_fmf = -1, p_core = -1, p_agc = -1, p_mpf = -1, p_core2 = -1, p_pcut = -1, p_tail = -1, p_fused = -1;
   FmCoreParams core;
   FmTailParams tail;
 
@@ -312,6 +314,7 @@ static fmr_status fm_build(fmr_fm *h) {
   h->ifres.p_fi = h->prof.add("if_polyphase");
   h->p_hist = h->prof.add("save_hist");
   h->p_fmf = h->prof.add("fm_if_filter");
+  h->p_fused = h->prof.add("fm_core_fused");
   h->p_agc = h->prof.add("fm_agc");
   h->p_mpf = h->prof.add("fm_multipath");
   h->p_core = h->prof.add("fm_discriminator_stats");
@@ -342,6 +345,7 @@ extern "C" fmr_status fmr_fm_create(const fmr_fm_config *cfg, fmr_fm **out) {
   h->want_serial_sms = 0;
   if (const char *e = getenv("FMR_SERIAL_SMS")) h->want_serial_sms = std::max(0, atoi(e));
   if (const char *e = getenv("FMR_SERIAL_V2")) h->serial_v2 = atoi(e) != 0;
+  if (const char *e = getenv("FMR_CORE_FUSED")) h->core_fused = atoi(e) != 0;
   fmr_status s = fm_build(h);
   if (s != FMR_OK) {
     std::string keep = g_err;
@@ -619,50 +623,62 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
       pf.end(h->p_fmf, sB);
       launches++;
     }
-    // ---- 384 kHz core: AGC (serial) -> [multipath] -> discriminator + statistics (parallel) -> PLL (serial)
+    // ---- 384 kHz core. Stereo without the multipath filter: one warp-specialised kernel (fmr_core.cuh);
+    // otherwise AGC (serial) -> [multipath] -> discriminator + statistics (parallel) -> PLL (serial).
+    const bool fused = h->core_fused && h->cfg.stereo && h->cfg.multipath_stages == 0 && h->max_time_chunks == 1;
     dim3 cgrid((C + 31) / 32);
-    if (h->cfg.fmfilter) FMR_CUDA(hop(sB, sG, h->ev_p[k][0]));
-    pf.begin(h->p_agc, sG);
-    tr.begin("agc", k, sG);
-    if (h->serial_v2) {
-      k_fm_agc2<<<cgrid, 32, 0, sG>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
-    } else {
-      k_fm_agc<<<cgrid, 32, 0, sG>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
-    }
-    tr.end(sG);
-    pf.end(h->p_agc, sG);
-    launches++;
-    FMR_CUDA(hop(sG, sB, h->ev_p[k][1]));
-    Ring<float2> disc_in = h->r_agc;
-    if (h->cfg.multipath_stages > 0) {
-      pf.begin(h->p_mpf, sB);
-      h->mpf.run(h->r_agc, h->r_mpf, h->d_state, d_e384, (int)nb, t0k, sB, 0, C);
-      pf.end(h->p_mpf, sB);
+    if (fused) {
+      dim3 fgrid((C + 31) / 32);
+      pf.begin(h->p_fused, sB);
+      k_fm_core_fused<<<fgrid, kCfThreads, 0, sB>>>(h->r_if, h->r_iff, h->r_384, h->d_state, d_flags, h->d_pps, d_e384,
+                                                   (int)nb, t0k, h->core, h->d_atan, (int)(flag_b0 + b0),
+                                                   (k == 0 && flag_b0 == 0) ? 1 : 0);
+      pf.end(h->p_fused, sB);
       launches++;
-      disc_in = h->r_mpf;
-    }
-    pf.begin(h->p_core, sB);
-    {
-      dim3 g1((n384k + 255) / 256, C);
-      k_fm_disc<<<g1, 256, 0, sB>>>(disc_in, h->r_mpx, (int)n384k, t0k, h->core);
-      dim3 g2((nb + 3) / 4, C);
-      k_fm_call_stats<<<g2, 128, 0, sB>>>(h->r_if, h->r_mpx, d_stats, d_e384, (int)nb, t0k);
-    }
-    pf.end(h->p_core, sB);
-    FMR_CUDA(hop(sB, sL, h->ev_p[k][2]));
-    pf.begin(h->p_core2, sL);
-    tr.begin("pll", k, sL);
-    if (h->serial_v2) {
-      k_fm_pll2<<<cgrid, 32, 0, sL>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
-                                      h->core, h->d_atan, (int)(flag_b0 + b0), (k == 0 && flag_b0 == 0) ? 1 : 0);
     } else {
-      k_fm_pll<<<cgrid, 32, 0, sL>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
-                                     h->core, h->d_atan, (int)(flag_b0 + b0), (k == 0 && flag_b0 == 0) ? 1 : 0);
+      if (h->cfg.fmfilter) FMR_CUDA(hop(sB, sG, h->ev_p[k][0]));
+      pf.begin(h->p_agc, sG);
+      tr.begin("agc", k, sG);
+      if (h->serial_v2) {
+        k_fm_agc2<<<cgrid, 32, 0, sG>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
+      } else {
+        k_fm_agc<<<cgrid, 32, 0, sG>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
+      }
+      tr.end(sG);
+      pf.end(h->p_agc, sG);
+      launches++;
+      FMR_CUDA(hop(sG, sB, h->ev_p[k][1]));
+      Ring<float2> disc_in = h->r_agc;
+      if (h->cfg.multipath_stages > 0) {
+        pf.begin(h->p_mpf, sB);
+        h->mpf.run(h->r_agc, h->r_mpf, h->d_state, d_e384, (int)nb, t0k, sB, 0, C);
+        pf.end(h->p_mpf, sB);
+        launches++;
+        disc_in = h->r_mpf;
+      }
+      pf.begin(h->p_core, sB);
+      {
+        dim3 g1((n384k + 255) / 256, C);
+        k_fm_disc<<<g1, 256, 0, sB>>>(disc_in, h->r_mpx, (int)n384k, t0k, h->core);
+        dim3 g2((nb + 3) / 4, C);
+        k_fm_call_stats<<<g2, 128, 0, sB>>>(h->r_if, h->r_mpx, d_stats, d_e384, (int)nb, t0k);
+      }
+      pf.end(h->p_core, sB);
+      FMR_CUDA(hop(sB, sL, h->ev_p[k][2]));
+      pf.begin(h->p_core2, sL);
+      tr.begin("pll", k, sL);
+      if (h->serial_v2) {
+        k_fm_pll2<<<cgrid, 32, 0, sL>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
+                                        h->core, h->d_atan, (int)(flag_b0 + b0), (k == 0 && flag_b0 == 0) ? 1 : 0);
+      } else {
+        k_fm_pll<<<cgrid, 32, 0, sL>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
+                                       h->core, h->d_atan, (int)(flag_b0 + b0), (k == 0 && flag_b0 == 0) ? 1 : 0);
+      }
+      tr.end(sL);
+      pf.end(h->p_core2, sL);
+      FMR_CUDA(hop(sL, sU, h->ev_p[k][3]));
+      launches += 3;
     }
-    tr.end(sL);
-    pf.end(h->p_core2, sL);
-    FMR_CUDA(hop(sL, sU, h->ev_p[k][3]));
-    launches += 3;
     // ---- audio resamplers (mono and L-R in lock step, FmDecode.cpp:172-183)
     InSrc<double2> asrc;
     memset(&asrc, 0, sizeof(asrc));

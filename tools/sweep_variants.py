@@ -15,13 +15,11 @@ import bench  # noqa: E402
 VARIANTS = [
     # name, env, blocks per step, channels
     ("all_on_128", {}, 128, 8192),
-    ("serial_v1", {"FMR_SERIAL_V2": "0"}, 128, 8192),
-    ("chunks2_sms8", {"FMR_TIME_CHUNKS": "2", "FMR_SERIAL_SMS": "8"}, 128, 8192),
-    ("chunks4_sms8", {"FMR_TIME_CHUNKS": "4", "FMR_SERIAL_SMS": "8"}, 256, 8192),
-    ("chunks2_nosms", {"FMR_TIME_CHUNKS": "2"}, 128, 8192),
+    ("core_unfused", {"FMR_CORE_FUSED": "0"}, 128, 8192),
     ("all_on_329", {}, 329, 8192),
     ("all_on_128_c1024", {}, 128, 1024),
     ("all_on_128_c148", {}, 128, 148),
+    ("all_on_128_c4096", {}, 128, 4096),
 ]
 
 
@@ -42,7 +40,7 @@ def main():
     iq = bench.gen_iq_device(torch, dev, fs, Cgen, Tmax, mode)
     stream = torch.cuda.current_stream()
     for name, env, nblk, C in variants:
-        for k in ("FMR_HB_STREAM", "FMR_FUSE_FI", "FMR_FFT_F64", "FMR_HBS_TILE", "FMR_FFT", "FMR_SERIAL_V2", "FMR_TIME_CHUNKS", "FMR_SERIAL_SMS"):
+        for k in ("FMR_HB_STREAM", "FMR_FUSE_FI", "FMR_FFT_F64", "FMR_HBS_TILE", "FMR_FFT", "FMR_SERIAL_V2", "FMR_TIME_CHUNKS", "FMR_SERIAL_SMS", "FMR_CORE_FUSED"):
             os.environ.pop(k, None)
         os.environ.update(env)
         C = min(C, Cgen)
