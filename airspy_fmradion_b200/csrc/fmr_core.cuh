@@ -5,14 +5,14 @@
 // deemphasis filters) with time-parallel work in between (PhaseDiscriminator, the L-R mix,
 // statistics). As separate launches (k_fm_agc2 -> k_fm_disc/k_fm_call_stats -> k_fm_pll2) their
 // latencies add up and every hand-over goes through HBM. Here a CTA owns 32 channels (lane =
-// channel) and three warps run as a pipeline over chunks of kCfT samples:
-//   warp 0  AGC           global IF ring -> gain recurrence -> shared memory (float2)
-//   warp 1  disc + post   atan2/phase difference/statistics -> shared memory (MPX);
-//                         and, two chunks behind, 2*x*sin(2 phi), both deemphasis filters -> HBM
-//   warp 2  PLL           the pilot phase lock recurrence only (its dependent chain is the
-//                         critical path of the whole kernel); hands sin/cos of the pilot phase on
+// channel) and four warps run as a pipeline over chunks of kCfT samples:
+//   warp 0  AGC    global IF ring -> gain recurrence -> shared memory (float2); IF RMS
+//   warp 1  disc   atan2 / phase difference / baseband statistics -> shared memory (MPX)
+//   warp 2  PLL    the pilot phase lock recurrence only (its dependent chain is the critical
+//                  path of the whole kernel); hands sin/cos of the pilot phase on
+//   warp 3  post   2*x*sin(2 phi), both deemphasis filters -> HBM
 // Chunks are handed over through double-buffered shared memory with named barriers
-// (bar.arrive / bar.sync, producer/consumer pairs of 64 threads); nothing of the core except
+// (bar.arrive / bar.sync between producer and consumer warps); nothing of the core except
 // the (mono, L-R) result touches HBM. Step time = the PLL chain alone instead of
 // AGC + discriminator + PLL.
 //
@@ -27,7 +27,7 @@
 namespace fmr {
 
 constexpr int kCfT = 8;        // samples per chunk
-constexpr int kCfThreads = 96; // three warps
+constexpr int kCfThreads = 128; // four warps
 
 struct CfSmem {
   float2 iq[2][kCfT][32];
@@ -35,11 +35,14 @@ struct CfSmem {
   double ps[2][kCfT][32];
   double pc[2][kCfT][32];
   float2 tab[256];
+  double kc[16]; // loop constants of the PLL, read back into registers (see warp 2)
 };
 
-// named barriers: producer/consumer pairs of two warps
+// named barriers between producer and consumer warps (64 threads; 96 where a slot has two readers)
 __device__ __forceinline__ void cf_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void cf_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void cf_sync3(int id) { asm volatile("bar.sync %0, 96;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void cf_arrive3(int id) { asm volatile("bar.arrive %0, 96;" ::"r"(id) : "memory"); }
 // link 0: AGC -> disc, link 1: disc -> PLL, link 2: PLL -> post
 __device__ __forceinline__ int cf_full(int link, int slot) { return 1 + link * 4 + slot; }
 __device__ __forceinline__ int cf_empty(int link, int slot) { return 3 + link * 4 + slot; }
@@ -144,90 +147,91 @@ static __global__ void __launch_bounds__(kCfThreads)
       st[c].if_rms = if_rms;
     }
   } else if (warp == 1) {
-    // =============================== discriminator + statistics, and the post stage
+    // =============================== PhaseDiscriminator::process (PhaseDiscriminator.cpp:33-46)
+    // + samples_mean_rms and the EMA of FmDecode.cpp:146-150
     FmChanState *sp = st + c;
     float prev = sp->disc_prev;
     float bmean = sp->baseband_mean, blevel = sp->baseband_level;
-    double dem = sp->de_m_x1, des = sp->de_s_x1;
     float vs = 0.f, vq = 0.f;
-    const bool shift = P.pilot_shift != 0, de_st = P.deemph_on_stereo != 0;
-    double2 *__restrict__ orow = out384.base + (size_t)c * out384.cap;
-    const uint32_t omask = out384.cap - 1;
+    const float inv_norm = P.disc_inv_norm, bound = P.disc_bound;
     CfCalls cl;
     cl.init(call_end, n_calls);
     cf_arrive(cf_empty(0, 0));
     cf_arrive(cf_empty(0, 1));
-    cf_arrive(cf_empty(2, 0));
-    cf_arrive(cf_empty(2, 1));
-    for (int j = 0; j <= K; j++) {
-      if (j < K) {
-        // ---- PhaseDiscriminator::process (PhaseDiscriminator.cpp:33-46) on chunk j
-        const int slot = j & 1, p0 = j * kCfT;
-        cf_sync(cf_full(0, slot));
-        float2 x[kCfT];
-#pragma unroll
-        for (int u = 0; u < kCfT; u++) x[u] = S.iq[slot][u][lane];
-        if (j + 2 < K) cf_arrive(cf_empty(0, slot));
-        float ph[kCfT];
-#pragma unroll
-        for (int u = 0; u < kCfT; u++) ph[u] = atan2f(x[u].y, x[u].x) * P.disc_inv_norm;
-        cf_sync(cf_empty(1, slot));
-#pragma unroll
-        for (int u = 0; u < kCfT; u++) {
-          const int p = p0 + u;
-          if (p < n_total) {
-            if ((uint32_t)p == cl.end) cl.next();
-            float d = ph[u] - prev;
-            prev = ph[u];
-            if (d > P.disc_bound) d -= 2 * P.disc_bound;
-            if (d < -P.disc_bound) d += 2 * P.disc_bound;
-            if (isnan(d)) d = 0.0f;
-            S.mpx[slot][u][lane] = d;
-            vs += d;
-            vq += d * d;
-            if ((uint32_t)(p + 1) == cl.end) {
-              // samples_mean_rms + the EMA of FmDecode.cpp:146-150
-              const float n = (float)(cl.end - cl.beg);
-              const float mean = vs / n, rms = sqrtf(vq / n);
-              bmean = (float)(0.95 * (double)bmean + 0.05 * (double)mean);
-              blevel = (float)(0.95 * (double)blevel + 0.05 * (double)rms);
-              vs = 0.f;
-              vq = 0.f;
-            }
-          }
+    for (int j = 0; j < K; j++) {
+      const int slot = j & 1, p0 = j * kCfT;
+      const int valid = (n_total - p0 < kCfT) ? (n_total - p0) : kCfT;
+      cf_sync(cf_full(0, slot));
+      cf_sync3(cf_empty(1, slot));
+#pragma unroll 2
+      for (int u = 0; u < valid; u++) {
+        const int p = p0 + u;
+        if ((uint32_t)p == cl.end) cl.next();
+        const float2 x = S.iq[slot][u][lane];
+        const float ph = atan2f(x.y, x.x) * inv_norm;
+        float d = ph - prev;
+        prev = ph;
+        if (d > bound) d -= 2 * bound;
+        if (d < -bound) d += 2 * bound;
+        if (isnan(d)) d = 0.0f;
+        S.mpx[slot][u][lane] = d;
+        vs += d;
+        vq += d * d;
+        if ((uint32_t)(p + 1) == cl.end) {
+          const float n = (float)(cl.end - cl.beg);
+          const float mean = vs / n, rms = sqrtf(vq / n);
+          bmean = (float)(0.95 * (double)bmean + 0.05 * (double)mean);
+          blevel = (float)(0.95 * (double)blevel + 0.05 * (double)rms);
+          vs = 0.f;
+          vq = 0.f;
         }
-        cf_arrive(cf_full(1, slot));
       }
-      if (j >= 1) {
-        // ---- post stage on chunk j-1: demod_stereo (FmDecode.cpp:224-239) + LowPassFilterRC x2
-        const int kk = j - 1, slot = kk & 1, p0 = kk * kCfT;
-        cf_sync(cf_full(2, slot));
-#pragma unroll
-        for (int u = 0; u < kCfT; u++) {
-          const int p = p0 + u;
-          if (p < n_total) {
-            const double xd = (double)S.mpx[slot][u][lane];
-            const double ps = S.ps[slot][u][lane], pc = S.pc[slot][u][lane];
-            const double tone = shift ? (2 * pc * pc - 1) : (2 * ps * pc);
-            double ster = (tone * xd) * 2.0;
-            if (de_st) {
-              const double x0 = ster - P.de_a1 * des;
-              ster = P.de_b0 * x0;
-              des = x0;
-            }
-            const double m0 = xd - P.de_a1 * dem;
-            const double mono = P.de_b0 * m0;
-            dem = m0;
-            if (act) orow[(t0lo + (uint32_t)p) & omask] = make_double2(mono, ster);
-          }
-        }
-        if (kk + 2 < K) cf_arrive(cf_empty(2, slot));
-      }
+      cf_arrive(cf_full(1, slot));
+      if (j + 2 < K) cf_arrive(cf_empty(0, slot));
     }
     if (act) {
       sp->disc_prev = prev;
       sp->baseband_mean = bmean;
       sp->baseband_level = blevel;
+    }
+  } else if (warp == 3) {
+    // =============================== demod_stereo (FmDecode.cpp:224-239) + LowPassFilterRC x2
+    FmChanState *sp = st + c;
+    double dem = sp->de_m_x1, des = sp->de_s_x1;
+    const bool shift = P.pilot_shift != 0, de_st = P.deemph_on_stereo != 0;
+    const double de_a1 = P.de_a1, de_b0 = P.de_b0;
+    double2 *__restrict__ orow = out384.base + (size_t)c * out384.cap;
+    const uint32_t omask = out384.cap - 1;
+    cf_arrive(cf_empty(2, 0));
+    cf_arrive(cf_empty(2, 1));
+    cf_arrive3(cf_empty(1, 0));
+    cf_arrive3(cf_empty(1, 1));
+    for (int k = 0; k < K; k++) {
+      const int slot = k & 1, p0 = k * kCfT;
+      const int valid = (n_total - p0 < kCfT) ? (n_total - p0) : kCfT;
+      cf_sync(cf_full(2, slot));
+#pragma unroll 2
+      for (int u = 0; u < valid; u++) {
+        const double xd = (double)S.mpx[slot][u][lane];
+        const double ps = S.ps[slot][u][lane], pc = S.pc[slot][u][lane];
+        const double tone = shift ? (2 * pc * pc - 1) : (2 * ps * pc);
+        double ster = (tone * xd) * 2.0;
+        if (de_st) {
+          const double x0 = ster - de_a1 * des;
+          ster = de_b0 * x0;
+          des = x0;
+        }
+        const double m0 = xd - de_a1 * dem;
+        const double mono = de_b0 * m0;
+        dem = m0;
+        if (act) orow[(t0lo + (uint32_t)(p0 + u)) & omask] = make_double2(mono, ster);
+      }
+      if (k + 2 < K) {
+        cf_arrive(cf_empty(2, slot));
+        cf_arrive3(cf_empty(1, slot));
+      }
+    }
+    if (act) {
       sp->de_m_x1 = dem;
       sp->de_s_x1 = des;
     }
@@ -235,15 +239,37 @@ static __global__ void __launch_bounds__(kCfThreads)
     // =============================== PilotPhaseLock::process (PilotPhaseLock.cpp:56-171)
     FmChanState s = st[c];
     if (reset_pps) s.n_pps = 0;
-    const double kTwoPi = 2.0 * 3.14159265358979323846;
-    const double f0 = (19000.0 / 384000.0) * kTwoPi;
-    double sf0, cf0;
-    sincos(f0, &sf0, &cf0);
-    double minf = P.pll_minfreq, maxf = P.pll_maxfreq, lf_b0 = P.lf_b0, lf_b1 = P.lf_b1, bq_b0 = P.bq_b0;
-    double bq_a1 = P.bq_a1, bq_a2 = P.bq_a2;
-    double dlmin = minf - f0, dlmax = maxf - f0;
-    asm volatile("" : "+d"(minf), "+d"(maxf), "+d"(lf_b0), "+d"(lf_b1), "+d"(bq_b0), "+d"(dlmin), "+d"(dlmax),
-                 "+d"(bq_a1), "+d"(bq_a2));
+    // Loop constants take a round trip through shared memory: kernel parameters and immediates
+    // get re-materialised from the constant bank / uniform moves INSIDE the recurrence otherwise,
+    // and every such instruction is a latency on the critical path of a one-warp kernel.
+    {
+      const double two_pi = 2.0 * 3.14159265358979323846;
+      const double f0c = (19000.0 / 384000.0) * two_pi;
+      double sf, cf;
+      sincos(f0c, &sf, &cf);
+      if (lane == 0) {
+        S.kc[0] = two_pi;
+        S.kc[1] = f0c;
+        S.kc[2] = sf;
+        S.kc[3] = cf;
+        S.kc[4] = P.pll_minfreq;
+        S.kc[5] = P.pll_maxfreq;
+        S.kc[6] = P.pll_minfreq - f0c;
+        S.kc[7] = P.pll_maxfreq - f0c;
+        S.kc[8] = P.lf_b0;
+        S.kc[9] = P.lf_b1;
+        S.kc[10] = P.bq_b0;
+        S.kc[11] = P.bq_a1;
+        S.kc[12] = P.bq_a2;
+        S.kc[13] = -1.0 / 6.0;
+        S.kc[14] = -0.5;
+      }
+      __syncwarp();
+    }
+    const volatile double *kc = S.kc;
+    const double kTwoPi = kc[0], f0 = kc[1], sf0 = kc[2], cf0 = kc[3], minf = kc[4], maxf = kc[5], dlmin = kc[6],
+                 dlmax = kc[7], lf_b0 = kc[8], lf_b1 = kc[9], bq_b0 = kc[10], bq_a1 = kc[11], bq_a2 = kc[12],
+                 k_m16 = kc[13], k_mh = kc[14];
     double bi1 = s.bi_x1, bi2 = s.bi_x2, bq1 = s.bq_x1, bq2 = s.bq_x2, lf1 = s.lf_x1;
     double freq = s.pll_freq, phase = s.pll_phase, ferr = s.freq_err;
     int periods = s.pilot_periods;
@@ -252,8 +278,8 @@ static __global__ void __launch_bounds__(kCfThreads)
     CfCalls cl;
     cl.init(call_end, n_calls);
     int b_flag = 0; // next call whose flag has not been written
-    cf_arrive(cf_empty(1, 0));
-    cf_arrive(cf_empty(1, 1));
+    cf_arrive3(cf_empty(1, 0));
+    cf_arrive3(cf_empty(1, 1));
     for (int k = 0; k < K; k++) {
       const int slot = k & 1, p0 = k * kCfT;
       const int valid = (n_total - p0 < kCfT) ? (n_total - p0) : kCfT;
@@ -304,9 +330,9 @@ static __global__ void __launch_bounds__(kCfThreads)
         const double dl = below_max ? (above_min ? dlr : dlmin) : dlmax;
         {
           const double d2 = dl * dl;
-          const double sd = fma(dl * d2, -1.0 / 6.0, dl);
-          psin = fma(ac, sd, fma(-0.5 * as, d2, as));
-          pcos = fma(-as, sd, fma(-0.5 * ac, d2, ac));
+          const double sd = fma(dl * d2, k_m16, dl);
+          psin = fma(ac, sd, fma(k_mh * as, d2, as));
+          pcos = fma(-as, sd, fma(k_mh * ac, d2, ac));
         }
         phase += freq;
         const bool wrap = phase > kTwoPi;
@@ -352,7 +378,7 @@ static __global__ void __launch_bounds__(kCfThreads)
         }
       }
       cf_arrive(cf_full(2, slot));
-      if (k + 2 < K) cf_arrive(cf_empty(1, slot));
+      if (k + 2 < K) cf_arrive3(cf_empty(1, slot));
     }
     if (act) {
       for (; b_flag < n_calls; b_flag++) flags[(size_t)c * n_calls + b_flag] = (uint8_t)s.stereo_detected;

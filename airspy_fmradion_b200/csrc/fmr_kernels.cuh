@@ -1183,9 +1183,12 @@ __device__ __forceinline__ float fast_atan2f_bf(float y, float x, const float2 *
   float z = num * r;
   z = fmaf(fmaf(-den, z, num), r, z);
   float alpha = z * 255.0f;
-  const int index = (int)alpha; // 0..255 because num <= den
-  alpha -= (float)index;
-  const float2 te = tab[index & 0xff];
+  // index = (int)alpha and (float)index without the two conversion instructions (~12 cycles each
+  // on the critical path): adding 2^23 with round-towards-zero leaves trunc(alpha) in the low
+  // mantissa bits, and subtracting 2^23 again gives it back as a float, both exactly (0 <= alpha <= 255)
+  const float t = __fadd_rz(alpha, 8388608.0f);
+  alpha -= t - 8388608.0f;
+  const float2 te = tab[__float_as_int(t) & 0xff];
   float base = fmaf(te.y, alpha, te.x);
   base = (z < __int_as_float(0x3b808082)) ? z : base; // (double)z < 0.003921569, see fast_atan2f_dev
   const float angle = fmaf(sg, base, K);
