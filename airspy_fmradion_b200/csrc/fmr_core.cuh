@@ -280,18 +280,23 @@ static __global__ void __launch_bounds__(kCfThreads)
     int b_flag = 0; // next call whose flag has not been written
     cf_arrive3(cf_empty(1, 0));
     cf_arrive3(cf_empty(1, 1));
+    // 32-bit shared-window addresses of this lane's columns (explicit ld/st.shared below: a generic
+    // pointer would be converted again for every access, inside the recurrence)
+    const unsigned a_mpx = (unsigned)__cvta_generic_to_shared(&S.mpx[0][0][lane]);
+    const unsigned a_ps = (unsigned)__cvta_generic_to_shared(&S.ps[0][0][lane]);
+    const unsigned a_pc = (unsigned)__cvta_generic_to_shared(&S.pc[0][0][lane]);
+    const unsigned a_tab = (unsigned)__cvta_generic_to_shared(&S.tab[0]);
+    uint32_t p = 0; // flat sample index
     for (int k = 0; k < K; k++) {
-      const int slot = k & 1, p0 = k * kCfT;
-      const int valid = (n_total - p0 < kCfT) ? (n_total - p0) : kCfT;
+      const int slot = k & 1;
+      const uint32_t p_chunk_end = min((uint32_t)n_total, (uint32_t)(k + 1) * kCfT);
       cf_sync(cf_full(1, slot));
       cf_sync(cf_empty(2, slot));
-      float x_next = S.mpx[slot][0][lane];
-#pragma unroll 1
-      for (int u = 0; u < valid; u++) {
-        const int p = p0 + u;
-        const double xd = (double)x_next;
-        if (u + 1 < valid) x_next = S.mpx[slot][u + 1][lane];
-        if ((uint32_t)p == cl.end) {
+      unsigned am = a_mpx + slot * (kCfT * 32 * 4), aps = a_ps + slot * (kCfT * 32 * 8), apc = a_pc + slot * (kCfT * 32 * 8);
+      float x_next;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x_next) : "r"(am));
+      while (p < p_chunk_end) {
+        if (p == cl.end) {
           // ---- a reference call begins: flags of skipped empty calls, lock state, exact re-anchor
           cl.next();
           if (act) {
@@ -301,60 +306,70 @@ static __global__ void __launch_bounds__(kCfThreads)
           was_locked = (s.lock_cnt >= P.lock_delay);
           sincos(phase, &psin, &pcos);
         }
-        S.ps[slot][u][lane] = psin;
-        S.pc[slot][u][lane] = pcos;
-        // ---- off the critical path
-        const double fb_i = bq_a1 * bi1 + bq_a2 * bi2;
-        const double fb_q = bq_a1 * bq1 + bq_a2 * bq2;
-        const double fb_l = __dmul_rn(lf_b1, lf1);
-        const double as = psin * cf0 + pcos * sf0;
-        const double ac = pcos * cf0 - psin * sf0;
-        // ---- critical path (see k_fm_pll2)
-        const double i0v = psin * xd - fb_i;
-        const double q0v = pcos * xd - fb_q;
-        const double new_i = bq_b0 * i0v;
-        const double new_q = bq_b0 * q0v;
-        bi2 = bi1;
-        bi1 = i0v;
-        bq2 = bq1;
-        bq1 = q0v;
-        const double perr = (double)fast_atan2f_bf((float)new_q, (float)new_i, S.tab);
-        last_i = new_i;
-        last_q = new_q;
-        ferr = fma(lf_b0, perr, fb_l);
-        lf1 = perr;
-        const double fraw = freq + ferr;
-        const bool below_max = fraw < maxf, above_min = minf < fraw;
-        const double dlr = fraw - f0;
-        freq = below_max ? (above_min ? fraw : minf) : maxf;
-        const double dl = below_max ? (above_min ? dlr : dlmin) : dlmax;
-        {
-          const double d2 = dl * dl;
-          const double sd = fma(dl * d2, k_m16, dl);
-          psin = fma(ac, sd, fma(k_mh * as, d2, as));
-          pcos = fma(-as, sd, fma(k_mh * ac, d2, ac));
-        }
-        phase += freq;
-        const bool wrap = phase > kTwoPi;
-        phase = wrap ? phase - kTwoPi : phase;
-        periods += wrap ? 1 : 0;
-        if (wrap && periods == 19000) {
-          periods = 0;
-          if (was_locked) {
-            if (s.n_pps < (uint32_t)kMaxPps && act) {
-              PpsEventDev ev;
-              ev.pps_index = s.pps_cnt;
-              ev.sample_index = s.sample_cnt + (unsigned long long)((uint32_t)p - cl.beg);
-              ev.block_position = (double)((uint32_t)p - cl.beg) / (double)(cl.end - cl.beg);
-              ev.block = (uint32_t)(cl.b + block_off);
-              ev.pad = 0;
-              pps[(size_t)c * kMaxPps + s.n_pps] = ev;
+        // samples up to the end of the chunk or of the reference call, whichever comes first
+        const uint32_t run_end = min(p_chunk_end, cl.end);
+#pragma unroll 1
+        for (; p < run_end; p++) {
+          const double xd = (double)x_next;
+          am += 32 * 4;
+          if (p + 1 < p_chunk_end) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x_next) : "r"(am));
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(aps), "d"(psin) : "memory");
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(apc), "d"(pcos) : "memory");
+          aps += 32 * 8;
+          apc += 32 * 8;
+          // ---- off the critical path
+          const double fb_i = bq_a1 * bi1 + bq_a2 * bi2;
+          const double fb_q = bq_a1 * bq1 + bq_a2 * bq2;
+          const double fb_l = __dmul_rn(lf_b1, lf1);
+          const double as = psin * cf0 + pcos * sf0;
+          const double ac = pcos * cf0 - psin * sf0;
+          // ---- critical path (see k_fm_pll2)
+          const double i0v = psin * xd - fb_i;
+          const double q0v = pcos * xd - fb_q;
+          const double new_i = bq_b0 * i0v;
+          const double new_q = bq_b0 * q0v;
+          bi2 = bi1;
+          bi1 = i0v;
+          bq2 = bq1;
+          bq1 = q0v;
+          const double perr = (double)fast_atan2f_bf_s((float)new_q, (float)new_i, a_tab);
+          last_i = new_i;
+          last_q = new_q;
+          ferr = fma(lf_b0, perr, fb_l);
+          lf1 = perr;
+          const double fraw = freq + ferr;
+          const bool below_max = fraw < maxf, above_min = minf < fraw;
+          const double dlr = fraw - f0;
+          freq = below_max ? (above_min ? fraw : minf) : maxf;
+          const double dl = below_max ? (above_min ? dlr : dlmin) : dlmax;
+          {
+            const double d2 = dl * dl;
+            const double sd = fma(dl * d2, k_m16, dl);
+            psin = fma(ac, sd, fma(k_mh * as, d2, as));
+            pcos = fma(-as, sd, fma(k_mh * ac, d2, ac));
+          }
+          phase += freq;
+          const bool wrap = phase > kTwoPi;
+          phase = wrap ? phase - kTwoPi : phase;
+          periods += wrap ? 1 : 0;
+          if (wrap && periods == 19000) {
+            periods = 0;
+            if (was_locked) {
+              if (s.n_pps < (uint32_t)kMaxPps && act) {
+                PpsEventDev ev;
+                ev.pps_index = s.pps_cnt;
+                ev.sample_index = s.sample_cnt + (unsigned long long)(p - cl.beg);
+                ev.block_position = (double)(p - cl.beg) / (double)(cl.end - cl.beg);
+                ev.block = (uint32_t)(cl.b + block_off);
+                ev.pad = 0;
+                pps[(size_t)c * kMaxPps + s.n_pps] = ev;
+              }
+              s.n_pps++;
+              s.pps_cnt++;
             }
-            s.n_pps++;
-            s.pps_cnt++;
           }
         }
-        if ((uint32_t)(p + 1) == cl.end) {
+        if (p == cl.end) {
           // ---- the reference call ends (PilotPhaseLock.cpp:106,153-170)
           const int n = (int)(cl.end - cl.beg);
           s.pilot_level = sqrt(last_i * last_i + last_q * last_q);

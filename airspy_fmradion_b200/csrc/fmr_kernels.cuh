@@ -1166,7 +1166,8 @@ struct PllTab {
   float2 e[256]; // (tbl[i], tbl[i+1] - tbl[i])
 };
 
-__device__ __forceinline__ float fast_atan2f_bf(float y, float x, const float2 *__restrict__ tab) {
+// TAB: callable index -> (tbl[i], tbl[i+1]-tbl[i])
+template <typename TAB> __device__ __forceinline__ float fast_atan2f_bf_t(float y, float x, TAB tab) {
   const float ya = fabsf(y), xa = fabsf(x);
   const float num = fminf(ya, xa), den = fmaxf(ya, xa);
   const bool xbig = xa > ya, xpos = x >= 0.0f, ypos = y >= 0.0f;
@@ -1188,11 +1189,24 @@ __device__ __forceinline__ float fast_atan2f_bf(float y, float x, const float2 *
   // mantissa bits, and subtracting 2^23 again gives it back as a float, both exactly (0 <= alpha <= 255)
   const float t = __fadd_rz(alpha, 8388608.0f);
   alpha -= t - 8388608.0f;
-  const float2 te = tab[__float_as_int(t) & 0xff];
+  const float2 te = tab(__float_as_int(t) & 0xff);
   float base = fmaf(te.y, alpha, te.x);
   base = (z < __int_as_float(0x3b808082)) ? z : base; // (double)z < 0.003921569, see fast_atan2f_dev
   const float angle = fmaf(sg, base, K);
   return (den > 0.0f) ? angle : 0.0f; // both inputs zero (Utility.h:245-247)
+}
+
+__device__ __forceinline__ float fast_atan2f_bf(float y, float x, const float2 *__restrict__ tab) {
+  return fast_atan2f_bf_t(y, x, [tab](int i) { return tab[i]; });
+}
+// table in shared memory addressed by its 32-bit shared-window address (no generic-pointer
+// conversion inside the recurrence)
+__device__ __forceinline__ float fast_atan2f_bf_s(float y, float x, unsigned tab_s) {
+  return fast_atan2f_bf_t(y, x, [tab_s](int i) {
+    float2 v;
+    asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(tab_s + 8u * (unsigned)i));
+    return v;
+  });
 }
 
 static __global__ void __launch_bounds__(32)
