@@ -142,10 +142,9 @@ template <int N1, int N2, int N3, int U> struct HbsCascade {
 #if defined(__CUDACC__)
 constexpr int kHbsThreads = 128;
 constexpr int kHbsU = 4;                         // macro-steps per block step
-constexpr int kHbsStages = 4;                    // cp.async ring depth (chunks per stream)
 constexpr int kHbsPitch = 144;                   // bytes per stream row: 128 + 16 (bank skew)
 constexpr int kHbsStageBytes = 32 * kHbsPitch;   // per warp
-constexpr int kHbsSmemBytes = (kHbsThreads / 32) * kHbsStages * kHbsStageBytes;
+constexpr int hbs_smem_bytes(int stages) { return (kHbsThreads / 32) * stages * kHbsStageBytes; }
 
 struct HbsParams {
   const float2 *lin; // [C][stride] caller's buffer of this call; lin[c][0] has absolute index `start`
@@ -156,13 +155,14 @@ struct HbsParams {
   int tiles_per_ch;
   int n_streams;     // channels * tiles_per_ch
   int n_block_steps; // block steps every stream runs: ceil((kWarm + tile/2) / U)
+  int l2_prefetch;   // > 0: every 8 chunks a lane asks the L2 for the 1 KB that lies this many chunks ahead
   float t1[8], t2[8], t3[8];
 };
 
 // k_hb_stream: outputs [a_out, a_out + tiles_per_ch*tile) of every channel. All input samples the
 // streams touch must lie inside the call's buffer and be 16-byte aligned (the host checks).
-template <int N1, int N2, int N3, int U>
-__global__ void __launch_bounds__(kHbsThreads, 3) k_hb_stream(HbsParams P, Ring<float2> out) {
+template <int N1, int N2, int N3, int U, int kHbsStages>
+__global__ void __launch_bounds__(kHbsThreads, (kHbsStages <= 4 ? 3 : 2)) k_hb_stream(HbsParams P, Ring<float2> out) {
   using D = HbsDelays<N1, N2, N3>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -200,6 +200,10 @@ __global__ void __launch_bounds__(kHbsThreads, 3) k_hb_stream(HbsParams P, Ring<
       }
     }
     asm volatile("cp.async.commit_group;\n" ::);
+    if (P.l2_prefetch > 0 && (step & 7) == 0 && step + P.l2_prefetch + 8 <= n_steps) {
+      // DRAM-friendly read-ahead: one 1 KB request per stream instead of eight 128-byte ones
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], 1024;\n" ::"l"(my_src + (size_t)(step + P.l2_prefetch) * 128));
+    }
   };
 #pragma unroll
   for (int s = 0; s < kHbsStages - 1; s++) issue(s);
@@ -253,6 +257,136 @@ __global__ void __launch_bounds__(kHbsThreads, 3) k_hb_stream(HbsParams P, Ring<
     m += 2 * U;
   }
   asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_hb_stream_tma — the same streaming cascade with the staging done by the TMA unit: every lane
+// issues ONE bulk copy (cp.async.bulk.shared.global, SASS UBLKCP) of ROWSTEPS*128 contiguous
+// bytes of its own stream into its own shared-memory row; completion is counted in bytes on an
+// mbarrier per (warp, stage). Compared with the LDGSTS version the requests are 2-4x larger
+// (friendlier to the DRAM pages), do not occupy L1 miss-tracking resources, and cost one
+// instruction per row instead of eight per 128 bytes.
+template <int ROWSTEPS> struct HbsTma {
+  static constexpr int kRowBytes = ROWSTEPS * 128;
+  static constexpr int kPitch = kRowBytes + 16; // odd multiple of 16 bytes: conflict-free LDS.128
+  static constexpr int kStageBytes = 32 * kPitch;
+  static constexpr int smem_bytes(int stages, int warps) { return 256 + warps * stages * kStageBytes; }
+};
+
+__device__ __forceinline__ void mbar_init(unsigned a, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned a, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
+template <int N1, int N2, int N3, int U, int ROWSTEPS, int STAGES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_hb_stream_tma(HbsParams P, Ring<float2> out) {
+  using D = HbsDelays<N1, N2, N3>;
+  using T = HbsTma<ROWSTEPS>;
+  static_assert(U % ROWSTEPS == 0, "a block step must be a whole number of rows");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem_raw);
+  const unsigned mbar0 = smem_s + warp * (STAGES * 8);
+  const unsigned ring_s = smem_s + 256 + warp * (STAGES * T::kStageBytes);
+  static_assert(WARPS * STAGES * 8 <= 256, "mbarrier area");
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < STAGES; st++) mbar_init(mbar0 + 8 * st, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  int sid = blockIdx.x * (WARPS * 32) + threadIdx.x;
+  const bool live = sid < P.n_streams;
+  if (!live) sid = P.n_streams - 1; // duplicate work, no stores: keeps the byte count per stage fixed
+  const int ch = sid / P.tiles_per_ch, tl = sid - ch * P.tiles_per_ch;
+  const long long m_lo = P.a_out + (long long)tl * P.tile;
+  const long long i_out = (m_lo + D::A3) >> 1;
+  const long long i_first = i_out - D::kWarm;
+  const char *my_src = reinterpret_cast<const char *>(P.lin + (size_t)ch * P.stride) + (16 * i_first - P.start) * 8;
+  const unsigned row_s = ring_s + lane * T::kPitch;
+  const int n_rows = P.n_block_steps * (U / ROWSTEPS);
+  auto issue = [&](int r) {
+    if (r < n_rows) {
+      const int st = r % STAGES;
+      if (lane == 0) mbar_expect_tx(mbar0 + 8 * st, 32 * T::kRowBytes);
+      bulk_g2s(row_s + st * T::kStageBytes, my_src + (size_t)r * T::kRowBytes, T::kRowBytes, mbar0 + 8 * st);
+    }
+  };
+#pragma unroll
+  for (int r = 0; r < STAGES; r++) issue(r);
+
+  HbsCascade<N1, N2, N3, U> cas;
+  cas.clear();
+  float t1[N1], t2[N2], t3[N3];
+#pragma unroll
+  for (int k = 0; k < N1; k++) t1[k] = P.t1[k];
+#pragma unroll
+  for (int k = 0; k < N2; k++) t2[k] = P.t2[k];
+#pragma unroll
+  for (int k = 0; k < N3; k++) t3[k] = P.t3[k];
+  float2 *__restrict__ orow = out.base + (size_t)ch * out.cap;
+  const unsigned omask = out.cap - 1;
+  const long long m_hi = m_lo + P.tile;
+  long long m = 2 * i_first - D::A3;
+  int r = 0;
+  for (int bs = 0; bs < P.n_block_steps; bs++) {
+#pragma unroll
+    for (int q = 0; q < U / ROWSTEPS; q++, r++) {
+      const int st = r % STAGES;
+      mbar_wait(mbar0 + 8 * st, (unsigned)((r / STAGES) & 1));
+      const unsigned a = row_s + st * T::kStageBytes;
+#pragma unroll
+      for (int ms = 0; ms < ROWSTEPS; ms++) {
+        float2 x[16];
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                       : "r"(a + ms * 128 + w * 16));
+          x[2 * w] = make_float2(v.x, v.y);
+          x[2 * w + 1] = make_float2(v.z, v.w);
+        }
+        cas.feed(q * ROWSTEPS + ms, x, t1);
+      }
+      // every lane has consumed its row (the loads feed the arithmetic above): hand the stage back
+      __syncwarp();
+      issue(r + STAGES);
+    }
+    float2 y[2 * U];
+    cas.finish(t2, t3, y);
+    if (live) {
+#pragma unroll
+      for (int q = 0; q < 2 * U; q += 2) {
+        const long long mq = m + q;
+        if (mq >= m_lo && mq < m_hi) {
+          float4 v = make_float4(y[q].x, y[q].y, y[q + 1].x, y[q + 1].y);
+          *reinterpret_cast<float4 *>(orow + ((unsigned)mq & omask)) = v;
+        }
+      }
+    }
+    m += 2 * U;
+  }
 }
 #endif // __CUDACC__
 

@@ -213,6 +213,9 @@ template <typename S> struct Resampler {
   bool fuse_fi = true;   // FMR_FUSE_FI=0: keep the polyphase bank as its own launch
   bool hb_stream = false; // streaming register-resident half-band cascade (10 MHz chain, cf32 input)
   int hbs_tile = 0;       // FMR_HBS_TILE: outputs per stream tile (0 = choose by problem size)
+  int hbs_stages = 4;     // FMR_HBS_STAGES: cp.async ring depth (2, 4 or 6)
+  int hbs_l2pf = 0;       // FMR_HBS_L2PF: L2 read-ahead distance in 128-byte chunks (0 = off)
+  int hbs_tma = 1;        // FMR_HBS_TMA: 0 = cp.async (LDGSTS) staging; 1..7 = TMA bulk-copy staging configurations
   int sm_count = 148;
   int fft_min_out = 0;
 
@@ -271,10 +274,31 @@ template <typename S> struct Resampler {
     FMR_CUDA(e);
     if constexpr (sizeof(S) == sizeof(float)) {
       if (lin && d->n_hb == 3 && hbt.n[0] == 4 && hbt.n[1] == 5 && hbt.n[2] == 8 && !env_off("FMR_HB_STREAM")) {
-        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream<4, 5, 8, kHbsU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kHbsSmemBytes)));
+        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream<4, 5, 8, kHbsU, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       hbs_smem_bytes(2))));
+        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream<4, 5, 8, kHbsU, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       hbs_smem_bytes(4))));
+        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream<4, 5, 8, kHbsU, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       hbs_smem_bytes(6))));
         hb_stream = true;
         if (const char *ev = getenv("FMR_HBS_TILE")) hbs_tile = atoi(ev);
+        if (const char *ev = getenv("FMR_HBS_STAGES")) hbs_stages = atoi(ev);
+        if (const char *ev = getenv("FMR_HBS_L2PF")) hbs_l2pf = atoi(ev);
+        if (const char *ev = getenv("FMR_HBS_TMA")) hbs_tma = atoi(ev);
+        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 2, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       HbsTma<2>::smem_bytes(3, 4))));
+        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 4, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       HbsTma<4>::smem_bytes(3, 2))));
+        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 2, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       HbsTma<2>::smem_bytes(6, 2))));
+        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 1, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       HbsTma<1>::smem_bytes(6, 4))));
+        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       HbsTma<2>::smem_bytes(2, 4))));
+        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       HbsTma<2>::smem_bytes(4, 3))));
+        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 2, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       HbsTma<2>::smem_bytes(3, 2))));
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -497,7 +521,29 @@ template <typename S> struct Resampler {
       P.t3[k] = hbt.t[2][k];
     }
     const int grid = (P.n_streams + kHbsThreads - 1) / kHbsThreads;
-    k_hb_stream<4, 5, 8, kHbsU><<<grid, kHbsThreads, kHbsSmemBytes, st>>>(P, o);
+    P.l2_prefetch = hbs_l2pf;
+    auto blocks = [&](int threads) { return (P.n_streams + threads - 1) / threads; };
+    if (hbs_tma == 1) {
+      k_hb_stream_tma<4, 5, 8, kHbsU, 2, 3, 4><<<blocks(128), 128, HbsTma<2>::smem_bytes(3, 4), st>>>(P, o);
+    } else if (hbs_tma == 2) {
+      k_hb_stream_tma<4, 5, 8, kHbsU, 4, 3, 2><<<blocks(64), 64, HbsTma<4>::smem_bytes(3, 2), st>>>(P, o);
+    } else if (hbs_tma == 3) {
+      k_hb_stream_tma<4, 5, 8, kHbsU, 2, 6, 2><<<blocks(64), 64, HbsTma<2>::smem_bytes(6, 2), st>>>(P, o);
+    } else if (hbs_tma == 4) {
+      k_hb_stream_tma<4, 5, 8, kHbsU, 1, 6, 4><<<blocks(128), 128, HbsTma<1>::smem_bytes(6, 4), st>>>(P, o);
+    } else if (hbs_tma == 5) {
+      k_hb_stream_tma<4, 5, 8, kHbsU, 2, 2, 4><<<blocks(128), 128, HbsTma<2>::smem_bytes(2, 4), st>>>(P, o);
+    } else if (hbs_tma == 6) {
+      k_hb_stream_tma<4, 5, 8, kHbsU, 2, 4, 3><<<blocks(96), 96, HbsTma<2>::smem_bytes(4, 3), st>>>(P, o);
+    } else if (hbs_tma == 7) {
+      k_hb_stream_tma<4, 5, 8, kHbsU, 2, 3, 2><<<blocks(64), 64, HbsTma<2>::smem_bytes(3, 2), st>>>(P, o);
+    } else if (hbs_stages <= 2) {
+      k_hb_stream<4, 5, 8, kHbsU, 2><<<grid, kHbsThreads, hbs_smem_bytes(2), st>>>(P, o);
+    } else if (hbs_stages >= 6) {
+      k_hb_stream<4, 5, 8, kHbsU, 6><<<grid, kHbsThreads, hbs_smem_bytes(6), st>>>(P, o);
+    } else {
+      k_hb_stream<4, 5, 8, kHbsU, 4><<<grid, kHbsThreads, hbs_smem_bytes(4), st>>>(P, o);
+    }
     (*launches)++;
     *sa = a;
     return a + tiles * tile;

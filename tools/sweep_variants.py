@@ -14,12 +14,14 @@ import bench  # noqa: E402
 
 VARIANTS = [
     # name, env, blocks per step, channels
-    ("all_on_128", {}, 128, 8192),
-    ("core_unfused", {"FMR_CORE_FUSED": "0"}, 128, 8192),
-    ("all_on_329", {}, 329, 8192),
-    ("all_on_128_c1024", {}, 128, 1024),
-    ("all_on_128_c148", {}, 128, 148),
-    ("all_on_128_c4096", {}, 128, 4096),
+    ("tma1_r2s3w4", {"FMR_HBS_TMA": "1"}, 128, 8192),
+    ("tma5_r2s2w4", {"FMR_HBS_TMA": "5"}, 128, 8192),
+    ("tma6_r2s4w3", {"FMR_HBS_TMA": "6"}, 128, 8192),
+    ("tma7_r2s3w2", {"FMR_HBS_TMA": "7"}, 128, 8192),
+    ("tma1_tile1024", {"FMR_HBS_TMA": "1", "FMR_HBS_TILE": "1024"}, 128, 8192),
+    ("tma1_tile256", {"FMR_HBS_TMA": "1", "FMR_HBS_TILE": "256"}, 128, 8192),
+    ("tma1_c1024", {"FMR_HBS_TMA": "1"}, 128, 1024),
+    ("tma7_c1024", {"FMR_HBS_TMA": "7"}, 128, 1024),
 ]
 
 
@@ -40,7 +42,7 @@ def main():
     iq = bench.gen_iq_device(torch, dev, fs, Cgen, Tmax, mode)
     stream = torch.cuda.current_stream()
     for name, env, nblk, C in variants:
-        for k in ("FMR_HB_STREAM", "FMR_FUSE_FI", "FMR_FFT_F64", "FMR_HBS_TILE", "FMR_FFT", "FMR_SERIAL_V2", "FMR_TIME_CHUNKS", "FMR_SERIAL_SMS", "FMR_CORE_FUSED"):
+        for k in ("FMR_HB_STREAM", "FMR_FUSE_FI", "FMR_FFT_F64", "FMR_HBS_TILE", "FMR_FFT", "FMR_SERIAL_V2", "FMR_TIME_CHUNKS", "FMR_SERIAL_SMS", "FMR_CORE_FUSED", "FMR_HBS_STAGES", "FMR_HBS_L2PF", "FMR_HBS_TMA"):
             os.environ.pop(k, None)
         os.environ.update(env)
         C = min(C, Cgen)
