@@ -65,6 +65,21 @@ template <typename V> __device__ __forceinline__ void fft4(V &a0, V &a1, V &a2, 
   a1 = cmk<V>(d02.x + d13.y, d02.y - d13.x); // d02 - j d13
   a3 = cmk<V>(d02.x - d13.y, d02.y + d13.x); // d02 + j d13
 }
+// FP32: a complex add is one packed FADD2, a complex subtract one FFMA2 with the scalar -1 (exact,
+// the same IEEE results as the scalar form) — Blackwell's packed FP32 pipe issues both lanes of a
+// (re, im) pair in one slot. Only the two "times -+j" outputs need a component swap.
+__device__ __forceinline__ float2 csub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+template <> __device__ __forceinline__ void fft4<float2>(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
+  const float2 s02 = __fadd2_rn(a0, a2);
+  const float2 d02 = csub2(a0, a2);
+  const float2 s13 = __fadd2_rn(a1, a3);
+  const float2 d13 = csub2(a1, a3);
+  a0 = __fadd2_rn(s02, s13);
+  a2 = csub2(s02, s13);
+  const float2 t = make_float2(d13.y, -d13.x); // -j d13
+  a1 = __fadd2_rn(d02, t);
+  a3 = csub2(d02, t);
+}
 
 // 16-point forward DFT in registers; result X[m] is left in v[4*(m&3) + (m>>2)].
 template <typename V> __device__ __forceinline__ void fft16(V (&v)[16]) {
@@ -124,34 +139,36 @@ template <typename V> __device__ __forceinline__ void twiddle16(V (&v)[16], V w1
 template <typename CFG> __device__ __forceinline__ void pass16_first_smem(typename CFG::V *buf) {
   using V = typename CFG::V;
   V v[CFG::kSets][16];
+  // fpad(i + r*Q) = fpad(i) + r*(Q + Q/16) and fpad(16 i + r) = 17 i + r: one base address per
+  // set, compile-time offsets for the 16 elements
 #pragma unroll
   for (int s = 0; s < CFG::kSets; s++) {
-    const int i = threadIdx.x + s * kFftThreads;
+    const V *src = buf + fpad(threadIdx.x + s * kFftThreads);
 #pragma unroll
-    for (int r = 0; r < 16; r++) v[s][r] = buf[fpad(i + r * CFG::kQ)];
+    for (int r = 0; r < 16; r++) v[s][r] = src[r * (CFG::kQ + CFG::kQ / 16)];
   }
   __syncthreads();
 #pragma unroll
   for (int s = 0; s < CFG::kSets; s++) {
-    const int i = threadIdx.x + s * kFftThreads;
+    V *dst = buf + 17 * (threadIdx.x + s * kFftThreads);
     fft16(v[s]);
 #pragma unroll
-    for (int r = 0; r < 16; r++) buf[fpad(i * 16 + r)] = v[s][4 * (r & 3) + (r >> 2)];
+    for (int r = 0; r < 16; r++) dst[r] = v[s][4 * (r & 3) + (r >> 2)];
   }
   __syncthreads();
 }
 
 // One radix-16 Stockham pass over the whole buffer, in place: p = 16 or 256.
-template <typename CFG>
-__device__ __forceinline__ void pass16_smem(typename CFG::V *buf, const typename CFG::V *tw, int p) {
+template <typename CFG, int p>
+__device__ __forceinline__ void pass16_smem(typename CFG::V *buf, const typename CFG::V *tw) {
   using V = typename CFG::V;
-  const int scale = CFG::kN / (16 * p);
+  constexpr int scale = CFG::kN / (16 * p);
   V v[CFG::kSets][16];
 #pragma unroll
   for (int s = 0; s < CFG::kSets; s++) {
-    const int i = threadIdx.x + s * kFftThreads;
+    const V *src = buf + fpad(threadIdx.x + s * kFftThreads);
 #pragma unroll
-    for (int r = 0; r < 16; r++) v[s][r] = buf[fpad(i + r * CFG::kQ)];
+    for (int r = 0; r < 16; r++) v[s][r] = src[r * (CFG::kQ + CFG::kQ / 16)];
   }
   __syncthreads();
 #pragma unroll
@@ -161,8 +178,11 @@ __device__ __forceinline__ void pass16_smem(typename CFG::V *buf, const typename
     twiddle16(v[s], tw_lookup(tw, k * scale));
     fft16(v[s]);
     const int j = (i - k) * 16 + k;
+    // p is 16 or 256: fpad(j + r*p) = fpad(j) + r*(p + p/16)
+    V *dst = buf + fpad(j);
+    const int step = p + (p >> 4);
 #pragma unroll
-    for (int r = 0; r < 16; r++) buf[fpad(j + r * p)] = v[s][4 * (r & 3) + (r >> 2)];
+    for (int r = 0; r < 16; r++) dst[r * step] = v[s][4 * (r & 3) + (r >> 2)];
   }
   __syncthreads();
 }
@@ -174,10 +194,11 @@ __device__ __forceinline__ void last_pass_load(const typename CFG::V *buf, const
   using V = typename CFG::V;
   const V w1 = tw_lookup(tw, i);
   if (CFG::kR4 == 4) {
-    a[0] = buf[fpad(i)];
-    a[1] = buf[fpad(i + 4096)];
-    a[2] = buf[fpad(i + 8192)];
-    a[3] = buf[fpad(i + 12288)];
+    const V *src = buf + fpad(i);
+    a[0] = src[0];
+    a[1] = src[4352];
+    a[2] = src[2 * 4352];
+    a[3] = src[3 * 4352];
     const V w2 = cmulv(w1, w1);
     a[1] = cmulv(a[1], w1);
     a[2] = cmulv(a[2], w2);
@@ -185,7 +206,7 @@ __device__ __forceinline__ void last_pass_load(const typename CFG::V *buf, const
     fft4(a[0], a[1], a[2], a[3]);
   } else {
     const V x0 = buf[fpad(i)];
-    const V x1 = cmulv(buf[fpad(i + 4096)], w1);
+    const V x1 = cmulv(buf[fpad(i) + 4352], w1);
     a[0] = cmk<V>(x0.x + x1.x, x0.y + x1.y);
     a[1] = cmk<V>(x0.x - x1.x, x0.y - x1.y);
     a[2] = a[0];
@@ -272,15 +293,15 @@ __global__ void __launch_bounds__(kFftThreads, 1)
     }
 #pragma unroll
     for (int s = 0; s < CFG::kSets; s++) {
-      const int i = threadIdx.x + s * kFftThreads;
+      V *dst = buf + 17 * (threadIdx.x + s * kFftThreads);
       fft16(v[s]);
 #pragma unroll
-      for (int r = 0; r < 16; r++) buf[fpad(i * 16 + r)] = v[s][4 * (r & 3) + (r >> 2)];
+      for (int r = 0; r < 16; r++) dst[r] = v[s][4 * (r & 3) + (r >> 2)];
     }
     __syncthreads();
   }
-  pass16_smem<CFG>(buf, tw, 16);
-  pass16_smem<CFG>(buf, tw, 256);
+  pass16_smem<CFG, 16>(buf, tw);
+  pass16_smem<CFG, 256>(buf, tw);
   // ---- forward last pass fused with Y = conj(X * H)
 #pragma unroll 2
   for (int b = 0; b < 4096 / kFftThreads; b++) {
@@ -288,13 +309,13 @@ __global__ void __launch_bounds__(kFftThreads, 1)
     V a[4];
     last_pass_load<CFG>(buf, tw, i, a);
 #pragma unroll
-    for (int r = 0; r < CFG::kR4; r++) buf[fpad(i + r * 4096)] = cconjv(cmulv(a[r], H[i + r * 4096]));
+    for (int r = 0; r < CFG::kR4; r++) buf[fpad(i) + r * 4352] = cconjv(cmulv(a[r], H[i + r * 4096]));
   }
   __syncthreads();
   // ---- inverse = conj(FFT(conj(.)))
   pass16_first_smem<CFG>(buf);
-  pass16_smem<CFG>(buf, tw, 16);
-  pass16_smem<CFG>(buf, tw, 256);
+  pass16_smem<CFG, 16>(buf, tw);
+  pass16_smem<CFG, 256>(buf, tw);
   if (!FUSE) {
     // ---- inverse last pass, outputs straight to the global ring (only the alias-free part)
 #pragma unroll 2
@@ -325,7 +346,7 @@ __global__ void __launch_bounds__(kFftThreads, 1)
         const int n = i + r * 4096;
         const int64_t t = qb + (n - (klen - 1));
         const V y = (t >= 0) ? cconjv(a[r]) : cmk<V>(0, 0);
-        buf[fpad(n)] = y;
+        buf[fpad(i) + r * 4352] = y;
         if (t >= fz.tail_lo && t < fz.tail_hi && n >= klen - 1 && blk == (int)gridDim.x - 1) {
           Ring<V>{reinterpret_cast<V *>(fz.tail_base), fz.tail_cap}.st(c, t, y);
         }

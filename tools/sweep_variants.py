@@ -14,14 +14,9 @@ import bench  # noqa: E402
 
 VARIANTS = [
     # name, env, blocks per step, channels
-    ("tma1_r2s3w4", {"FMR_HBS_TMA": "1"}, 128, 8192),
-    ("tma5_r2s2w4", {"FMR_HBS_TMA": "5"}, 128, 8192),
-    ("tma6_r2s4w3", {"FMR_HBS_TMA": "6"}, 128, 8192),
-    ("tma7_r2s3w2", {"FMR_HBS_TMA": "7"}, 128, 8192),
-    ("tma1_tile1024", {"FMR_HBS_TMA": "1", "FMR_HBS_TILE": "1024"}, 128, 8192),
-    ("tma1_tile256", {"FMR_HBS_TMA": "1", "FMR_HBS_TILE": "256"}, 128, 8192),
-    ("tma1_c1024", {"FMR_HBS_TMA": "1"}, 128, 1024),
-    ("tma7_c1024", {"FMR_HBS_TMA": "7"}, 128, 1024),
+    ("all_on_128", {}, 128, 8192),
+    ("fi_unfused", {"FMR_FUSE_FI": "0"}, 128, 8192),
+    ("all_on_329", {}, 329, 8192),
 ]
 
 
