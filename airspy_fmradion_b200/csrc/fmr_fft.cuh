@@ -214,6 +214,50 @@ __device__ __forceinline__ void last_pass_load(const typename CFG::V *buf, const
   }
 }
 
+// Whole-step polyphase interpolator (r8b::CDSPFracInterpolator::convolve0) over one filtered block
+// in shared memory (plain order). Output i = p + outstep*q of the block has bank row
+// ph(p) = (p*instep + rem) mod outstep and its window starts instep*q samples after that of
+// output p. So the warp fixes p — one bank row, loaded once into registers and shared by all
+// lanes — and spreads q over the lanes: consecutive lanes then read addresses `instep` elements
+// apart, and instep is odd for every shipped chain, i.e. conflict free. When a block holds fewer
+// than 32 periods the warp takes several p at once (G groups of L lanes).
+template <typename V, int FLEN>
+__device__ __forceinline__ void fi_epilogue(const V *__restrict__ buf, const decltype(V().x) *__restrict__ bank, int instep,
+                                            int outstep, int klen, int rem_b, int cnt, Ring<V> out, uint32_t c, int64_t mb) {
+  using S = decltype(V().x);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kFftThreads / 32;
+  const int nq = (cnt + outstep - 1) / outstep;
+  const int L = nq < 32 ? nq : 32;
+  const int G = 32 / L;
+  const int sgrp = lane / L, ql = lane - sgrp * L;
+  if (sgrp >= G) return;
+  for (int pg = warp * G; pg < outstep; pg += nwarps * G) {
+    const int p = pg + sgrp;
+    if (p >= outstep) continue;
+    const int pp = p * instep + rem_b;
+    const int dp = pp / outstep;
+    const int ph = pp - dp * outstep;
+    const S *__restrict__ row = bank + (size_t)ph * FLEN;
+    S h[FLEN];
+#pragma unroll
+    for (int k = 0; k < FLEN; k++) h[k] = __ldg(row + k);
+    for (int q = ql; q < nq; q += L) {
+      const int i = p + outstep * q;
+      if (i < cnt) {
+        const V *__restrict__ w = buf + (klen - 1) + dp + instep * q;
+        V acc = cmk<V>(0, 0);
+#pragma unroll
+        for (int k = 0; k < FLEN; k++) {
+          const V x = w[k];
+          acc.x += h[k] * x.x;
+          acc.y += h[k] * x.y;
+        }
+        out.st(c, mb + i, acc);
+      }
+    }
+  }
+}
+
 struct FftFuse {
   const void *bank; // [outstep][flen] interpolator bank, scalar type of the chain
   int instep, outstep, flen;
@@ -234,7 +278,7 @@ struct FftFuse {
 //          it holds (down must be 1); samples with negative index read as zero like the ring does.
 //   n_in_avail: number of valid input samples in the ring (indices >= it read as zero)
 template <typename S, int N, bool FUSE>
-__global__ void __launch_bounds__(kFftThreads, 1)
+__global__ void __launch_bounds__(kFftThreads, (N == 8192 && sizeof(S) == 4) ? 2 : 1)
     k_fir_fft(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out, const typename V2<S>::type *__restrict__ H,
               int klen, int down, int64_t q0, int n_out, int64_t n_in_avail, int lq, FftFuse fz) {
   using CFG = FftCfg<S, N>;
@@ -334,10 +378,13 @@ __global__ void __launch_bounds__(kFftThreads, 1)
       }
     }
   } else {
-    // ---- inverse last pass in place (slot n holds filter output qb + n - (klen-1)), then the
-    // polyphase interpolator straight from shared memory
-#pragma unroll 2
-    for (int b = 0; b < 4096 / kFftThreads; b++) {
+    // ---- inverse last pass into registers, then back to shared memory in PLAIN order (slot n
+    // holds filter output qb + n - (klen-1)): the interpolator below reads windows whose start
+    // advances by `instep` per lane, which is conflict free only without the FFT's skew
+    constexpr int NB = 4096 / kFftThreads;
+    V y[NB][CFG::kR4];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
       const int i = threadIdx.x + b * kFftThreads;
       V a[4];
       last_pass_load<CFG>(buf, tw, i, a);
@@ -345,33 +392,42 @@ __global__ void __launch_bounds__(kFftThreads, 1)
       for (int r = 0; r < CFG::kR4; r++) {
         const int n = i + r * 4096;
         const int64_t t = qb + (n - (klen - 1));
-        const V y = (t >= 0) ? cconjv(a[r]) : cmk<V>(0, 0);
-        buf[fpad(i) + r * 4352] = y;
+        y[b][r] = (t >= 0) ? cconjv(a[r]) : cmk<V>(0, 0);
         if (t >= fz.tail_lo && t < fz.tail_hi && n >= klen - 1 && blk == (int)gridDim.x - 1) {
-          Ring<V>{reinterpret_cast<V *>(fz.tail_base), fz.tail_cap}.st(c, t, y);
+          Ring<V>{reinterpret_cast<V *>(fz.tail_base), fz.tail_cap}.st(c, t, y[b][r]);
         }
       }
     }
     __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+#pragma unroll
+      for (int r = 0; r < CFG::kR4; r++) buf[threadIdx.x + b * kFftThreads + r * 4096] = y[b][r];
+    }
+    __syncthreads();
     const S *__restrict__ bank = reinterpret_cast<const S *>(fz.bank);
-    const int64_t pos_b = mb * fz.instep;
-    const int64_t ip_b = pos_b / fz.outstep;
-    const int rem_b = (int)(pos_b - ip_b * fz.outstep);
-    // slot of the first tap of output mb: ip_b - (flen/2-1) - qb + klen-1 = klen-1
-    for (int i = threadIdx.x; i < cnt; i += kFftThreads) {
-      const int prel = i * fz.instep + rem_b;
-      const int dip = prel / fz.outstep;
-      const int ph = prel - dip * fz.outstep;
-      const S *__restrict__ row = bank + (size_t)ph * fz.flen;
-      const int n0 = (klen - 1) + dip;
-      V acc = cmk<V>(0, 0);
-      for (int k = 0; k < fz.flen; k++) {
-        const V x = buf[fpad(n0 + k)];
-        const S h = __ldg(row + k);
-        acc.x += h * x.x;
-        acc.y += h * x.y;
+    const int rem_b = (int)((mb * fz.instep) % fz.outstep);
+    if (fz.flen == 18) {
+      fi_epilogue<V, 18>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
+    } else if (fz.flen == 24) {
+      fi_epilogue<V, 24>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
+    } else {
+      // generic bank length: one output per thread, taps in a loop
+      for (int i = threadIdx.x; i < cnt; i += kFftThreads) {
+        const int prel = i * fz.instep + rem_b;
+        const int dip = prel / fz.outstep;
+        const int ph = prel - dip * fz.outstep;
+        const S *__restrict__ row = bank + (size_t)ph * fz.flen;
+        const int n0 = (klen - 1) + dip;
+        V acc = cmk<V>(0, 0);
+        for (int k = 0; k < fz.flen; k++) {
+          const V x = buf[n0 + k];
+          const S h = __ldg(row + k);
+          acc.x += h * x.x;
+          acc.y += h * x.y;
+        }
+        out.st(c, mb + i, acc);
       }
-      out.st(c, mb + i, acc);
     }
   }
 }

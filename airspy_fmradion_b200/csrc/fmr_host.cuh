@@ -381,7 +381,9 @@ template <typename S> struct Resampler {
   static void fft_plan(int n, int per16, int per8, bool have16, int *nb16, int *nb8) {
     *nb16 = 0;
     *nb8 = 0;
-    if (!have16 || per16 <= 0) {
+    const char *fn = getenv("FMR_FFT_N");
+    const bool force8 = fn && atoi(fn) == 8192;
+    if (!have16 || per16 <= 0 || force8) {
       *nb8 = (n + per8 - 1) / per8;
       return;
     }
