@@ -76,9 +76,13 @@ static __global__ void __launch_bounds__(kCfThreads)
     k_fm_core_fused(Ring<float2> if_raw, Ring<float2> iq_in, Ring<double2> out384, FmChanState *__restrict__ st,
                     uint8_t *__restrict__ flags, PpsEventDev *__restrict__ pps, const uint32_t *__restrict__ call_end,
                     int n_calls, int64_t t0, FmCoreParams P, const float *__restrict__ atan_tbl, int block_off,
-                    int reset_pps) {
+                    int reset_pps, int sm_count) {
   __shared__ CfSmem S;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rot = (int)(blockIdx.x / (unsigned)sm_count); // CTAs b and b + #SMs tend to share an SM
+  // Role of this warp. Hardware warp w of a CTA issues on SM sub-partition w % 4; CTAs that share
+  // an SM rotate the roles so that their PLL warps (the critical recurrence) do not queue on the
+  // same scheduler.
+  const int lane = threadIdx.x & 31, warp = ((threadIdx.x >> 5) + rot) & 3;
   for (int i = threadIdx.x; i < 256; i += kCfThreads) S.tab[i] = make_float2(atan_tbl[i], atan_tbl[i + 1] - atan_tbl[i]);
   __syncthreads();
   const int c_raw = blockIdx.x * 32 + lane;

@@ -72,6 +72,7 @@ struct fmr_fm {
   int want_serial_sms = 0;
   bool serial_v2 = true;  // FMR_SERIAL_V2=0: the first-generation AGC / PLL kernels
   bool core_fused = true; // FMR_CORE_FUSED=0: AGC / discriminator / PLL as separate launches
+  int rot_sms = 148;      // FMR_CORE_ROT=0 disables the per-CTA rotation of warp roles in the fused core
   int C = 0;
   const ChainDesc *ifc = nullptr; // null when input_rate == 384000 (no IfResampler, main.cpp:778)
   const ChainDesc *auc = nullptr;
@@ -346,6 +347,13 @@ extern "C" fmr_status fmr_fm_create(const fmr_fm_config *cfg, fmr_fm **out) {
   if (const char *e = getenv("FMR_SERIAL_SMS")) h->want_serial_sms = std::max(0, atoi(e));
   if (const char *e = getenv("FMR_SERIAL_V2")) h->serial_v2 = atoi(e) != 0;
   if (const char *e = getenv("FMR_CORE_FUSED")) h->core_fused = atoi(e) != 0;
+  {
+    int sms = fmr_device_sm_count(cfg->device);
+    h->rot_sms = sms > 0 ? sms : 148;
+    if (const char *e = getenv("FMR_CORE_ROT")) {
+      if (atoi(e) == 0) h->rot_sms = 1 << 30;
+    }
+  }
   fmr_status s = fm_build(h);
   if (s != FMR_OK) {
     std::string keep = g_err;
@@ -632,7 +640,7 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
       pf.begin(h->p_fused, sB);
       k_fm_core_fused<<<fgrid, kCfThreads, 0, sB>>>(h->r_if, h->r_iff, h->r_384, h->d_state, d_flags, h->d_pps, d_e384,
                                                    (int)nb, t0k, h->core, h->d_atan, (int)(flag_b0 + b0),
-                                                   (k == 0 && flag_b0 == 0) ? 1 : 0);
+                                                   (k == 0 && flag_b0 == 0) ? 1 : 0, h->rot_sms);
       pf.end(h->p_fused, sB);
       launches++;
     } else {

@@ -15,9 +15,10 @@ import bench  # noqa: E402
 VARIANTS = [
     # name, env, blocks per step, channels
     ("all_on_128", {}, 128, 8192),
-    ("fft8192", {"FMR_FFT_N": "8192"}, 128, 8192),
+    ("no_rot", {"FMR_CORE_ROT": "0"}, 128, 8192),
+    ("serial_v1_tail", {"FMR_SERIAL_V2": "0"}, 128, 8192),
     ("all_on_329", {}, 329, 8192),
-    ("fft8192_329", {"FMR_FFT_N": "8192"}, 329, 8192),
+    ("all_on_128_c16384", {}, 128, 16384),
 ]
 
 
@@ -38,7 +39,7 @@ def main():
     iq = bench.gen_iq_device(torch, dev, fs, Cgen, Tmax, mode)
     stream = torch.cuda.current_stream()
     for name, env, nblk, C in variants:
-        for k in ("FMR_HB_STREAM", "FMR_FUSE_FI", "FMR_FFT_F64", "FMR_HBS_TILE", "FMR_FFT", "FMR_SERIAL_V2", "FMR_TIME_CHUNKS", "FMR_SERIAL_SMS", "FMR_CORE_FUSED", "FMR_HBS_STAGES", "FMR_HBS_L2PF", "FMR_HBS_TMA", "FMR_FFT_N"):
+        for k in ("FMR_HB_STREAM", "FMR_FUSE_FI", "FMR_FFT_F64", "FMR_HBS_TILE", "FMR_FFT", "FMR_SERIAL_V2", "FMR_TIME_CHUNKS", "FMR_SERIAL_SMS", "FMR_CORE_FUSED", "FMR_HBS_STAGES", "FMR_HBS_L2PF", "FMR_HBS_TMA", "FMR_FFT_N", "FMR_CORE_ROT"):
             os.environ.pop(k, None)
         os.environ.update(env)
         C = min(C, Cgen)
