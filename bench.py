@@ -7,7 +7,10 @@
 
 A "step" is one pass of the hot path over one batch of synthetic IQ: every channel of the
 handle consumes `--blocks` source blocks of 2048 samples (FileSource's default block,
-FileSource.h:34). Streams are continuous across steps (filter/PLL/AGC state carries over).
+FileSource.h:34) handed over as one super-block with its block partition. The default of 329
+blocks (673 792 samples, 67 ms of signal per channel) makes the overlap-save blocks of both
+resamplers come out whole (6 x 16384-point IF blocks, 1 x 8192-point audio block per channel).
+Streams are continuous across steps (filter/PLL/AGC state carries over).
 Metric = IQ Msamples/s consumed, summed over channels and GPUs (BASELINE.json).
 Prints ONE JSON line on rank 0.
 """
@@ -161,7 +164,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2_fm_stereo_10Msps", choices=sorted(WORKLOADS))
     ap.add_argument("--channels", type=int, default=0, help="channels per GPU (default per workload)")
-    ap.add_argument("--blocks", type=int, default=128, help="source blocks of 2048 samples per channel per step")
+    ap.add_argument("--blocks", type=int, default=329, help="source blocks of 2048 samples per channel per step")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu", action="store_true")
@@ -268,18 +271,32 @@ def main():
     peak, peak_src = peaks()
     alg_bytes = C * T * 8 + C * int(lens.sum()) * 8  # IQ read + audio written, per launch/step
     roof = None
-    traffic = None
-    try:  # DRAM bytes per input sample of the dominant kernel from the committed ncu capture
+    tj = {}
+    try:  # DRAM bytes per input sample of the profiled kernels from the committed ncu captures
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
-        if dom in tj:
-            traffic = tj[dom]["bytes_per_input_sample"] * C * T
     except Exception:
-        traffic = None
+        tj = {}
+
+    def traffic_of(name):
+        e = tj.get(name)
+        return e["bytes_per_input_sample"] * C * T if isinstance(e, dict) and "bytes_per_input_sample" in e else None
+
     if dom:
         ach = alg_bytes / (stage[dom] * 1e-3) / 1e9
+        # the same arithmetic for every stage that takes more than 10 % of the step, so that the kernel
+        # that actually streams the input from HBM (if_halfband_cascade) is always listed
+        per_stage = {}
+        tot = sum(stage.values())
+        for k, v in stage.items():
+            if v >= 0.1 * tot:
+                a = alg_bytes / (v * 1e-3) / 1e9
+                per_stage[k] = {"ms": round(v, 4), "achieved": round(a, 1), "frac": round(a / peak, 4),
+                                "traffic": traffic_of(k)}
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "kernel_ms": stage[dom],
+                "traffic": traffic_of(dom), "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "kernel_ms": stage[dom],
                 "whole_step_frac": (alg_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
+                "stages": per_stage,
                 "stage_ms": {k: round(v, 4) for k, v in stage.items()}}
 
     # end to end through the host-buffer entry point (pinned host memory, H2D + D2H inside)
