@@ -46,12 +46,13 @@ class AmConfig(C.Structure):
     _fields_ = [("input_rate", C.c_double), ("fs4_shift", C.c_int), ("amfilter", C.c_int),
                 ("mode", C.c_int), ("n_channels", C.c_uint32), ("max_samples_per_call", C.c_uint32),
                 ("max_blocks_per_call", C.c_uint32), ("device", C.c_int), ("amfilter_coeff", C.c_void_p),
-                ("amfilter_ntaps", C.c_uint32)]
+                ("amfilter_ntaps", C.c_uint32), ("nbfm_freq_dev", C.c_double)]
 
 
 class AmStats(C.Structure):
     _fields_ = [("baseband_level", C.c_double), ("af_agc_gain", C.c_float),
-                ("if_agc_gain", C.c_float), ("if_rms", C.c_float), ("decoder_calls", C.c_uint64)]
+                ("if_agc_gain", C.c_float), ("if_rms", C.c_float), ("decoder_calls", C.c_uint64),
+                ("tuning_offset", C.c_float)]
 
 
 # every symbol include/fmradion_b200.h declares

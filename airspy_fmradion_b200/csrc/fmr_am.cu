@@ -1,5 +1,6 @@
-// fmr_am.cu — AM handle: FourthConverterIQ -> IfResampler -> AmDecoder::process for
-// ModType::AM (main.cpp:912-971, AmDecode.cpp:96-218), many channels per launch.
+// fmr_am.cu — the 48 kHz decoders: FourthConverterIQ -> IfResampler -> AmDecoder::process for
+// ModType::AM (main.cpp:912-971, AmDecode.cpp:96-218) and NbfmDecoder::process for ModType::NBFM
+// (main.cpp:959-962, NbfmDecode.cpp:47-96), many channels per launch.
 #include <complex>
 #include <cmath>
 
@@ -12,6 +13,7 @@ namespace {
 struct AmChanState {
   float if_gain;                          // IfSimpleAgc m_current_gain
   float baseband_mean, baseband_level, if_rms;
+  float disc_prev;                        // NBFM: PhaseDiscriminator m_save_value
   double af_gain;                         // AfSimpleAgc m_current_gain
   double dc_x1, dc_x2;                    // HighPassFilterIir delay line
   double de_x1;                           // LowPassFilterRC delay line
@@ -99,6 +101,79 @@ __global__ void k_am_core(Ring<float2> in, double *__restrict__ audio, size_t au
   st[c] = s;
 }
 
+struct NbfmCoreParams {
+  float if_max, if_rate;         // IfSimpleAgc(1.0, 100000.0, 0.0001)  NbfmDecode.cpp:43
+  float disc_inv_norm, disc_bound; // PhaseDiscriminator(freq_dev / 48000) NbfmDecode.cpp:35, PhaseDiscriminator.cpp:27-30
+  int n_channels;
+};
+
+// NbfmDecoder::process between the IF filter and the audio filter (NbfmDecode.cpp:54-86): IF RMS of
+// the filtered block, IF AGC, phase discriminator, float -> double, baseband mean / RMS with their
+// EMA. The AGC is a serial recurrence at 48 kHz, so one lane per channel runs the lot; the MPX goes
+// out as the real part of a double2 stream for the audio FIR kernel.
+__global__ void k_nbfm_core(Ring<float2> in, Ring<double2> bb, AmChanState *__restrict__ st,
+                            const uint32_t *__restrict__ call_end, int n_calls, int64_t t0, NbfmCoreParams P) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.n_channels) return;
+  AmChanState s = st[c];
+  uint32_t prev_end = 0;
+  for (int b = 0; b < n_calls; b++) {
+    const uint32_t end = call_end[b];
+    const int n = (int)(end - prev_end);
+    if (n == 0) continue; // main.cpp:933-936: the decoder is not called
+    const int64_t tb = t0 + prev_end;
+    prev_end = end;
+    s.decoder_calls++;
+    float sumsq = 0.f, vsum = 0.f, vsq = 0.f;
+    for (int i0 = 0; i0 < n; i0 += kCoreChunk) {
+      float2 xin[kCoreChunk];
+#pragma unroll
+      for (int u = 0; u < kCoreChunk; u++) xin[u] = (i0 + u < n) ? in.ld(c, tb + i0 + u) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kCoreChunk; u++) {
+        const int i = i0 + u;
+        if (i >= n) break;
+        const float2 x = xin[u];
+        sumsq += x.x * x.x + x.y * x.y; // Utility::rms_level_sample on the filtered block (NbfmDecode.cpp:54)
+        // IfSimpleAgc::process (IfSimpleAgc.cpp:37-57)
+        const float xr = x.x * s.if_gain, xi = x.y * s.if_gain;
+        const float nrm = xr * xr + xi * xi;
+        const float z = (float)(1.0 + ((double)P.if_rate * (1.0 - (double)nrm)));
+        s.if_gain *= z;
+        if (!isfinite(s.if_gain)) {
+          s.if_gain = 1.0f;
+        } else if (s.if_gain > P.if_max) {
+          s.if_gain = P.if_max;
+        }
+        // PhaseDiscriminator::process (PhaseDiscriminator.cpp:33-46)
+        const float ph = atan2f(xi, xr) * P.disc_inv_norm;
+        float d = ph - s.disc_prev;
+        s.disc_prev = ph;
+        if (d > P.disc_bound) d -= 2 * P.disc_bound;
+        if (d < -P.disc_bound) d += 2 * P.disc_bound;
+        if (isnan(d)) d = 0.0f;
+        vsum += d;
+        vsq += d * d;
+        bb.st(c, tb + i, make_double2((double)d, 0.0));
+      }
+    }
+    s.if_rms = sqrtf(sumsq / (float)n);
+    const float mean = vsum / (float)n, rms = sqrtf(vsq / (float)n); // samples_mean_rms, NbfmDecode.cpp:83-86
+    s.baseband_mean = (float)(0.95 * (double)s.baseband_mean + 0.05 * (double)mean);
+    s.baseband_level = (float)(0.95 * (double)s.baseband_level + 0.05 * (double)rms);
+  }
+  st[c] = s;
+}
+
+// audio = filtered baseband * 10^(-3/20) (NbfmDecode.cpp:92-96), thread per output sample
+__global__ void k_nbfm_out(Ring<double2> in, double *__restrict__ audio, size_t audio_stride, int64_t t0, int n,
+                           double gain) {
+  const uint32_t c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  audio[(size_t)c * audio_stride + i] = in.ld(c, t0 + i).x * gain;
+}
+
 } // namespace
 
 struct fmr_am {
@@ -120,6 +195,14 @@ struct fmr_am {
   Prof prof;
   int p_hist = -1, p_flt = -1, p_core = -1;
   AmCoreParams core;
+  // NBFM (mode 1)
+  bool nbfm = false;
+  NbfmCoreParams ncore;
+  double freq_dev = 8000.0;
+  Ring<double2> r_bb{nullptr, 0};  // discriminator output as double
+  Ring<double2> r_aud{nullptr, 0}; // after the audio FIR
+  double *d_audiofilter = nullptr;
+  int p_aud = -1, p_out = -1;
   int64_t cum_in = 0, cum48 = 0;
   uint32_t last_launches = 0;
   float *d_iq = nullptr;
@@ -154,7 +237,10 @@ static fmr_status am_build(fmr_am *h) {
   const int C = h->C = (int)cfg.n_channels;
   const int64_t max_in = cfg.max_samples_per_call;
   const int max_blocks = (int)cfg.max_blocks_per_call;
-  if (cfg.mode != 2) return fail(FMR_ERR_UNSUPPORTED, "only ModType::AM (2) is implemented");
+  if (cfg.mode != 2 && cfg.mode != 1) {
+    return fail(FMR_ERR_UNSUPPORTED, "only ModType::AM (2) and ModType::NBFM (1) are implemented");
+  }
+  h->nbfm = (cfg.mode == 1);
   if (cfg.input_rate != 48000.0) {
     h->ifc = find_chain(cfg.input_rate, 48000.0, 0);
     if (!h->ifc) return fail(FMR_ERR_UNSUPPORTED, "no resampler tables for this input_rate -> 48000");
@@ -186,6 +272,13 @@ static fmr_status am_build(fmr_am *h) {
     if (cfg.amfilter == 3) {
       tbl = k_jj1bdx_am_48khz_wide;
       h->amfilter_taps = 127;
+    }
+    if (h->nbfm) {
+      h->amfilter_taps = 127;
+      tbl = k_jj1bdx_nbfm_48khz_default;
+      if (cfg.amfilter == 1) tbl = k_jj1bdx_nbfm_48khz_medium;
+      if (cfg.amfilter == 2) tbl = k_jj1bdx_nbfm_48khz_narrow;
+      if (cfg.amfilter == 3) tbl = k_jj1bdx_nbfm_48khz_wide;
     }
     if (cfg.amfilter == 4) {
       if (!cfg.amfilter_coeff || cfg.amfilter_ntaps < 2 || cfg.amfilter_ntaps > 4096) {
@@ -237,6 +330,24 @@ static fmr_status am_build(fmr_am *h) {
     P.de_b0 = 1 + P.de_a1;
   }
   P.n_channels = C;
+  if (h->nbfm) {
+    h->freq_dev = cfg.nbfm_freq_dev > 0 ? cfg.nbfm_freq_dev : 8000.0; // NbfmDecoder::freq_dev_normal
+    NbfmCoreParams &N = h->ncore;
+    N.if_max = 100000.0f;
+    N.if_rate = 0.0001f;
+    const double max_freq_dev = h->freq_dev / 48000.0; // NbfmDecode.cpp:35
+    N.disc_inv_norm = 1.0f / (float)(max_freq_dev * 2.0 * M_PI);
+    N.disc_bound = (float)(1.0 / (max_freq_dev * 2.0));
+    N.n_channels = C;
+    h->r_bb.cap = h->r_if.cap;
+    FMR_CUDA(h->mem.alloc(&h->r_bb.base, (size_t)C * h->r_bb.cap));
+    h->r_aud.cap = h->r_if.cap;
+    FMR_CUDA(h->mem.alloc(&h->r_aud.base, (size_t)C * h->r_aud.cap));
+    FMR_CUDA(h->mem.alloc(&h->d_audiofilter, 63, false));
+    FMR_CUDA(cudaMemcpy(h->d_audiofilter, k_jj1bdx_48khz_nbfmaudio, 63 * sizeof(double), cudaMemcpyHostToDevice));
+    FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fq_smem(63, sizeof(double2), sizeof(double))));
+  }
   h->audio_cap = (size_t)max48;
   h->ifres.prof = &h->prof;
   h->ifres.p_hb = h->prof.add("if_halfband_cascade");
@@ -244,7 +355,9 @@ static fmr_status am_build(fmr_am *h) {
   h->ifres.p_fi = h->prof.add("if_polyphase");
   h->p_hist = h->prof.add("save_hist");
   h->p_flt = h->prof.add("am_channel_filter");
-  h->p_core = h->prof.add("am_core_48k");
+  h->p_core = h->prof.add(h->nbfm ? "nbfm_core_48k" : "am_core_48k");
+  h->p_aud = h->prof.add("nbfm_audio_fir");
+  h->p_out = h->prof.add("nbfm_gain_out");
   return FMR_OK;
 }
 
@@ -367,10 +480,25 @@ extern "C" fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t
                                              h->d_e48, (int)n_blocks);
     pf.end(h->p_flt, st);
     pf.begin(h->p_core, st);
-    k_am_core<<<(C + 31) / 32, 32, 0, st>>>(h->r_flt, d_audio, audio_stride, h->d_state, h->d_e48, (int)n_blocks, t0,
-                                            h->core);
-    pf.end(h->p_core, st);
-    launches += 2;
+    if (h->nbfm) {
+      k_nbfm_core<<<(C + 31) / 32, 32, 0, st>>>(h->r_flt, h->r_bb, h->d_state, h->d_e48, (int)n_blocks, t0, h->ncore);
+      pf.end(h->p_core, st);
+      // LowPassFilterFirAudio (jj1bdx_48khz_nbfmaudio, 63 taps, per-call head loop), NbfmDecode.cpp:89
+      pf.begin(h->p_aud, st);
+      k_fir_quirk<double><<<grid, kQThreads, fq_smem(63, sizeof(double2), sizeof(double)), st>>>(
+          h->r_bb, h->r_aud, h->d_audiofilter, 63, t0, (int)n48, h->d_e48, (int)n_blocks);
+      pf.end(h->p_aud, st);
+      pf.begin(h->p_out, st);
+      dim3 og((n48 + 255) / 256, C);
+      k_nbfm_out<<<og, 256, 0, st>>>(h->r_aud, d_audio, audio_stride, t0, (int)n48, std::pow(10.0, (-3.0 / 20.0)));
+      pf.end(h->p_out, st);
+      launches += 4;
+    } else {
+      k_am_core<<<(C + 31) / 32, 32, 0, st>>>(h->r_flt, d_audio, audio_stride, h->d_state, h->d_e48, (int)n_blocks, t0,
+                                              h->core);
+      pf.end(h->p_core, st);
+      launches += 2;
+    }
   }
   FMR_CUDA(cudaGetLastError());
   h->cum_in += (int64_t)total_in;
@@ -424,6 +552,7 @@ extern "C" fmr_status fmr_am_stats(fmr_am *h, uint32_t channel, fmr_am_stats_t *
   out->if_agc_gain = s.if_gain;
   out->if_rms = s.if_rms;
   out->decoder_calls = s.decoder_calls;
+  out->tuning_offset = h->nbfm ? (float)(s.baseband_mean * h->freq_dev) : 0.0f; // NbfmDecode.h:59
   return FMR_OK;
 }
 

@@ -217,7 +217,8 @@ class AmDecoder(_Base):
             amfilter = 4
         cfg = _capi.AmConfig(float(input_rate), int(fs4_shift), int(amfilter), int(mode), int(n_channels),
                              int(max_samples_per_call), int(max_blocks_per_call), int(device),
-                             coeff.ctypes.data if coeff is not None else None, len(coeff) if coeff is not None else 0)
+                             coeff.ctypes.data if coeff is not None else None, len(coeff) if coeff is not None else 0,
+                             float(getattr(self, "_freq_dev", 0.0)))
         h = C.c_void_p()
         check(L.fmr_am_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -241,3 +242,24 @@ class AmDecoder(_Base):
 
     def last_launches(self):
         return int(_capi.lib().fmr_am_last_launches(self._h))
+
+
+class NbfmDecoder(AmDecoder):
+    """Mirror of the reference's NbfmDecoder (include/NbfmDecode.h:30-63): narrow-band FM at 48 kHz,
+    mono audio. Same handle type as AmDecoder on the C side (mode = ModType::NBFM)."""
+    sample_rate_pcm = 48000.0
+    internal_rate_pcm = 48000.0
+    freq_dev_normal = 8000.0   # include/NbfmDecode.h:38
+    freq_dev_wide = 17000.0    # include/NbfmDecode.h:41
+    MODTYPE_NBFM = 1           # include/SoftFM.h:49
+
+    def __init__(self, nbfmfilter=0, freq_dev=8000.0, *, input_rate=48000.0, fs4_shift=False, n_channels=1,
+                 max_samples_per_call=1 << 20, max_blocks_per_call=4096, device=0, nbfmfilter_coeff=None):
+        """nbfmfilter: 0 default, 1 medium, 2 narrow, 3 wide (main.cpp:785-810); freq_dev: full-scale deviation, Hz."""
+        self._freq_dev = float(freq_dev)
+        super().__init__(nbfmfilter, self.MODTYPE_NBFM, input_rate=input_rate, fs4_shift=fs4_shift,
+                         n_channels=n_channels, max_samples_per_call=max_samples_per_call,
+                         max_blocks_per_call=max_blocks_per_call, device=device, amfilter_coeff=nbfmfilter_coeff)
+
+    def get_tuning_offset(self, channel=0):
+        return self.stats(channel).tuning_offset

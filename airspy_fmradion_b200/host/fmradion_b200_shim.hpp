@@ -151,7 +151,7 @@ public:
   static constexpr double bandwidth_pcm = 4500;
   static constexpr double deemphasis_time = 100;
 
-  // Arguments as include/AmDecode.h:42-48. Only ModType::AM is implemented on the GPU.
+  // Arguments as include/AmDecode.h:42-48. ModType::AM is implemented on the GPU (NBFM: see NbfmDecoder).
   AmDecoder(IQSampleCoeff &amfilter_coeff, const ModType mode, double input_rate = internal_rate_pcm,
             bool fs4_shift = false, int device = 0) {
     fmr_am_config cfg{};
@@ -189,6 +189,58 @@ public:
   double get_baseband_level() const { return m_stats.baseband_level; }
   float get_af_agc_current_gain() const { return m_stats.af_agc_gain; }
   float get_if_agc_current_gain() const { return m_stats.if_agc_gain; }
+  float get_if_rms() const { return m_stats.if_rms; }
+
+private:
+  fmr_am *m_h = nullptr;
+  fmr_am_stats_t m_stats{};
+};
+
+// Narrow-band FM decoder with the reference's interface (include/NbfmDecode.h:30-63).
+class NbfmDecoder {
+public:
+  static constexpr double sample_rate_pcm = 48000;
+  static constexpr double internal_rate_pcm = 48000;
+  static constexpr double freq_dev_normal = 8000;
+  static constexpr double freq_dev_wide = 17000;
+
+  NbfmDecoder(IQSampleCoeff &nbfmfilter_coeff, const double freq_dev, double input_rate = internal_rate_pcm,
+              bool fs4_shift = false, int device = 0) {
+    fmr_am_config cfg{};
+    cfg.input_rate = input_rate;
+    cfg.fs4_shift = fs4_shift ? 1 : 0;
+    cfg.amfilter = 4; // caller-supplied coefficients
+    cfg.amfilter_coeff = nbfmfilter_coeff.data();
+    cfg.amfilter_ntaps = (uint32_t)nbfmfilter_coeff.size();
+    cfg.mode = static_cast<int>(ModType::NBFM);
+    cfg.nbfm_freq_dev = freq_dev;
+    cfg.n_channels = 1;
+    cfg.max_samples_per_call = 65536;
+    cfg.max_blocks_per_call = 1;
+    cfg.device = device;
+    fmr_b200_detail::check(fmr_am_create(&cfg, &m_h));
+  }
+  ~NbfmDecoder() { fmr_am_destroy(m_h); }
+  NbfmDecoder(const NbfmDecoder &) = delete;
+  NbfmDecoder &operator=(const NbfmDecoder &) = delete;
+
+  void process(const IQSampleVector &samples_in, SampleVector &audio) {
+    const uint32_t n = (uint32_t)samples_in.size();
+    if (n == 0) {
+      audio.resize(0);
+      return;
+    }
+    uint64_t total = 0;
+    fmr_b200_detail::check(fmr_am_query_output(m_h, &n, 1, &total, nullptr));
+    audio.resize(total ? (size_t)total : 1);
+    uint32_t len = 0;
+    fmr_b200_detail::check(fmr_am_process_host(m_h, reinterpret_cast<const float *>(samples_in.data()), n, &n, 1,
+                                               audio.data(), audio.size(), &len));
+    audio.resize((size_t)total);
+    fmr_b200_detail::check(fmr_am_stats(m_h, 0, &m_stats));
+  }
+  float get_tuning_offset() const { return m_stats.tuning_offset; }
+  float get_baseband_level() const { return (float)m_stats.baseband_level; }
   float get_if_rms() const { return m_stats.if_rms; }
 
 private:

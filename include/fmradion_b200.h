@@ -162,7 +162,11 @@ uint32_t fmr_fm_last_launches(fmr_fm *h);
 fmr_status fmr_fm_set_profiling(fmr_fm *h, int enable);
 fmr_status fmr_fm_stage_times(fmr_fm *h, float *ms, const char **names, uint32_t cap, uint32_t *n);
 
-/* ------------------------------------------------------------------------- AM ------- */
+/* ------------------------------------------------------ AM and narrow-band FM ------- */
+/* One handle type serves the two 48 kHz decoders of the reference:
+ *   mode 2 (ModType::AM)   AmDecoder::process    include/AmDecode.h:48-65, sfmbase/AmDecode.cpp:96-218
+ *   mode 1 (ModType::NBFM) NbfmDecoder::process  include/NbfmDecode.h:43-63, sfmbase/NbfmDecode.cpp:47-96
+ * both behind FourthConverterIQ + IfResampler(input_rate -> 48 kHz) exactly as main.cpp:912-971 runs them. */
 
 typedef struct fmr_am fmr_am;
 
@@ -171,21 +175,25 @@ typedef struct fmr_am_config {
   int fs4_shift;
   int amfilter;         /* 0 default, 1 medium, 2 narrow, 3 wide (main.cpp:785-810),
                            4 = amfilter_coeff[amfilter_ntaps] (AmDecoder ctor `amfilter_coeff`) */
-  int mode;             /* ModType value; only 2 (AM) is implemented */
+  int mode;             /* ModType value (include/SoftFM.h:49): 1 = NBFM, 2 = AM; others FMR_ERR_UNSUPPORTED.
+                           For NBFM `amfilter` selects jj1bdx_nbfm_48khz_{default,medium,narrow,wide}
+                           (main.cpp:785-810) or, with 4, the caller's `amfilter_coeff` (ctor `nbfmfilter_coeff`) */
   uint32_t n_channels;
   uint32_t max_samples_per_call;
   uint32_t max_blocks_per_call;
   int device;
   const float *amfilter_coeff; /* used when amfilter == 4 */
   uint32_t amfilter_ntaps;
+  double nbfm_freq_dev; /* NBFM: full-scale deviation in Hz (NbfmDecoder ctor `freq_dev`); 0 = freq_dev_normal = 8000 */
 } fmr_am_config;
 
 typedef struct fmr_am_stats_t {
   double baseband_level;  /* AmDecoder::get_baseband_level()        */
   float af_agc_gain;      /* AmDecoder::get_af_agc_current_gain()   */
   float if_agc_gain;      /* AmDecoder::get_if_agc_current_gain()   */
-  float if_rms;           /* AmDecoder::get_if_rms()                */
+  float if_rms;           /* AmDecoder::get_if_rms() / NbfmDecoder::get_if_rms() */
   uint64_t decoder_calls;
+  float tuning_offset;    /* NbfmDecoder::get_tuning_offset() (0 for AM) */
 } fmr_am_stats_t;
 
 fmr_status fmr_am_create(const fmr_am_config *cfg, fmr_am **out);

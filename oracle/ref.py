@@ -29,6 +29,9 @@ def lib():
         L.ref_fm_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint]
         L.ref_am_create.restype = C.c_void_p
         L.ref_am_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int]
+        L.ref_nbfm_create.restype = C.c_void_p
+        L.ref_nbfm_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_double]
+        L.ref_nbfm_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_destroy.argtypes = [C.c_void_p]
         L.ref_process_block.restype = C.c_int
         L.ref_process_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -71,19 +74,27 @@ class AmStats(C.Structure):
                 ("if_agc_gain", C.c_float), ("if_rms", C.c_float), ("decoder_calls", C.c_uint64)]
 
 
-MODTYPE_AM = 2  # include/SoftFM.h:56 enum class ModType { FM, NBFM, AM, ... }
+class NbfmStats(C.Structure):
+    _fields_ = [("tuning_offset", C.c_float), ("baseband_level", C.c_float), ("if_rms", C.c_float),
+                ("if_agc_gain", C.c_float), ("decoder_calls", C.c_uint64)]
+
+
+MODTYPE_AM = 2  # include/SoftFM.h:49 enum class ModType { FM, NBFM, AM, ... }
+MODTYPE_NBFM = 1
 
 
 class RefChain:
     """One reference receive chain (front end + decoder) fed block by block."""
 
     def __init__(self, mode="fm", ifrate=384000.0, fs4=False, filter=0, stereo=True,
-                 deemphasis_us=50.0, pilot_shift=False, mpf_stages=0):
+                 deemphasis_us=50.0, pilot_shift=False, mpf_stages=0, freq_dev=8000.0):
         L = lib()
         self.mode = mode
         if mode == "fm":
             self.h = L.ref_fm_create(ifrate, int(fs4), filter, int(stereo), deemphasis_us,
                                      int(pilot_shift), mpf_stages)
+        elif mode == "nbfm":
+            self.h = L.ref_nbfm_create(ifrate, int(fs4), filter, float(freq_dev))
         else:
             self.h = L.ref_am_create(ifrate, int(fs4), filter, MODTYPE_AM)
         self._audio = np.empty(1 << 18, dtype=np.float64)
@@ -143,6 +154,9 @@ class RefChain:
         if self.mode == "fm":
             s = FmStats()
             lib().ref_fm_stats(self.h, C.byref(s))
+        elif self.mode == "nbfm":
+            s = NbfmStats()
+            lib().ref_nbfm_stats(self.h, C.byref(s))
         else:
             s = AmStats()
             lib().ref_am_stats(self.h, C.byref(s))

@@ -50,13 +50,15 @@
 namespace {
 
 struct RefChain {
-  int mode; // 0 = FM, 1 = AM
+  int mode; // 0 = FM, 1 = AM, 2 = NBFM
   double ifrate;
   double demod_rate;
   bool fs4;
   bool downsample;
   IQSampleCoeff fmfilter_coeff;
   IQSampleCoeff amfilter_coeff;
+  IQSampleCoeff nbfmfilter_coeff;
+  std::unique_ptr<NbfmDecoder> nbfm;
   std::unique_ptr<FourthConverterIQ> fourth;
   std::unique_ptr<IfResampler> ifres;
   std::unique_ptr<FmDecoder> fm;
@@ -149,6 +151,35 @@ void *ref_am_create(double ifrate, int fs4_shift, int filter, int modtype) {
   return c;
 }
 
+// filter: 0 default, 1 medium, 2 narrow, 3 wide (main.cpp:785-810); freq_dev in Hz
+// (NbfmDecoder::freq_dev_normal = 8000, main.cpp:828-830).
+void *ref_nbfm_create(double ifrate, int fs4_shift, int filter, double freq_dev) {
+  RefChain *c = new RefChain();
+  c->mode = 2;
+  c->ifrate = ifrate;
+  c->demod_rate = NbfmDecoder::internal_rate_pcm;
+  c->fs4 = fs4_shift != 0;
+  c->downsample = (ifrate != c->demod_rate);
+  switch (filter) {
+  case 1:
+    c->nbfmfilter_coeff = FilterParameters::jj1bdx_nbfm_48khz_medium;
+    break;
+  case 2:
+    c->nbfmfilter_coeff = FilterParameters::jj1bdx_nbfm_48khz_narrow;
+    break;
+  case 3:
+    c->nbfmfilter_coeff = FilterParameters::jj1bdx_nbfm_48khz_wide;
+    break;
+  default:
+    c->nbfmfilter_coeff = FilterParameters::jj1bdx_nbfm_48khz_default;
+    break;
+  }
+  c->fourth = std::make_unique<FourthConverterIQ>(false);
+  c->ifres = std::make_unique<IfResampler>(ifrate, c->demod_rate);
+  c->nbfm = std::make_unique<NbfmDecoder>(c->nbfmfilter_coeff, freq_dev);
+  return c;
+}
+
 void ref_destroy(void *h) { delete static_cast<RefChain *>(h); }
 
 // One source block. Returns the number of doubles written to `audio`
@@ -166,6 +197,8 @@ int ref_process_block(void *h, const float *iq, int n, double *audio, int cap) {
   SampleVector out;
   if (c->mode == 0) {
     c->fm->process(std::move(if_samples), out);
+  } else if (c->mode == 2) {
+    c->nbfm->process(if_samples, out);
   } else {
     c->am->process(std::move(if_samples), out);
   }
@@ -293,6 +326,23 @@ void ref_am_stats(void *h, RefAmStats *s) {
   s->decoder_calls = c->decoder_calls;
 }
 
+struct RefNbfmStats {
+  float tuning_offset;
+  float baseband_level;
+  float if_rms;
+  float if_agc_gain;
+  uint64_t decoder_calls;
+};
+
+void ref_nbfm_stats(void *h, RefNbfmStats *s) {
+  RefChain *c = static_cast<RefChain *>(h);
+  s->tuning_offset = c->nbfm->get_tuning_offset();
+  s->baseband_level = c->nbfm->get_baseband_level();
+  s->if_rms = c->nbfm->get_if_rms();
+  s->if_agc_gain = c->nbfm->m_ifagc.get_current_gain();
+  s->decoder_calls = c->decoder_calls;
+}
+
 // ---- stand-alone resampler access (for the schedule / table checks) ----
 // kind 0: IfResampler-style CDSPResampler24 (one real lane); kind 1: AudioResampler-style.
 void *ref_r8b_create(double src, double dst, int kind) {
@@ -405,6 +455,14 @@ int ref_filter_table(const char *name, double *out, int cap) {
     cd(FilterParameters::jj1bdx_48khz_fmaudio);
   else if (s == "jj1bdx_48khz_nbfmaudio")
     cd(FilterParameters::jj1bdx_48khz_nbfmaudio);
+  else if (s == "jj1bdx_nbfm_48khz_default")
+    cf(FilterParameters::jj1bdx_nbfm_48khz_default);
+  else if (s == "jj1bdx_nbfm_48khz_medium")
+    cf(FilterParameters::jj1bdx_nbfm_48khz_medium);
+  else if (s == "jj1bdx_nbfm_48khz_narrow")
+    cf(FilterParameters::jj1bdx_nbfm_48khz_narrow);
+  else if (s == "jj1bdx_nbfm_48khz_wide")
+    cf(FilterParameters::jj1bdx_nbfm_48khz_wide);
   else if (s == "jj1bdx_am_48khz_narrow")
     cf(FilterParameters::jj1bdx_am_48khz_narrow);
   else if (s == "jj1bdx_am_48khz_medium")

@@ -23,6 +23,11 @@ class AmStats(C.Structure):
                 ("if_rms", C.c_float), ("decoder_calls", C.c_uint64)]
 
 
+class NbfmStats(C.Structure):
+    _fields_ = [("tuning_offset", C.c_float), ("baseband_level", C.c_float), ("if_rms", C.c_float),
+                ("if_agc_gain", C.c_float), ("decoder_calls", C.c_uint64)]
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -33,10 +38,13 @@ def lib():
         L.orc_fm_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint]
         L.orc_am_create.restype = C.c_void_p
         L.orc_am_create.argtypes = [C.c_double, C.c_int, C.c_int]
-        for n in ("orc_fm_destroy", "orc_am_destroy", "orc_r8_destroy"):
+        L.orc_nbfm_create.restype = C.c_void_p
+        L.orc_nbfm_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_double]
+        L.orc_nbfm_stats.argtypes = [C.c_void_p, C.c_void_p]
+        for n in ("orc_fm_destroy", "orc_am_destroy", "orc_r8_destroy", "orc_nbfm_destroy"):
             getattr(L, n).argtypes = [C.c_void_p]
             getattr(L, n).restype = None
-        for n in ("orc_fm_process_block", "orc_am_process_block"):
+        for n in ("orc_fm_process_block", "orc_am_process_block", "orc_nbfm_process_block"):
             getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         for n in ("orc_fm_tap_if", "orc_fm_mpf_coeffs", "orc_fm_pps"):
             getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -111,6 +119,26 @@ def am_run(iq, fs, blk, filter=0, fs4=False):
     L.orc_am_stats(h, C.byref(s))
     st = _copy_stats(s)
     L.orc_am_destroy(h)
+    return (np.concatenate(out) if out else np.empty(0)), np.array(lens, dtype=np.int64), {}, st
+
+
+def nbfm_run(iq, fs, blk, filter=0, fs4=False, freq_dev=8000.0):
+    L = lib()
+    h = L.orc_nbfm_create(fs, int(fs4), filter, float(freq_dev))
+    assert h
+    iq = np.ascontiguousarray(iq, dtype=np.complex64)
+    audio = np.empty(1 << 17, dtype=np.float64)
+    out, lens = [], []
+    for o in range(0, len(iq), blk):
+        b = iq[o:o + blk]
+        m = L.orc_nbfm_process_block(h, b.ctypes.data, len(b), audio.ctypes.data, len(audio))
+        assert m >= 0
+        out.append(audio[:m].copy())
+        lens.append(m)
+    s = NbfmStats()
+    L.orc_nbfm_stats(h, C.byref(s))
+    st = _copy_stats(s)
+    L.orc_nbfm_destroy(h)
     return (np.concatenate(out) if out else np.empty(0)), np.array(lens, dtype=np.int64), {}, st
 
 

@@ -715,6 +715,93 @@ void orc_am_stats(void *p, OrcAmStats *s) {
   s->if_rms = h->if_rms; s->decoder_calls = h->decoder_calls;
 }
 
+/* ------------------------------------------------------------------ NBFM chain -------- */
+typedef struct {
+  double ifrate; int fs4; unsigned fs4_idx;
+  const ChainDesc *ifc; R8Lane if_re, if_im;
+  FirIQ nbf; FirAudio audiof;
+  float agc_gain, agc_max, agc_rate, if_rms, baseband_mean, baseband_level;
+  float disc_norm, disc_bound, disc_save;
+  double freq_dev;
+  uint64_t decoder_calls;
+} OrcNbfm;
+
+/* NbfmDecoder::NbfmDecoder (NbfmDecode.cpp:24-45), filter choice main.cpp:785-810 */
+void *orc_nbfm_create(double ifrate, int fs4, int filter, double freq_dev) {
+  OrcNbfm *h = (OrcNbfm *)calloc(1, sizeof(OrcNbfm));
+  h->ifrate = ifrate; h->fs4 = fs4; h->freq_dev = freq_dev;
+  if (ifrate != 48000.0) {
+    h->ifc = find_chain(ifrate, 48000.0, 0);
+    if (!h->ifc) { free(h); return 0; }
+    r8_init(&h->if_re, h->ifc); r8_init(&h->if_im, h->ifc);
+  }
+  const float *c = k_jj1bdx_nbfm_48khz_default;
+  if (filter == 1) c = k_jj1bdx_nbfm_48khz_medium; else if (filter == 2) c = k_jj1bdx_nbfm_48khz_narrow;
+  else if (filter == 3) c = k_jj1bdx_nbfm_48khz_wide;
+  firiq_init(&h->nbf, c, 127);
+  fira_init(&h->audiof, k_jj1bdx_48khz_nbfmaudio, 63);                            /* NbfmDecode.cpp:39 */
+  {
+    const double max_freq_dev = freq_dev / 48000.0;                               /* NbfmDecode.cpp:35 */
+    h->disc_norm = (float)(max_freq_dev * 2.0 * M_PI);                            /* PhaseDiscriminator.cpp:27-30 */
+    h->disc_bound = (float)(1.0 / (max_freq_dev * 2.0));
+  }
+  h->agc_gain = 1.0f; h->agc_max = 100000.0f; h->agc_rate = 0.0001f;              /* NbfmDecode.cpp:43 */
+  return h;
+}
+void orc_nbfm_destroy(void *p) {
+  OrcNbfm *h = (OrcNbfm *)p;
+  if (!h) return;
+  if (h->ifc) { r8_free(&h->if_re); r8_free(&h->if_im); }
+  free(h->nbf.sre); free(h->nbf.sim); free(h->audiof.state); free(h);
+}
+/* main.cpp:912-961 + NbfmDecoder::process (NbfmDecode.cpp:47-96) */
+int orc_nbfm_process_block(void *p, const float *iq, int n, double *audio, int cap) {
+  OrcNbfm *h = (OrcNbfm *)p;
+  float *ifs = 0;
+  const int m = front_end(h->fs4, &h->fs4_idx, h->ifc, &h->if_re, &h->if_im, iq, n, &ifs);
+  if (m == 0) { free(ifs); return 0; }
+  if (m > cap) { free(ifs); return -1; }
+  h->decoder_calls++;
+  float *x = (float *)malloc(sizeof(float) * 2 * (size_t)m);
+  firiq_process(&h->nbf, ifs, m, x);                                              /* :51 */
+  {
+    float level = 0;
+    for (int i = 0; i < m; i++) level += x[2 * i] * x[2 * i] + x[2 * i + 1] * x[2 * i + 1];
+    h->if_rms = sqrtf(level / (float)m);                                          /* :54 */
+  }
+  if_agc(&h->agc_gain, h->agc_max, h->agc_rate, x, m);                            /* :57 */
+  double *bb = (double *)malloc(sizeof(double) * (size_t)m), *flt = (double *)malloc(sizeof(double) * (size_t)m);
+  float vsum = 0, vsq = 0;
+  {
+    const float inv = 1.0f / h->disc_norm;                                        /* :60, PhaseDiscriminator.cpp:33-46 */
+    float prev = h->disc_save, last = 0;
+    for (int i = 0; i < m; i++) {
+      const float ph = atan2f(x[2 * i + 1], x[2 * i]) * inv;
+      float d = ph - prev;
+      if (d > h->disc_bound) d -= 2 * h->disc_bound;
+      if (d < -h->disc_bound) d += 2 * h->disc_bound;
+      prev = ph; last = ph;
+      if (isnan(d)) d = 0.0f;
+      bb[i] = (double)d; vsum += d; vsq += d * d;                                 /* :71-72, :84 */
+    }
+    h->disc_save = last;
+  }
+  h->baseband_mean = (float)(0.95 * h->baseband_mean + 0.05 * (vsum / (float)m));  /* :85-86 */
+  h->baseband_level = (float)(0.95 * h->baseband_level + 0.05 * sqrtf(vsq / (float)m));
+  fira_process(&h->audiof, bb, m, flt);                                           /* :89 */
+  const double audio_gain = pow(10.0, (-3.0 / 20.0));                             /* :92-93 */
+  for (int i = 0; i < m; i++) audio[i] = flt[i] * audio_gain;
+  free(x); free(ifs); free(bb); free(flt);
+  return m;
+}
+typedef struct { float tuning_offset, baseband_level, if_rms, if_agc_gain; uint64_t decoder_calls; } OrcNbfmStats;
+void orc_nbfm_stats(void *p, OrcNbfmStats *s) {
+  OrcNbfm *h = (OrcNbfm *)p;
+  s->tuning_offset = (float)(h->baseband_mean * h->freq_dev);                      /* NbfmDecode.h:59 */
+  s->baseband_level = h->baseband_level; s->if_rms = h->if_rms; s->if_agc_gain = h->agc_gain;
+  s->decoder_calls = h->decoder_calls;
+}
+
 /* Cumulative release schedule of a chain (same integer model the product's host code uses,
    restated independently): outputs released after N inputs. */
 int64_t orc_chain_out(double src, double dst, int kind, int64_t n) {

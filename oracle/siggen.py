@@ -53,3 +53,18 @@ def am_iq(fs, n, channel=0, sigma=0.005):
     out.real = env.astype(np.float32) + noise[:, 0]
     out.imag = noise[:, 1]
     return out
+
+
+def nbfm_iq(fs, n, channel=0, sigma=0.005, amp=0.5, dev=3000.0):
+    """Narrow-band FM test signal: a two-tone voice-band message (600 + 37c Hz, 1700 + 53c Hz)
+    with +-`dev` Hz peak deviation on a carrier 300 Hz off the centre (so that the tuning-offset
+    getter has something to report), + N(0, sigma^2), seed 11+c."""
+    t = np.arange(n, dtype=np.float64) / fs
+    msg = 0.6 * np.sin(2 * np.pi * (600.0 + 37.0 * channel) * t) + 0.4 * np.sin(2 * np.pi * (1700.0 + 53.0 * channel) * t)
+    phi = np.cumsum(2 * np.pi * (300.0 + dev * msg) / fs)
+    rng = np.random.Generator(np.random.PCG64(11 + channel))
+    noise = rng.standard_normal((n, 2), dtype=np.float32) * np.float32(sigma)
+    out = np.empty(n, dtype=np.complex64)
+    out.real = (amp * np.cos(phi)).astype(np.float32) + noise[:, 0]
+    out.imag = (amp * np.sin(phi)).astype(np.float32) + noise[:, 1]
+    return out

@@ -40,3 +40,15 @@ def oracle_am_run(iq, fs, blk, filter=0, fs4=False, prefer="ref"):
         return audio, lens
     audio, lens, _, _ = _restate().am_run(iq, fs, blk, filter=filter, fs4=fs4)
     return audio, lens
+
+
+def oracle_nbfm_run(iq, fs, blk, filter=0, fs4=False, freq_dev=8000.0, prefer="ref"):
+    """Returns (audio, per_call_len, stats)."""
+    if prefer == "ref" and have_ref():
+        c = ref.RefChain("nbfm", fs, fs4=fs4, filter=filter, freq_dev=freq_dev)
+        audio, lens, _ = c.run(iq, blk)
+        st = c.stats()
+        c.close()
+        return audio, lens, st
+    audio, lens, _, st = _restate().nbfm_run(iq, fs, blk, filter=filter, fs4=fs4, freq_dev=freq_dev)
+    return audio, lens, st
