@@ -166,32 +166,39 @@ static __global__ void __launch_bounds__(kCfThreads)
       const int slot = j & 1, p0 = j * kCfT;
       const int valid = (n_total - p0 < kCfT) ? (n_total - p0) : kCfT;
       cf_sync(cf_full(0, slot));
-      cf_sync3(cf_empty(1, slot));
-#pragma unroll 2
-      for (int u = 0; u < valid; u++) {
-        const int p = p0 + u;
-        if ((uint32_t)p == cl.end) cl.next();
+      // the eight arctangents of the chunk are independent: all in flight together
+      float ph[kCfT];
+#pragma unroll
+      for (int u = 0; u < kCfT; u++) {
         const float2 x = S.iq[slot][u][lane];
-        const float ph = atan2f(x.y, x.x) * inv_norm;
-        float d = ph - prev;
-        prev = ph;
-        if (d > bound) d -= 2 * bound;
-        if (d < -bound) d += 2 * bound;
-        if (isnan(d)) d = 0.0f;
-        S.mpx[slot][u][lane] = d;
-        vs += d;
-        vq += d * d;
-        if ((uint32_t)(p + 1) == cl.end) {
-          const float n = (float)(cl.end - cl.beg);
-          const float mean = vs / n, rms = sqrtf(vq / n);
-          bmean = (float)(0.95 * (double)bmean + 0.05 * (double)mean);
-          blevel = (float)(0.95 * (double)blevel + 0.05 * (double)rms);
-          vs = 0.f;
-          vq = 0.f;
+        ph[u] = fmr_atan2f(x.y, x.x) * inv_norm;
+      }
+      if (j + 2 < K) cf_arrive(cf_empty(0, slot)); // the AGC warp may refill this slot now
+      cf_sync3(cf_empty(1, slot));                 // PLL and post are done with this MPX slot
+#pragma unroll
+      for (int u = 0; u < kCfT; u++) {
+        const int p = p0 + u;
+        if (u < valid) {
+          if ((uint32_t)p == cl.end) cl.next();
+          float d = ph[u] - prev;
+          prev = ph[u];
+          if (d > bound) d -= 2 * bound;
+          if (d < -bound) d += 2 * bound;
+          if (isnan(d)) d = 0.0f;
+          S.mpx[slot][u][lane] = d;
+          vs += d;
+          vq += d * d;
+          if ((uint32_t)(p + 1) == cl.end) {
+            const float n = (float)(cl.end - cl.beg);
+            const float mean = vs / n, rms = sqrtf(vq / n);
+            bmean = (float)(0.95 * (double)bmean + 0.05 * (double)mean);
+            blevel = (float)(0.95 * (double)blevel + 0.05 * (double)rms);
+            vs = 0.f;
+            vq = 0.f;
+          }
         }
       }
       cf_arrive(cf_full(1, slot));
-      if (j + 2 < K) cf_arrive(cf_empty(0, slot));
     }
     if (act) {
       sp->disc_prev = prev;

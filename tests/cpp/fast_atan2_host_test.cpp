@@ -46,7 +46,54 @@ static float bf_atan2(float y, float x, int exactdiv) {
   float angle = fmaf(sg, base, K);
   return (den > 0.0f) ? angle : 0.0f;
 }
+// fmr_atan2f (csrc/fmr_kernels.cuh): the discriminator's branch-free atan2f, same operations;
+// the device's rcp.approx is modelled as the rounded reciprocal perturbed by +-1 ulp.
+static inline float poly_atan2f(float y, float x) {
+  const float ya = fabsf(y), xa = fabsf(x);
+  const float mn = fminf(ya, xa), mx = fmaxf(ya, xa);
+  float r0 = (float)(1.0 / (double)mx);
+  { uint32_t u; memcpy(&u, &r0, 4); u += (rand() % 3) - 1; memcpy(&r0, &u, 4); }
+  const float r1 = fmaf(fmaf(-mx, r0, 1.0f), r0, r0);
+  float z = mn * r1;
+  z = fmaf(fmaf(-mx, z, mn), r1, z);
+  const float s = z * z;
+  float p = 0.0028662257f;
+  p = fmaf(p, s, -0.0161657367f);
+  p = fmaf(p, s, 0.0429096138f);
+  p = fmaf(p, s, -0.0752896400f);
+  p = fmaf(p, s, 0.1065626393f);
+  p = fmaf(p, s, -0.1420889944f);
+  p = fmaf(p, s, 0.1999355085f);
+  p = fmaf(p, s, -0.3333314528f);
+  float r = fmaf(p * s, z, z);
+  r = (ya > xa) ? 1.57079632679489661923f - r : r;
+  r = (x < 0.0f) ? 3.14159265358979323846f - r : r;
+  r = (mx > 0.0f) ? r : 0.0f;
+  return copysignf(r, y);
+}
+static int check_poly_atan2() {
+  double maxe = 0, sum2 = 0;
+  long n = 0;
+  for (long it = 0; it < 4000000; it++) {
+    float y = ((float)rand() / RAND_MAX - 0.5f) * powf(10.f, (rand() % 6) - 3);
+    float x = ((float)rand() / RAND_MAX - 0.5f) * powf(10.f, (rand() % 6) - 3);
+    if (it % 1001 == 0) y = 0;
+    if (it % 1777 == 0) x = 0;
+    if (it % 5003 == 0) y = x;
+    const double ref = atan2((double)y, (double)x);
+    double e = fabs((double)poly_atan2f(y, x) - ref);
+    if (e > 3.2) e = fabs(e - 2 * M_PI); // -pi vs +pi on the cut
+    if (e > maxe) maxe = e;
+    sum2 += e * e;
+    n++;
+  }
+  const int zero_ok = (poly_atan2f(0.f, 0.f) == 0.0f);
+  printf("polynomial atan2f: n=%ld max abs err %.3e rad, rms %.3e rad, atan2(0,0)==0: %d\n", n, maxe, sqrt(sum2 / n), zero_ok);
+  return (maxe < 4e-7 && sqrt(sum2 / n) < 1e-7 && zero_ok) ? 0 : 1;
+}
+
 int main() {
+  if (check_poly_atan2()) return 2;
   srand(1); long bad0 = 0, bad1 = 0, n = 0; double maxd = 0;
   for (int it = 0; it < 4000000; it++) {
     float y = ((float)rand()/RAND_MAX - 0.5f) * powf(10.f, (rand()%8) - 6), x = ((float)rand()/RAND_MAX - 0.5f) * powf(10.f, (rand()%8) - 6);

@@ -14,11 +14,10 @@ import bench  # noqa: E402
 
 VARIANTS = [
     # name, env, blocks per step, channels
-    ("all_on_128", {}, 128, 8192),
-    ("no_rot", {"FMR_CORE_ROT": "0"}, 128, 8192),
-    ("serial_v1_tail", {"FMR_SERIAL_V2": "0"}, 128, 8192),
     ("all_on_329", {}, 329, 8192),
-    ("all_on_128_c16384", {}, 128, 16384),
+    ("all_on_128", {}, 128, 8192),
+    ("all_on_128_c1024", {}, 128, 1024),
+    ("all_on_128_c148", {}, 128, 148),
 ]
 
 
