@@ -8,6 +8,11 @@
 // call passed through unfiltered. One warp owns one channel: the 4*stages+1 complex
 // coefficients live in registers (tap k on lane k%32), the delay line in a shared-memory
 // ring, the dot product is reduced with warp shuffles, so a sample costs no block barrier.
+// The ring is stored twice back to back so that the N-tap window is always contiguous (tap
+// loads with immediate offsets, no per-tap wrap arithmetic); a lane's partial dot product runs
+// as four independent accumulator chains (the summation order differs from VOLK's SIMD order
+// either way); the window stays in registers for the coefficient update; input samples are
+// prefetched one batch of eight ahead.
 #ifndef FMR_MPF_CUH
 #define FMR_MPF_CUH
 
@@ -16,7 +21,7 @@
 namespace fmr {
 
 constexpr int kMpfRing = 1024;
-constexpr int kMpfWarps = 4;
+constexpr int kMpfWarps = 3; // 3 x 16 KB of mirrored ring = the 48 KB static shared-memory limit; 4 CTAs per SM
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -25,11 +30,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 template <int J>
-__global__ void __launch_bounds__(32 * kMpfWarps)
+__global__ void __launch_bounds__(32 * kMpfWarps, 4)
     k_mpf(Ring<float2> in, Ring<float2> out, FmChanState *__restrict__ st, float2 *__restrict__ g_coeff,
           float2 *__restrict__ g_state, int N, int ref_idx, const uint32_t *__restrict__ call_end, int n_calls,
           int64_t t0, int C) {
-  __shared__ float2 ring_all[kMpfWarps][kMpfRing];
+  __shared__ float2 ring_all[kMpfWarps][2 * kMpfRing];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * kMpfWarps + warp;
   if (c >= C) return;
@@ -41,10 +46,13 @@ __global__ void __launch_bounds__(32 * kMpfWarps)
     cf[j] = (k < N) ? g_coeff[(size_t)c * kMpfRing + k] : make_float2(0.f, 0.f);
   }
   for (int k = lane; k < kMpfRing; k += 32) {
-    ring[k] = (k < N) ? g_state[(size_t)c * kMpfRing + k] : make_float2(0.f, 0.f);
+    const float2 v = (k < N) ? g_state[(size_t)c * kMpfRing + k] : make_float2(0.f, 0.f);
+    ring[k] = v;
+    ring[k + kMpfRing] = v;
   }
   __syncwarp();
   uint32_t cnt = (uint32_t)(N - 1); // ring index of the newest sample
+  const int jf = N >> 5;            // number of full rows of 32 taps
   uint32_t wait = st[c].mpf_wait;
   double err_keep = st[c].mpf_error;
   uint32_t prev_end = 0;
@@ -61,11 +69,17 @@ __global__ void __launch_bounds__(32 * kMpfWarps)
       continue;
     }
     bool ok = true;
-    float2 xbuf[8]; // samples are fetched 8 at a time so their latency is not paid per sample
+    // samples are fetched 8 at a time, one batch ahead, so their latency is not paid per sample
+    float2 xbuf[8], xnext[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) xnext[u] = (u < n) ? in.ld(c, tb + u) : make_float2(0.f, 0.f);
     for (int i = 0; i < n; i++) {
       if ((i & 7) == 0) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) xbuf[u] = (i + u < n) ? in.ld(c, tb + i + u) : make_float2(0.f, 0.f);
+        for (int u = 0; u < 8; u++) {
+          xbuf[u] = xnext[u];
+          xnext[u] = (i + 8 + u < n) ? in.ld(c, tb + i + 8 + u) : make_float2(0.f, 0.f);
+        }
       }
       float2 x = xbuf[0];
 #pragma unroll
@@ -73,20 +87,29 @@ __global__ void __launch_bounds__(32 * kMpfWarps)
         if ((i & 7) == u) x = xbuf[u];
       }
       cnt++;
-      if (lane == 0) ring[cnt & (kMpfRing - 1)] = x;
+      if (lane == 0) {
+        ring[cnt & (kMpfRing - 1)] = x;
+        ring[(cnt & (kMpfRing - 1)) + kMpfRing] = x;
+      }
       __syncwarp();
       const bool upd = ((i & 3) == 0);
-      float yr = 0.f, yi = 0.f, ms = 0.f;
+      // tap k = lane + 32 j reads the sample N-1-k steps behind the newest: contiguous from `wbase`
+      const float2 *__restrict__ w = ring + ((cnt - (uint32_t)(N - 1)) & (kMpfRing - 1)) + lane;
+      // rows j < N/32 are full for every lane; only the rows behind them need the per-lane k < N
+      // test. Explicit FMAs: two per tap and component, no separate add.
+      float2 sv[J];
+      float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < J; j++) {
-        const int k = lane + 32 * j;
-        if (k < N) {
-          const float2 s = ring[(cnt - (uint32_t)(N - 1 - k)) & (kMpfRing - 1)];
-          yr += s.x * cf[j].x - s.y * cf[j].y;
-          yi += s.x * cf[j].y + s.y * cf[j].x;
-          ms += s.x * s.x + s.y * s.y;
+        if (j < jf || lane + 32 * j < N) {
+          sv[j] = w[32 * j];
+        } else {
+          sv[j] = make_float2(0.f, 0.f);
         }
+        ar[j & 3] = fmaf(-sv[j].y, cf[j].y, fmaf(sv[j].x, cf[j].x, ar[j & 3]));
+        ai[j & 3] = fmaf(sv[j].y, cf[j].x, fmaf(sv[j].x, cf[j].y, ai[j & 3]));
       }
+      float yr = (ar[0] + ar[1]) + (ar[2] + ar[3]), yi = (ai[0] + ai[1]) + (ai[2] + ai[3]);
       yr = warp_sum(yr);
       yi = warp_sum(yi);
       if (!isfinite(yr) || !isfinite(yi)) {
@@ -96,20 +119,26 @@ __global__ void __launch_bounds__(32 * kMpfWarps)
       if (lane == 0) out.st(c, tb + i, make_float2(yr, yi));
       if (upd) {
         // MultipathFilter::update_coeff (MultipathFilter.cpp:108-161)
-        ms = warp_sum(ms);
+        float m4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < J; j++) m4[j & 3] = fmaf(sv[j].y, sv[j].y, fmaf(sv[j].x, sv[j].x, m4[j & 3]));
+        const float ms = warp_sum((m4[0] + m4[1]) + (m4[2] + m4[3]));
         const double env = (double)(yr * yr + yi * yi);
         const double err = 1.0 - env;
         const float mu = (float)(0.1 / ((double)ms + 1e-10));
         const float factor = (float)(err * (double)mu);
         const float fr = factor * yr, fi = factor * yi;
+        // taps beyond N keep a zero coefficient because their window sample was read as zero
 #pragma unroll
         for (int j = 0; j < J; j++) {
-          const int k = lane + 32 * j;
-          if (k < N) {
-            const float2 s = ring[(cnt - (uint32_t)(N - 1 - k)) & (kMpfRing - 1)];
-            cf[j].x += fr * s.x + fi * s.y;
-            cf[j].y += fi * s.x - fr * s.y;
-            if (k == ref_idx) cf[j] = make_float2(1.f, 0.f);
+          cf[j].x = fmaf(fi, sv[j].y, fmaf(fr, sv[j].x, cf[j].x));
+          cf[j].y = fmaf(-fr, sv[j].y, fmaf(fi, sv[j].x, cf[j].y));
+        }
+        // the reference tap is pinned to 1+0j (MultipathFilter.cpp:158-160)
+        if (lane == (ref_idx & 31)) {
+#pragma unroll
+          for (int j = 0; j < J; j++) {
+            if (j == (ref_idx >> 5)) cf[j] = make_float2(1.f, 0.f);
           }
         }
         err_keep = err;
@@ -191,6 +220,7 @@ struct MpfDev {
     dim3 block(32 * kMpfWarps);
 #define FMR_MPF_CASE(j)                                                                                          \
   case j:                                                                                                        \
+    cudaFuncSetAttribute(k_mpf<j>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
     k_mpf<j><<<grid, block, 0, s>>>(in, out, st, d_coeff, d_state, N, ref_idx, call_end, n_calls, t0, C);         \
     break;
     switch (J) {
@@ -201,6 +231,7 @@ struct MpfDev {
       FMR_MPF_CASE(20)
       FMR_MPF_CASE(26)
     default:
+      cudaFuncSetAttribute(k_mpf<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       k_mpf<32><<<grid, block, 0, s>>>(in, out, st, d_coeff, d_state, N, ref_idx, call_end, n_calls, t0, C);
       break;
     }

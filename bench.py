@@ -217,7 +217,7 @@ def main():
     T = nblk * BLK
     C = args.channels or {"fm": 8192, "am": 8192}[mode]
     if mpf:
-        C = args.channels or 1776  # 444 CTAs of 4 channels = one wave of the multipath kernel (3 CTAs/SM)
+        C = args.channels or 1776  # 592 CTAs of 3 channels = one wave of the multipath kernel (4 CTAs/SM)
     dec = make_decoder(wl, C, T, nblk, dev_index)
     iq = gen_iq_device(torch, dev, fs, C, T, mode)
     width = 2 if (mode == "fm" and stereo) else 1
