@@ -355,7 +355,11 @@ template <typename S> struct Resampler {
     smem_fir = ((size_t)(kFirTile - 1) * d->bc.down + d->bc.klen) * sizeof(V) + (size_t)d->bc.klen * sizeof(S);
     FMR_CUDA(cudaFuncSetAttribute(k_fir_long<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fir));
     if (d->has_fi) {
-      const int64_t max_bc = max_hb / d->bc.down + 4;
+      int64_t max_bc = max_hb / d->bc.down + 4;
+      // With the polyphase bank fused behind the FFT low-pass the intermediate ring only ever holds
+      // what the unfused kernels of SMALL calls produce (fewer than fft_min_out filter outputs) plus
+      // the history tail the fused kernel leaves for them.
+      if (use_fft && fuse_fi && d->bc.down == 1 && max_bc > fft_min_out + 64) max_bc = fft_min_out + 64;
       r_bc.cap = pow2ceil((uint64_t)(max_bc + 4 * d->fi.flen + 64));
       FMR_CUDA(mem.alloc(&r_bc.base, (size_t)C * r_bc.cap));
       const size_t nt = (size_t)d->fi.outstep * d->fi.flen;

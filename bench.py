@@ -215,7 +215,7 @@ def main():
 
     nblk = args.blocks
     T = nblk * BLK
-    C = args.channels or {"fm": 8192, "am": 8192}[mode]
+    C = args.channels or {"fm": 16384, "am": 8192}[mode]
     if mpf:
         C = args.channels or 1776  # 592 CTAs of 3 channels = one wave of the multipath kernel (4 CTAs/SM)
     dec = make_decoder(wl, C, T, nblk, dev_index)

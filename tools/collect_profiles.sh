@@ -12,7 +12,7 @@ ncu --set full --clock-control none --import-source on -k regex:k_hb_stream_tma 
 ncu --set full --clock-control none --import-source on -k regex:k_fir_fft -s 4 -c 3 -f -o gpurun_out/prof_fft_${R} $B --steps 1 --warmup 3 --channels 1024 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_fm_core_fused -s 3 -c 1 -f -o gpurun_out/prof_core_${R} $B --steps 1 --warmup 3 --channels 1024 > /dev/null 2>&1
 # 3. bench sweep (device-resident value) over channel counts and workloads
-for ch in 148 1024 4096 8192 16384; do
+for ch in 148 1024 4096 8192 16384; do  # 16384 is the bench default
   $B --steps 4 --warmup 3 --channels $ch 2>&1 | tail -1 > gpurun_out/sweep_cfg2_${ch}_${R}.json
 done
 $B --steps 4 --warmup 3 --blocks 128 2>&1 | tail -1 > gpurun_out/sweep_cfg2_8192_b128_${R}.json
