@@ -4,6 +4,7 @@
 #include <complex>
 #include <cmath>
 
+#include "fmr_core.cuh"
 #include "fmr_host.cuh"
 
 using namespace fmr;
@@ -101,6 +102,159 @@ __global__ void k_am_core(Ring<float2> in, double *__restrict__ audio, size_t au
   st[c] = s;
 }
 
+// k_am_core_fused — the same block as k_am_core with its three recurrences on three warps of one
+// CTA (lane = channel), pipelined over chunks of kCfT samples through shared memory with named
+// barriers, exactly like the FM core (fmr_core.cuh):
+//   warp 0  IF RMS, IfSimpleAgc, envelope |x|, baseband statistics      (float recurrence)
+//   warp 1  DC block biquad, AfSimpleAgc                                (double recurrence)
+//   warp 2  deemphasis, store
+// k_am_core runs them back to back per sample (~520 cycles of dependent latency); here the step
+// time is the longest single recurrence.
+struct AmSmem {
+  float mag[2][kCfT][32];
+  double y[2][kCfT][32];
+};
+
+__global__ void __launch_bounds__(96)
+    k_am_core_fused(Ring<float2> in, double *__restrict__ audio, size_t audio_stride, AmChanState *__restrict__ st,
+                    const uint32_t *__restrict__ call_end, int n_calls, int64_t t0, AmCoreParams P) {
+  __shared__ AmSmem S;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c_raw = blockIdx.x * 32 + lane;
+  const bool act = c_raw < P.n_channels;
+  const int c = act ? c_raw : (P.n_channels - 1); // idle lanes shadow the last channel, store nothing
+  const int n_total = n_calls ? (int)call_end[n_calls - 1] : 0;
+  const int K = (n_total + kCfT - 1) / kCfT;
+  const uint32_t t0lo = (uint32_t)t0;
+  // link 0: warp 0 -> warp 1 (mag), link 1: warp 1 -> warp 2 (y)
+  if (warp == 0) {
+    AmChanState *sp = st + c;
+    float g = sp->if_gain, if_rms = sp->if_rms, bmean = sp->baseband_mean, blevel = sp->baseband_level;
+    unsigned long long calls = sp->decoder_calls;
+    float sumsq = 0.f, vsum = 0.f, vsq = 0.f;
+    const float2 *__restrict__ irow = in.base + (size_t)c * in.cap;
+    const uint32_t imask = in.cap - 1;
+    const double rate = (double)P.if_rate;
+    CfCalls cl;
+    cl.init(call_end, n_calls);
+    float2 nx[kCfT];
+#pragma unroll
+    for (int u = 0; u < kCfT; u++) nx[u] = (u < n_total) ? irow[(t0lo + (uint32_t)u) & imask] : make_float2(0.f, 0.f);
+    for (int k = 0; k < K; k++) {
+      const int slot = k & 1, p0 = k * kCfT;
+      float2 x[kCfT];
+#pragma unroll
+      for (int u = 0; u < kCfT; u++) x[u] = nx[u];
+#pragma unroll
+      for (int u = 0; u < kCfT; u++) {
+        const int p = p0 + kCfT + u;
+        nx[u] = (p < n_total) ? irow[(t0lo + (uint32_t)p) & imask] : make_float2(0.f, 0.f);
+      }
+      cf_sync(cf_empty(0, slot));
+#pragma unroll
+      for (int u = 0; u < kCfT; u++) {
+        const int p = p0 + u;
+        if (p < n_total) {
+          if ((uint32_t)p == cl.end) {
+            cl.next();
+            calls++;
+          }
+          sumsq += x[u].x * x[u].x + x[u].y * x[u].y; // Utility::rms_level_sample (AmDecode.cpp:154)
+          // IfSimpleAgc::process (IfSimpleAgc.cpp:37-57)
+          const float xr = x[u].x * g, xi = x[u].y * g;
+          const float nrm = xr * xr + xi * xi;
+          const float z = (float)(1.0 + (rate * (1.0 - (double)nrm)));
+          g *= z;
+          g = isfinite(g) ? ((g > P.if_max) ? P.if_max : g) : 1.0f;
+          const float mag = sqrtf(xr * xr + xi * xi); // demodulate_am (AmDecode.cpp:221-226)
+          vsum += mag;
+          vsq += mag * mag;
+          S.mag[slot][u][lane] = mag;
+          if ((uint32_t)(p + 1) == cl.end) {
+            const float n = (float)(cl.end - cl.beg);
+            if_rms = sqrtf(sumsq / n);
+            const float mean = vsum / n, rms = sqrtf(vsq / n);
+            bmean = (float)(0.95 * (double)bmean + 0.05 * (double)mean);
+            blevel = (float)(0.95 * (double)blevel + 0.05 * (double)rms);
+            sumsq = 0.f;
+            vsum = 0.f;
+            vsq = 0.f;
+          }
+        }
+      }
+      cf_arrive(cf_full(0, slot));
+    }
+    if (act) {
+      sp->if_gain = g;
+      sp->if_rms = if_rms;
+      sp->baseband_mean = bmean;
+      sp->baseband_level = blevel;
+      sp->decoder_calls = calls;
+    }
+  } else if (warp == 1) {
+    AmChanState *sp = st + c;
+    double x1 = sp->dc_x1, x2s = sp->dc_x2, ag = sp->af_gain;
+    const double a1 = P.a1, a2 = P.a2, b0 = P.b0, b1 = P.b1, b2 = P.b2;
+    const double af_ref = P.af_ref, af_rate = P.af_rate, af_max = P.af_max;
+    cf_arrive(cf_empty(0, 0));
+    cf_arrive(cf_empty(0, 1));
+    for (int k = 0; k < K; k++) {
+      const int slot = k & 1, p0 = k * kCfT;
+      cf_sync(cf_full(0, slot));
+      float m[kCfT];
+#pragma unroll
+      for (int u = 0; u < kCfT; u++) m[u] = S.mag[slot][u][lane];
+      if (k + 2 < K) cf_arrive(cf_empty(0, slot));
+      cf_sync(cf_empty(1, slot));
+#pragma unroll
+      for (int u = 0; u < kCfT; u++) {
+        if (p0 + u < n_total) {
+          // DC block (AmDecode.cpp:194; Filter.cpp:243-250)
+          const double d0 = (double)m[u] - (a1 * x1 + a2 * x2s);
+          const double v = b0 * d0 + b1 * x1 + b2 * x2s;
+          x2s = x1;
+          x1 = d0;
+          // AfSimpleAgc::process (AfSimpleAgc.cpp:36-58)
+          const double xa = v * ag;
+          const double y = xa * af_ref;
+          const double za = 1.0 + (af_rate * (1.0 - (xa * xa)));
+          ag *= za;
+          ag = isfinite(ag) ? ((ag > af_max) ? af_max : ag) : 1.0;
+          S.y[slot][u][lane] = y;
+        }
+      }
+      cf_arrive(cf_full(1, slot));
+    }
+    if (act) {
+      sp->dc_x1 = x1;
+      sp->dc_x2 = x2s;
+      sp->af_gain = ag;
+    }
+  } else {
+    AmChanState *sp = st + c;
+    double e1 = sp->de_x1;
+    const double de_a1 = P.de_a1, de_b0 = P.de_b0;
+    double *__restrict__ o = audio + (size_t)c * audio_stride;
+    cf_arrive(cf_empty(1, 0));
+    cf_arrive(cf_empty(1, 1));
+    for (int k = 0; k < K; k++) {
+      const int slot = k & 1, p0 = k * kCfT;
+      cf_sync(cf_full(1, slot));
+#pragma unroll
+      for (int u = 0; u < kCfT; u++) {
+        if (p0 + u < n_total) {
+          // deemphasis (AmDecode.cpp:212-214)
+          const double e0 = S.y[slot][u][lane] - de_a1 * e1;
+          if (act) o[p0 + u] = de_b0 * e0;
+          e1 = e0;
+        }
+      }
+      if (k + 2 < K) cf_arrive(cf_empty(1, slot));
+    }
+    if (act) sp->de_x1 = e1;
+  }
+}
+
 struct NbfmCoreParams {
   float if_max, if_rate;         // IfSimpleAgc(1.0, 100000.0, 0.0001)  NbfmDecode.cpp:43
   float disc_inv_norm, disc_bound; // PhaseDiscriminator(freq_dev / 48000) NbfmDecode.cpp:35, PhaseDiscriminator.cpp:27-30
@@ -195,6 +349,7 @@ struct fmr_am {
   Prof prof;
   int p_hist = -1, p_flt = -1, p_core = -1;
   AmCoreParams core;
+  bool core_fused = true; // FMR_CORE_FUSED=0: the single-warp k_am_core
   // NBFM (mode 1)
   bool nbfm = false;
   NbfmCoreParams ncore;
@@ -373,6 +528,7 @@ extern "C" fmr_status fmr_am_create(const fmr_am_config *cfg, fmr_am **out) {
   }
   fmr_am *h = new fmr_am();
   h->cfg = *cfg;
+  if (const char *e = getenv("FMR_CORE_FUSED")) h->core_fused = atoi(e) != 0;
   fmr_status s = am_build(h);
   if (s != FMR_OK) {
     std::string keep = g_err;
@@ -494,8 +650,13 @@ extern "C" fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t
       pf.end(h->p_out, st);
       launches += 4;
     } else {
-      k_am_core<<<(C + 31) / 32, 32, 0, st>>>(h->r_flt, d_audio, audio_stride, h->d_state, h->d_e48, (int)n_blocks, t0,
-                                              h->core);
+      if (h->core_fused) {
+        k_am_core_fused<<<(C + 31) / 32, 96, 0, st>>>(h->r_flt, d_audio, audio_stride, h->d_state, h->d_e48,
+                                                      (int)n_blocks, t0, h->core);
+      } else {
+        k_am_core<<<(C + 31) / 32, 32, 0, st>>>(h->r_flt, d_audio, audio_stride, h->d_state, h->d_e48, (int)n_blocks, t0,
+                                                h->core);
+      }
       pf.end(h->p_core, st);
       launches += 2;
     }
