@@ -215,9 +215,12 @@ def main():
 
     nblk = args.blocks
     T = nblk * BLK
-    C = args.channels or {"fm": 16384, "am": 8192}[mode]
-    if mpf:
-        C = args.channels or 1776  # 592 CTAs of 3 channels = one wave of the multipath kernel (4 CTAs/SM)
+    # channels per GPU: as many as fit comfortably in 180 GB with their rings (the serial recurrences cost
+    # the same for 1 or 16384 channels, so throughput grows with the channel count); cfg4's 384 kHz
+    # rings are 10x larger per input sample; cfg3: 592 CTAs of 3 channels = one wave of the multipath
+    # kernel (4 CTAs/SM)
+    C = args.channels or {"cfg2_fm_stereo_10Msps": 16384, "cfg3_fm_stereo_10Msps_E200": 1776,
+                          "cfg4_fm_stereo_1Msps": 8192, "cfg5_am_384ksps": 8192}[wl]
     dec = make_decoder(wl, C, T, nblk, dev_index)
     iq = gen_iq_device(torch, dev, fs, C, T, mode)
     width = 2 if (mode == "fm" and stereo) else 1
