@@ -26,6 +26,8 @@ struct AmCoreParams {
   double af_max, af_ref, af_rate;         // AfSimpleAgc(1.0, 1.5, 0.6, 0.001)    AmDecode.cpp:54-66
   double b0, b1, b2, a1, a2;              // HighPassFilterIir(60/48000)          AmDecode.cpp:45
   double de_a1, de_b0;                    // LowPassFilterRC(100us * 48 kHz)      AmDecode.cpp:49
+  int demod_real;                         // demodulate_dsb (real part) instead of demodulate_am (magnitude)
+  int deemph;                             // deemphasis runs for ModType::AM only (AmDecode.cpp:212-214)
   int n_channels;
 };
 
@@ -69,8 +71,8 @@ __global__ void k_am_core(Ring<float2> in, double *__restrict__ audio, size_t au
         } else if (s.if_gain > P.if_max) {
           s.if_gain = P.if_max;
         }
-        // demodulate_am (AmDecode.cpp:221-226): volk_32fc_magnitude_32f
-        const float mag = sqrtf(xr * xr + xi * xi);
+        // demodulate_am (AmDecode.cpp:221-226): volk_32fc_magnitude_32f; demodulate_dsb (:229-234): real part
+        const float mag = P.demod_real ? xr : sqrtf(xr * xr + xi * xi);
         vsum += mag;
         vsq += mag * mag;
         // DC block (AmDecode.cpp:194; Filter.cpp:243-250)
@@ -88,10 +90,14 @@ __global__ void k_am_core(Ring<float2> in, double *__restrict__ audio, size_t au
         } else if (s.af_gain > P.af_max) {
           s.af_gain = P.af_max;
         }
-        // deemphasis (AmDecode.cpp:212-214)
-        const double e0 = y - P.de_a1 * s.de_x1;
-        o[ob + i] = P.de_b0 * e0;
-        s.de_x1 = e0;
+        // deemphasis (AmDecode.cpp:212-214), ModType::AM only
+        if (P.deemph) {
+          const double e0 = y - P.de_a1 * s.de_x1;
+          o[ob + i] = P.de_b0 * e0;
+          s.de_x1 = e0;
+        } else {
+          o[ob + i] = y;
+        }
       }
     }
     s.if_rms = sqrtf(sumsq / (float)n);
@@ -166,7 +172,8 @@ __global__ void __launch_bounds__(96)
           const float z = (float)(1.0 + (rate * (1.0 - (double)nrm)));
           g *= z;
           g = isfinite(g) ? ((g > P.if_max) ? P.if_max : g) : 1.0f;
-          const float mag = sqrtf(xr * xr + xi * xi); // demodulate_am (AmDecode.cpp:221-226)
+          // demodulate_am (AmDecode.cpp:221-226) / demodulate_dsb (:229-234)
+          const float mag = P.demod_real ? xr : sqrtf(xr * xr + xi * xi);
           vsum += mag;
           vsq += mag * mag;
           S.mag[slot][u][lane] = mag;
@@ -243,16 +250,37 @@ __global__ void __launch_bounds__(96)
 #pragma unroll
       for (int u = 0; u < kCfT; u++) {
         if (p0 + u < n_total) {
-          // deemphasis (AmDecode.cpp:212-214)
-          const double e0 = S.y[slot][u][lane] - de_a1 * e1;
-          if (act) o[p0 + u] = de_b0 * e0;
-          e1 = e0;
+          // deemphasis (AmDecode.cpp:212-214), ModType::AM only
+          const double yv = S.y[slot][u][lane];
+          if (P.deemph) {
+            const double e0 = yv - de_a1 * e1;
+            if (act) o[p0 + u] = de_b0 * e0;
+            e1 = e0;
+          } else if (act) {
+            o[p0 + u] = yv;
+          }
         }
       }
       if (k + 2 < K) cf_arrive(cf_empty(1, slot));
     }
     if (act) sp->de_x1 = e1;
   }
+}
+
+// FineTuner::process (FineTuner.cpp:55-70): out[i] = in[i] * table[(index + i) mod size], complex
+// float product with the reference's separate roundings (no FMA contraction). All channels of a
+// handle have consumed the same number of samples, so the table index is one scalar per tuner.
+__global__ void k_finetune(Ring<float2> in, Ring<float2> out, const float2 *__restrict__ table, int size,
+                           uint32_t idx0, int64_t t0, int n) {
+  const uint32_t c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 x = in.ld(c, t0 + i);
+  const float2 w = table[(idx0 + (uint32_t)i) % (uint32_t)size];
+  float2 y;
+  y.x = __fsub_rn(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
+  y.y = __fadd_rn(__fmul_rn(x.x, w.y), __fmul_rn(x.y, w.x));
+  out.st(c, t0 + i, y);
 }
 
 struct NbfmCoreParams {
@@ -350,6 +378,12 @@ struct fmr_am {
   int p_hist = -1, p_flt = -1, p_core = -1;
   AmCoreParams core;
   bool core_fused = true; // FMR_CORE_FUSED=0: the single-warp k_am_core
+  // USB / LSB / CW / WSPR (AmDecode.cpp:103-137): FineTuner -> 2049-tap filter -> FineTuner
+  Ring<float2> r_t1{nullptr, 0}, r_t2{nullptr, 0};
+  float *d_cwfilter = nullptr, *d_ssbfilter = nullptr;
+  float2 *d_tab_cw = nullptr, *d_tab_up = nullptr, *d_tab_down = nullptr; // FineTuner tables (480 entries)
+  uint32_t idx_cw = 0, idx_up = 0, idx_down = 0;                         // FineTuner m_index
+  int p_tune = -1;
   // NBFM (mode 1)
   bool nbfm = false;
   NbfmCoreParams ncore;
@@ -392,9 +426,7 @@ static fmr_status am_build(fmr_am *h) {
   const int C = h->C = (int)cfg.n_channels;
   const int64_t max_in = cfg.max_samples_per_call;
   const int max_blocks = (int)cfg.max_blocks_per_call;
-  if (cfg.mode != 2 && cfg.mode != 1) {
-    return fail(FMR_ERR_UNSUPPORTED, "only ModType::AM (2) and ModType::NBFM (1) are implemented");
-  }
+  if (cfg.mode < 1 || cfg.mode > 7) return fail(FMR_ERR_UNSUPPORTED, "mode must be a ModType value 1 (NBFM) .. 7 (WSPR)");
   h->nbfm = (cfg.mode == 1);
   if (cfg.input_rate != 48000.0) {
     h->ifc = find_chain(cfg.input_rate, 48000.0, 0);
@@ -485,6 +517,44 @@ static fmr_status am_build(fmr_am *h) {
     P.de_b0 = 1 + P.de_a1;
   }
   P.n_channels = C;
+  {
+    // AmDecoder::AmDecoder (AmDecode.cpp:54-77): AGC references and rates depend on the mode
+    const int m = cfg.mode;
+    const bool ssbcw = (m == 4 || m == 5 || m == 6 || m == 7), cw = (m == 6 || m == 7);
+    P.af_ref = ssbcw ? 0.24 : 0.6;
+    P.af_rate = cw ? 0.00125 : 0.001;
+    P.if_rate = cw ? 0.0006f : 0.0003f;
+    P.demod_real = (m != 2) ? 1 : 0;
+    P.deemph = (m == 2) ? 1 : 0;
+    if (ssbcw) {
+      h->r_t1.cap = h->r_if.cap;
+      FMR_CUDA(h->mem.alloc(&h->r_t1.base, (size_t)C * h->r_t1.cap));
+      h->r_t2.cap = h->r_if.cap;
+      FMR_CUDA(h->mem.alloc(&h->r_t2.base, (size_t)C * h->r_t2.cap));
+      FMR_CUDA(h->mem.alloc(&h->d_cwfilter, 2049, false));
+      FMR_CUDA(cudaMemcpy(h->d_cwfilter, k_jj1bdx_cw_48khz_500hz, 2049 * sizeof(float), cudaMemcpyHostToDevice));
+      FMR_CUDA(h->mem.alloc(&h->d_ssbfilter, 2049, false));
+      FMR_CUDA(cudaMemcpy(h->d_ssbfilter, k_jj1bdx_ssb_48khz_1500hz, 2049 * sizeof(float), cudaMemcpyHostToDevice));
+      FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)fq_smem(2049, sizeof(float2), sizeof(float))));
+      // FineTuner::set_freq_shift (FineTuner.cpp:32-52): table_size 480 = 48000/100, shifts +5, +15, -15
+      auto make_tab = [&](int shift, float2 **dst) -> cudaError_t {
+        std::vector<float2> t(480);
+        const double step = 2.0 * M_PI / 480.0;
+        for (unsigned i = 0; i < 480; i++) {
+          const int64_t r = ((int64_t)shift * (int64_t)i) % (int64_t)480;
+          const double phi = (double)r * step;
+          t[i] = make_float2((float)std::cos(phi), (float)std::sin(phi));
+        }
+        cudaError_t e = h->mem.alloc(dst, (size_t)480, false);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, t.data(), sizeof(float2) * 480, cudaMemcpyHostToDevice);
+      };
+      FMR_CUDA(make_tab(5, &h->d_tab_cw));
+      FMR_CUDA(make_tab(15, &h->d_tab_up));
+      FMR_CUDA(make_tab(-15, &h->d_tab_down));
+    }
+  }
   if (h->nbfm) {
     h->freq_dev = cfg.nbfm_freq_dev > 0 ? cfg.nbfm_freq_dev : 8000.0; // NbfmDecoder::freq_dev_normal
     NbfmCoreParams &N = h->ncore;
@@ -510,6 +580,7 @@ static fmr_status am_build(fmr_am *h) {
   h->ifres.p_fi = h->prof.add("if_polyphase");
   h->p_hist = h->prof.add("save_hist");
   h->p_flt = h->prof.add("am_channel_filter");
+  h->p_tune = h->prof.add("am_finetuners");
   h->p_core = h->prof.add(h->nbfm ? "nbfm_core_48k" : "am_core_48k");
   h->p_aud = h->prof.add("nbfm_audio_fir");
   h->p_out = h->prof.add("nbfm_gain_out");
@@ -631,10 +702,36 @@ extern "C" fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t
   }
   if (n48 > 0) {
     dim3 grid((n48 + kQTile - 1) / kQTile, C);
-    pf.begin(h->p_flt, st);
-    k_fir_quirk<float><<<grid, kQThreads, fq_smem(h->amfilter_taps, sizeof(float2), sizeof(float)), st>>>(h->r_if, h->r_flt, h->d_amfilter, h->amfilter_taps, t0, (int)n48,
-                                             h->d_e48, (int)n_blocks);
-    pf.end(h->p_flt, st);
+    const int mode = h->cfg.mode;
+    if (mode >= 4 && mode <= 7) {
+      // USB: down, ssb filter, up. LSB: up, ssb filter, down. CW: cw filter, cw tuner. WSPR: down, cw filter, up
+      // (AmDecode.cpp:103-137)
+      dim3 tg((n48 + 255) / 256, C);
+      auto tune = [&](Ring<float2> a, Ring<float2> b, const float2 *tab, uint32_t *idx) {
+        k_finetune<<<tg, 256, 0, st>>>(a, b, tab, 480, *idx, t0, (int)n48);
+        *idx = (uint32_t)((*idx + n48) % 480u);
+        launches++;
+      };
+      auto filt = [&](Ring<float2> a, Ring<float2> b, const float *taps) {
+        k_fir_quirk<float><<<grid, kQThreads, fq_smem(2049, sizeof(float2), sizeof(float)), st>>>(a, b, taps, 2049, t0, (int)n48,
+                                                                                             h->d_e48, (int)n_blocks);
+      };
+      pf.begin(h->p_tune, st);
+      if (mode == 4 || mode == 7) tune(h->r_if, h->r_t1, h->d_tab_down, &h->idx_down);
+      if (mode == 5) tune(h->r_if, h->r_t1, h->d_tab_up, &h->idx_up);
+      pf.end(h->p_tune, st);
+      pf.begin(h->p_flt, st);
+      filt(mode == 6 ? h->r_if : h->r_t1, h->r_t2, (mode == 4 || mode == 5) ? h->d_ssbfilter : h->d_cwfilter);
+      pf.end(h->p_flt, st);
+      if (mode == 4 || mode == 7) tune(h->r_t2, h->r_flt, h->d_tab_up, &h->idx_up);
+      if (mode == 5) tune(h->r_t2, h->r_flt, h->d_tab_down, &h->idx_down);
+      if (mode == 6) tune(h->r_t2, h->r_flt, h->d_tab_cw, &h->idx_cw);
+    } else {
+      pf.begin(h->p_flt, st);
+      k_fir_quirk<float><<<grid, kQThreads, fq_smem(h->amfilter_taps, sizeof(float2), sizeof(float)), st>>>(h->r_if, h->r_flt, h->d_amfilter, h->amfilter_taps, t0, (int)n48,
+                                               h->d_e48, (int)n_blocks);
+      pf.end(h->p_flt, st);
+    }
     pf.begin(h->p_core, st);
     if (h->nbfm) {
       k_nbfm_core<<<(C + 31) / 32, 32, 0, st>>>(h->r_flt, h->r_bb, h->d_state, h->d_e48, (int)n_blocks, t0, h->ncore);

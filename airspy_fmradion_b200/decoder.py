@@ -205,7 +205,8 @@ class AmDecoder(_Base):
 
     def __init__(self, amfilter=0, mode=2, *, input_rate=48000.0, fs4_shift=False, n_channels=1,
                  max_samples_per_call=1 << 20, max_blocks_per_call=4096, device=0, amfilter_coeff=None):
-        """amfilter: 0 default, 1 medium, 2 narrow, 3 wide (main.cpp:785-810); mode: ModType value."""
+        """amfilter: 0 default, 1 medium, 2 narrow, 3 wide (main.cpp:785-810); mode: ModType value
+        (include/SoftFM.h:49): 2 AM, 3 DSB, 4 USB, 5 LSB, 6 CW, 7 WSPR."""
         L = _capi.lib()
         self._destroy, self._query = L.fmr_am_destroy, L.fmr_am_query_output
         self._process_host, self._process_device = L.fmr_am_process_host, L.fmr_am_process_device

@@ -151,7 +151,7 @@ public:
   static constexpr double bandwidth_pcm = 4500;
   static constexpr double deemphasis_time = 100;
 
-  // Arguments as include/AmDecode.h:42-48. ModType::AM is implemented on the GPU (NBFM: see NbfmDecoder).
+  // Arguments as include/AmDecode.h:42-48; ModType AM, DSB, USB, LSB, CW and WSPR (NBFM: see NbfmDecoder).
   AmDecoder(IQSampleCoeff &amfilter_coeff, const ModType mode, double input_rate = internal_rate_pcm,
             bool fs4_shift = false, int device = 0) {
     fmr_am_config cfg{};

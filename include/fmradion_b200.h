@@ -175,7 +175,8 @@ typedef struct fmr_am_config {
   int fs4_shift;
   int amfilter;         /* 0 default, 1 medium, 2 narrow, 3 wide (main.cpp:785-810),
                            4 = amfilter_coeff[amfilter_ntaps] (AmDecoder ctor `amfilter_coeff`) */
-  int mode;             /* ModType value (include/SoftFM.h:49): 1 = NBFM, 2 = AM; others FMR_ERR_UNSUPPORTED.
+  int mode;             /* ModType value (include/SoftFM.h:49): 1 NBFM, 2 AM, 3 DSB, 4 USB, 5 LSB, 6 CW, 7 WSPR
+                           (AmDecoder::process, AmDecode.cpp:96-218; FineTuner.cpp:55-70 for the pitch shifts).
                            For NBFM `amfilter` selects jj1bdx_nbfm_48khz_{default,medium,narrow,wide}
                            (main.cpp:785-810) or, with 4, the caller's `amfilter_coeff` (ctor `nbfmfilter_coeff`) */
   uint32_t n_channels;

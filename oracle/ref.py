@@ -87,7 +87,7 @@ class RefChain:
     """One reference receive chain (front end + decoder) fed block by block."""
 
     def __init__(self, mode="fm", ifrate=384000.0, fs4=False, filter=0, stereo=True,
-                 deemphasis_us=50.0, pilot_shift=False, mpf_stages=0, freq_dev=8000.0):
+                 deemphasis_us=50.0, pilot_shift=False, mpf_stages=0, freq_dev=8000.0, modtype=MODTYPE_AM):
         L = lib()
         self.mode = mode
         if mode == "fm":
@@ -96,7 +96,7 @@ class RefChain:
         elif mode == "nbfm":
             self.h = L.ref_nbfm_create(ifrate, int(fs4), filter, float(freq_dev))
         else:
-            self.h = L.ref_am_create(ifrate, int(fs4), filter, MODTYPE_AM)
+            self.h = L.ref_am_create(ifrate, int(fs4), filter, int(modtype))
         self._audio = np.empty(1 << 18, dtype=np.float64)
 
     def close(self):

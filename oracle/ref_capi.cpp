@@ -463,6 +463,10 @@ int ref_filter_table(const char *name, double *out, int cap) {
     cf(FilterParameters::jj1bdx_nbfm_48khz_narrow);
   else if (s == "jj1bdx_nbfm_48khz_wide")
     cf(FilterParameters::jj1bdx_nbfm_48khz_wide);
+  else if (s == "jj1bdx_cw_48khz_500hz")
+    cf(FilterParameters::jj1bdx_cw_48khz_500hz);
+  else if (s == "jj1bdx_ssb_48khz_1500hz")
+    cf(FilterParameters::jj1bdx_ssb_48khz_1500hz);
   else if (s == "jj1bdx_am_48khz_narrow")
     cf(FilterParameters::jj1bdx_am_48khz_narrow);
   else if (s == "jj1bdx_am_48khz_medium")

@@ -38,6 +38,8 @@ def lib():
         L.orc_fm_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint]
         L.orc_am_create.restype = C.c_void_p
         L.orc_am_create.argtypes = [C.c_double, C.c_int, C.c_int]
+        L.orc_am_create_mode.restype = C.c_void_p
+        L.orc_am_create_mode.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int]
         L.orc_nbfm_create.restype = C.c_void_p
         L.orc_nbfm_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_double]
         L.orc_nbfm_stats.argtypes = [C.c_void_p, C.c_void_p]
@@ -102,9 +104,9 @@ def fm_run(iq, fs, blk, stereo=True, fs4=False, filter=0, deemphasis_us=50.0, pi
     return (np.concatenate(out) if out else np.empty(0)), np.array(lens, dtype=np.int64), td, st
 
 
-def am_run(iq, fs, blk, filter=0, fs4=False):
+def am_run(iq, fs, blk, filter=0, fs4=False, modtype=2):
     L = lib()
-    h = L.orc_am_create(fs, int(fs4), filter)
+    h = L.orc_am_create_mode(fs, int(fs4), filter, int(modtype))
     assert h
     iq = np.ascontiguousarray(iq, dtype=np.complex64)
     audio = np.empty(1 << 17, dtype=np.float64)

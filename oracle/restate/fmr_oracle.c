@@ -640,19 +640,45 @@ int orc_fm_pps(void *p, double *out, int cap) {
 }
 
 /* ------------------------------------------------------------------ AM chain ---------- */
+/* FineTuner (FineTuner.cpp:25-72): table-driven NCO multiply, index carried across calls. */
+typedef struct { float *re, *im; unsigned size, index; } Tuner;
+static void tuner_init(Tuner *t, unsigned table_size, int freq_shift) {
+  t->size = table_size; t->index = 0;
+  t->re = (float *)malloc(sizeof(float) * table_size); t->im = (float *)malloc(sizeof(float) * table_size);
+  const double phase_step = 2.0 * M_PI / (double)table_size;                     /* FineTuner.cpp:41 */
+  for (unsigned i = 0; i < table_size; i++) {
+    /* ((int64_t)freq_shift * i) % m_table_size with m_table_size unsigned int: int64 remainder,
+       sign of the dividend (FineTuner.cpp:43) */
+    const int64_t r = ((int64_t)freq_shift * (int64_t)i) % (int64_t)table_size;
+    const double phi = (double)r * phase_step;
+    t->re[i] = (float)cos(phi); t->im[i] = (float)sin(phi);
+  }
+}
+static void tuner_process(Tuner *t, const float *in, int n, float *out) {        /* FineTuner.cpp:55-70 */
+  unsigned idx = t->index;
+  for (int i = 0; i < n; i++) {
+    const float a = in[2 * i], b = in[2 * i + 1], c = t->re[idx], d = t->im[idx];
+    out[2 * i] = a * c - b * d;
+    out[2 * i + 1] = a * d + b * c;
+    if (++idx == t->size) idx = 0;
+  }
+  t->index = idx;
+}
 typedef struct {
-  double ifrate; int fs4; unsigned fs4_idx;
+  double ifrate; int fs4; unsigned fs4_idx; int mode;
   const ChainDesc *ifc; R8Lane if_re, if_im;
-  FirIQ amf;
+  FirIQ amf, cwf, ssbf;
+  Tuner cw_up, ws_up, ws_down;
   float if_gain, if_max, if_rate, if_rms, baseband_mean, baseband_level;
   Biquad dcblock; FoIir deemph;
   double af_gain, af_max, af_ref, af_rate;
   uint64_t decoder_calls;
 } OrcAm;
 
-void *orc_am_create(double ifrate, int fs4, int filter) {
+/* mode: ModType value (include/SoftFM.h:49): 2 AM, 3 DSB, 4 USB, 5 LSB, 6 CW, 7 WSPR */
+void *orc_am_create_mode(double ifrate, int fs4, int filter, int mode) {
   OrcAm *h = (OrcAm *)calloc(1, sizeof(OrcAm));
-  h->ifrate = ifrate; h->fs4 = fs4;
+  h->ifrate = ifrate; h->fs4 = fs4; h->mode = mode;
   if (ifrate != 48000.0) {
     h->ifc = find_chain(ifrate, 48000.0, 0);
     if (!h->ifc) { free(h); return 0; }
@@ -662,19 +688,27 @@ void *orc_am_create(double ifrate, int fs4, int filter) {
   if (filter == 1) c = k_jj1bdx_am_48khz_medium; else if (filter == 2) c = k_jj1bdx_am_48khz_narrow;
   else if (filter == 3) { c = k_jj1bdx_am_48khz_wide; nt = 127; }
   firiq_init(&h->amf, c, nt);
+  firiq_init(&h->cwf, k_jj1bdx_cw_48khz_500hz, 2049);                           /* AmDecode.cpp:35 */
+  firiq_init(&h->ssbf, k_jj1bdx_ssb_48khz_1500hz, 2049);                        /* AmDecode.cpp:39 */
   hp_init(&h->dcblock, 60.0 / 48000.0);                                         /* AmDecode.cpp:45 */
   rc_init(&h->deemph, 100.0 * 48000.0 * 1.0e-6);                                /* AmDecode.cpp:49 */
-  h->af_gain = 1.0; h->af_max = 1.5; h->af_ref = 0.6; h->af_rate = 0.001;       /* AmDecode.cpp:54-66 */
-  h->if_gain = 1.0f; h->if_max = 1000000.0f; h->if_rate = 0.0003f;              /* AmDecode.cpp:71-77 */
+  const int ssbcw = (mode == 4 || mode == 5 || mode == 6 || mode == 7), cw = (mode == 6 || mode == 7);
+  h->af_gain = 1.0; h->af_max = 1.5; h->af_ref = ssbcw ? 0.24 : 0.6; h->af_rate = cw ? 0.00125 : 0.001; /* :54-66 */
+  h->if_gain = 1.0f; h->if_max = 1000000.0f; h->if_rate = cw ? 0.0006f : 0.0003f;                      /* :71-77 */
+  tuner_init(&h->cw_up, 480, 5);                                                /* AmDecode.cpp:82 */
+  tuner_init(&h->ws_up, 480, 15); tuner_init(&h->ws_down, 480, -15);            /* AmDecode.cpp:88-89 */
   return h;
 }
+void *orc_am_create(double ifrate, int fs4, int filter) { return orc_am_create_mode(ifrate, fs4, filter, 2); }
 void orc_am_destroy(void *p) {
   OrcAm *h = (OrcAm *)p;
   if (!h) return;
   if (h->ifc) { r8_free(&h->if_re); r8_free(&h->if_im); }
-  free(h->amf.sre); free(h->amf.sim); free(h);
+  free(h->amf.sre); free(h->amf.sim); free(h->cwf.sre); free(h->cwf.sim); free(h->ssbf.sre); free(h->ssbf.sim);
+  free(h->cw_up.re); free(h->cw_up.im); free(h->ws_up.re); free(h->ws_up.im); free(h->ws_down.re); free(h->ws_down.im);
+  free(h);
 }
-/* main.cpp:912-971 + AmDecoder::process for ModType::AM (AmDecode.cpp:96-218) */
+/* main.cpp:912-971 + AmDecoder::process (AmDecode.cpp:96-218), all modes */
 int orc_am_process_block(void *p, const float *iq, int n, double *audio, int cap) {
   OrcAm *h = (OrcAm *)p;
   float *ifs = 0;
@@ -682,8 +716,15 @@ int orc_am_process_block(void *p, const float *iq, int n, double *audio, int cap
   if (m == 0) { free(ifs); return 0; }
   if (m > cap) { free(ifs); return -1; }
   h->decoder_calls++;
-  float *x = (float *)malloc(sizeof(float) * 2 * (size_t)m);
-  firiq_process(&h->amf, ifs, m, x);                                            /* :101 */
+  float *x = (float *)malloc(sizeof(float) * 2 * (size_t)m), *t1 = (float *)malloc(sizeof(float) * 2 * (size_t)m);
+  switch (h->mode) {                                                            /* :97-152 */
+  case 4: tuner_process(&h->ws_down, ifs, m, x); firiq_process(&h->ssbf, x, m, t1); tuner_process(&h->ws_up, t1, m, x); break;
+  case 5: tuner_process(&h->ws_up, ifs, m, x); firiq_process(&h->ssbf, x, m, t1); tuner_process(&h->ws_down, t1, m, x); break;
+  case 6: firiq_process(&h->cwf, ifs, m, t1); tuner_process(&h->cw_up, t1, m, x); break;
+  case 7: tuner_process(&h->ws_down, ifs, m, x); firiq_process(&h->cwf, x, m, t1); tuner_process(&h->ws_up, t1, m, x); break;
+  default: firiq_process(&h->amf, ifs, m, x); break;                            /* AM, DSB :101 */
+  }
+  free(t1);
   {
     float level = 0;
     for (int i = 0; i < m; i++) level += x[2 * i] * x[2 * i] + x[2 * i + 1] * x[2 * i + 1];
@@ -692,7 +733,8 @@ int orc_am_process_block(void *p, const float *iq, int n, double *audio, int cap
   if_agc(&h->if_gain, h->if_max, h->if_rate, x, m);                             /* :157 */
   float vsum = 0, vsq = 0;
   for (int i = 0; i < m; i++) {
-    const float mag = sqrtf(x[2 * i] * x[2 * i] + x[2 * i + 1] * x[2 * i + 1]);  /* demodulate_am :221-226 */
+    /* demodulate_am :221-226 (magnitude) / demodulate_dsb :229-234 (real part) */
+    const float mag = (h->mode == 2) ? sqrtf(x[2 * i] * x[2 * i] + x[2 * i + 1] * x[2 * i + 1]) : x[2 * i];
     vsum += mag; vsq += mag * mag;
     double v = bq_process(&h->dcblock, (double)mag);                            /* :194 */
     /* AfSimpleAgc::process (AfSimpleAgc.cpp:36-58) */
@@ -701,7 +743,7 @@ int orc_am_process_block(void *p, const float *iq, int n, double *audio, int cap
     const double z = 1.0 + (h->af_rate * (1.0 - (x2 * x2)));
     h->af_gain *= z;
     if (!isfinite(h->af_gain)) h->af_gain = 1.0; else if (h->af_gain > h->af_max) h->af_gain = h->af_max;
-    audio[i] = fo_process(&h->deemph, o);                                       /* :212-214 */
+    audio[i] = (h->mode == 2) ? fo_process(&h->deemph, o) : o;                  /* :212-214: deemphasis for AM only */
   }
   h->baseband_mean = (float)(0.95 * h->baseband_mean + 0.05 * (vsum / (float)m));  /* :206-209 */
   h->baseband_level = (float)(0.95 * h->baseband_level + 0.05 * sqrtf(vsq / (float)m));

@@ -68,3 +68,19 @@ def nbfm_iq(fs, n, channel=0, sigma=0.005, amp=0.5, dev=3000.0):
     out.real = (amp * np.cos(phi)).astype(np.float32) + noise[:, 0]
     out.imag = (amp * np.sin(phi)).astype(np.float32) + noise[:, 1]
     return out
+
+
+def ssb_iq(fs, n, channel=0, sigma=0.003):
+    """Test signal for the DSB/USB/LSB/CW/WSPR branches of AmDecoder: complex tones on both sides of
+    the carrier (+700 + 17c Hz and +1900 Hz: upper sideband; -1100 Hz: lower sideband; +120 Hz: inside
+    the 500 Hz CW filter; +1480 Hz: inside the WSPR band) + N(0, sigma^2), seed 23+c."""
+    t = np.arange(n, dtype=np.float64) / fs
+    x = (0.30 * np.exp(2j * np.pi * (700.0 + 17.0 * channel) * t) + 0.15 * np.exp(2j * np.pi * 1900.0 * t)
+         + 0.20 * np.exp(-2j * np.pi * 1100.0 * t) + 0.25 * np.exp(2j * np.pi * 120.0 * t)
+         + 0.10 * np.exp(2j * np.pi * 1480.0 * t))
+    rng = np.random.Generator(np.random.PCG64(23 + channel))
+    noise = rng.standard_normal((n, 2), dtype=np.float32) * np.float32(sigma)
+    out = np.empty(n, dtype=np.complex64)
+    out.real = x.real.astype(np.float32) + noise[:, 0]
+    out.imag = x.imag.astype(np.float32) + noise[:, 1]
+    return out
