@@ -55,6 +55,19 @@ class AmStats(C.Structure):
                 ("tuning_offset", C.c_float)]
 
 
+class OutputConfig(C.Structure):
+    _fields_ = [("out_format", C.c_int), ("squelch_level", C.c_double), ("gain", C.c_double)]
+
+
+class BlockLevel(C.Structure):
+    _fields_ = [("if_rms", C.c_float), ("audio_mean", C.c_float), ("audio_rms", C.c_float), ("gain", C.c_float)]
+
+
+# enum values of include/fmradion_b200.h
+IQ_CF32, IQ_S16, IQ_S8, IQ_U8, IQ_S24 = range(5)
+OUT_F64, OUT_F32, OUT_S16 = range(3)
+IQ_BYTES = {IQ_CF32: 8, IQ_S16: 4, IQ_S8: 2, IQ_U8: 2, IQ_S24: 6}
+
 # every symbol include/fmradion_b200.h declares
 EXPORTS = [
     "fmr_last_error", "fmr_version", "fmr_device_sm_count",
@@ -66,6 +79,8 @@ EXPORTS = [
     "fmr_am_create", "fmr_am_destroy", "fmr_am_process_host", "fmr_am_process_device",
     "fmr_am_query_output", "fmr_am_stats", "fmr_am_last_launches", "fmr_am_set_profiling",
     "fmr_am_stage_times",
+    "fmr_fm_process_host_io", "fmr_fm_process_device_io", "fmr_fm_block_levels",
+    "fmr_am_process_host_io", "fmr_am_process_device_io", "fmr_am_block_levels",
 ]
 
 _lib = None
@@ -115,6 +130,13 @@ def lib():
     L.fmr_am_stats.argtypes = [vp, C.c_uint32, C.POINTER(AmStats)]
     L.fmr_am_last_launches.argtypes = [vp]
     L.fmr_am_last_launches.restype = C.c_uint32
+    proc_io = [vp, vp, C.c_int, C.c_size_t, vp, C.c_uint32, C.POINTER(OutputConfig), vp, C.c_size_t, vp]
+    L.fmr_fm_process_host_io.argtypes = proc_io
+    L.fmr_fm_process_device_io.argtypes = proc_io + [vp]
+    L.fmr_fm_block_levels.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
+    L.fmr_am_process_host_io.argtypes = proc_io
+    L.fmr_am_process_device_io.argtypes = proc_io + [vp]
+    L.fmr_am_block_levels.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
     _lib = L
     return L
 

@@ -6,6 +6,7 @@
 
 #include "fmr_core.cuh"
 #include "fmr_host.cuh"
+#include "fmr_io.cuh"
 
 using namespace fmr;
 
@@ -397,6 +398,13 @@ struct fmr_am {
   float *d_iq = nullptr;
   double *d_audio = nullptr;
   size_t audio_cap = 0;
+  // file-format ingest and output stage (fmr_am_process_*_io, fmr_io.cuh)
+  uint8_t *d_raw = nullptr;
+  size_t raw_cap = 0;
+  uint8_t *d_out = nullptr;
+  BlockLevelDev *d_levels = nullptr;
+  bool have_levels = false;
+  uint32_t last_blocks = 0;
 };
 
 static int64_t am_out_total(const ChainDesc *ifc, int64_t n) { return ifc ? chain_out(ifc, n) : n; }
@@ -796,6 +804,139 @@ extern "C" fmr_status fmr_am_process_host(fmr_am *h, const float *iq, size_t iq_
                                cudaMemcpyDeviceToHost, st));
   }
   FMR_CUDA(cudaStreamSynchronize(st));
+  return FMR_OK;
+}
+
+static fmr_status am_ensure_staging(fmr_am *h, size_t raw_bytes, bool want_sink) {
+  const int C = h->C;
+  if (!h->d_iq) {
+    FMR_CUDA(h->mem.alloc(&h->d_iq, (size_t)C * h->cfg.max_samples_per_call * 2, false));
+    FMR_CUDA(h->mem.alloc(&h->d_audio, (size_t)C * h->audio_cap, false));
+  }
+  if (raw_bytes > h->raw_cap) {
+    FMR_CUDA(cudaDeviceSynchronize());
+    FMR_CUDA(h->mem.alloc(&h->d_raw, raw_bytes, false));
+    h->raw_cap = raw_bytes;
+  }
+  if (want_sink && !h->d_levels) {
+    FMR_CUDA(h->mem.alloc(&h->d_out, (size_t)C * h->audio_cap * 8, false));
+    FMR_CUDA(h->mem.alloc(&h->d_levels, (size_t)C * h->cfg.max_blocks_per_call));
+  }
+  return FMR_OK;
+}
+
+// FileSource sample formats in, the block loop's output stage out (main.cpp:977-1002), around
+// fmr_am_process_device; everything is enqueued on `stream`.
+extern "C" fmr_status fmr_am_process_device_io(fmr_am *h, const void *d_iq, int iq_format, size_t iq_stride,
+                                               const uint32_t *block_len, uint32_t n_blocks,
+                                               const fmr_output_config *out_cfg, void *d_audio, size_t audio_stride,
+                                               uint32_t *audio_len, void *stream) {
+  if (!h || !d_iq || !block_len || !d_audio) return fail(FMR_ERR_INVALID, "null argument");
+  if (iq_format_bytes(iq_format) == 0) return fail(FMR_ERR_INVALID, "unknown iq_format");
+  if (out_cfg && out_format_bytes(out_cfg->out_format) == 0) return fail(FMR_ERR_INVALID, "unknown out_format");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < n_blocks; b++) total += block_len[b];
+  if (total > h->cfg.max_samples_per_call) return fail(FMR_ERR_CAPACITY, "sum(block_len) > max_samples_per_call");
+  if (total > iq_stride) return fail(FMR_ERR_INVALID, "iq_stride < sum(block_len)");
+  if (n_blocks > h->cfg.max_blocks_per_call) return fail(FMR_ERR_CAPACITY, "n_blocks > max_blocks_per_call");
+  const bool direct = (iq_format == FMR_IQ_CF32);
+  fmr_status s = FMR_OK;
+  if (!direct || out_cfg) {
+    s = am_ensure_staging(h, 0, out_cfg != nullptr);
+    if (s != FMR_OK) return s;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const float *d_in = reinterpret_cast<const float *>(d_iq);
+  size_t stride = iq_stride;
+  uint32_t extra = 0;
+  if (!direct) {
+    FMR_CUDA(launch_ingest_convert(d_iq, iq_format, iq_stride, reinterpret_cast<float2 *>(h->d_iq), (size_t)total, total,
+                                   h->C, st));
+    d_in = h->d_iq;
+    stride = (size_t)total;
+    extra++;
+  }
+  h->have_levels = false;
+  h->last_blocks = n_blocks;
+  if (!out_cfg) {
+    s = fmr_am_process_device(h, d_in, stride, block_len, n_blocks, reinterpret_cast<double *>(d_audio), audio_stride,
+                              audio_len, stream);
+    if (s == FMR_OK) h->last_launches += extra;
+    return s;
+  }
+  uint64_t out_total = 0;
+  s = fmr_am_query_output(h, block_len, n_blocks, &out_total, nullptr);
+  if (s != FMR_OK) return s;
+  if (out_total > audio_stride) return fail(FMR_ERR_CAPACITY, "audio_stride too small for this call");
+  const int64_t t0 = h->cum48;
+  s = fmr_am_process_device(h, d_in, stride, block_len, n_blocks, h->d_audio, h->audio_cap, audio_len, stream);
+  if (s != FMR_OK) return s;
+  if (n_blocks > 0) {
+    SinkParams P;
+    P.out_fmt = out_cfg->out_format;
+    P.w = 1; // AmDecoder / NbfmDecoder produce mono (AmDecode.h:53, NbfmDecode.h:48)
+    P.gain = out_cfg->gain;
+    P.squelch = out_cfg->squelch_level;
+    dim3 sg(n_blocks, h->C);
+    // decoder input and audio share the 48 kHz call table
+    k_audio_sink<<<sg, kSinkThreads, 0, st>>>(h->r_if, t0, h->d_e48, h->d_audio, h->audio_cap, h->d_e48, (int)n_blocks,
+                                              d_audio, audio_stride, h->d_levels, P);
+    FMR_CUDA(cudaGetLastError());
+    extra++;
+  }
+  h->last_launches += extra;
+  h->have_levels = true;
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_am_process_host_io(fmr_am *h, const void *iq, int iq_format, size_t iq_stride,
+                                             const uint32_t *block_len, uint32_t n_blocks,
+                                             const fmr_output_config *out_cfg, void *audio, size_t audio_stride,
+                                             uint32_t *audio_len) {
+  if (!h || !iq || !block_len || !audio) return fail(FMR_ERR_INVALID, "null argument");
+  const size_t esz = (size_t)iq_format_bytes(iq_format);
+  if (esz == 0) return fail(FMR_ERR_INVALID, "unknown iq_format");
+  if (out_cfg && out_format_bytes(out_cfg->out_format) == 0) return fail(FMR_ERR_INVALID, "unknown out_format");
+  const size_t osz = out_cfg ? (size_t)out_format_bytes(out_cfg->out_format) : 8;
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < n_blocks; b++) total += block_len[b];
+  if (total > h->cfg.max_samples_per_call) return fail(FMR_ERR_CAPACITY, "sum(block_len) > max_samples_per_call");
+  if (total > iq_stride) return fail(FMR_ERR_INVALID, "iq_stride < sum(block_len)");
+  const int C = h->C;
+  fmr_status s = am_ensure_staging(h, (size_t)C * h->cfg.max_samples_per_call * esz, true);
+  if (s != FMR_OK) return s;
+  cudaStream_t st = h->own_stream;
+  if (total > 0) {
+    FMR_CUDA(cudaMemcpy2DAsync(h->d_raw, (size_t)total * esz, iq, iq_stride * esz, (size_t)total * esz, C,
+                               cudaMemcpyHostToDevice, st));
+  }
+  uint64_t out_total = 0;
+  s = fmr_am_query_output(h, block_len, n_blocks, &out_total, nullptr);
+  if (s != FMR_OK) return s;
+  if (out_total > audio_stride) return fail(FMR_ERR_CAPACITY, "audio_stride too small for this call");
+  s = fmr_am_process_device_io(h, h->d_raw, iq_format, (size_t)total, block_len, n_blocks, out_cfg, h->d_out, h->audio_cap,
+                               audio_len, (void *)st);
+  if (s != FMR_OK) return s;
+  if (out_total > 0) {
+    FMR_CUDA(cudaMemcpy2DAsync(audio, audio_stride * osz, h->d_out, h->audio_cap * osz, (size_t)out_total * osz, C,
+                               cudaMemcpyDeviceToHost, st));
+  }
+  FMR_CUDA(cudaStreamSynchronize(st));
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_am_block_levels(fmr_am *h, uint32_t channel, fmr_block_level_t *out, uint32_t n_blocks) {
+  if (!h || !out || channel >= (uint32_t)h->C || n_blocks != h->last_blocks) {
+    return fail(FMR_ERR_INVALID, "bad argument (n_blocks must equal the last call's)");
+  }
+  if (!h->have_levels) return fail(FMR_ERR_INVALID, "the last call had no output stage");
+  static_assert(sizeof(BlockLevelDev) == sizeof(fmr_block_level_t), "level record layout");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  FMR_CUDA(cudaDeviceSynchronize());
+  FMR_CUDA(cudaMemcpy(out, h->d_levels + (size_t)channel * n_blocks, n_blocks * sizeof(BlockLevelDev),
+                      cudaMemcpyDeviceToHost));
   return FMR_OK;
 }
 

@@ -8,6 +8,7 @@
 
 #include "fmr_core.cuh"
 #include "fmr_host.cuh"
+#include "fmr_io.cuh"
 #include "fmr_mpf.cuh"
 #include "fmr_partition.cuh"
 
@@ -126,6 +127,17 @@ struct fmr_fm {
   float *d_iq = nullptr;
   double *d_audio = nullptr;
   size_t audio_cap = 0; // doubles per channel
+
+  // file-format ingest and output stage (fmr_fm_process_*_io, fmr_io.cuh)
+  uint8_t *d_raw = nullptr; // raw file samples of formats that are converted by their own launch
+  size_t raw_cap = 0;       // bytes
+  uint8_t *d_out = nullptr; // sink-format audio of the host entry point, [C][audio_cap] values
+  BlockLevelDev *d_levels = nullptr; // chunk-major like d_flags
+  bool sink_on = false;     // set for the duration of an *_io call with an out_cfg
+  SinkParams sink{};
+  uint8_t *sink_out = nullptr; // where the launch in progress stores value (c, i): sink_out[(c*stride + i) * bytes]
+  size_t sink_out_stride = 0;
+  bool have_levels = false;
 };
 
 static int64_t if_out_total(const fmr_fm *h, int64_t n) { return h->ifc ? chain_out(h->ifc, n) : n; }
@@ -508,7 +520,7 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
   // run as a two-stream pipeline: stream A does the front end (half-band cascade, FFT low-pass,
   // polyphase bank) of chunk k+1 while stream B does the 384 kHz core and the audio tail of chunk k.
   int n_chunks = 1;
-  if (!pf.on && n_blocks >= 2 * (uint32_t)h->chunk_min_blocks) {
+  if (!pf.on && !h->sink_on && n_blocks >= 2 * (uint32_t)h->chunk_min_blocks) {
     n_chunks = (int)(n_blocks / h->chunk_min_blocks);
     if (n_chunks > h->max_time_chunks) n_chunks = h->max_time_chunks;
     if (n_chunks < 1) n_chunks = 1;
@@ -710,6 +722,14 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
       pf.end(h->p_tail, sT);
       launches += 2;
     }
+    if (h->sink_on && nb > 0) {
+      // ---- output stage of the block loop (main.cpp:977-1002): levels, squelch gain, sink format
+      dim3 sg(nb, C);
+      k_audio_sink<<<sg, kSinkThreads, 0, sT>>>(h->r_if, t0k, d_e384, d_audio + (size_t)s48 * w, audio_stride, d_e48, (int)nb,
+                                                h->sink_out + (size_t)s48 * w * out_format_bytes(h->sink.out_fmt),
+                                                h->sink_out_stride, h->d_levels + (size_t)C * (flag_b0 + b0), h->sink);
+      launches++;
+    }
   }
   if (n_chunks > 1) {
     FMR_CUDA(cudaEventRecord(h->ev_join[0], sA));
@@ -747,39 +767,8 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
   return FMR_OK;
 }
 
-// Host-buffer entry point. The super-block is cut into a few time chunks so that the H2D copy
-// of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap (three streams,
-// events); with pinned host memory the call is PCIe-bound instead of copy + compute + copy.
-static fmr_status fm_process_host_impl(fmr_fm *h, const float *iq, size_t iq_stride, const uint32_t *block_len,
-                                       uint32_t n_blocks, double *audio, size_t audio_stride, uint32_t *audio_len,
-                                       int fmt);
-
-extern "C" fmr_status fmr_fm_process_host(fmr_fm *h, const float *iq, size_t iq_stride, const uint32_t *block_len,
-                                          uint32_t n_blocks, double *audio, size_t audio_stride,
-                                          uint32_t *audio_len) {
-  return fm_process_host_impl(h, iq, iq_stride, block_len, n_blocks, audio, audio_stride, audio_len, 0);
-}
-
-extern "C" fmr_status fmr_fm_process_host_i16(fmr_fm *h, const int16_t *iq, size_t iq_stride,
-                                              const uint32_t *block_len, uint32_t n_blocks, double *audio,
-                                              size_t audio_stride, uint32_t *audio_len) {
-  if (h && h->cfg.input_rate == 384000.0) return fail(FMR_ERR_UNSUPPORTED, "int16 ingest needs an IF resampler stage");
-  return fm_process_host_impl(h, reinterpret_cast<const float *>(iq), iq_stride, block_len, n_blocks, audio,
-                              audio_stride, audio_len, 1);
-}
-
-static fmr_status fm_process_host_impl(fmr_fm *h, const float *iq, size_t iq_stride, const uint32_t *block_len,
-                                       uint32_t n_blocks, double *audio, size_t audio_stride, uint32_t *audio_len,
-                                       int fmt) {
-  if (!h || !iq || !block_len || !audio) return fail(FMR_ERR_INVALID, "null argument");
-  const size_t esz = fmt ? 4 : 8;               // bytes per complex sample
-  const size_t fstep = fmt ? 1 : 2;             // float-pointer units per complex sample
-  FMR_CUDA(cudaSetDevice(h->cfg.device));
-  uint64_t total = 0;
-  for (uint32_t b = 0; b < n_blocks; b++) total += block_len[b];
-  if (total > h->cfg.max_samples_per_call) return fail(FMR_ERR_CAPACITY, "sum(block_len) > max_samples_per_call");
-  if (total > iq_stride) return fail(FMR_ERR_INVALID, "iq_stride < sum(block_len)");
-  if (n_blocks > h->cfg.max_blocks_per_call) return fail(FMR_ERR_CAPACITY, "n_blocks > max_blocks_per_call");
+// Staging buffers of the *_host and *_io entry points, allocated on first use.
+static fmr_status fm_ensure_staging(fmr_fm *h, size_t raw_bytes, bool want_sink) {
   const int C = h->C;
   if (!h->d_iq) {
     FMR_CUDA(h->mem.alloc(&h->d_iq, (size_t)C * h->cfg.max_samples_per_call * 2, false));
@@ -791,8 +780,80 @@ static fmr_status fm_process_host_impl(fmr_fm *h, const float *iq, size_t iq_str
       FMR_CUDA(cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
     }
   }
+  if (raw_bytes > h->raw_cap) {
+    FMR_CUDA(cudaDeviceSynchronize());
+    FMR_CUDA(h->mem.alloc(&h->d_raw, raw_bytes, false));
+    h->raw_cap = raw_bytes;
+  }
+  if (want_sink && !h->d_levels) {
+    FMR_CUDA(h->mem.alloc(&h->d_out, (size_t)C * h->audio_cap * 8, false));
+    FMR_CUDA(h->mem.alloc(&h->d_levels, (size_t)C * h->cfg.max_blocks_per_call));
+  }
+  return FMR_OK;
+}
+
+static fmr_status check_io_args(int iq_format, const fmr_output_config *oc) {
+  if (iq_format_bytes(iq_format) == 0) return fail(FMR_ERR_INVALID, "unknown iq_format");
+  if (oc && out_format_bytes(oc->out_format) == 0) return fail(FMR_ERR_INVALID, "unknown out_format");
+  return FMR_OK;
+}
+
+// Host-buffer entry point. The super-block is cut into a few time chunks so that the H2D copy
+// of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap (three streams,
+// events); with pinned host memory the call is PCIe-bound instead of copy + compute + copy.
+// `fmt` is the sample format of `iq` (cf32, and int16 when an IF resampler follows, are converted inside the
+// first kernel's load; the others by k_ingest_convert); `oc` != null adds the block loop's output stage, and
+// then only the sink's format travels back.
+static fmr_status fm_process_host_impl(fmr_fm *h, const void *iq_v, size_t iq_stride, const uint32_t *block_len,
+                                       uint32_t n_blocks, void *audio_v, size_t audio_stride, uint32_t *audio_len,
+                                       int fmt, const fmr_output_config *oc);
+
+extern "C" fmr_status fmr_fm_process_host(fmr_fm *h, const float *iq, size_t iq_stride, const uint32_t *block_len,
+                                          uint32_t n_blocks, double *audio, size_t audio_stride,
+                                          uint32_t *audio_len) {
+  return fm_process_host_impl(h, iq, iq_stride, block_len, n_blocks, audio, audio_stride, audio_len, FMR_IQ_CF32,
+                              nullptr);
+}
+
+extern "C" fmr_status fmr_fm_process_host_i16(fmr_fm *h, const int16_t *iq, size_t iq_stride,
+                                              const uint32_t *block_len, uint32_t n_blocks, double *audio,
+                                              size_t audio_stride, uint32_t *audio_len) {
+  if (h && h->cfg.input_rate == 384000.0) return fail(FMR_ERR_UNSUPPORTED, "int16 ingest needs an IF resampler stage");
+  return fm_process_host_impl(h, iq, iq_stride, block_len, n_blocks, audio, audio_stride, audio_len, FMR_IQ_S16,
+                              nullptr);
+}
+
+extern "C" fmr_status fmr_fm_process_host_io(fmr_fm *h, const void *iq, int iq_format, size_t iq_stride,
+                                             const uint32_t *block_len, uint32_t n_blocks,
+                                             const fmr_output_config *out_cfg, void *audio, size_t audio_stride,
+                                             uint32_t *audio_len) {
+  fmr_status s = check_io_args(iq_format, out_cfg);
+  if (s != FMR_OK) return s;
+  return fm_process_host_impl(h, iq, iq_stride, block_len, n_blocks, audio, audio_stride, audio_len, iq_format,
+                              out_cfg);
+}
+
+static fmr_status fm_process_host_impl(fmr_fm *h, const void *iq_v, size_t iq_stride, const uint32_t *block_len,
+                                       uint32_t n_blocks, void *audio_v, size_t audio_stride, uint32_t *audio_len,
+                                       int fmt, const fmr_output_config *oc) {
+  if (!h || !iq_v || !block_len || !audio_v) return fail(FMR_ERR_INVALID, "null argument");
+  const uint8_t *iq = reinterpret_cast<const uint8_t *>(iq_v);
+  uint8_t *audio = reinterpret_cast<uint8_t *>(audio_v);
+  const size_t esz = (size_t)iq_format_bytes(fmt); // bytes per complex sample
+  // formats the first kernel reads directly; the rest goes through k_ingest_convert
+  const bool direct = (fmt == FMR_IQ_CF32) || (fmt == FMR_IQ_S16 && h->cfg.input_rate != 384000.0);
+  const size_t osz = oc ? (size_t)out_format_bytes(oc->out_format) : 8;
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < n_blocks; b++) total += block_len[b];
+  if (total > h->cfg.max_samples_per_call) return fail(FMR_ERR_CAPACITY, "sum(block_len) > max_samples_per_call");
+  if (total > iq_stride) return fail(FMR_ERR_INVALID, "iq_stride < sum(block_len)");
+  if (n_blocks > h->cfg.max_blocks_per_call) return fail(FMR_ERR_CAPACITY, "n_blocks > max_blocks_per_call");
+  const int C = h->C;
+  fmr_status s = fm_ensure_staging(h, direct ? 0 : (size_t)C * h->cfg.max_samples_per_call * esz, oc != nullptr);
+  if (s != FMR_OK) return s;
   uint64_t out_total = 0;
-  fmr_status s = fmr_fm_query_output(h, block_len, n_blocks, &out_total, nullptr);
+  s = fmr_fm_query_output(h, block_len, n_blocks, &out_total, nullptr);
   if (s != FMR_OK) return s;
   if (out_total > audio_stride) return fail(FMR_ERR_CAPACITY, "audio_stride too small for this call");
   if (n_blocks == 0) return FMR_OK;
@@ -806,19 +867,30 @@ static fmr_status fm_process_host_impl(fmr_fm *h, const float *iq, size_t iq_str
   h->last_launches = 0;
   h->last_t0 = h->cum384;
   h->last_blocks = n_blocks;
+  h->have_levels = false;
+  if (oc) {
+    h->sink_on = true;
+    h->sink.out_fmt = oc->out_format;
+    h->sink.w = h->cfg.stereo ? 2 : 1;
+    h->sink.gain = oc->gain;
+    h->sink.squelch = oc->squelch_level;
+    h->sink_out_stride = h->audio_cap;
+  }
   struct Guard {
     fmr_fm *h;
     ~Guard() {
       h->in_host_call = false;
       h->iq_fmt = 0;
+      h->sink_on = false;
     }
   } guard{h};
+  uint8_t *d_in = direct ? reinterpret_cast<uint8_t *>(h->d_iq) : h->d_raw;
   for (int k = 0; k < n_chunks; k++) {
     const uint32_t b0 = (uint32_t)((uint64_t)n_blocks * k / n_chunks), b1 = (uint32_t)((uint64_t)n_blocks * (k + 1) / n_chunks);
     uint64_t n_in = 0;
     for (uint32_t b = b0; b < b1; b++) n_in += block_len[b];
     if (n_in > 0) {
-      FMR_CUDA(cudaMemcpy2DAsync(h->d_iq + fstep * in_off, (size_t)total * esz, iq + fstep * in_off, iq_stride * esz,
+      FMR_CUDA(cudaMemcpy2DAsync(d_in + esz * in_off, (size_t)total * esz, iq + esz * in_off, iq_stride * esz,
                                  (size_t)n_in * esz, C, cudaMemcpyHostToDevice, h->s_h2d));
     }
     FMR_CUDA(cudaEventRecord(h->ev_in[k], h->s_h2d));
@@ -827,21 +899,109 @@ static fmr_status fm_process_host_impl(fmr_fm *h, const float *iq, size_t iq_str
     s = fmr_fm_query_output(h, block_len + b0, b1 - b0, &n_out, nullptr);
     if (s != FMR_OK) return s;
     h->host_b0 = b0;
-    h->iq_fmt = fmt;
-    s = fm_process_device_impl(h, h->d_iq + fstep * in_off, (size_t)total, block_len + b0, b1 - b0,
-                               h->d_audio + out_off, h->audio_cap, audio_len ? audio_len + b0 : nullptr, (void *)st);
+    const float *d_chunk;
+    if (direct) {
+      h->iq_fmt = fmt;
+      d_chunk = reinterpret_cast<const float *>(d_in + esz * in_off);
+    } else {
+      FMR_CUDA(launch_ingest_convert(h->d_raw + esz * in_off, fmt, (size_t)total,
+                                     reinterpret_cast<float2 *>(h->d_iq) + in_off, (size_t)total, n_in, C, st));
+      h->last_launches++;
+      h->iq_fmt = FMR_IQ_CF32;
+      d_chunk = h->d_iq + 2 * in_off;
+    }
+    if (oc) h->sink_out = h->d_out + out_off * osz;
+    s = fm_process_device_impl(h, d_chunk, (size_t)total, block_len + b0, b1 - b0, h->d_audio + out_off, h->audio_cap,
+                               audio_len ? audio_len + b0 : nullptr, (void *)st);
     if (s != FMR_OK) return s;
     FMR_CUDA(cudaEventRecord(h->ev_done[k], st));
     if (n_out > 0) {
+      const uint8_t *d_res = oc ? h->d_out : reinterpret_cast<const uint8_t *>(h->d_audio);
       FMR_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_done[k], 0));
-      FMR_CUDA(cudaMemcpy2DAsync(audio + out_off, audio_stride * 8, h->d_audio + out_off, h->audio_cap * 8,
-                                 (size_t)n_out * 8, C, cudaMemcpyDeviceToHost, h->s_d2h));
+      FMR_CUDA(cudaMemcpy2DAsync(audio + out_off * osz, audio_stride * osz, d_res + out_off * osz, h->audio_cap * osz,
+                                 (size_t)n_out * osz, C, cudaMemcpyDeviceToHost, h->s_d2h));
     }
     in_off += (size_t)n_in;
     out_off += (size_t)n_out;
   }
   FMR_CUDA(cudaStreamSynchronize(st));
   FMR_CUDA(cudaStreamSynchronize(h->s_d2h));
+  h->have_levels = (oc != nullptr);
+  return FMR_OK;
+}
+
+// Device-pointer form: conversion (if the format needs its own launch) and the output stage run on `stream`.
+extern "C" fmr_status fmr_fm_process_device_io(fmr_fm *h, const void *d_iq, int iq_format, size_t iq_stride,
+                                               const uint32_t *block_len, uint32_t n_blocks,
+                                               const fmr_output_config *out_cfg, void *d_audio, size_t audio_stride,
+                                               uint32_t *audio_len, void *stream) {
+  if (!h || !d_iq || !block_len || !d_audio) return fail(FMR_ERR_INVALID, "null argument");
+  fmr_status s = check_io_args(iq_format, out_cfg);
+  if (s != FMR_OK) return s;
+  if (h->in_host_call) return fail(FMR_ERR_INVALID, "handle is inside a host call");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  const bool direct = (iq_format == FMR_IQ_CF32) || (iq_format == FMR_IQ_S16 && h->cfg.input_rate != 384000.0);
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < n_blocks; b++) total += block_len[b];
+  if (total > h->cfg.max_samples_per_call) return fail(FMR_ERR_CAPACITY, "sum(block_len) > max_samples_per_call");
+  if (total > iq_stride) return fail(FMR_ERR_INVALID, "iq_stride < sum(block_len)");
+  if (!direct || out_cfg) {
+    s = fm_ensure_staging(h, 0, out_cfg != nullptr);
+    if (s != FMR_OK) return s;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const float *d_in = reinterpret_cast<const float *>(d_iq);
+  size_t stride = iq_stride;
+  uint32_t extra = 0;
+  h->iq_fmt = direct ? iq_format : FMR_IQ_CF32;
+  if (!direct) {
+    FMR_CUDA(launch_ingest_convert(d_iq, iq_format, iq_stride, reinterpret_cast<float2 *>(h->d_iq), (size_t)total, total,
+                                   h->C, st));
+    d_in = h->d_iq;
+    stride = (size_t)total;
+    extra = 1;
+  }
+  h->have_levels = false;
+  double *d_dec = reinterpret_cast<double *>(d_audio);
+  size_t dec_stride = audio_stride;
+  if (out_cfg) {
+    uint64_t out_total = 0;
+    s = fmr_fm_query_output(h, block_len, n_blocks, &out_total, nullptr);
+    if (s != FMR_OK) return s;
+    if (out_total > audio_stride) return fail(FMR_ERR_CAPACITY, "audio_stride too small for this call");
+    h->sink_on = true;
+    h->sink.out_fmt = out_cfg->out_format;
+    h->sink.w = h->cfg.stereo ? 2 : 1;
+    h->sink.gain = out_cfg->gain;
+    h->sink.squelch = out_cfg->squelch_level;
+    h->sink_out = reinterpret_cast<uint8_t *>(d_audio);
+    h->sink_out_stride = audio_stride;
+    d_dec = h->d_audio;
+    dec_stride = h->audio_cap;
+  }
+  s = fm_process_device_impl(h, d_in, stride, block_len, n_blocks, d_dec, dec_stride, audio_len, stream);
+  h->sink_on = false;
+  h->iq_fmt = 0;
+  if (s != FMR_OK) return s;
+  h->last_launches += extra;
+  h->have_levels = (out_cfg != nullptr);
+  return FMR_OK;
+}
+
+extern "C" fmr_status fmr_fm_block_levels(fmr_fm *h, uint32_t channel, fmr_block_level_t *out, uint32_t n_blocks) {
+  if (!h || !out || channel >= (uint32_t)h->C || n_blocks != h->last_blocks) {
+    return fail(FMR_ERR_INVALID, "bad argument (n_blocks must equal the last call's)");
+  }
+  if (!h->have_levels) return fail(FMR_ERR_INVALID, "the last call had no output stage");
+  static_assert(sizeof(BlockLevelDev) == sizeof(fmr_block_level_t), "level record layout");
+  FMR_CUDA(cudaSetDevice(h->cfg.device));
+  FMR_CUDA(cudaDeviceSynchronize());
+  for (const auto &ch : h->last_chunks) {
+    const uint32_t b0 = ch.first, nb = ch.second;
+    if (nb == 0) continue;
+    FMR_CUDA(cudaMemcpy(out + b0, h->d_levels + (size_t)h->C * b0 + (size_t)channel * nb, nb * sizeof(BlockLevelDev),
+                        cudaMemcpyDeviceToHost));
+  }
   return FMR_OK;
 }
 

@@ -77,6 +77,44 @@ class _Base:
                                    audio_stride, lens.ctypes.data, stream))
         return lens
 
+    # ---- FileSource sample formats in, the block loop's output stage out -------
+    _OUT_DTYPES = {_capi.OUT_F64: np.float64, _capi.OUT_F32: np.float32, _capi.OUT_S16: np.int16}
+
+    def process_blocks_io(self, raw, iq_format, block_len, out_format=None, squelch_level=0.0, gain=0.5, out=None):
+        """raw: the file's own sample bytes per channel, uint8 [C, T * bytes_per_complex_sample] (or any
+        C-contiguous array with that many bytes per row: int16 [C, T, 2], complex64 [C, T], ...).
+        out_format None: the decoder's doubles unchanged; otherwise main.cpp:977-1002 is applied on the
+        device (levels, squelch gain, sink sample format) and `block_levels()` holds the per-block levels.
+        Returns (audio [C, n] in the sink dtype, audio_len[n_blocks])."""
+        raw = np.ascontiguousarray(raw)
+        if raw.ndim == 1 or (self.n_channels == 1 and raw.shape[0] != 1):
+            raw = raw[None, ...]
+        assert raw.shape[0] == self.n_channels
+        esz = _capi.IQ_BYTES[iq_format]
+        row_bytes = raw.nbytes // self.n_channels
+        assert row_bytes % esz == 0
+        stride = row_bytes // esz
+        bl, total = self._blocks(block_len)
+        assert total <= stride
+        out_total, _ = self.query_output(bl)
+        dt = self._OUT_DTYPES[_capi.OUT_F64 if out_format is None else out_format]
+        if out is None:
+            out = np.zeros((self.n_channels, max(out_total, 1)), dtype=dt)
+        assert out.dtype == dt and out.ndim == 2 and out.shape[0] == self.n_channels and out.shape[1] >= out_total
+        oc = None if out_format is None else C.byref(_capi.OutputConfig(int(out_format), float(squelch_level), float(gain)))
+        lens = np.zeros(len(bl), dtype=np.uint32)
+        check(self._process_host_io(self._h, raw.ctypes.data, int(iq_format), stride, bl.ctypes.data, len(bl), oc,
+                                    out.ctypes.data, out.shape[1], lens.ctypes.data))
+        self._last_io_blocks = len(bl)
+        return out[:, :out_total], lens
+
+    def block_levels(self, channel=0):
+        """Per-block (if_rms, audio_mean, audio_rms, gain) of the last process_blocks_io call with an out_format."""
+        n = self._last_io_blocks
+        arr = (_capi.BlockLevel * n)()
+        check(self._block_levels(self._h, channel, arr, n))
+        return np.array([(a.if_rms, a.audio_mean, a.audio_rms, a.gain) for a in arr], dtype=np.float32).reshape(n, 4)
+
     def set_profiling(self, enable=True):
         check(self._set_profiling(self._h, int(enable)))
 
@@ -115,6 +153,7 @@ class FmDecoder(_Base):
         L = _capi.lib()
         self._destroy, self._query = L.fmr_fm_destroy, L.fmr_fm_query_output
         self._process_host, self._process_device = L.fmr_fm_process_host, L.fmr_fm_process_device
+        self._process_host_io, self._block_levels = L.fmr_fm_process_host_io, L.fmr_fm_block_levels
         self._set_profiling, self._stage_times = L.fmr_fm_set_profiling, L.fmr_fm_stage_times
         self.n_channels = int(n_channels)
         self.stereo = bool(stereo)
@@ -210,6 +249,7 @@ class AmDecoder(_Base):
         L = _capi.lib()
         self._destroy, self._query = L.fmr_am_destroy, L.fmr_am_query_output
         self._process_host, self._process_device = L.fmr_am_process_host, L.fmr_am_process_device
+        self._process_host_io, self._block_levels = L.fmr_am_process_host_io, L.fmr_am_block_levels
         self._set_profiling, self._stage_times = L.fmr_am_set_profiling, L.fmr_am_stage_times
         self.n_channels = int(n_channels)
         coeff = None

@@ -162,6 +162,43 @@ uint32_t fmr_fm_last_launches(fmr_fm *h);
 fmr_status fmr_fm_set_profiling(fmr_fm *h, int enable);
 fmr_status fmr_fm_stage_times(fmr_fm *h, float *ms, const char **names, uint32_t cap, uint32_t *n);
 
+/* ------------------------------------------- file formats in, sink formats out ---- */
+/* IQ sample formats FileSource accepts (sfmbase/FileSource.cpp:120-138,206-216), as sf_read_float
+ * delivers them (FileSource.cpp:491-531): integer value / 2^(bits-1), U8 as (value-128)/128. The decode
+ * runs on the device, so only the file's own bytes cross PCIe (S16: 4, S8/U8: 2, S24: 6 instead of 8). */
+enum { FMR_IQ_CF32 = 0, FMR_IQ_S16 = 1, FMR_IQ_S8 = 2, FMR_IQ_U8 = 3, FMR_IQ_S24 = 4 };
+/* Audio sample formats of the reference's SndfileOutput (main.cpp:592-623, AudioOutput.cpp:153-167):
+ * F64 = the decoder's own doubles, F32 = (float)x, S16 = lrint(x * 32767) (sf_write_double, no clipping). */
+enum { FMR_OUT_F64 = 0, FMR_OUT_F32 = 1, FMR_OUT_S16 = 2 };
+
+/* The block loop's output stage, main.cpp:977-1002: per-block audio level (Utility::samples_mean_rms on the
+ * float copy), Utility::adjust_gain(audio, if_rms >= squelch_level ? gain : 0) and the sink's sample format. */
+typedef struct fmr_output_config {
+  int out_format;        /* FMR_OUT_*                                                   */
+  double squelch_level;  /* linear IF level, main.cpp:484-489 (0 = squelch always open) */
+  double gain;           /* 0.5 = the reference's nominal -6 dB (main.cpp:1000)         */
+} fmr_output_config;
+
+typedef struct fmr_block_level_t { /* what the block loop derives per source block */
+  float if_rms;      /* decoder's get_if_rms() after this block's process call (main.cpp:956-976);
+                        -1 when the block produced no IF samples (the loop `continue`s, main.cpp:933-936) */
+  float audio_mean;  /* Utility::samples_mean_rms of the block's audio as float (main.cpp:989-996) */
+  float audio_rms;
+  float gain;        /* gain applied: cfg.gain or 0 (squelch closed)                */
+} fmr_block_level_t;
+
+/* process_host / process_device with the input in `iq_format` and, when out_cfg != NULL, the output stage
+ * applied on the device: `audio` then receives values of out_cfg->out_format (audio_stride and audio_len
+ * count values, not bytes). out_cfg == NULL: `audio` receives the decoder's doubles unchanged. */
+fmr_status fmr_fm_process_host_io(fmr_fm *h, const void *iq, int iq_format, size_t iq_stride,
+                                  const uint32_t *block_len, uint32_t n_blocks, const fmr_output_config *out_cfg,
+                                  void *audio, size_t audio_stride, uint32_t *audio_len);
+fmr_status fmr_fm_process_device_io(fmr_fm *h, const void *d_iq, int iq_format, size_t iq_stride,
+                                    const uint32_t *block_len, uint32_t n_blocks, const fmr_output_config *out_cfg,
+                                    void *d_audio, size_t audio_stride, uint32_t *audio_len, void *stream);
+/* Per-block levels of the last *_io call that had an out_cfg; n_blocks must equal that call's. */
+fmr_status fmr_fm_block_levels(fmr_fm *h, uint32_t channel, fmr_block_level_t *out, uint32_t n_blocks);
+
 /* ------------------------------------------------------ AM and narrow-band FM ------- */
 /* One handle type serves the two 48 kHz decoders of the reference:
  *   mode 2 (ModType::AM)   AmDecoder::process    include/AmDecode.h:48-65, sfmbase/AmDecode.cpp:96-218
@@ -214,6 +251,15 @@ fmr_status fmr_am_stats(fmr_am *h, uint32_t channel, fmr_am_stats_t *out);
 uint32_t fmr_am_last_launches(fmr_am *h);
 fmr_status fmr_am_set_profiling(fmr_am *h, int enable);
 fmr_status fmr_am_stage_times(fmr_am *h, float *ms, const char **names, uint32_t cap, uint32_t *n);
+
+/* Same as the fmr_fm_*_io entry points, for the 48 kHz decoders. */
+fmr_status fmr_am_process_host_io(fmr_am *h, const void *iq, int iq_format, size_t iq_stride,
+                                  const uint32_t *block_len, uint32_t n_blocks, const fmr_output_config *out_cfg,
+                                  void *audio, size_t audio_stride, uint32_t *audio_len);
+fmr_status fmr_am_process_device_io(fmr_am *h, const void *d_iq, int iq_format, size_t iq_stride,
+                                    const uint32_t *block_len, uint32_t n_blocks, const fmr_output_config *out_cfg,
+                                    void *d_audio, size_t audio_stride, uint32_t *audio_len, void *stream);
+fmr_status fmr_am_block_levels(fmr_am *h, uint32_t channel, fmr_block_level_t *out, uint32_t n_blocks);
 
 #ifdef __cplusplus
 }
