@@ -879,8 +879,9 @@ extern "C" fmr_status fmr_am_process_device_io(fmr_am *h, const void *d_iq, int 
     P.gain = out_cfg->gain;
     P.squelch = out_cfg->squelch_level;
     dim3 sg(n_blocks, h->C);
-    // decoder input and audio share the 48 kHz call table
-    k_audio_sink<<<sg, kSinkThreads, 0, st>>>(h->r_if, t0, h->d_e48, h->d_audio, h->audio_cap, h->d_e48, (int)n_blocks,
+    // both 48 kHz decoders measure the IF level behind their channel filter / tuner chain (m_buf_filtered2,
+    // AmDecode.cpp:153-154; m_buf_filtered, NbfmDecode.cpp:50-54) = r_flt; it shares the call table with the audio
+    k_audio_sink<<<sg, kSinkThreads, 0, st>>>(h->r_flt, t0, h->d_e48, h->d_audio, h->audio_cap, h->d_e48, (int)n_blocks,
                                               d_audio, audio_stride, h->d_levels, P);
     FMR_CUDA(cudaGetLastError());
     extra++;

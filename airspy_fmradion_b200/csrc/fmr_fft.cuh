@@ -31,6 +31,16 @@
 namespace fmr {
 
 constexpr int kFftThreads = 512;
+// Build-time experiment (-DFMR_FFT_REGCAP_THREADS=608): compiling the 16384-point FP32 kernel for a nominal
+// 608-thread block caps it at 96 registers per thread (no spills, +0.8 % run time) instead of 111; at 512 threads
+// that leaves room for one CTA of the fused 384 kHz core (128 threads x 96 registers) on the same SM, which the
+// time-chunk pipeline (fmr_fm.cu, FMR_TIME_CHUNKS + FMR_FUSED_CHUNKS) needs to run the latency-bound core of chunk
+// k underneath the front end of chunk k+1. Measured: the overlap happens but chunking costs more than it hides
+// (profiles/README.md), so the default stays 512 = no cap.
+#ifndef FMR_FFT_REGCAP_THREADS
+#define FMR_FFT_REGCAP_THREADS 512
+#endif
+constexpr int kFftRegCapThreads = FMR_FFT_REGCAP_THREADS;
 
 template <typename S, int N> struct FftCfg {
   using V = typename V2<S>::type;
@@ -278,7 +288,8 @@ struct FftFuse {
 //          it holds (down must be 1); samples with negative index read as zero like the ring does.
 //   n_in_avail: number of valid input samples in the ring (indices >= it read as zero)
 template <typename S, int N, bool FUSE>
-__global__ void __launch_bounds__(kFftThreads, (N == 8192 && sizeof(S) == 4) ? 2 : 1)
+__global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThreads : kFftThreads,
+                                  (N == 8192 && sizeof(S) == 4) ? 2 : 1)
     k_fir_fft(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out, const typename V2<S>::type *__restrict__ H,
               int klen, int down, int64_t q0, int n_out, int64_t n_in_avail, int lq, FftFuse fz) {
   using CFG = FftCfg<S, N>;

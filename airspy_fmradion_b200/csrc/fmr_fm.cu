@@ -73,6 +73,7 @@ struct fmr_fm {
   int want_serial_sms = 0;
   bool serial_v2 = true;  // FMR_SERIAL_V2=0: the first-generation AGC / PLL kernels
   bool core_fused = true; // FMR_CORE_FUSED=0: AGC / discriminator / PLL as separate launches
+  bool fused_chunks = false; // FMR_FUSED_CHUNKS=1: keep the fused core inside the time-chunk pipeline
   int rot_sms = 148;      // FMR_CORE_ROT=0 disables the per-CTA rotation of warp roles in the fused core
   int C = 0;
   const ChainDesc *ifc = nullptr; // null when input_rate == 384000 (no IfResampler, main.cpp:778)
@@ -359,6 +360,12 @@ extern "C" fmr_status fmr_fm_create(const fmr_fm_config *cfg, fmr_fm **out) {
   if (const char *e = getenv("FMR_SERIAL_SMS")) h->want_serial_sms = std::max(0, atoi(e));
   if (const char *e = getenv("FMR_SERIAL_V2")) h->serial_v2 = atoi(e) != 0;
   if (const char *e = getenv("FMR_CORE_FUSED")) h->core_fused = atoi(e) != 0;
+  if (const char *e = getenv("FMR_FUSED_CHUNKS")) h->fused_chunks = atoi(e) != 0;
+  if (h->fused_chunks && !Resampler<float>::env_off("FMR_CORE_CARVEOUT")) {
+    // Kernels that want different shared-memory carve-outs do not share an SM: ask for the same (maximum)
+    // carve-out the front-end kernels need, so that core CTAs can be placed beside them.
+    cudaFuncSetAttribute(k_fm_core_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   {
     int sms = fmr_device_sm_count(cfg->device);
     h->rot_sms = sms > 0 ? sms : 148;
@@ -645,14 +652,16 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
     }
     // ---- 384 kHz core. Stereo without the multipath filter: one warp-specialised kernel (fmr_core.cuh);
     // otherwise AGC (serial) -> [multipath] -> discriminator + statistics (parallel) -> PLL (serial).
-    const bool fused = h->core_fused && h->cfg.stereo && h->cfg.multipath_stages == 0 && h->max_time_chunks == 1;
+    const bool fused = h->core_fused && h->cfg.stereo && h->cfg.multipath_stages == 0 && (h->max_time_chunks == 1 || h->fused_chunks);
     dim3 cgrid((C + 31) / 32);
     if (fused) {
       dim3 fgrid((C + 31) / 32);
       pf.begin(h->p_fused, sB);
+      tr.begin("core", k, sB);
       k_fm_core_fused<<<fgrid, kCfThreads, 0, sB>>>(h->r_if, h->r_iff, h->r_384, h->d_state, d_flags, h->d_pps, d_e384,
                                                    (int)nb, t0k, h->core, h->d_atan, (int)(flag_b0 + b0),
                                                    (k == 0 && flag_b0 == 0) ? 1 : 0, h->rot_sms);
+      tr.end(sB);
       pf.end(h->p_fused, sB);
       launches++;
     } else {

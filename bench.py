@@ -346,6 +346,33 @@ def main():
             e2e["int16_ingest"] = {"value": world * Ce * T * args.e2e_steps / dt / 1e6, "unit": "Msamples/s",
                                    "h2d_bytes_per_step": Ce * T * 4,
                                    "note": "fmr_fm_process_host_i16: IQ as int16 pairs, converted in the first kernel"}
+        try:
+            # the whole file path (SURVEY.md 8 f1 + f4) on 8-bit IQ, the narrowest format FileSource accepts
+            # (format=U8_LE): sample decode, decoder, level metering, squelch gain and the int16 sink format all on
+            # the device, so 2 B per IQ sample go up and 2 B per audio value come back
+            from airspy_fmradion_b200 import _capi
+            h_u8 = torch.empty((Ce, T, 2), dtype=torch.uint8, pin_memory=True)
+            h_u8.copy_((torch.view_as_real(iq[:Ce]) * 127.0).round_().clamp_(-128, 127).add_(128).to(torch.uint8))
+            u_np = h_u8.numpy().reshape(Ce, -1)
+            o_i16 = torch.empty((Ce, audio_cap), dtype=torch.int16, pin_memory=True).numpy()
+            for _ in range(2):
+                a, l = dec2.process_blocks_io(u_np, _capi.IQ_U8, bl, out_format=_capi.OUT_S16, out=o_i16)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                a, l = dec2.process_blocks_io(u_np, _capi.IQ_U8, bl, out_format=_capi.OUT_S16, out=o_i16)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if dist is not None:
+                tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            e2e["u8_file_path"] = {"value": world * Ce * T * args.e2e_steps / dt / 1e6, "unit": "Msamples/s",
+                                   "h2d_bytes_per_step": Ce * T * 2, "d2h_bytes_per_step": int(a.shape[1]) * 2 * Ce,
+                                   "note": "fmr_fm_process_host_io: U8 IQ in, output stage (levels, -6 dB, int16) on "
+                                           "the device, int16 audio out"}
+        except Exception as ex:  # optional sub-measurement: the bench line must still print
+            e2e["u8_file_path"] = {"error": str(ex)}
         dec2.close()
 
     cpu = None
