@@ -49,6 +49,7 @@ template <typename S, int N> struct FftCfg {
   static constexpr int kSets = N / 16 / kFftThreads; // butterflies of 16 per thread per pass
   static constexpr int kR4 = N / 4096;          // radix of the last pass
   static constexpr int kSmemBytes = (N + N / 16) * (int)sizeof(V) + 256 * (int)sizeof(V);
+  static constexpr int kSmemBytesTw = kSmemBytes + (256 + 4096) * (int)sizeof(V); // + the full twiddle tables
   static_assert(kSets >= 1 && (kR4 == 2 || kR4 == 4), "unsupported FFT size");
 };
 
@@ -168,9 +169,17 @@ template <typename CFG> __device__ __forceinline__ void pass16_first_smem(typena
   __syncthreads();
 }
 
-// One radix-16 Stockham pass over the whole buffer, in place: p = 16 or 256.
-template <typename CFG, int p>
-__device__ __forceinline__ void pass16_smem(typename CFG::V *buf, const typename CFG::V *tw) {
+// Full twiddle tables of the two twiddled radix-16 passes (TW instantiations): entry (r, k) of pass p is
+// W_N^(k * scale_p * r) = exp(-2 pi i k r / (16 p)), stored [r][k] so that consecutive lanes (consecutive k) read
+// consecutive words. 16 x 16 entries for p = 16 followed by 16 x 256 for p = 256; the values do not depend on N.
+constexpr int kTwTabP16 = 0, kTwTabP256 = 256, kTwTabLen = 256 + 4096;
+
+// One radix-16 Stockham pass over the whole buffer, in place: p = 16 or 256. With TW the fifteen twiddles of a
+// butterfly come from the table (fifteen independent shared-memory loads) instead of one looked-up root and a
+// chain of fourteen complex multiplications for its powers.
+template <typename CFG, int p, bool TW = false>
+__device__ __forceinline__ void pass16_smem(typename CFG::V *buf, const typename CFG::V *tw,
+                                            const typename CFG::V *twtab = nullptr) {
   using V = typename CFG::V;
   constexpr int scale = CFG::kN / (16 * p);
   V v[CFG::kSets][16];
@@ -185,7 +194,13 @@ __device__ __forceinline__ void pass16_smem(typename CFG::V *buf, const typename
   for (int s = 0; s < CFG::kSets; s++) {
     const int i = threadIdx.x + s * kFftThreads;
     const int k = i & (p - 1);
-    twiddle16(v[s], tw_lookup(tw, k * scale));
+    if (TW) {
+      const V *tp = twtab + (p == 16 ? kTwTabP16 : kTwTabP256) + k;
+#pragma unroll
+      for (int r = 1; r < 16; r++) v[s][r] = cmulv(v[s][r], tp[r * p]);
+    } else {
+      twiddle16(v[s], tw_lookup(tw, k * scale));
+    }
     fft16(v[s]);
     const int j = (i - k) * 16 + k;
     // p is 16 or 256: fpad(j + r*p) = fpad(j) + r*(p + p/16)
@@ -280,6 +295,7 @@ struct FftFuse {
   void *tail_base;
   uint32_t tail_cap;
   int64_t tail_lo, tail_hi;
+  const void *twtab; // TW instantiations: [kTwTabLen] twiddles in the chain's complex type (global memory)
 };
 
 // k_fir_fft: y[q] = sum_j h[j] x[q*down - fl2 + j].
@@ -287,7 +303,7 @@ struct FftFuse {
 //   fused: block b produces interpolator outputs m in [m0 + b*mo, ...) from the filtered samples
 //          it holds (down must be 1); samples with negative index read as zero like the ring does.
 //   n_in_avail: number of valid input samples in the ring (indices >= it read as zero)
-template <typename S, int N, bool FUSE>
+template <typename S, int N, bool FUSE, bool TW = false>
 __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThreads : kFftThreads,
                                   (N == 8192 && sizeof(S) == 4) ? 2 : 1)
     k_fir_fft(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out, const typename V2<S>::type *__restrict__ H,
@@ -297,6 +313,7 @@ __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThr
   extern __shared__ __align__(16) unsigned char smem_raw[];
   V *buf = reinterpret_cast<V *>(smem_raw);
   V *tw = buf + (N + N / 16);
+  V *twtab = tw + 256;
   const uint32_t c = blockIdx.y;
   const int blk = blockIdx.x;
   int cnt;        // plain: filter outputs of this block; fused: interpolator outputs of this block
@@ -334,16 +351,31 @@ __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThr
     }
     tw[q] = cmk<V>(co, s);
   }
+  if (TW) {
+    const V *__restrict__ g = reinterpret_cast<const V *>(fz.twtab);
+    for (int i = threadIdx.x; i < kTwTabLen; i += kFftThreads) twtab[i] = __ldg(g + i);
+  }
   // ---- forward pass 1 (p = 1, no twiddles), inputs straight from the global ring
   {
     V v[CFG::kSets][16];
+    // block entirely inside the valid, unwrapped part of the ring (CTA-uniform): one pointer, constant offsets
+    const uint32_t pos0 = (uint32_t)base & (in.cap - 1);
+    if (TW && base >= 0 && base + N <= n_in_avail && pos0 + (uint32_t)N <= in.cap) {
+      const V *__restrict__ row = in.base + (size_t)c * in.cap + pos0 + threadIdx.x;
 #pragma unroll
-    for (int s = 0; s < CFG::kSets; s++) {
-      const int i = threadIdx.x + s * kFftThreads;
+      for (int s = 0; s < CFG::kSets; s++) {
 #pragma unroll
-      for (int r = 0; r < 16; r++) {
-        const int64_t t = base + i + r * CFG::kQ;
-        v[s][r] = (t < n_in_avail) ? in.ld(c, t) : cmk<V>(0, 0);
+        for (int r = 0; r < 16; r++) v[s][r] = row[s * kFftThreads + r * CFG::kQ];
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < CFG::kSets; s++) {
+        const int i = threadIdx.x + s * kFftThreads;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+          const int64_t t = base + i + r * CFG::kQ;
+          v[s][r] = (t < n_in_avail) ? in.ld(c, t) : cmk<V>(0, 0);
+        }
       }
     }
 #pragma unroll
@@ -355,8 +387,8 @@ __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThr
     }
     __syncthreads();
   }
-  pass16_smem<CFG, 16>(buf, tw);
-  pass16_smem<CFG, 256>(buf, tw);
+  pass16_smem<CFG, 16, TW>(buf, tw, twtab);
+  pass16_smem<CFG, 256, TW>(buf, tw, twtab);
   // ---- forward last pass fused with Y = conj(X * H)
 #pragma unroll 2
   for (int b = 0; b < 4096 / kFftThreads; b++) {
@@ -369,8 +401,8 @@ __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThr
   __syncthreads();
   // ---- inverse = conj(FFT(conj(.)))
   pass16_first_smem<CFG>(buf);
-  pass16_smem<CFG, 16>(buf, tw);
-  pass16_smem<CFG, 256>(buf, tw);
+  pass16_smem<CFG, 16, TW>(buf, tw, twtab);
+  pass16_smem<CFG, 256, TW>(buf, tw, twtab);
   if (!FUSE) {
     // ---- inverse last pass, outputs straight to the global ring (only the alias-free part)
 #pragma unroll 2

@@ -208,6 +208,8 @@ template <typename S> struct Resampler {
   Prof *prof = nullptr;
   int p_hb = -1, p_bc = -1, p_fi = -1;
   V *d_H16 = nullptr, *d_H8 = nullptr; // filter spectra for k_fir_fft (16384: float chains only)
+  V *d_twtab = nullptr;                // full twiddle tables of the 16384-point kernel (FMR_FFT_TW=0: off)
+  bool fft_tw = false;
   bool use_fft = false;
   bool use_dec2 = false; // double chains with a decimate-by-2 low-pass (audio resampler)
   bool fuse_fi = true;   // FMR_FUSE_FI=0: keep the polyphase bank as its own launch
@@ -341,6 +343,25 @@ template <typename S> struct Resampler {
                                        FftCfg<S, 16384>::kSmemBytes)));
         FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<S, 16384, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        FftCfg<S, 16384>::kSmemBytes)));
+        FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<S, 16384, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       FftCfg<S, 16384>::kSmemBytesTw)));
+        // full twiddle tables of the two twiddled radix-16 passes, computed in double (fmr_fft.cuh, kTwTab*)
+        std::vector<V> tt(kTwTabLen);
+        for (int r = 0; r < 16; r++) {
+          for (int k = 0; k < 16; k++) {
+            const double a = -2.0 * M_PI * (double)(k * r) / 256.0;
+            tt[kTwTabP16 + r * 16 + k].x = (S)std::cos(a);
+            tt[kTwTabP16 + r * 16 + k].y = (S)std::sin(a);
+          }
+          for (int k = 0; k < 256; k++) {
+            const double a = -2.0 * M_PI * (double)(k * r) / 4096.0;
+            tt[kTwTabP256 + r * 256 + k].x = (S)std::cos(a);
+            tt[kTwTabP256 + r * 256 + k].y = (S)std::sin(a);
+          }
+        }
+        FMR_CUDA(mem.alloc(&d_twtab, tt.size(), false));
+        FMR_CUDA(cudaMemcpy(d_twtab, tt.data(), sizeof(V) * tt.size(), cudaMemcpyHostToDevice));
+        fft_tw = !env_off("FMR_FFT_TW");
       }
       use_fft = true;
       fft_min_out = (sizeof(S) == sizeof(float)) ? kFftMinOutF32 : kFftMinOutF64;
@@ -456,8 +477,14 @@ template <typename S> struct Resampler {
         fz.tail_hi = last ? b1 : 0;
         fz.tail_lo = last ? b1 - (2 * d->fi.flen + 16) : 0;
         dim3 grid(nb16, gcn);
-        k_fir_fft<S, 16384, true><<<grid, kFftThreads, FftCfg<S, 16384>::kSmemBytes, st>>>(in, o, d_H16, klen, 1, 0, 0,
-                                                                                         avail, lq16, fz);
+        if (fft_tw) {
+          fz.twtab = d_twtab;
+          k_fir_fft<S, 16384, true, true><<<grid, kFftThreads, FftCfg<S, 16384>::kSmemBytesTw, st>>>(in, o, d_H16, klen, 1,
+                                                                                                   0, 0, avail, lq16, fz);
+        } else {
+          k_fir_fft<S, 16384, true><<<grid, kFftThreads, FftCfg<S, 16384>::kSmemBytes, st>>>(in, o, d_H16, klen, 1, 0, 0,
+                                                                                           avail, lq16, fz);
+        }
         done = cnt;
         launched++;
       }
