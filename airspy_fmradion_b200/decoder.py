@@ -108,6 +108,18 @@ class _Base:
         self._last_io_blocks = len(bl)
         return out[:, :out_total], lens
 
+    def process_device_io(self, d_raw_ptr, iq_format, iq_stride, block_len, d_audio_ptr, audio_stride, out_format=None,
+                          squelch_level=0.0, gain=0.5, stream=0):
+        """Device-pointer form of process_blocks_io (addresses as ints); asynchronous on `stream`. iq_stride in complex
+        samples, audio_stride in values of the sink format. Returns audio_len per block."""
+        bl, _ = self._blocks(block_len)
+        oc = None if out_format is None else C.byref(_capi.OutputConfig(int(out_format), float(squelch_level), float(gain)))
+        lens = np.zeros(len(bl), dtype=np.uint32)
+        check(self._process_device_io(self._h, d_raw_ptr, int(iq_format), iq_stride, bl.ctypes.data, len(bl), oc,
+                                      d_audio_ptr, audio_stride, lens.ctypes.data, stream))
+        self._last_io_blocks = len(bl)
+        return lens
+
     def block_levels(self, channel=0):
         """Per-block (if_rms, audio_mean, audio_rms, gain) of the last process_blocks_io call with an out_format."""
         n = self._last_io_blocks
@@ -154,6 +166,7 @@ class FmDecoder(_Base):
         self._destroy, self._query = L.fmr_fm_destroy, L.fmr_fm_query_output
         self._process_host, self._process_device = L.fmr_fm_process_host, L.fmr_fm_process_device
         self._process_host_io, self._block_levels = L.fmr_fm_process_host_io, L.fmr_fm_block_levels
+        self._process_device_io = L.fmr_fm_process_device_io
         self._set_profiling, self._stage_times = L.fmr_fm_set_profiling, L.fmr_fm_stage_times
         self.n_channels = int(n_channels)
         self.stereo = bool(stereo)
@@ -250,6 +263,7 @@ class AmDecoder(_Base):
         self._destroy, self._query = L.fmr_am_destroy, L.fmr_am_query_output
         self._process_host, self._process_device = L.fmr_am_process_host, L.fmr_am_process_device
         self._process_host_io, self._block_levels = L.fmr_am_process_host_io, L.fmr_am_block_levels
+        self._process_device_io = L.fmr_am_process_device_io
         self._set_profiling, self._stage_times = L.fmr_am_set_profiling, L.fmr_am_stage_times
         self.n_channels = int(n_channels)
         coeff = None

@@ -169,6 +169,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--single-homed", type=int, default=0, metavar="CH_PER_GPU",
+                    help="opt-in, N>1: also time the single-homed I/O mode (int16 IQ of all channels enters at rank 0, "
+                         "is scattered over NCCL/NVLink, decoded on the owning GPU, int16 audio gathered back)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -375,6 +378,35 @@ def main():
             e2e["u8_file_path"] = {"error": str(ex)}
         dec2.close()
 
+    single_homed = None
+    if args.single_homed > 0 and dist is not None and mode == "fm":
+        # every rank takes part in the same collectives; any failure here fails the run (opt-in measurement)
+        from airspy_fmradion_b200 import _capi
+        from airspy_fmradion_b200.shard import ShardedDecoder
+        Cs = args.single_homed * world
+        sd = ShardedDecoder(Cs, lambda n: make_decoder(wl, n, T, nblk, dev_index))
+        raw_root = None
+        if rank == 0:
+            rows = torch.arange(Cs, device=dev) % C
+            raw_root = (torch.view_as_real(iq[rows]) * 32768.0).clamp_(-32768, 32767).round_().to(torch.int16)
+            raw_root = raw_root.reshape(Cs, T * 2).view(torch.uint8)
+        for _ in range(2):
+            sd.process_blocks_from_root(raw_root, _capi.IQ_S16, bl, _capi.OUT_S16, device=dev)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(args.e2e_steps):
+            full, _l = sd.process_blocks_from_root(raw_root, _capi.IQ_S16, bl, _capi.OUT_S16, device=dev)
+        s1.record(stream)
+        barrier()
+        tt = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        single_homed = {"value": Cs * T * args.e2e_steps / (float(tt.item()) * 1e-3) / 1e6, "unit": "Msamples/s",
+                        "channels_total": Cs, "scatter_bytes_per_step": Cs * T * 4,
+                        "note": "int16 IQ of all channels resident on rank 0 -> NCCL scatter -> decode + output stage on "
+                                "the owning GPU -> NCCL gather of int16 audio to rank 0 (SURVEY.md 8 e)"}
+        sd.dec.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -392,6 +424,8 @@ def main():
                            "l2": "input per step (%.0f MB) exceeds the 126 MB L2" % (C * T * 8 / 1e6),
                            "parallelism": "channels sharded %d per GPU, no data-path collective" % C},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+        if single_homed is not None:
+            line["single_homed"] = single_homed
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
