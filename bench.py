@@ -349,6 +349,7 @@ def main():
             e2e["int16_ingest"] = {"value": world * Ce * T * args.e2e_steps / dt / 1e6, "unit": "Msamples/s",
                                    "h2d_bytes_per_step": Ce * T * 4,
                                    "note": "fmr_fm_process_host_i16: IQ as int16 pairs, converted in the first kernel"}
+            h_i16 = q_np = None  # release the pinned staging before the next sub-measurement
         try:
             # the whole file path (SURVEY.md 8 f1 + f4) on 8-bit IQ, the narrowest format FileSource accepts
             # (format=U8_LE): sample decode, decoder, level metering, squelch gain and the int16 sink format all on
