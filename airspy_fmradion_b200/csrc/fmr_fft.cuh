@@ -42,11 +42,12 @@ constexpr int kFftThreads = 512;
 #endif
 constexpr int kFftRegCapThreads = FMR_FFT_REGCAP_THREADS;
 
-template <typename S, int N> struct FftCfg {
+template <typename S, int N, int THREADS = kFftThreads> struct FftCfg {
   using V = typename V2<S>::type;
   static constexpr int kN = N;
+  static constexpr int kThreads = THREADS;      // threads per CTA (512; 1024 = the 32-warp form of the 16384-point kernel)
   static constexpr int kQ = N / 16;             // stride of the radix-16 passes
-  static constexpr int kSets = N / 16 / kFftThreads; // butterflies of 16 per thread per pass
+  static constexpr int kSets = N / 16 / THREADS; // butterflies of 16 per thread per pass
   static constexpr int kR4 = N / 4096;          // radix of the last pass
   static constexpr int kSmemBytes = (N + N / 16) * (int)sizeof(V) + 256 * (int)sizeof(V);
   static constexpr int kSmemBytesTw = kSmemBytes + (256 + 4096) * (int)sizeof(V); // + the full twiddle tables
@@ -154,14 +155,14 @@ template <typename CFG> __device__ __forceinline__ void pass16_first_smem(typena
   // set, compile-time offsets for the 16 elements
 #pragma unroll
   for (int s = 0; s < CFG::kSets; s++) {
-    const V *src = buf + fpad(threadIdx.x + s * kFftThreads);
+    const V *src = buf + fpad(threadIdx.x + s * CFG::kThreads);
 #pragma unroll
     for (int r = 0; r < 16; r++) v[s][r] = src[r * (CFG::kQ + CFG::kQ / 16)];
   }
   __syncthreads();
 #pragma unroll
   for (int s = 0; s < CFG::kSets; s++) {
-    V *dst = buf + 17 * (threadIdx.x + s * kFftThreads);
+    V *dst = buf + 17 * (threadIdx.x + s * CFG::kThreads);
     fft16(v[s]);
 #pragma unroll
     for (int r = 0; r < 16; r++) dst[r] = v[s][4 * (r & 3) + (r >> 2)];
@@ -185,14 +186,14 @@ __device__ __forceinline__ void pass16_smem(typename CFG::V *buf, const typename
   V v[CFG::kSets][16];
 #pragma unroll
   for (int s = 0; s < CFG::kSets; s++) {
-    const V *src = buf + fpad(threadIdx.x + s * kFftThreads);
+    const V *src = buf + fpad(threadIdx.x + s * CFG::kThreads);
 #pragma unroll
     for (int r = 0; r < 16; r++) v[s][r] = src[r * (CFG::kQ + CFG::kQ / 16)];
   }
   __syncthreads();
 #pragma unroll
   for (int s = 0; s < CFG::kSets; s++) {
-    const int i = threadIdx.x + s * kFftThreads;
+    const int i = threadIdx.x + s * CFG::kThreads;
     const int k = i & (p - 1);
     if (TW) {
       const V *tp = twtab + (p == 16 ? kTwTabP16 : kTwTabP256) + k;
@@ -246,11 +247,11 @@ __device__ __forceinline__ void last_pass_load(const typename CFG::V *buf, const
 // lanes — and spreads q over the lanes: consecutive lanes then read addresses `instep` elements
 // apart, and instep is odd for every shipped chain, i.e. conflict free. When a block holds fewer
 // than 32 periods the warp takes several p at once (G groups of L lanes).
-template <typename V, int FLEN>
+template <typename V, int FLEN, int NT>
 __device__ __forceinline__ void fi_epilogue(const V *__restrict__ buf, const decltype(V().x) *__restrict__ bank, int instep,
                                             int outstep, int klen, int rem_b, int cnt, Ring<V> out, uint32_t c, int64_t mb) {
   using S = decltype(V().x);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kFftThreads / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = NT / 32;
   const int nq = (cnt + outstep - 1) / outstep;
   const int L = nq < 32 ? nq : 32;
   const int G = 32 / L;
@@ -303,12 +304,13 @@ struct FftFuse {
 //   fused: block b produces interpolator outputs m in [m0 + b*mo, ...) from the filtered samples
 //          it holds (down must be 1); samples with negative index read as zero like the ring does.
 //   n_in_avail: number of valid input samples in the ring (indices >= it read as zero)
-template <typename S, int N, bool FUSE, bool TW = false>
-__global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThreads : kFftThreads,
+template <typename S, int N, bool FUSE, bool TW = false, int THREADS = kFftThreads>
+__global__ void __launch_bounds__((THREADS != kFftThreads) ? THREADS
+                                  : (N == 16384 && sizeof(S) == 4) ? kFftRegCapThreads : kFftThreads,
                                   (N == 8192 && sizeof(S) == 4) ? 2 : 1)
     k_fir_fft(Ring<typename V2<S>::type> in, Ring<typename V2<S>::type> out, const typename V2<S>::type *__restrict__ H,
               int klen, int down, int64_t q0, int n_out, int64_t n_in_avail, int lq, FftFuse fz) {
-  using CFG = FftCfg<S, N>;
+  using CFG = FftCfg<S, N, THREADS>;
   using V = typename CFG::V;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   V *buf = reinterpret_cast<V *>(smem_raw);
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThr
   }
   if (TW) {
     const V *__restrict__ g = reinterpret_cast<const V *>(fz.twtab);
-    for (int i = threadIdx.x; i < kTwTabLen; i += kFftThreads) twtab[i] = __ldg(g + i);
+    for (int i = threadIdx.x; i < kTwTabLen; i += CFG::kThreads) twtab[i] = __ldg(g + i);
   }
   // ---- forward pass 1 (p = 1, no twiddles), inputs straight from the global ring
   {
@@ -365,12 +367,12 @@ __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThr
 #pragma unroll
       for (int s = 0; s < CFG::kSets; s++) {
 #pragma unroll
-        for (int r = 0; r < 16; r++) v[s][r] = row[s * kFftThreads + r * CFG::kQ];
+        for (int r = 0; r < 16; r++) v[s][r] = row[s * CFG::kThreads + r * CFG::kQ];
       }
     } else {
 #pragma unroll
       for (int s = 0; s < CFG::kSets; s++) {
-        const int i = threadIdx.x + s * kFftThreads;
+        const int i = threadIdx.x + s * CFG::kThreads;
 #pragma unroll
         for (int r = 0; r < 16; r++) {
           const int64_t t = base + i + r * CFG::kQ;
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThr
     }
 #pragma unroll
     for (int s = 0; s < CFG::kSets; s++) {
-      V *dst = buf + 17 * (threadIdx.x + s * kFftThreads);
+      V *dst = buf + 17 * (threadIdx.x + s * CFG::kThreads);
       fft16(v[s]);
 #pragma unroll
       for (int r = 0; r < 16; r++) dst[r] = v[s][4 * (r & 3) + (r >> 2)];
@@ -391,8 +393,8 @@ __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThr
   pass16_smem<CFG, 256, TW>(buf, tw, twtab);
   // ---- forward last pass fused with Y = conj(X * H)
 #pragma unroll 2
-  for (int b = 0; b < 4096 / kFftThreads; b++) {
-    const int i = threadIdx.x + b * kFftThreads;
+  for (int b = 0; b < 4096 / CFG::kThreads; b++) {
+    const int i = threadIdx.x + b * CFG::kThreads;
     V a[4];
     last_pass_load<CFG>(buf, tw, i, a);
 #pragma unroll
@@ -406,8 +408,8 @@ __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThr
   if (!FUSE) {
     // ---- inverse last pass, outputs straight to the global ring (only the alias-free part)
 #pragma unroll 2
-    for (int b = 0; b < 4096 / kFftThreads; b++) {
-      const int i = threadIdx.x + b * kFftThreads;
+    for (int b = 0; b < 4096 / CFG::kThreads; b++) {
+      const int i = threadIdx.x + b * CFG::kThreads;
       V a[4];
       last_pass_load<CFG>(buf, tw, i, a);
 #pragma unroll
@@ -424,11 +426,11 @@ __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThr
     // ---- inverse last pass into registers, then back to shared memory in PLAIN order (slot n
     // holds filter output qb + n - (klen-1)): the interpolator below reads windows whose start
     // advances by `instep` per lane, which is conflict free only without the FFT's skew
-    constexpr int NB = 4096 / kFftThreads;
+    constexpr int NB = 4096 / CFG::kThreads;
     V y[NB][CFG::kR4];
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-      const int i = threadIdx.x + b * kFftThreads;
+      const int i = threadIdx.x + b * CFG::kThreads;
       V a[4];
       last_pass_load<CFG>(buf, tw, i, a);
 #pragma unroll
@@ -445,18 +447,18 @@ __global__ void __launch_bounds__((N == 16384 && sizeof(S) == 4) ? kFftRegCapThr
 #pragma unroll
     for (int b = 0; b < NB; b++) {
 #pragma unroll
-      for (int r = 0; r < CFG::kR4; r++) buf[threadIdx.x + b * kFftThreads + r * 4096] = y[b][r];
+      for (int r = 0; r < CFG::kR4; r++) buf[threadIdx.x + b * CFG::kThreads + r * 4096] = y[b][r];
     }
     __syncthreads();
     const S *__restrict__ bank = reinterpret_cast<const S *>(fz.bank);
     const int rem_b = (int)((mb * fz.instep) % fz.outstep);
     if (fz.flen == 18) {
-      fi_epilogue<V, 18>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
+      fi_epilogue<V, 18, CFG::kThreads>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
     } else if (fz.flen == 24) {
-      fi_epilogue<V, 24>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
+      fi_epilogue<V, 24, CFG::kThreads>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
     } else {
       // generic bank length: one output per thread, taps in a loop
-      for (int i = threadIdx.x; i < cnt; i += kFftThreads) {
+      for (int i = threadIdx.x; i < cnt; i += CFG::kThreads) {
         const int prel = i * fz.instep + rem_b;
         const int dip = prel / fz.outstep;
         const int ph = prel - dip * fz.outstep;

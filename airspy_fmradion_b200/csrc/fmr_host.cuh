@@ -19,6 +19,7 @@
 #include <complex>
 
 #include "fmr_fft.cuh"
+#include "fmr_fft_inplace.cuh"
 #include "fmr_hbstream.cuh"
 #include "fmr_kernels.cuh"
 #include "fmr_tables.h"
@@ -210,6 +211,9 @@ template <typename S> struct Resampler {
   V *d_H16 = nullptr, *d_H8 = nullptr; // filter spectra for k_fir_fft (16384: float chains only)
   V *d_twtab = nullptr;                // full twiddle tables of the 16384-point kernel (FMR_FFT_TW=0: off)
   bool fft_tw = false;
+  V *d_H16rev = nullptr, *d_iptab = nullptr; // in-place form (fmr_fft_inplace.cuh)
+  bool fft_inplace = false;                  // FMR_FFT_INPLACE=1
+  int fft_threads = 512;               // FMR_FFT_THREADS=1024: the 32-warp form of the fused 16384-point kernel
   bool use_fft = false;
   bool use_dec2 = false; // double chains with a decimate-by-2 low-pass (audio resampler)
   bool fuse_fi = true;   // FMR_FUSE_FI=0: keep the polyphase bank as its own launch
@@ -362,6 +366,45 @@ template <typename S> struct Resampler {
         FMR_CUDA(mem.alloc(&d_twtab, tt.size(), false));
         FMR_CUDA(cudaMemcpy(d_twtab, tt.data(), sizeof(V) * tt.size(), cudaMemcpyHostToDevice));
         fft_tw = !env_off("FMR_FFT_TW");
+        {
+          // in-place (DIF / DIT) form of the same block, fmr_fft_inplace.cuh: spectrum in digit-reversed order,
+          // its twiddle tables; FMR_FFT_INPLACE=1 selects it
+          using namespace ipfft;
+          std::vector<std::complex<double>> hc(kN, std::complex<double>(0.0, 0.0));
+          for (int i = 0; i < d->bc.klen; i++) hc[i] = d->bc.taps[i];
+          host_fft(hc);
+          std::vector<V> hr(kN), tb(kTabLen);
+          for (int pz = 0; pz < kN; pz++) {
+            const std::complex<double> hv = hc[freq_of_pos(pz)] / (double)kN;
+            hr[pz].x = (S)hv.real();
+            hr[pz].y = (S)hv.imag();
+          }
+          auto wv = [](double num, double den) {
+            const double a = -2.0 * M_PI * num / den;
+            V v;
+            v.x = (S)std::cos(a);
+            v.y = (S)std::sin(a);
+            return v;
+          };
+          for (int q = 0; q < 128; q++) {
+            tb[kTw + q] = wv(128.0 * q, (double)kN);
+            tb[kTw + 128 + q] = wv((double)q, (double)kN);
+          }
+          for (int dd = 0; dd < 16; dd++) {
+            for (int b = 0; b < 64; b++) tb[kT64 + dd * 64 + b] = wv((double)(b * dd), 1024.0);
+            for (int b = 0; b < 4; b++) tb[kT4 + dd * 4 + b] = wv((double)(b * dd), 64.0);
+          }
+          FMR_CUDA(mem.alloc(&d_H16rev, hr.size(), false));
+          FMR_CUDA(cudaMemcpy(d_H16rev, hr.data(), sizeof(V) * hr.size(), cudaMemcpyHostToDevice));
+          FMR_CUDA(mem.alloc(&d_iptab, tb.size(), false));
+          FMR_CUDA(cudaMemcpy(d_iptab, tb.data(), sizeof(V) * tb.size(), cudaMemcpyHostToDevice));
+          FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
+          FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
+          if (const char *ev = getenv("FMR_FFT_INPLACE")) fft_inplace = atoi(ev) != 0;
+        }
+        FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<S, 16384, true, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       FftCfg<S, 16384>::kSmemBytesTw)));
+        if (const char *ev = getenv("FMR_FFT_THREADS")) fft_threads = atoi(ev);
       }
       use_fft = true;
       fft_min_out = (sizeof(S) == sizeof(float)) ? kFftMinOutF32 : kFftMinOutF64;
@@ -477,7 +520,19 @@ template <typename S> struct Resampler {
         fz.tail_hi = last ? b1 : 0;
         fz.tail_lo = last ? b1 - (2 * d->fi.flen + 16) : 0;
         dim3 grid(nb16, gcn);
-        if (fft_tw) {
+        if (fft_inplace) {
+          fz.twtab = d_iptab;
+          if (fft_threads == 1024) {
+            k_fir_fft_ip<1024><<<grid, 1024, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
+          } else {
+            k_fir_fft_ip<512><<<grid, 512, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
+          }
+        } else if (fft_tw && fft_threads == 1024) {
+          // 32 warps per SM on the same 16384-point block: one butterfly set per thread, 64 registers
+          fz.twtab = d_twtab;
+          k_fir_fft<S, 16384, true, true, 1024><<<grid, 1024, FftCfg<S, 16384>::kSmemBytesTw, st>>>(in, o, d_H16, klen, 1, 0,
+                                                                                                  0, avail, lq16, fz);
+        } else if (fft_tw) {
           fz.twtab = d_twtab;
           k_fir_fft<S, 16384, true, true><<<grid, kFftThreads, FftCfg<S, 16384>::kSmemBytesTw, st>>>(in, o, d_H16, klen, 1,
                                                                                                    0, 0, avail, lq16, fz);

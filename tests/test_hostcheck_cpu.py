@@ -28,3 +28,15 @@ def test_streaming_halfband_bookkeeping(tmp_path):
 def test_branch_free_fast_atan2(tmp_path):
     out = _build_and_run("tests/cpp/fast_atan2_host_test.cpp", tmp_path, extra=("-frounding-math",))
     assert "exact-division form mismatches=0" in out
+
+
+def test_inplace_fft_host_emulation(tmp_path):
+    """k_fir_fft_ip's per-thread pass bodies (fmr_fft_inplace.cuh, __host__ __device__) run on the CPU, threads of a
+    pass in scrambled order, against the direct circular convolution in double; pad words must stay untouched."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    exe = str(tmp_path / "fft_inplace_host_test")
+    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-arch=sm_100a", "-x", "cu",
+                           os.path.join(ROOT, "tests/cpp/fft_inplace_host_test.cu"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    sys.stdout.write(out.stdout)
+    assert out.returncode == 0 and "inplace fft: ok" in out.stdout
