@@ -212,7 +212,7 @@ template <typename S> struct Resampler {
   V *d_twtab = nullptr;                // full twiddle tables of the 16384-point kernel (FMR_FFT_TW=0: off)
   bool fft_tw = false;
   V *d_H16rev = nullptr, *d_iptab = nullptr; // in-place form (fmr_fft_inplace.cuh)
-  bool fft_inplace = false;                  // FMR_FFT_INPLACE=1
+  bool fft_inplace = true;                   // FMR_FFT_INPLACE=0: the Stockham form (k_fir_fft)
   int fft_threads = 512;               // FMR_FFT_THREADS=1024: the 32-warp form of the fused 16384-point kernel
   bool use_fft = false;
   bool use_dec2 = false; // double chains with a decimate-by-2 low-pass (audio resampler)

@@ -49,7 +49,8 @@ def raw_page(rep):
 def main():
     traffic = {"note": "dram__bytes_read.sum + dram__bytes_write.sum per IQ input sample, one ncu --set full "
                        "capture per kernel (profiles/ncu_*_%s.txt), C=1024 channels" % R}
-    stage_of = {"hbs": "if_halfband_cascade", "fft": "if_lowpass", "core": "fm_core_fused"}
+    # "fftip" (the in-place form, the default since the end of round 1) overrides "fft" (Stockham form) for the stage
+    stage_of = {"hbs": "if_halfband_cascade", "fft": "if_lowpass", "fftip": "if_lowpass", "core": "fm_core_fused"}
     # samples per channel of the profiled run = bench default blocks
     import re
     blocks = int(re.search(r'"--blocks", type=int, default=(\d+)', open(os.path.join(ROOT, "bench.py")).read()).group(1))
@@ -66,7 +67,7 @@ def main():
                     if k in d:
                         f.write("%-80s %s %s\n" % (k, d[k], units.get(k, "")))
         # several launches may have been captured: take the kernel the stage is named after
-        want = {"fft": "k_fir_fft<float, 16384"}.get(tag)
+        want = {"fft": "k_fir_fft<float, 16384", "fftip": "k_fir_fft_ip"}.get(tag)
         d = next((k for k in ks if want and want in k.get("Kernel Name", "")), ks[0])
 
         def gb(k):
