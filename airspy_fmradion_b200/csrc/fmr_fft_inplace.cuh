@@ -205,6 +205,178 @@ FMR_IP_HD void dit_last(int b, const float2 *buf, const float2 *tab, float2 (&y)
 FMR_IP_HD int freq_of_pos(int p) { return (p >> 10) + 16 * ((p >> 6) & 15) + 256 * ((p >> 2) & 15) + 4096 * (p & 3); }
 
 } // namespace ipfft
+
+// ---------------------------------------------------------------------------------------------------------------
+// Radix 32 x 32 x 16 form of the same in-place scheme: three passes each way instead of four, i.e. 9 instead of 13
+// sweeps of the block through shared memory (the in-place radix-16 kernel sits on the shared-memory pipe).
+//   position p = 512 d1 + 16 d2 + d3 holds frequency k = d1 + 32 d2 + 1024 d3 (d1, d2 < 32, d3 < 16)
+//   DIF stride 512: butterfly b < 512 takes {b + 512 a}, 32-point DFT, times W_N^(b d), stored at {b + 512 d}
+//   DIF stride 16 : chunk c < 32 of 512, b < 16: {512 c + b + 16 a}, 32-point DFT, times W_512^(b d)
+//   middle        : 16 contiguous slots: 16-point DFT, times H (digit-reversed), conjugate, 16-point DFT back
+//   DIT stride 16 / stride 512: the mirror images (twiddle first).
+// One 32-point butterfly per thread and pass (512 threads), two 16-point ones in the middle.
+namespace ipfft32 {
+using ipfft::cadd;
+using ipfft::cconj;
+using ipfft::cmul;
+using ipfft::csub;
+using ipfft::fft16;
+using ipfft::mk;
+using ipfft::nat;
+using ipfft::pad;
+constexpr int kN = 16384;
+constexpr int kBufLen = kN + kN / 16;
+constexpr int kTabLen = 256; // two-level table of W_N: [q] q < 128: W^(128 q), [128 + l]: W^l
+
+FMR_IP_HD float2 tw_lookup(const float2 *tab, int m) { return cmul(tab[m >> 7], tab[128 + (m & 127)]); }
+
+// 32-point forward DFT. In: e[n] = x[2 n], o[n] = x[2 n + 1]. Out: X[k] in e[nat(k)], X[k + 16] in o[nat(k)], k < 16.
+FMR_IP_HD void fft32(float2 (&e)[16], float2 (&o)[16]) {
+  fft16(e);
+  fft16(o);
+  // W_32^k, k = 0 .. 15
+  const float c[16] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                       0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f,
+                       0.0f, -0.19509032201612826785f, -0.38268343236508977173f, -0.55557023301960222474f,
+                       -0.70710678118654752440f, -0.83146961230254523708f, -0.92387953251128675613f, -0.98078528040323044913f};
+  const float sn[16] = {0.0f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                        0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f, 0.98078528040323044913f,
+                        1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                        0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f};
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int r = nat(k);
+    float2 t;
+    if (k == 0) {
+      t = o[r];
+    } else if (k == 8) {
+      t = mk(o[r].y, -o[r].x); // times -j
+    } else {
+      t = cmul(o[r], mk(c[k], -sn[k]));
+    }
+    const float2 a = e[r];
+    e[r] = cadd(a, t);
+    o[r] = csub(a, t);
+  }
+}
+
+// powers of a root: w[j] = w1^j (j < 8), w8, w16, w24
+struct Pow32 {
+  float2 w[8], w8, w16, w24;
+};
+// m: exponent of the root (W_N^m); the three coarse powers come from the table instead of repeated squaring, which
+// would multiply the rounding error of the root by 8, 16 and 24 (24 m < N for every caller)
+FMR_IP_HD void powers32(const float2 *tab, int m, Pow32 &P) {
+  const float2 w1 = tw_lookup(tab, m);
+  P.w[0] = mk(1.0f, 0.0f);
+  P.w[1] = w1;
+  P.w[2] = cmul(w1, w1);
+  P.w[3] = cmul(P.w[2], w1);
+  P.w[4] = cmul(P.w[2], P.w[2]);
+  P.w[5] = cmul(P.w[4], w1);
+  P.w[6] = cmul(P.w[3], P.w[3]);
+  P.w[7] = cmul(P.w[4], P.w[3]);
+  P.w8 = tw_lookup(tab, 8 * m);
+  P.w16 = tw_lookup(tab, 16 * m);
+  P.w24 = tw_lookup(tab, 24 * m);
+}
+FMR_IP_HD float2 pow_of(const Pow32 &P, int d) { // w1^d, d = 1 .. 31 (compile-time d after unrolling)
+  const int j = d & 7, g = d >> 3;
+  if (g == 0) return P.w[j];
+  const float2 wg = (g == 1) ? P.w8 : (g == 2) ? P.w16 : P.w24;
+  return (j == 0) ? wg : cmul(wg, P.w[j]);
+}
+
+// ---- DIF, stride 512: butterfly b in [0, 512); inputs x[b + 512 a] from `ld`
+template <typename LD> FMR_IP_HD void dif_first(int b, LD ld, float2 *buf, const float2 *tab) {
+  float2 e[16], o[16];
+#pragma unroll
+  for (int n = 0; n < 16; n++) {
+    e[n] = ld(b + 512 * (2 * n));
+    o[n] = ld(b + 512 * (2 * n + 1));
+  }
+  fft32(e, o);
+  Pow32 P;
+  powers32(tab, b, P);
+  float2 *dst = buf + pad(b); // pad(b + 512 d) = pad(b) + 544 d
+  dst[0] = e[nat(0)];
+#pragma unroll
+  for (int d = 1; d < 32; d++) dst[544 * d] = cmul((d < 16) ? e[nat(d)] : o[nat(d - 16)], pow_of(P, d));
+}
+// ---- DIF, stride 16: i in [0, 512): chunk c = i >> 4 of 512, b = i & 15
+FMR_IP_HD void dif_16(int i, float2 *buf, const float2 *tab) {
+  const int b = i & 15, c = i >> 4;
+  float2 *p = buf + 544 * c + b; // pad(512 c + b + 16 a) = 544 c + b + 17 a
+  float2 e[16], o[16];
+#pragma unroll
+  for (int n = 0; n < 16; n++) {
+    e[n] = p[17 * (2 * n)];
+    o[n] = p[17 * (2 * n + 1)];
+  }
+  fft32(e, o);
+  Pow32 P;
+  powers32(tab, 32 * b, P); // W_512^b = W_N^(32 b)
+  p[0] = e[nat(0)];
+#pragma unroll
+  for (int d = 1; d < 32; d++) p[17 * d] = cmul((d < 16) ? e[nat(d)] : o[nat(d - 16)], pow_of(P, d));
+}
+// ---- middle: 16 contiguous slots, i in [0, 1024)
+FMR_IP_HD void mid_r16(int i, float2 *buf, const float2 *__restrict__ hrev) {
+  float2 *p = buf + 17 * i; // pad(16 i + r) = 17 i + r
+  float2 v[16];
+#pragma unroll
+  for (int r = 0; r < 16; r++) v[r] = p[r];
+  fft16(v);
+  const float4 *__restrict__ h4 = reinterpret_cast<const float4 *>(hrev) + 8 * i;
+  float2 u[16];
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const float4 h = h4[q];
+    u[2 * q] = cconj(cmul(v[nat(2 * q)], mk(h.x, h.y)));
+    u[2 * q + 1] = cconj(cmul(v[nat(2 * q + 1)], mk(h.z, h.w)));
+  }
+  fft16(u);
+#pragma unroll
+  for (int a = 0; a < 16; a++) p[a] = u[nat(a)];
+}
+// ---- DIT, stride 16
+FMR_IP_HD void dit_16(int i, float2 *buf, const float2 *tab) {
+  const int b = i & 15, c = i >> 4;
+  float2 *p = buf + 544 * c + b;
+  Pow32 P;
+  powers32(tab, 32 * b, P);
+  float2 e[16], o[16];
+  e[0] = p[0];
+  o[0] = cmul(p[17], pow_of(P, 1));
+#pragma unroll
+  for (int n = 1; n < 16; n++) {
+    e[n] = cmul(p[17 * (2 * n)], pow_of(P, 2 * n));
+    o[n] = cmul(p[17 * (2 * n + 1)], pow_of(P, 2 * n + 1));
+  }
+  fft32(e, o);
+#pragma unroll
+  for (int a = 0; a < 32; a++) p[17 * a] = (a < 16) ? e[nat(a)] : o[nat(a - 16)];
+}
+// ---- DIT, stride 512, into registers: y[a] = filtered sample of buffer slot b + 512 a
+FMR_IP_HD void dit_last(int b, const float2 *buf, const float2 *tab, float2 (&y)[32]) {
+  const float2 *p = buf + pad(b);
+  Pow32 P;
+  powers32(tab, b, P);
+  float2 e[16], o[16];
+  e[0] = p[0];
+  o[0] = cmul(p[544], pow_of(P, 1));
+#pragma unroll
+  for (int n = 1; n < 16; n++) {
+    e[n] = cmul(p[544 * (2 * n)], pow_of(P, 2 * n));
+    o[n] = cmul(p[544 * (2 * n + 1)], pow_of(P, 2 * n + 1));
+  }
+  fft32(e, o);
+#pragma unroll
+  for (int a = 0; a < 32; a++) y[a] = cconj((a < 16) ? e[nat(a)] : o[nat(a - 16)]);
+}
+FMR_IP_HD int freq_of_pos(int p) { return (p >> 9) + 32 * ((p >> 4) & 31) + 1024 * (p & 15); }
+
+} // namespace ipfft32
 } // namespace fmr
 
 #if defined(__CUDACC__) && defined(FMR_FFT_CUH)
@@ -315,7 +487,89 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
+// Radix 32 x 32 x 16 form (ipfft32), 512 threads = one 32-point butterfly per thread and pass. Same parameters; Hrev
+// in ipfft32's digit-reversed order, fz.twtab = its 256-entry table.
+__global__ void __launch_bounds__(512, 1)
+    k_fir_fft_ip32(Ring<float2> in, Ring<float2> out, const float2 *__restrict__ Hrev, int klen, int64_t n_in_avail, FftFuse fz) {
+  using namespace ipfft32;
+  constexpr int THREADS = 512;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+  float2 *tab = buf + kBufLen;
+  const uint32_t c = blockIdx.y;
+  const int blk = blockIdx.x;
+  int cnt = fz.n_m - blk * fz.mo;
+  if (cnt > fz.mo) cnt = fz.mo;
+  if (cnt <= 0) return;
+  const int64_t mb = fz.m0 + (int64_t)blk * fz.mo;
+  const int64_t qb = (mb * fz.instep) / fz.outstep - (fz.flen / 2 - 1);
+  const int fl2 = (klen - 1) / 2;
+  const int64_t base = qb - fl2;
+  if (threadIdx.x < kTabLen) tab[threadIdx.x] = __ldg(reinterpret_cast<const float2 *>(fz.twtab) + threadIdx.x);
+  __syncthreads();
+  {
+    const uint32_t pos0 = (uint32_t)base & (in.cap - 1);
+    if (base >= 0 && base + kN <= n_in_avail && pos0 + (uint32_t)kN <= in.cap) {
+      const float2 *__restrict__ row = in.base + (size_t)c * in.cap + pos0;
+      dif_first(threadIdx.x, [&](int n) { return row[n]; }, buf, tab);
+    } else {
+      dif_first(threadIdx.x,
+                [&](int n) {
+                  const int64_t t = base + n;
+                  return (t < n_in_avail) ? in.ld(c, t) : make_float2(0.f, 0.f);
+                },
+                buf, tab);
+    }
+  }
+  __syncthreads();
+  dif_16(threadIdx.x, buf, tab);
+  __syncthreads();
+  mid_r16(threadIdx.x, buf, Hrev);
+  mid_r16(threadIdx.x + THREADS, buf, Hrev);
+  __syncthreads();
+  dit_16(threadIdx.x, buf, tab);
+  __syncthreads();
+  float2 y[32];
+  dit_last(threadIdx.x, buf, tab, y);
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 32; a++) {
+    const int n = threadIdx.x + 512 * a;
+    const int64_t t = qb + (n - (klen - 1));
+    const float2 v = (t >= 0) ? y[a] : make_float2(0.f, 0.f);
+    if (t >= fz.tail_lo && t < fz.tail_hi && n >= klen - 1 && blk == (int)gridDim.x - 1) {
+      Ring<float2>{reinterpret_cast<float2 *>(fz.tail_base), fz.tail_cap}.st(c, t, v);
+    }
+    buf[n] = v;
+  }
+  __syncthreads();
+  const float *__restrict__ bank = reinterpret_cast<const float *>(fz.bank);
+  const int rem_b = (int)((mb * fz.instep) % fz.outstep);
+  if (fz.flen == 18) {
+    fi_epilogue<float2, 18, THREADS>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
+  } else if (fz.flen == 24) {
+    fi_epilogue<float2, 24, THREADS>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
+  } else {
+    for (int i = threadIdx.x; i < cnt; i += THREADS) {
+      const int prel = i * fz.instep + rem_b;
+      const int dip = prel / fz.outstep;
+      const int ph = prel - dip * fz.outstep;
+      const float *__restrict__ row = bank + (size_t)ph * fz.flen;
+      const int n0 = (klen - 1) + dip;
+      float2 acc = make_float2(0.f, 0.f);
+      for (int k = 0; k < fz.flen; k++) {
+        const float2 x = buf[n0 + k];
+        const float h = __ldg(row + k);
+        acc.x += h * x.x;
+        acc.y += h * x.y;
+      }
+      out.st(c, mb + i, acc);
+    }
+  }
+}
+
 constexpr int kIpSmemBytes = (ipfft::kBufLen + ipfft::kTabLen) * (int)sizeof(float2);
+constexpr int kIp32SmemBytes = (ipfft32::kBufLen + ipfft32::kTabLen) * (int)sizeof(float2);
 
 } // namespace fmr
 #endif

@@ -213,6 +213,8 @@ template <typename S> struct Resampler {
   bool fft_tw = false;
   V *d_H16rev = nullptr, *d_iptab = nullptr; // in-place form (fmr_fft_inplace.cuh)
   bool fft_inplace = true;                   // FMR_FFT_INPLACE=0: the Stockham form (k_fir_fft)
+  V *d_H16rev32 = nullptr;                   // spectrum in the digit-reversed order of the radix 32 x 32 x 16 form
+  bool fft_inplace32 = false;                // FMR_FFT_INPLACE=2: k_fir_fft_ip32 (host-checked, not yet measured)
   int fft_threads = 512;               // FMR_FFT_THREADS=1024: the 32-warp form of the fused 16384-point kernel
   bool use_fft = false;
   bool use_dec2 = false; // double chains with a decimate-by-2 low-pass (audio resampler)
@@ -400,7 +402,20 @@ template <typename S> struct Resampler {
           FMR_CUDA(cudaMemcpy(d_iptab, tb.data(), sizeof(V) * tb.size(), cudaMemcpyHostToDevice));
           FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
           FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
-          if (const char *ev = getenv("FMR_FFT_INPLACE")) fft_inplace = atoi(ev) != 0;
+          // radix 32 x 32 x 16 form (FMR_FFT_INPLACE=2): its own digit-reversed order, the two-level table only
+          std::vector<V> hr32(kN);
+          for (int pz = 0; pz < kN; pz++) {
+            const std::complex<double> hv = hc[ipfft32::freq_of_pos(pz)] / (double)kN;
+            hr32[pz].x = (S)hv.real();
+            hr32[pz].y = (S)hv.imag();
+          }
+          FMR_CUDA(mem.alloc(&d_H16rev32, hr32.size(), false));
+          FMR_CUDA(cudaMemcpy(d_H16rev32, hr32.data(), sizeof(V) * hr32.size(), cudaMemcpyHostToDevice));
+          FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip32, cudaFuncAttributeMaxDynamicSharedMemorySize, kIp32SmemBytes)));
+          if (const char *ev = getenv("FMR_FFT_INPLACE")) {
+            fft_inplace = atoi(ev) != 0;
+            fft_inplace32 = atoi(ev) == 2;
+          }
         }
         FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<S, 16384, true, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        FftCfg<S, 16384>::kSmemBytesTw)));
@@ -520,7 +535,10 @@ template <typename S> struct Resampler {
         fz.tail_hi = last ? b1 : 0;
         fz.tail_lo = last ? b1 - (2 * d->fi.flen + 16) : 0;
         dim3 grid(nb16, gcn);
-        if (fft_inplace) {
+        if (fft_inplace && fft_inplace32) {
+          fz.twtab = d_iptab; // its first 256 entries are the two-level table of W_N
+          k_fir_fft_ip32<<<grid, 512, kIp32SmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev32), klen, avail, fz);
+        } else if (fft_inplace) {
           fz.twtab = d_iptab;
           if (fft_threads == 1024) {
             k_fir_fft_ip<1024><<<grid, 1024, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);

@@ -30,6 +30,8 @@ VARIANTS = [
     ("fft_1024thr", {"FMR_FFT_THREADS": "1024"}, 329, 8192),
     ("fft_inplace_512", {"FMR_FFT_INPLACE": "1"}, 329, 8192),
     ("fft_inplace_1024", {"FMR_FFT_INPLACE": "1", "FMR_FFT_THREADS": "1024"}, 329, 8192),
+    ("fft_stockham", {"FMR_FFT_INPLACE": "0"}, 329, 8192),
+    ("fft_inplace_r32", {"FMR_FFT_INPLACE": "2"}, 329, 8192),
 ]
 
 
