@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 // Radix 32 x 32 x 16 form (ipfft32), 512 threads = one 32-point butterfly per thread and pass. Same parameters; Hrev
 // in ipfft32's digit-reversed order, fz.twtab = its 256-entry table.
-__global__ void __launch_bounds__(512, 1)
+static __global__ void __launch_bounds__(512, 1)
     k_fir_fft_ip32(Ring<float2> in, Ring<float2> out, const float2 *__restrict__ Hrev, int klen, int64_t n_in_avail, FftFuse fz) {
   using namespace ipfft32;
   constexpr int THREADS = 512;
