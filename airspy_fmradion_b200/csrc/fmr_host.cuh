@@ -402,19 +402,22 @@ template <typename S> struct Resampler {
           FMR_CUDA(cudaMemcpy(d_iptab, tb.data(), sizeof(V) * tb.size(), cudaMemcpyHostToDevice));
           FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
           FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
-          // radix 32 x 32 x 16 form (FMR_FFT_INPLACE=2): its own digit-reversed order, the two-level table only
-          std::vector<V> hr32(kN);
-          for (int pz = 0; pz < kN; pz++) {
-            const std::complex<double> hv = hc[ipfft32::freq_of_pos(pz)] / (double)kN;
-            hr32[pz].x = (S)hv.real();
-            hr32[pz].y = (S)hv.imag();
-          }
-          FMR_CUDA(mem.alloc(&d_H16rev32, hr32.size(), false));
-          FMR_CUDA(cudaMemcpy(d_H16rev32, hr32.data(), sizeof(V) * hr32.size(), cudaMemcpyHostToDevice));
-          FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip32, cudaFuncAttributeMaxDynamicSharedMemorySize, kIp32SmemBytes)));
           if (const char *ev = getenv("FMR_FFT_INPLACE")) {
             fft_inplace = atoi(ev) != 0;
             fft_inplace32 = atoi(ev) == 2;
+          }
+          if (fft_inplace32) {
+            // radix 32 x 32 x 16 form: its own digit-reversed order, the two-level table only. Set up only on request:
+            // the kernel has not run on a GPU yet, nothing of it may touch the default path
+            std::vector<V> hr32(kN);
+            for (int pz = 0; pz < kN; pz++) {
+              const std::complex<double> hv = hc[ipfft32::freq_of_pos(pz)] / (double)kN;
+              hr32[pz].x = (S)hv.real();
+              hr32[pz].y = (S)hv.imag();
+            }
+            FMR_CUDA(mem.alloc(&d_H16rev32, hr32.size(), false));
+            FMR_CUDA(cudaMemcpy(d_H16rev32, hr32.data(), sizeof(V) * hr32.size(), cudaMemcpyHostToDevice));
+            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip32, cudaFuncAttributeMaxDynamicSharedMemorySize, kIp32SmemBytes)));
           }
         }
         FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<S, 16384, true, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
