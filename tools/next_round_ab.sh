@@ -1,0 +1,9 @@
+#!/bin/bash
+# First GPU call of the next round: parity + A/B of the kernel variants that were written and host-checked at the
+# end of round 1 but have not been measured (the round's GPU budget was spent).
+#   FMR_FFT_INPLACE=2  k_fir_fft_ip32 (radix 32 x 32 x 16 in-place form of the 16384-point FFT low-pass)
+# Flip the default in fmr_host.cuh (fft_inplace32) only if the parity tests pass and the sweep shows a gain.
+set -u
+mkdir -p gpurun_out
+FMR_FFT_INPLACE=2 timeout 200 python -m pytest tests/test_fm_gpu.py tests/test_golden_gpu.py tests/test_edge_gpu.py -q -x 2>&1 | tail -4 | tee gpurun_out/pytest_ip32.log
+timeout 200 python tools/sweep_variants.py all_on_329 fft_inplace_r32 fft_stockham 2>gpurun_out/sweep_ip32.err | tee gpurun_out/sweep_ip32.log
