@@ -384,8 +384,12 @@ namespace fmr {
 
 // Fused form only (IF chain): block -> filtered block in shared memory (plain order) -> polyphase bank.
 // Parameters as k_fir_fft<float, 16384, true>; H is the digit-reversed spectrum, fz.twtab the ipfft table.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
+// BOUND > THREADS compiles for a nominal larger block, i.e. caps the registers (65536 / BOUND): <512, 896> = 72
+// registers, which leaves room for one half-band stream CTA or fused-core CTAs of ANOTHER handle on the same SM
+// (bench.py --handles: independent handles on their own streams overlap their HBM-, shared-memory- and latency-bound
+// kernels).
+template <int THREADS, int BOUND = THREADS>
+__global__ void __launch_bounds__(BOUND, 1)
     k_fir_fft_ip(Ring<float2> in, Ring<float2> out, const float2 *__restrict__ Hrev, int klen, int64_t n_in_avail, FftFuse fz) {
   using namespace ipfft;
   constexpr int SETS = 1024 / THREADS, NB4 = 4096 / THREADS;

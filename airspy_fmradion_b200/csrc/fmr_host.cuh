@@ -214,6 +214,7 @@ template <typename S> struct Resampler {
   V *d_H16rev = nullptr, *d_iptab = nullptr; // in-place form (fmr_fft_inplace.cuh)
   bool fft_inplace = true;                   // FMR_FFT_INPLACE=0: the Stockham form (k_fir_fft)
   V *d_H16rev32 = nullptr;                   // spectrum in the digit-reversed order of the radix 32 x 32 x 16 form
+  bool fft_regcap = false;                   // FMR_FFT_REGCAP=1: k_fir_fft_ip<512, 896> (72 registers; for --handles overlap)
   bool fft_inplace32 = false;                // FMR_FFT_INPLACE=2: k_fir_fft_ip32 (host-checked, not yet measured)
   int fft_threads = 512;               // FMR_FFT_THREADS=1024: the 32-warp form of the fused 16384-point kernel
   bool use_fft = false;
@@ -402,6 +403,10 @@ template <typename S> struct Resampler {
           FMR_CUDA(cudaMemcpy(d_iptab, tb.data(), sizeof(V) * tb.size(), cudaMemcpyHostToDevice));
           FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
           FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
+          if (const char *ev = getenv("FMR_FFT_REGCAP")) fft_regcap = atoi(ev) != 0;
+          if (fft_regcap) { // set up only on request (not measured yet)
+            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<512, 896>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
+          }
           if (const char *ev = getenv("FMR_FFT_INPLACE")) {
             fft_inplace = atoi(ev) != 0;
             fft_inplace32 = atoi(ev) == 2;
@@ -543,7 +548,9 @@ template <typename S> struct Resampler {
           k_fir_fft_ip32<<<grid, 512, kIp32SmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev32), klen, avail, fz);
         } else if (fft_inplace) {
           fz.twtab = d_iptab;
-          if (fft_threads == 1024) {
+          if (fft_regcap) {
+            k_fir_fft_ip<512, 896><<<grid, 512, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
+          } else if (fft_threads == 1024) {
             k_fir_fft_ip<1024><<<grid, 1024, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
           } else {
             k_fir_fft_ip<512><<<grid, 512, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);

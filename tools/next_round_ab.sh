@@ -7,3 +7,18 @@ set -u
 mkdir -p gpurun_out
 FMR_FFT_INPLACE=2 timeout 200 python -m pytest tests/test_fm_gpu.py tests/test_golden_gpu.py tests/test_edge_gpu.py -q -x 2>&1 | tail -4 | tee gpurun_out/pytest_ip32.log
 timeout 200 python tools/sweep_variants.py all_on_329 fft_inplace_r32 fft_stockham 2>gpurun_out/sweep_ip32.err | tee gpurun_out/sweep_ip32.log
+# Independent handles per GPU on their own streams (bench.py --handles): overlap of the HBM-bound half-band stream,
+# the shared-memory-bound FFT and the latency-bound core ACROSS handles, with no library change. The second / third
+# runs make the kernels small enough to share an SM: FFT capped at 72 registers (FMR_FFT_REGCAP=1), half-band stream
+# with two TMA stages = 68 KB (FMR_HBS_TMA=5, measured as fast as three stages).
+B="python bench.py --no-cpu --no-e2e --steps 6 --warmup 3"
+for g in 2 4; do
+  $B --handles $g 2>/dev/null | tail -1 > gpurun_out/multi_handle_${g}.json
+  FMR_FFT_REGCAP=1 FMR_HBS_TMA=5 $B --handles $g 2>/dev/null | tail -1 > gpurun_out/multi_handle_${g}_coresident.json
+done
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/multi_handle_*.json")):
+    d = json.load(open(f))
+    print(f, "single %.1f" % (d["value"] / 1e3), "multi", d.get("multi_handle"))
+PY
