@@ -9,14 +9,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from airspy_fmradion_b200 import FmDecoder  # noqa: E402
-from oracle import siggen  # noqa: E402
 
 
 def main():
     import torch
     fs, blk, per, calls, nch = 1.0e7, 2048, 160, 4, 4
     n = blk * per * calls
-    iq = np.stack([siggen.fm_stereo_iq(fs, n, c) for c in range(nch)])
+    # any FM signal does (the comparison is GPU schedule against GPU schedule): mono tone + 19 kHz pilot, some noise
+    t = np.arange(n) / fs
+    rng = np.random.default_rng(1)
+    rows = []
+    for c in range(nch):
+        mpx = 0.6 * np.sin(2 * np.pi * (1000.0 + 37 * c) * t) + 0.1 * np.sin(2 * np.pi * 19000.0 * t)
+        ph = 2 * np.pi * 75000.0 * np.cumsum(mpx) / fs
+        x = 0.5 * np.exp(1j * ph) + 0.01 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+        rows.append(x.astype(np.complex64))
+    iq = np.stack(rows)
     dev = torch.device("cuda", 0)
     d_iq = torch.from_numpy(iq.view(np.float32)).to(dev)
     kw = dict(stereo=True, input_rate=fs, n_channels=nch, max_samples_per_call=blk * per, max_blocks_per_call=per)
