@@ -18,6 +18,7 @@
 #define FMR_TABLES_H
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace fmr {
 
@@ -45,14 +46,19 @@ struct ChainDesc {
   BcStage bc;
   int has_fi;
   FiStage fi;
+  int verified; // 1: the GPU path for this pair has passed the parity suite on a B200 (tools/gen_tables.py)
 };
 
 #include "fmr_tables_generated.inc"
 
+// Pairs whose tables ship but whose GPU path has not passed the parity suite yet are refused (the caller gets
+// FMR_ERR_UNSUPPORTED, as for a pair without tables) unless FMR_EXPERIMENTAL_RATES=1.
 inline const ChainDesc *find_chain(double src, double dst, int kind) {
+  const char *e = getenv("FMR_EXPERIMENTAL_RATES");
+  const bool experimental = e && atoi(e) != 0;
   for (int i = 0; i < kNumChains; i++) {
     if (kChains[i].src == src && kChains[i].dst == dst && kChains[i].kind == kind) {
-      return &kChains[i];
+      return (kChains[i].verified || experimental) ? &kChains[i] : nullptr;
     }
   }
   return nullptr;

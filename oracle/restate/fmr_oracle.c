@@ -28,7 +28,7 @@
 typedef struct HbStage { int ntaps; const double *taps; } HbStage;
 typedef struct BcStage { int klen, inputlen, latency, down, outoffset; const double *taps; } BcStage;
 typedef struct FiStage { int instep, outstep, flen; const double *taps; } FiStage;
-typedef struct ChainDesc { double src, dst; int kind; int n_hb; HbStage hb[3]; BcStage bc; int has_fi; FiStage fi; } ChainDesc;
+typedef struct ChainDesc { double src, dst; int kind; int n_hb; HbStage hb[3]; BcStage bc; int has_fi; FiStage fi; int verified; } ChainDesc;
 #include "../../airspy_fmradion_b200/csrc/fmr_tables_generated.inc"
 
 static const ChainDesc *find_chain(double src, double dst, int kind) {

@@ -1,0 +1,48 @@
+"""Rate pairs whose tables were added at the end of round 1 (3 M, 2.4 M, 1.44 M, 1.2 M, 960 k, 912 k, 768 k -> 384 k):
+pinned on the CPU against the COMPILED REFERENCE — the plain-C restatement (which reads the same generated tables) must
+reproduce the reference's audio and per-call sizes, and the library's host-side schedule must reproduce the per-call
+sizes. Their GPU path is enabled only with FMR_EXPERIMENTAL_RATES=1 until it has passed tests/test_newrates_gpu.py."""
+import numpy as np
+import pytest
+
+from oracle import ref, restate, siggen
+
+RATES = [3.0e6, 2.4e6, 1.44e6, 1.2e6, 960000.0, 912000.0, 768000.0]
+needs_ref = pytest.mark.skipif(not ref.available(), reason="compiled reference (oracle/_ref) not built")
+
+
+def _blocks(fs):
+    # long enough to get past both resamplers' start-up latency (first audio after 29 591 IF samples)
+    return int(np.ceil(0.11 * fs / 2048)) + 8
+
+
+@needs_ref
+@pytest.mark.parametrize("fs", RATES)
+def test_restatement_and_schedule_match_reference(fs, monkeypatch):
+    monkeypatch.setenv("FMR_EXPERIMENTAL_RATES", "1")
+    blk, nblk = 2048, _blocks(fs)
+    iq = siggen.fm_stereo_iq(fs, blk * nblk, 1)
+    c = ref.RefChain("fm", fs, stereo=True)
+    ref_audio, ref_lens, _ = c.run(iq, blk)
+    c.close()
+    audio, lens, _, _ = restate.fm_run(iq, fs, blk, stereo=True)
+    assert list(lens) == list(ref_lens)
+    assert len(ref_audio) > 500
+    assert np.abs(audio - ref_audio).max() <= 1e-9
+    from airspy_fmradion_b200 import _capi
+    L = _capi.lib()
+    bl = np.full(nblk, blk, dtype=np.uint32)
+    out = np.zeros(nblk, dtype=np.uint32)
+    _capi.check(L.fmr_fm_schedule(fs, 1, 0, bl.ctypes.data, nblk, None, out.ctypes.data))
+    assert list(out) == list(ref_lens)
+
+
+def test_unverified_rates_are_refused_by_default(monkeypatch):
+    from airspy_fmradion_b200 import _capi
+    L = _capi.lib()
+    monkeypatch.delenv("FMR_EXPERIMENTAL_RATES", raising=False)
+    bl = np.full(4, 2048, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    for fs in RATES:
+        assert L.fmr_fm_schedule(fs, 1, 0, bl.ctypes.data, 4, None, out.ctypes.data) == 2  # FMR_ERR_UNSUPPORTED
+    assert L.fmr_fm_schedule(1.0e7, 1, 0, bl.ctypes.data, 4, None, out.ctypes.data) == 0

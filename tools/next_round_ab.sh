@@ -11,6 +11,9 @@ timeout 200 python tools/sweep_variants.py all_on_329 fft_inplace_r32 fft_stockh
 # the shared-memory-bound FFT and the latency-bound core ACROSS handles, with no library change. The second / third
 # runs make the kernels small enough to share an SM: FFT capped at 72 registers (FMR_FFT_REGCAP=1), half-band stream
 # with two TMA stages = 68 KB (FMR_HBS_TMA=5, measured as fast as three stages).
+# Rate pairs added without GPU budget: if green, set their `verified` flag to 1 in tools/gen_tables.py, regenerate, and
+# drop the gate of tests/test_newrates_gpu.py.
+FMR_EXPERIMENTAL_RATES=1 timeout 300 python -m pytest tests/test_newrates_gpu.py -q -s 2>&1 | tail -20 | tee gpurun_out/pytest_newrates.log
 B="python bench.py --no-cpu --no-e2e --steps 6 --warmup 3"
 for g in 2 4; do
   $B --handles $g 2>/dev/null | tail -1 > gpurun_out/multi_handle_${g}.json
