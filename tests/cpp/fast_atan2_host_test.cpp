@@ -10,7 +10,7 @@
 #include <cstdint>
 namespace fmr {
 struct HbStage{int ntaps; const double* taps;}; struct BcStage{int klen,inputlen,latency,down,outoffset; const double* taps;}; struct FiStage{int instep,outstep,flen; const double* taps;};
-struct ChainDesc{double src,dst;int kind;int n_hb;HbStage hb[3];BcStage bc;int has_fi;FiStage fi;};
+struct ChainDesc{double src,dst;int kind;int n_hb;HbStage hb[3];BcStage bc;int has_fi;FiStage fi;int verified;};
 #include "../../airspy_fmradion_b200/csrc/fmr_tables_generated.inc"
 }
 using namespace fmr;
