@@ -30,7 +30,7 @@ struct BcStage {
   int klen;      // kernel length (odd), zero-phase, includes the chain's final gain
   int inputlen;  // r8brain's FFT block payload (only documents where Latency comes from)
   int latency;   // samples of the convolver's output withheld at stream start
-  int down;      // 1 or 2
+  int down;      // 1, 2 or 3
   int outoffset; // (klen-1)/2
   const double *taps;
 };
@@ -75,7 +75,7 @@ inline int64_t hb_out(const ChainDesc *d, int64_t n) {
 inline int64_t bc_out(const ChainDesc *d, int64_t n) {
   int64_t c = n - d->bc.latency;
   if (c < 0) c = 0;
-  if (d->bc.down == 2) c = (c + 1) / 2;
+  if (d->bc.down > 1) c = (c + d->bc.down - 1) / d->bc.down; // every down-th sample, the first one kept
   return c;
 }
 inline int64_t fi_out(const ChainDesc *d, int64_t n) {

@@ -99,7 +99,7 @@ static int r8_process(R8Lane *r, const double *x, int n, Stream *out) {
     const int fl2 = (d->bc.klen - 1) / 2;
     int64_t c = a->n - d->bc.latency;
     if (c < 0) c = 0;
-    int64_t avail = (d->bc.down == 2) ? (c + 1) / 2 : c;
+    int64_t avail = (d->bc.down > 1) ? (c + d->bc.down - 1) / d->bc.down : c;
     int64_t q0 = d->has_fi ? b->n : r->emitted;
     int produced = 0;
     for (int64_t q = q0; q < avail; q++) {
@@ -851,7 +851,7 @@ int64_t orc_chain_out(double src, double dst, int kind, int64_t n) {
   if (!d) return -1;
   for (int s = 0; s < d->n_hb; s++) { n = n / 2 - (d->hb[s].ntaps - 1); if (n < 0) n = 0; }
   int64_t c = n - d->bc.latency; if (c < 0) c = 0;
-  if (d->bc.down == 2) c = (c + 1) / 2;
+  if (d->bc.down > 1) c = (c + d->bc.down - 1) / d->bc.down;
   if (!d->has_fi) return c;
   const int fl2 = d->fi.flen / 2;
   if (c < fl2 + 1) return 0;

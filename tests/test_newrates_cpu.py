@@ -1,4 +1,4 @@
-"""Rate pairs whose tables were added at the end of round 1 (3 M, 2.4 M, 1.44 M, 1.2 M, 960 k, 912 k, 768 k -> 384 k):
+"""Rate pairs whose tables were added at the end of round 1 (3 M, 2.4 M, 1.44 M, 1.2 M, 1.152 M, 960 k, 912 k, 768 k -> 384 k):
 pinned on the CPU against the COMPILED REFERENCE — the plain-C restatement (which reads the same generated tables) must
 reproduce the reference's audio and per-call sizes, and the library's host-side schedule must reproduce the per-call
 sizes. Their GPU path is enabled only with FMR_EXPERIMENTAL_RATES=1 until it has passed tests/test_newrates_gpu.py."""
@@ -7,7 +7,7 @@ import pytest
 
 from oracle import ref, restate, siggen
 
-RATES = [3.0e6, 2.4e6, 1.44e6, 1.2e6, 960000.0, 912000.0, 768000.0]
+RATES = [3.0e6, 2.4e6, 1.44e6, 1.2e6, 960000.0, 912000.0, 768000.0, 1152000.0]
 needs_ref = pytest.mark.skipif(not ref.available(), reason="compiled reference (oracle/_ref) not built")
 
 

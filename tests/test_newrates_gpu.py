@@ -14,7 +14,7 @@ pytestmark = [pytest.mark.gpu,
                                  reason="unverified rate pairs: set FMR_EXPERIMENTAL_RATES=1 (tools/next_round_ab.sh)")]
 
 
-@pytest.mark.parametrize("fs", [3.0e6, 2.4e6, 1.44e6, 1.2e6, 960000.0, 912000.0, 768000.0])
+@pytest.mark.parametrize("fs", [3.0e6, 2.4e6, 1.44e6, 1.2e6, 1152000.0, 960000.0, 912000.0, 768000.0])
 def test_new_rate_matches_oracle(fs):
     from airspy_fmradion_b200 import FmDecoder
     blk, per = 2048, 64
