@@ -256,6 +256,8 @@ template <typename S> struct Resampler {
     FMR_HB_COMBO(1, 8, 0, 0)  // 2.5 MHz
     FMR_HB_COMBO(2, 6, 11, 0) // 384 kHz -> 48 kHz (IfResampler spec, AM)
     FMR_HB_COMBO(2, 7, 13, 0) // 384 kHz -> 48 kHz (AudioResampler spec)
+    FMR_HB_COMBO(1, 11, 0, 0) // 2.048 MHz -> 384 kHz; 192 kHz, 256 kHz -> 48 kHz
+    FMR_HB_COMBO(3, 5, 6, 11) // 768 kHz, 1 MHz -> 48 kHz
 #undef FMR_HB_COMBO
     return false;
   }
