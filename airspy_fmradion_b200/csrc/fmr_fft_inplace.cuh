@@ -377,6 +377,95 @@ FMR_IP_HD void dit_last(int b, const float2 *buf, const float2 *tab, float2 (&y)
 FMR_IP_HD int freq_of_pos(int p) { return (p >> 9) + 32 * ((p >> 4) & 31) + 1024 * (p & 15); }
 
 } // namespace ipfft32
+
+// ---------------------------------------------------------------------------------------------------------------
+// 8192-point form, radix 32 x 16 x 16 (the remainder block of the 10 MHz chain, the 1 MHz-class chains whose filters
+// fit an 8192-point block, and the block size the fused persistent front end of DESIGN.md section 10 needs).
+//   position p = 256 d1 + 16 d2 + d3 holds frequency k = d1 + 32 d2 + 512 d3 (d1 < 32, d2, d3 < 16)
+// 256 threads: one 32-point butterfly per thread in the outer passes, two 16-point ones in the inner passes.
+namespace ipfft8k {
+using ipfft::cconj;
+using ipfft::cmul;
+using ipfft::fft16;
+using ipfft::mk;
+using ipfft::nat;
+using ipfft::pad;
+using ipfft::powers16;
+using ipfft32::fft32;
+using ipfft32::mid_r16; // 16 contiguous slots: identical (pad(16 i + r) = 17 i + r), i in [0, 512)
+using ipfft32::Pow32;
+using ipfft32::pow_of;
+constexpr int kN = 8192;
+constexpr int kBufLen = kN + kN / 16;
+constexpr int kTabLen = 256; // [q] q < 64: W_N^(128 q), [128 + l]: W_N^l
+
+// the two-level table has the same layout as ipfft32's (its contents are W_8192), so its lookup and power helpers serve
+using ipfft32::powers32; // 24 m < N for m < 256
+using ipfft32::tw_lookup;
+// ---- DIF, stride 256, radix 32: butterfly b in [0, 256)
+template <typename LD> FMR_IP_HD void dif_first(int b, LD ld, float2 *buf, const float2 *tab) {
+  float2 e[16], o[16];
+#pragma unroll
+  for (int n = 0; n < 16; n++) {
+    e[n] = ld(b + 256 * (2 * n));
+    o[n] = ld(b + 256 * (2 * n + 1));
+  }
+  fft32(e, o);
+  Pow32 P;
+  powers32(tab, b, P);
+  float2 *dst = buf + pad(b); // pad(b + 256 d) = pad(b) + 272 d
+  dst[0] = e[nat(0)];
+#pragma unroll
+  for (int d = 1; d < 32; d++) dst[272 * d] = cmul((d < 16) ? e[nat(d)] : o[nat(d - 16)], pow_of(P, d));
+}
+// ---- DIF, stride 16, radix 16: i in [0, 512): chunk c = i >> 4 of 256, b = i & 15
+FMR_IP_HD void dif_16(int i, float2 *buf, const float2 *tab) {
+  const int b = i & 15, c = i >> 4;
+  float2 *p = buf + 272 * c + b; // pad(256 c + b + 16 a) = 272 c + b + 17 a
+  float2 v[16];
+#pragma unroll
+  for (int r = 0; r < 16; r++) v[r] = p[17 * r];
+  fft16(v);
+  float2 w[16];
+  powers16(tw_lookup(tab, 32 * b), w); // W_256^b = W_N^(32 b)
+  p[0] = v[nat(0)];
+#pragma unroll
+  for (int d = 1; d < 16; d++) p[17 * d] = cmul(v[nat(d)], w[d]);
+}
+// ---- DIT, stride 16, radix 16
+FMR_IP_HD void dit_16(int i, float2 *buf, const float2 *tab) {
+  const int b = i & 15, c = i >> 4;
+  float2 *p = buf + 272 * c + b;
+  float2 w[16];
+  powers16(tw_lookup(tab, 32 * b), w);
+  float2 v[16];
+  v[0] = p[0];
+#pragma unroll
+  for (int d = 1; d < 16; d++) v[d] = cmul(p[17 * d], w[d]);
+  fft16(v);
+#pragma unroll
+  for (int a = 0; a < 16; a++) p[17 * a] = v[nat(a)];
+}
+// ---- DIT, stride 256, radix 32, into registers: y[a] = filtered sample of buffer slot b + 256 a
+FMR_IP_HD void dit_last(int b, const float2 *buf, const float2 *tab, float2 (&y)[32]) {
+  const float2 *p = buf + pad(b);
+  Pow32 P;
+  powers32(tab, b, P);
+  float2 e[16], o[16];
+  e[0] = p[0];
+  o[0] = cmul(p[272], pow_of(P, 1));
+#pragma unroll
+  for (int n = 1; n < 16; n++) {
+    e[n] = cmul(p[272 * (2 * n)], pow_of(P, 2 * n));
+    o[n] = cmul(p[272 * (2 * n + 1)], pow_of(P, 2 * n + 1));
+  }
+  fft32(e, o);
+#pragma unroll
+  for (int a = 0; a < 32; a++) y[a] = cconj((a < 16) ? e[nat(a)] : o[nat(a - 16)]);
+}
+FMR_IP_HD int freq_of_pos(int p) { return (p >> 8) + 32 * ((p >> 4) & 15) + 512 * (p & 15); }
+
+} // namespace ipfft8k
 } // namespace fmr
 
 #if defined(__CUDACC__) && defined(FMR_FFT_CUH)
@@ -572,6 +661,89 @@ static __global__ void __launch_bounds__(512, 1)
   }
 }
 
+// 8192-point form (ipfft8k), 256 threads, two CTAs per SM. Fused epilogue as above.
+static __global__ void __launch_bounds__(256, 2)
+    k_fir_fft_ip8k(Ring<float2> in, Ring<float2> out, const float2 *__restrict__ Hrev, int klen, int64_t n_in_avail, FftFuse fz) {
+  using namespace ipfft8k;
+  constexpr int THREADS = 256;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+  float2 *tab = buf + kBufLen;
+  const uint32_t c = blockIdx.y;
+  const int blk = blockIdx.x;
+  int cnt = fz.n_m - blk * fz.mo;
+  if (cnt > fz.mo) cnt = fz.mo;
+  if (cnt <= 0) return;
+  const int64_t mb = fz.m0 + (int64_t)blk * fz.mo;
+  const int64_t qb = (mb * fz.instep) / fz.outstep - (fz.flen / 2 - 1);
+  const int fl2 = (klen - 1) / 2;
+  const int64_t base = qb - fl2;
+  tab[threadIdx.x] = __ldg(reinterpret_cast<const float2 *>(fz.twtab) + threadIdx.x); // kTabLen == THREADS
+  __syncthreads();
+  {
+    const uint32_t pos0 = (uint32_t)base & (in.cap - 1);
+    if (base >= 0 && base + kN <= n_in_avail && pos0 + (uint32_t)kN <= in.cap) {
+      const float2 *__restrict__ row = in.base + (size_t)c * in.cap + pos0;
+      dif_first(threadIdx.x, [&](int n) { return row[n]; }, buf, tab);
+    } else {
+      dif_first(threadIdx.x,
+                [&](int n) {
+                  const int64_t t = base + n;
+                  return (t < n_in_avail) ? in.ld(c, t) : make_float2(0.f, 0.f);
+                },
+                buf, tab);
+    }
+  }
+  __syncthreads();
+  dif_16(threadIdx.x, buf, tab);
+  dif_16(threadIdx.x + THREADS, buf, tab);
+  __syncthreads();
+  mid_r16(threadIdx.x, buf, Hrev);
+  mid_r16(threadIdx.x + THREADS, buf, Hrev);
+  __syncthreads();
+  dit_16(threadIdx.x, buf, tab);
+  dit_16(threadIdx.x + THREADS, buf, tab);
+  __syncthreads();
+  float2 y[32];
+  dit_last(threadIdx.x, buf, tab, y);
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 32; a++) {
+    const int n = threadIdx.x + 256 * a;
+    const int64_t t = qb + (n - (klen - 1));
+    const float2 v = (t >= 0) ? y[a] : make_float2(0.f, 0.f);
+    if (t >= fz.tail_lo && t < fz.tail_hi && n >= klen - 1 && blk == (int)gridDim.x - 1) {
+      Ring<float2>{reinterpret_cast<float2 *>(fz.tail_base), fz.tail_cap}.st(c, t, v);
+    }
+    buf[n] = v;
+  }
+  __syncthreads();
+  const float *__restrict__ bank = reinterpret_cast<const float *>(fz.bank);
+  const int rem_b = (int)((mb * fz.instep) % fz.outstep);
+  if (fz.flen == 18) {
+    fi_epilogue<float2, 18, THREADS>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
+  } else if (fz.flen == 24) {
+    fi_epilogue<float2, 24, THREADS>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
+  } else {
+    for (int i = threadIdx.x; i < cnt; i += THREADS) {
+      const int prel = i * fz.instep + rem_b;
+      const int dip = prel / fz.outstep;
+      const int ph = prel - dip * fz.outstep;
+      const float *__restrict__ row = bank + (size_t)ph * fz.flen;
+      const int n0 = (klen - 1) + dip;
+      float2 acc = make_float2(0.f, 0.f);
+      for (int k = 0; k < fz.flen; k++) {
+        const float2 x = buf[n0 + k];
+        const float h = __ldg(row + k);
+        acc.x += h * x.x;
+        acc.y += h * x.y;
+      }
+      out.st(c, mb + i, acc);
+    }
+  }
+}
+
+constexpr int kIp8kSmemBytes = (ipfft8k::kBufLen + ipfft8k::kTabLen) * (int)sizeof(float2);
 constexpr int kIpSmemBytes = (ipfft::kBufLen + ipfft::kTabLen) * (int)sizeof(float2);
 constexpr int kIp32SmemBytes = (ipfft32::kBufLen + ipfft32::kTabLen) * (int)sizeof(float2);
 

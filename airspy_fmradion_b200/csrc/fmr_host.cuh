@@ -214,6 +214,8 @@ template <typename S> struct Resampler {
   V *d_H16rev = nullptr, *d_iptab = nullptr; // in-place form (fmr_fft_inplace.cuh)
   bool fft_inplace = true;                   // FMR_FFT_INPLACE=0: the Stockham form (k_fir_fft)
   V *d_H16rev32 = nullptr;                   // spectrum in the digit-reversed order of the radix 32 x 32 x 16 form
+  V *d_H8rev = nullptr, *d_iptab8 = nullptr; // 8192-point in-place form
+  bool fft_inplace8k = false;                // FMR_FFT_INPLACE8K=1: k_fir_fft_ip8k for the fused 8192-point blocks
   bool fft_regcap = false;                   // FMR_FFT_REGCAP=1: k_fir_fft_ip<512, 896> (72 registers; for --handles overlap)
   bool fft_inplace32 = false;                // FMR_FFT_INPLACE=2: k_fir_fft_ip32 (host-checked, not yet measured)
   int fft_threads = 512;               // FMR_FFT_THREADS=1024: the 32-warp form of the fused 16384-point kernel
@@ -413,6 +415,28 @@ template <typename S> struct Resampler {
             fft_inplace = atoi(ev) != 0;
             fft_inplace32 = atoi(ev) == 2;
           }
+          if (const char *ev = getenv("FMR_FFT_INPLACE8K")) fft_inplace8k = atoi(ev) != 0;
+          if (fft_inplace8k) {
+            // 8192-point in-place form for the remainder / short-filter blocks (set up only on request: not measured yet)
+            std::vector<std::complex<double>> h8(8192, std::complex<double>(0.0, 0.0));
+            for (int i = 0; i < d->bc.klen; i++) h8[i] = d->bc.taps[i];
+            host_fft(h8);
+            std::vector<V> hr8(8192), tb8(ipfft8k::kTabLen);
+            for (int pz = 0; pz < 8192; pz++) {
+              const std::complex<double> hv = h8[ipfft8k::freq_of_pos(pz)] / 8192.0;
+              hr8[pz].x = (S)hv.real();
+              hr8[pz].y = (S)hv.imag();
+            }
+            for (int q = 0; q < 128; q++) {
+              tb8[q] = wv(128.0 * q, 8192.0);
+              tb8[128 + q] = wv((double)q, 8192.0);
+            }
+            FMR_CUDA(mem.alloc(&d_H8rev, hr8.size(), false));
+            FMR_CUDA(cudaMemcpy(d_H8rev, hr8.data(), sizeof(V) * hr8.size(), cudaMemcpyHostToDevice));
+            FMR_CUDA(mem.alloc(&d_iptab8, tb8.size(), false));
+            FMR_CUDA(cudaMemcpy(d_iptab8, tb8.data(), sizeof(V) * tb8.size(), cudaMemcpyHostToDevice));
+            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip8k, cudaFuncAttributeMaxDynamicSharedMemorySize, kIp8kSmemBytes)));
+          }
           if (fft_inplace32) {
             // radix 32 x 32 x 16 form: its own digit-reversed order, the two-level table only. Set up only on request:
             // the kernel has not run on a GPU yet, nothing of it may touch the default path
@@ -581,6 +605,14 @@ template <typename S> struct Resampler {
       fz.tail_hi = b1;
       fz.tail_lo = b1 - (2 * d->fi.flen + 16);
       dim3 grid(nb8, gcn);
+      if constexpr (sizeof(S) == sizeof(float)) {
+        if (fft_inplace8k) {
+          fz.twtab = d_iptab8;
+          k_fir_fft_ip8k<<<grid, 256, kIp8kSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H8rev), klen, avail, fz);
+          launched++;
+          return launched;
+        }
+      }
       k_fir_fft<S, 8192, true><<<grid, kFftThreads, FftCfg<S, 8192>::kSmemBytes, st>>>(in, o, d_H8, klen, 1, 0, 0, avail,
                                                                                      lq8, fz);
       launched++;

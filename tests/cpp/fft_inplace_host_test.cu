@@ -187,5 +187,61 @@ int main() {
          maxerr32, maxdiff, pads32, kN / 16);
   const bool ok32 = maxerr32 < 2e-6 * std::max(1.0, maxref) * 4 && pads32 == kN / 16;
   printf(ok32 ? "inplace fft32: ok\n" : "FAIL\n");
-  return ok32 ? 0 : 1;
+  if (!ok32) return 1;
+
+  // ---------------- 8192-point form (ipfft8k), its own input block and a 1847-tap filter
+  namespace r8 = fmr::ipfft8k;
+  const int N8 = r8::kN, klen8 = 1847;
+  {
+    std::vector<int> seen(N8, 0);
+    for (int p = 0; p < N8; p++) seen[r8::freq_of_pos(p)]++;
+    for (int k = 0; k < N8; k++) {
+      if (seen[k] != 1) {
+        printf("FAIL: ipfft8k::freq_of_pos is not a permutation\n");
+        return 1;
+      }
+    }
+  }
+  std::vector<cd> hc8(N8, cd(0, 0));
+  for (int i = 0; i < klen8; i++) hc8[i] = h[i + (klen - klen8) / 2];
+  std::vector<double> h8(klen8);
+  for (int i = 0; i < klen8; i++) h8[i] = h[i + (klen - klen8) / 2];
+  host_fft(hc8);
+  std::vector<float2> hrev8(N8), tab8(r8::kTabLen);
+  for (int p = 0; p < N8; p++) {
+    const cd v = hc8[r8::freq_of_pos(p)] / (double)N8;
+    hrev8[p] = mk((float)v.real(), (float)v.imag());
+  }
+  for (int q = 0; q < 128; q++) {
+    tab8[q] = wv(128.0 * q, N8); // only q < 64 is ever read
+    tab8[128 + q] = wv(q, N8);
+  }
+  std::vector<float2> buf8(r8::kBufLen, mk(NAN, NAN));
+  for (int i : order(256)) r8::dif_first(i, LdVec{x.data()}, buf8.data(), tab8.data());
+  for (int i : order(512)) r8::dif_16(i, buf8.data(), tab8.data());
+  for (int i : order(512)) r8::mid_r16(i, buf8.data(), hrev8.data());
+  for (int i : order(512)) r8::dit_16(i, buf8.data(), tab8.data());
+  std::vector<float2> y8(N8);
+  for (int b : order(256)) {
+    float2 r[32];
+    r8::dit_last(b, buf8.data(), tab8.data(), r);
+    for (int a = 0; a < 32; a++) y8[b + 256 * a] = r[a];
+  }
+  int pads8 = 0;
+  for (int e = 0; e < r8::kBufLen; e++) pads8 += std::isnan(buf8[e].x) ? 1 : 0;
+  double maxerr8 = 0, maxref8 = 0;
+  for (int n = 0; n < N8; n += 3) {
+    cd acc(0, 0);
+    for (int j = 0; j < klen8; j++) {
+      const float2 v = x[(n - j + N8) & (N8 - 1)];
+      acc += h8[j] * cd(v.x, v.y);
+    }
+    maxerr8 = std::max(maxerr8, std::abs(acc - cd(y8[n].x, y8[n].y)));
+    maxref8 = std::max(maxref8, std::abs(acc));
+  }
+  printf("8192-point in-place FFT convolution: max |err| %.3e (signal max %.3e), poisoned pad words left %d of %d\n", maxerr8,
+         maxref8, pads8, N8 / 16);
+  const bool ok8 = maxerr8 < 2e-6 * std::max(1.0, maxref8) * 4 && pads8 == N8 / 16;
+  printf(ok8 ? "inplace fft8k: ok\n" : "FAIL\n");
+  return ok8 ? 0 : 1;
 }
