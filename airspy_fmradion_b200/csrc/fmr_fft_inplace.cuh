@@ -471,13 +471,63 @@ FMR_IP_HD int freq_of_pos(int p) { return (p >> 8) + 32 * ((p >> 4) & 15) + 512 
 #if defined(__CUDACC__) && defined(FMR_FFT_CUH)
 namespace fmr {
 
+// Polyphase epilogue with the bank and the per-row window offsets in shared memory. The source-level profile of
+// k_fir_fft_ip (profiles/README.md) attributes a third of the kernel's stall samples to fi_epilogue: per bank row a
+// warp does an integer division (MUFU.RCP + fix-up) and eighteen LDG.CONSTANT loads of the row's coefficients, which
+// miss the small L1 that is left beside 150 KB of shared memory, and only then starts its FFMA chain. Here the bank
+// (rows padded to kEpiRow floats) is copied to shared memory once per block and (window offset,
+// bank row) of every output phase are tabulated once per block, so a row costs one LDS.64 + flen/2 broadcast LDS.64
+// before the same eighteen LDS.64 + FFMA pairs in the same order (results are bit-identical to fi_epilogue).
+constexpr int kEpiRow = 24;       // floats per bank row in shared memory (covers flen 18 and 24; rows 16-byte aligned)
+constexpr int kEpiMaxRows = 192;  // output phases (outstep) the shared-memory tables hold
+template <int FLEN, int NT>
+__device__ __forceinline__ void fi_epilogue_smem(const float2 *__restrict__ buf, const float *__restrict__ sbank,
+                                                 const int2 *__restrict__ srow, int instep, int outstep, int klen, int cnt,
+                                                 Ring<float2> out, uint32_t c, int64_t mb) {
+  static_assert(FLEN <= kEpiRow && (FLEN % 2) == 0, "bank row layout");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = NT / 32;
+  const int nq = (cnt + outstep - 1) / outstep;
+  const int L = nq < 32 ? nq : 32;
+  const int G = 32 / L;
+  const int sgrp = lane / L, ql = lane - sgrp * L;
+  if (sgrp >= G) return;
+  for (int pg = warp * G; pg < outstep; pg += nwarps * G) {
+    const int p = pg + sgrp;
+    if (p >= outstep) continue;
+    const int2 r = srow[p]; // x: window offset dp, y: bank row ph
+    const float *__restrict__ row = sbank + r.y * kEpiRow;
+    float h[FLEN];
+#pragma unroll
+    for (int k = 0; k < FLEN; k += 2) {
+      const float2 hh = *reinterpret_cast<const float2 *>(row + k);
+      h[k] = hh.x;
+      h[k + 1] = hh.y;
+    }
+    for (int q = ql; q < nq; q += L) {
+      const int i = p + outstep * q;
+      if (i < cnt) {
+        const float2 *__restrict__ w = buf + (klen - 1) + r.x + instep * q;
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < FLEN; k++) {
+          const float2 x = w[k];
+          acc.x += h[k] * x.x;
+          acc.y += h[k] * x.y;
+        }
+        out.st(c, mb + i, acc);
+      }
+    }
+  }
+}
+
 // Fused form only (IF chain): block -> filtered block in shared memory (plain order) -> polyphase bank.
 // Parameters as k_fir_fft<float, 16384, true>; H is the digit-reversed spectrum, fz.twtab the ipfft table.
 // BOUND > THREADS compiles for a nominal larger block, i.e. caps the registers (65536 / BOUND): <512, 896> = 72
 // registers, which leaves room for one half-band stream CTA or fused-core CTAs of ANOTHER handle on the same SM
 // (bench.py --handles: independent handles on their own streams overlap their HBM-, shared-memory- and latency-bound
 // kernels).
-template <int THREADS, int BOUND = THREADS>
+// EPI = 1: fi_epilogue_smem (needs kIpEpiSmemBytes of dynamic shared memory; flen 18 or 24 and outstep <= kEpiMaxRows).
+template <int THREADS, int BOUND = THREADS, int EPI = 0>
 __global__ void __launch_bounds__(BOUND, 1)
     k_fir_fft_ip(Ring<float2> in, Ring<float2> out, const float2 *__restrict__ Hrev, int klen, int64_t n_in_avail, FftFuse fz) {
   using namespace ipfft;
@@ -497,6 +547,22 @@ __global__ void __launch_bounds__(BOUND, 1)
   {
     const float2 *__restrict__ g = reinterpret_cast<const float2 *>(fz.twtab);
     for (int i = threadIdx.x; i < kTabLen; i += THREADS) tab[i] = __ldg(g + i);
+  }
+  float *sbank = reinterpret_cast<float *>(tab + kTabLen);
+  int2 *srow = reinterpret_cast<int2 *>(sbank + kEpiMaxRows * kEpiRow);
+  if (EPI) {
+    const float *__restrict__ gb = reinterpret_cast<const float *>(fz.bank);
+    const int flen = fz.flen;
+    for (int i = threadIdx.x; i < fz.outstep * flen; i += THREADS) {
+      const int rr = i / flen;
+      sbank[rr * kEpiRow + (i - rr * flen)] = __ldg(gb + i);
+    }
+    const int rem0 = (int)((mb * fz.instep) % fz.outstep);
+    for (int pz = threadIdx.x; pz < fz.outstep; pz += THREADS) {
+      const int pp = pz * fz.instep + rem0;
+      const int dp = pp / fz.outstep;
+      srow[pz] = make_int2(dp, pp - dp * fz.outstep);
+    }
   }
   __syncthreads();
   // ---- forward, decimation in frequency
@@ -557,7 +623,11 @@ __global__ void __launch_bounds__(BOUND, 1)
   __syncthreads();
   const float *__restrict__ bank = reinterpret_cast<const float *>(fz.bank);
   const int rem_b = (int)((mb * fz.instep) % fz.outstep);
-  if (fz.flen == 18) {
+  if (EPI && fz.flen == 18) {
+    fi_epilogue_smem<18, THREADS>(buf, sbank, srow, fz.instep, fz.outstep, klen, cnt, out, c, mb);
+  } else if (EPI && fz.flen == 24) {
+    fi_epilogue_smem<24, THREADS>(buf, sbank, srow, fz.instep, fz.outstep, klen, cnt, out, c, mb);
+  } else if (fz.flen == 18) {
     fi_epilogue<float2, 18, THREADS>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
   } else if (fz.flen == 24) {
     fi_epilogue<float2, 24, THREADS>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
@@ -743,6 +813,8 @@ static __global__ void __launch_bounds__(256, 2)
   }
 }
 
+constexpr int kIpEpiSmemBytes = (ipfft::kBufLen + ipfft::kTabLen) * (int)sizeof(float2) + kEpiMaxRows * kEpiRow * (int)sizeof(float) +
+                                kEpiMaxRows * (int)sizeof(int2);
 constexpr int kIp8kSmemBytes = (ipfft8k::kBufLen + ipfft8k::kTabLen) * (int)sizeof(float2);
 constexpr int kIpSmemBytes = (ipfft::kBufLen + ipfft::kTabLen) * (int)sizeof(float2);
 constexpr int kIp32SmemBytes = (ipfft32::kBufLen + ipfft32::kTabLen) * (int)sizeof(float2);

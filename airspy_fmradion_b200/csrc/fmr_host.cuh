@@ -216,6 +216,7 @@ template <typename S> struct Resampler {
   V *d_H16rev32 = nullptr;                   // spectrum in the digit-reversed order of the radix 32 x 32 x 16 form
   V *d_H8rev = nullptr, *d_iptab8 = nullptr; // 8192-point in-place form
   bool fft_inplace8k = false;                // FMR_FFT_INPLACE8K=1: k_fir_fft_ip8k for the fused 8192-point blocks
+  bool fft_epi = false;                      // FMR_FFT_EPI=1: k_fir_fft_ip<512, 512, 1> (polyphase bank in shared memory)
   bool fft_regcap = false;                   // FMR_FFT_REGCAP=1: k_fir_fft_ip<512, 896> (72 registers; for --handles overlap)
   bool fft_inplace32 = false;                // FMR_FFT_INPLACE=2: k_fir_fft_ip32 (host-checked, not yet measured)
   int fft_threads = 512;               // FMR_FFT_THREADS=1024: the 32-warp form of the fused 16384-point kernel
@@ -415,6 +416,13 @@ template <typename S> struct Resampler {
             fft_inplace = atoi(ev) != 0;
             fft_inplace32 = atoi(ev) == 2;
           }
+          if (const char *ev = getenv("FMR_FFT_EPI")) fft_epi = atoi(ev) != 0;
+          if (fft_epi && d->has_fi && d->fi.outstep <= kEpiMaxRows && (d->fi.flen == 18 || d->fi.flen == 24)) {
+            // polyphase epilogue with the bank in shared memory (set up only on request: not measured yet)
+            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<512, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpEpiSmemBytes)));
+          } else {
+            fft_epi = false;
+          }
           if (const char *ev = getenv("FMR_FFT_INPLACE8K")) fft_inplace8k = atoi(ev) != 0;
           if (fft_inplace8k) {
             // 8192-point in-place form for the remainder / short-filter blocks (set up only on request: not measured yet)
@@ -574,7 +582,9 @@ template <typename S> struct Resampler {
           k_fir_fft_ip32<<<grid, 512, kIp32SmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev32), klen, avail, fz);
         } else if (fft_inplace) {
           fz.twtab = d_iptab;
-          if (fft_regcap) {
+          if (fft_epi) {
+            k_fir_fft_ip<512, 512, 1><<<grid, 512, kIpEpiSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
+          } else if (fft_regcap) {
             k_fir_fft_ip<512, 896><<<grid, 512, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
           } else if (fft_threads == 1024) {
             k_fir_fft_ip<1024><<<grid, 1024, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
