@@ -491,31 +491,41 @@ __device__ __forceinline__ void fi_epilogue_smem(const float2 *__restrict__ buf,
   const int G = 32 / L;
   const int sgrp = lane / L, ql = lane - sgrp * L;
   if (sgrp >= G) return;
-  for (int pg = warp * G; pg < outstep; pg += nwarps * G) {
-    const int p = pg + sgrp;
-    if (p >= outstep) continue;
-    const int2 r = srow[p]; // x: window offset dp, y: bank row ph
-    const float *__restrict__ row = sbank + r.y * kEpiRow;
-    float h[FLEN];
+  // two bank rows per iteration: their loads and FFMA chains are independent, so one hides the other's latency
+  const int pstep = nwarps * G;
+  for (int pg = warp * G; pg < outstep; pg += 2 * pstep) {
+    const int p0 = pg + sgrp, p1 = p0 + pstep;
+    const bool v0 = p0 < outstep, v1 = p1 < outstep;
+    const int2 r0 = srow[v0 ? p0 : 0], r1 = srow[v1 ? p1 : 0]; // x: window offset dp, y: bank row ph
+    const float *__restrict__ row0 = sbank + r0.y * kEpiRow;
+    const float *__restrict__ row1 = sbank + r1.y * kEpiRow;
+    float h0[FLEN], h1[FLEN];
 #pragma unroll
     for (int k = 0; k < FLEN; k += 2) {
-      const float2 hh = *reinterpret_cast<const float2 *>(row + k);
-      h[k] = hh.x;
-      h[k + 1] = hh.y;
+      const float2 a = *reinterpret_cast<const float2 *>(row0 + k);
+      const float2 b = *reinterpret_cast<const float2 *>(row1 + k);
+      h0[k] = a.x;
+      h0[k + 1] = a.y;
+      h1[k] = b.x;
+      h1[k + 1] = b.y;
     }
     for (int q = ql; q < nq; q += L) {
-      const int i = p + outstep * q;
-      if (i < cnt) {
-        const float2 *__restrict__ w = buf + (klen - 1) + r.x + instep * q;
-        float2 acc = make_float2(0.f, 0.f);
+      const int i0 = p0 + outstep * q, i1 = p1 + outstep * q;
+      const bool w0 = v0 && i0 < cnt, w1 = v1 && i1 < cnt;
+      // windows of outputs that do not exist are read from the first row's window (always inside the block)
+      const float2 *__restrict__ x0 = buf + (klen - 1) + r0.x + instep * (w0 ? q : 0);
+      const float2 *__restrict__ x1 = buf + (klen - 1) + r1.x + instep * (w1 ? q : 0);
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < FLEN; k++) {
-          const float2 x = w[k];
-          acc.x += h[k] * x.x;
-          acc.y += h[k] * x.y;
-        }
-        out.st(c, mb + i, acc);
+      for (int k = 0; k < FLEN; k++) {
+        const float2 a = x0[k], b = x1[k];
+        acc0.x += h0[k] * a.x;
+        acc0.y += h0[k] * a.y;
+        acc1.x += h1[k] * b.x;
+        acc1.y += h1[k] * b.y;
       }
+      if (w0) out.st(c, mb + i0, acc0);
+      if (w1) out.st(c, mb + i1, acc1);
     }
   }
 }
