@@ -468,9 +468,7 @@ FMR_IP_HD int freq_of_pos(int p) { return (p >> 8) + 32 * ((p >> 4) & 15) + 512 
 } // namespace ipfft8k
 } // namespace fmr
 
-#if defined(__CUDACC__) && defined(FMR_FFT_CUH)
 namespace fmr {
-
 // Polyphase epilogue with the bank and the per-row window offsets in shared memory. The source-level profile of
 // k_fir_fft_ip (profiles/README.md) attributes a third of the kernel's stall samples to fi_epilogue: per bank row a
 // warp does an integer division (MUFU.RCP + fix-up) and eighteen LDG.CONSTANT loads of the row's coefficients, which
@@ -480,12 +478,13 @@ namespace fmr {
 // before the same eighteen LDS.64 + FFMA pairs in the same order (results are bit-identical to fi_epilogue).
 constexpr int kEpiRow = 24;       // floats per bank row in shared memory (covers flen 18 and 24; rows 16-byte aligned)
 constexpr int kEpiMaxRows = 192;  // output phases (outstep) the shared-memory tables hold
-template <int FLEN, int NT>
-__device__ __forceinline__ void fi_epilogue_smem(const float2 *__restrict__ buf, const float *__restrict__ sbank,
-                                                 const int2 *__restrict__ srow, int instep, int outstep, int klen, int cnt,
-                                                 Ring<float2> out, uint32_t c, int64_t mb) {
+// `tid` is the thread index and st(i, value) stores interpolator output i of the block, so that the host test can run
+// the identical mapping thread by thread.
+template <int FLEN, int NT, typename ST>
+FMR_IP_HD void fi_epilogue_smem(int tid, const float2 *__restrict__ buf, const float *__restrict__ sbank,
+                                const int2 *__restrict__ srow, int instep, int outstep, int klen, int cnt, ST st) {
   static_assert(FLEN <= kEpiRow && (FLEN % 2) == 0, "bank row layout");
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = NT / 32;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = NT / 32;
   const int nq = (cnt + outstep - 1) / outstep;
   const int L = nq < 32 ? nq : 32;
   const int G = 32 / L;
@@ -515,7 +514,7 @@ __device__ __forceinline__ void fi_epilogue_smem(const float2 *__restrict__ buf,
       // windows of outputs that do not exist are read from the first row's window (always inside the block)
       const float2 *__restrict__ x0 = buf + (klen - 1) + r0.x + instep * (w0 ? q : 0);
       const float2 *__restrict__ x1 = buf + (klen - 1) + r1.x + instep * (w1 ? q : 0);
-      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+      float2 acc0 = ipfft::mk(0.f, 0.f), acc1 = ipfft::mk(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < FLEN; k++) {
         const float2 a = x0[k], b = x1[k];
@@ -524,11 +523,26 @@ __device__ __forceinline__ void fi_epilogue_smem(const float2 *__restrict__ buf,
         acc1.x += h1[k] * b.x;
         acc1.y += h1[k] * b.y;
       }
-      if (w0) out.st(c, mb + i0, acc0);
-      if (w1) out.st(c, mb + i1, acc1);
+      if (w0) st(i0, acc0);
+      if (w1) st(i1, acc1);
     }
   }
 }
+
+// (window offset, bank row) of output phase p of a block whose first output has remainder rem_b
+FMR_IP_HD int2 epi_row(int p, int instep, int outstep, int rem_b) {
+  const int pp = p * instep + rem_b;
+  const int dp = pp / outstep;
+  int2 r;
+  r.x = dp;
+  r.y = pp - dp * outstep;
+  return r;
+}
+
+} // namespace fmr
+
+#if defined(__CUDACC__) && defined(FMR_FFT_CUH)
+namespace fmr {
 
 // Fused form only (IF chain): block -> filtered block in shared memory (plain order) -> polyphase bank.
 // Parameters as k_fir_fft<float, 16384, true>; H is the digit-reversed spectrum, fz.twtab the ipfft table.
@@ -568,11 +582,7 @@ __global__ void __launch_bounds__(BOUND, 1)
       sbank[rr * kEpiRow + (i - rr * flen)] = __ldg(gb + i);
     }
     const int rem0 = (int)((mb * fz.instep) % fz.outstep);
-    for (int pz = threadIdx.x; pz < fz.outstep; pz += THREADS) {
-      const int pp = pz * fz.instep + rem0;
-      const int dp = pp / fz.outstep;
-      srow[pz] = make_int2(dp, pp - dp * fz.outstep);
-    }
+    for (int pz = threadIdx.x; pz < fz.outstep; pz += THREADS) srow[pz] = epi_row(pz, fz.instep, fz.outstep, rem0);
   }
   __syncthreads();
   // ---- forward, decimation in frequency
@@ -634,9 +644,11 @@ __global__ void __launch_bounds__(BOUND, 1)
   const float *__restrict__ bank = reinterpret_cast<const float *>(fz.bank);
   const int rem_b = (int)((mb * fz.instep) % fz.outstep);
   if (EPI && fz.flen == 18) {
-    fi_epilogue_smem<18, THREADS>(buf, sbank, srow, fz.instep, fz.outstep, klen, cnt, out, c, mb);
+    fi_epilogue_smem<18, THREADS>(threadIdx.x, buf, sbank, srow, fz.instep, fz.outstep, klen, cnt,
+                                  [&](int i, float2 v) { out.st(c, mb + i, v); });
   } else if (EPI && fz.flen == 24) {
-    fi_epilogue_smem<24, THREADS>(buf, sbank, srow, fz.instep, fz.outstep, klen, cnt, out, c, mb);
+    fi_epilogue_smem<24, THREADS>(threadIdx.x, buf, sbank, srow, fz.instep, fz.outstep, klen, cnt,
+                                  [&](int i, float2 v) { out.st(c, mb + i, v); });
   } else if (fz.flen == 18) {
     fi_epilogue<float2, 18, THREADS>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
   } else if (fz.flen == 24) {

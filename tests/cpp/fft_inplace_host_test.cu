@@ -133,6 +133,47 @@ int main() {
   printf(ok ? "inplace fft: ok\n" : "FAIL\n");
   if (!ok) return 1;
 
+  // ---------------- shared-memory polyphase epilogue (fi_epilogue_smem) on the filtered block y, geometry of the
+  // 10 MHz chain: 192 phases x 18 taps, step 625/192; every "thread" in scrambled order, each output exactly once,
+  // bit-identical to the straightforward evaluation in the same summation order
+  {
+    const int instep = 625, outstep = 192, flen = 18;
+    const int lq = kN - klen + 1, cnt = (int)(((long long)(lq - flen - 8) * outstep) / instep);
+    std::vector<float> bankv((size_t)outstep * flen), sbank((size_t)fmr::kEpiMaxRows * fmr::kEpiRow, NAN);
+    for (auto &v : bankv) v = nd(rng);
+    for (int i = 0; i < outstep * flen; i++) sbank[(i / flen) * fmr::kEpiRow + i % flen] = bankv[i];
+    for (int rem_b : {0, 77, 191}) {
+      std::vector<int2> srow(outstep);
+      for (int p = 0; p < outstep; p++) srow[p] = fmr::epi_row(p, instep, outstep, rem_b);
+      std::vector<float2> got(cnt, mk(NAN, NAN));
+      std::vector<int> hits(cnt, 0);
+      for (int tid : order(512)) {
+        fmr::fi_epilogue_smem<18, 512>(tid, y.data(), sbank.data(), srow.data(), instep, outstep, klen, cnt,
+                                       [&](int i, float2 v) {
+                                         got[i] = v;
+                                         hits[i]++;
+                                       });
+      }
+      int bad = 0;
+      for (int i = 0; i < cnt; i++) {
+        const int prel = i * instep + rem_b, dip = prel / outstep, ph = prel - dip * outstep;
+        float ax = 0.f, ay = 0.f;
+        for (int k = 0; k < flen; k++) {
+          const float2 v = y[(klen - 1) + dip + k];
+          ax += bankv[(size_t)ph * flen + k] * v.x;
+          ay += bankv[(size_t)ph * flen + k] * v.y;
+        }
+        if (hits[i] != 1 || got[i].x != ax || got[i].y != ay) bad++;
+      }
+      printf("epilogue rem_b=%d: %d outputs, %d mismatches\n", rem_b, cnt, bad);
+      if (bad) {
+        printf("FAIL\n");
+        return 1;
+      }
+    }
+    printf("inplace epilogue: ok\n");
+  }
+
   // ---------------- radix 32 x 32 x 16 form (ipfft32): same input, same taps
   namespace r32 = fmr::ipfft32;
   {
