@@ -674,7 +674,8 @@ __global__ void __launch_bounds__(BOUND, 1)
 
 // Radix 32 x 32 x 16 form (ipfft32), 512 threads = one 32-point butterfly per thread and pass. Same parameters; Hrev
 // in ipfft32's digit-reversed order, fz.twtab = its 256-entry table.
-static __global__ void __launch_bounds__(512, 1)
+template <int EPI>
+__global__ void __launch_bounds__(512, 1)
     k_fir_fft_ip32(Ring<float2> in, Ring<float2> out, const float2 *__restrict__ Hrev, int klen, int64_t n_in_avail, FftFuse fz) {
   using namespace ipfft32;
   constexpr int THREADS = 512;
@@ -691,6 +692,18 @@ static __global__ void __launch_bounds__(512, 1)
   const int fl2 = (klen - 1) / 2;
   const int64_t base = qb - fl2;
   if (threadIdx.x < kTabLen) tab[threadIdx.x] = __ldg(reinterpret_cast<const float2 *>(fz.twtab) + threadIdx.x);
+  float *sbank = reinterpret_cast<float *>(tab + kTabLen);
+  int2 *srow = reinterpret_cast<int2 *>(sbank + kEpiMaxRows * kEpiRow);
+  if (EPI) {
+    const float *__restrict__ gb = reinterpret_cast<const float *>(fz.bank);
+    const int flen = fz.flen;
+    for (int i = threadIdx.x; i < fz.outstep * flen; i += THREADS) {
+      const int rr = i / flen;
+      sbank[rr * kEpiRow + (i - rr * flen)] = __ldg(gb + i);
+    }
+    const int rem0 = (int)((mb * fz.instep) % fz.outstep);
+    for (int pz = threadIdx.x; pz < fz.outstep; pz += THREADS) srow[pz] = epi_row(pz, fz.instep, fz.outstep, rem0);
+  }
   __syncthreads();
   {
     const uint32_t pos0 = (uint32_t)base & (in.cap - 1);
@@ -730,7 +743,13 @@ static __global__ void __launch_bounds__(512, 1)
   __syncthreads();
   const float *__restrict__ bank = reinterpret_cast<const float *>(fz.bank);
   const int rem_b = (int)((mb * fz.instep) % fz.outstep);
-  if (fz.flen == 18) {
+  if (EPI && fz.flen == 18) {
+    fi_epilogue_smem<18, THREADS>(threadIdx.x, buf, sbank, srow, fz.instep, fz.outstep, klen, cnt,
+                                  [&](int i, float2 v) { out.st(c, mb + i, v); });
+  } else if (EPI && fz.flen == 24) {
+    fi_epilogue_smem<24, THREADS>(threadIdx.x, buf, sbank, srow, fz.instep, fz.outstep, klen, cnt,
+                                  [&](int i, float2 v) { out.st(c, mb + i, v); });
+  } else if (fz.flen == 18) {
     fi_epilogue<float2, 18, THREADS>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
   } else if (fz.flen == 24) {
     fi_epilogue<float2, 24, THREADS>(buf, bank, fz.instep, fz.outstep, klen, rem_b, cnt, out, c, mb);
@@ -840,6 +859,7 @@ constexpr int kIpEpiSmemBytes = (ipfft::kBufLen + ipfft::kTabLen) * (int)sizeof(
 constexpr int kIp8kSmemBytes = (ipfft8k::kBufLen + ipfft8k::kTabLen) * (int)sizeof(float2);
 constexpr int kIpSmemBytes = (ipfft::kBufLen + ipfft::kTabLen) * (int)sizeof(float2);
 constexpr int kIp32SmemBytes = (ipfft32::kBufLen + ipfft32::kTabLen) * (int)sizeof(float2);
+constexpr int kIp32EpiSmemBytes = kIp32SmemBytes + kEpiMaxRows * kEpiRow * (int)sizeof(float) + kEpiMaxRows * (int)sizeof(int2);
 
 } // namespace fmr
 #endif

@@ -456,7 +456,8 @@ template <typename S> struct Resampler {
             }
             FMR_CUDA(mem.alloc(&d_H16rev32, hr32.size(), false));
             FMR_CUDA(cudaMemcpy(d_H16rev32, hr32.data(), sizeof(V) * hr32.size(), cudaMemcpyHostToDevice));
-            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip32, cudaFuncAttributeMaxDynamicSharedMemorySize, kIp32SmemBytes)));
+            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip32<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIp32SmemBytes)));
+            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIp32EpiSmemBytes)));
           }
         }
         FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<S, 16384, true, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -579,7 +580,11 @@ template <typename S> struct Resampler {
         dim3 grid(nb16, gcn);
         if (fft_inplace && fft_inplace32) {
           fz.twtab = d_iptab; // its first 256 entries are the two-level table of W_N
-          k_fir_fft_ip32<<<grid, 512, kIp32SmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev32), klen, avail, fz);
+          if (fft_epi) {
+            k_fir_fft_ip32<1><<<grid, 512, kIp32EpiSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev32), klen, avail, fz);
+          } else {
+            k_fir_fft_ip32<0><<<grid, 512, kIp32SmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev32), klen, avail, fz);
+          }
         } else if (fft_inplace) {
           fz.twtab = d_iptab;
           if (fft_epi) {

@@ -10,7 +10,7 @@ FMR_FFT_INPLACE=2 FMR_FFT_INPLACE8K=1 timeout 200 python -m pytest tests/test_fm
 #   FMR_FFT_EPI=1      k_fir_fft_ip<512,512,1>: polyphase bank + window offsets in shared memory (the epilogue holds a third of
 #                      the FFT kernel's stall samples); results must be bit-identical (same checksum as all_on_329)
 FMR_FFT_EPI=1 timeout 120 python -m pytest tests/test_fm_gpu.py -q -x -k "if_stage or cfg2" 2>&1 | tail -3 | tee gpurun_out/pytest_epi.log
-timeout 200 python tools/sweep_variants.py all_on_329 fft_epi_smem fft_inplace_r32 fft_inplace_8k fft_inplace_r32_8k fft_stockham 2>gpurun_out/sweep_ip32.err | tee gpurun_out/sweep_ip32.log
+timeout 200 python tools/sweep_variants.py all_on_329 fft_epi_smem fft_inplace_r32 fft_inplace_r32_epi fft_inplace_8k fft_inplace_r32_8k fft_stockham 2>gpurun_out/sweep_ip32.err | tee gpurun_out/sweep_ip32.log
 # Independent handles per GPU on their own streams (bench.py --handles): overlap of the HBM-bound half-band stream,
 # the shared-memory-bound FFT and the latency-bound core ACROSS handles, with no library change. The second / third
 # runs make the kernels small enough to share an SM: FFT capped at 72 registers (FMR_FFT_REGCAP=1), half-band stream

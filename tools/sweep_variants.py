@@ -33,6 +33,7 @@ VARIANTS = [
     ("fft_stockham", {"FMR_FFT_INPLACE": "0"}, 329, 8192),
     ("fft_inplace_r32", {"FMR_FFT_INPLACE": "2"}, 329, 8192),
     ("fft_epi_smem", {"FMR_FFT_EPI": "1"}, 329, 8192),
+    ("fft_inplace_r32_epi", {"FMR_FFT_INPLACE": "2", "FMR_FFT_EPI": "1"}, 329, 8192),
     ("fft_inplace_8k", {"FMR_FFT_INPLACE8K": "1"}, 329, 8192),
     ("fft_inplace_r32_8k", {"FMR_FFT_INPLACE": "2", "FMR_FFT_INPLACE8K": "1"}, 329, 8192),
 ]
