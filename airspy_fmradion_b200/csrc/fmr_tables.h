@@ -51,14 +51,12 @@ struct ChainDesc {
 
 #include "fmr_tables_generated.inc"
 
-// Pairs whose tables ship but whose GPU path has not passed the parity suite yet are refused (the caller gets
-// FMR_ERR_UNSUPPORTED, as for a pair without tables) unless FMR_EXPERIMENTAL_RATES=1.
+// Every pair in kChains has passed the GPU parity suite on a B200 (profiles/pytest_newrates_r02.log); a pair whose
+// `verified` flag is 0 (tables shipped ahead of a GPU run, tools/gen_tables.py) is refused like a pair without tables.
 inline const ChainDesc *find_chain(double src, double dst, int kind) {
-  const char *e = getenv("FMR_EXPERIMENTAL_RATES");
-  const bool experimental = e && atoi(e) != 0;
   for (int i = 0; i < kNumChains; i++) {
     if (kChains[i].src == src && kChains[i].dst == dst && kChains[i].kind == kind) {
-      return (kChains[i].verified || experimental) ? &kChains[i] : nullptr;
+      return kChains[i].verified ? &kChains[i] : nullptr;
     }
   }
   return nullptr;

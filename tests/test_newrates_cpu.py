@@ -1,7 +1,7 @@
 """Rate pairs whose tables were added at the end of round 1 (3 M, 2.4 M, 1.44 M, 1.2 M, 1.152 M, 960 k, 912 k, 768 k -> 384 k):
 pinned on the CPU against the COMPILED REFERENCE — the plain-C restatement (which reads the same generated tables) must
 reproduce the reference's audio and per-call sizes, and the library's host-side schedule must reproduce the per-call
-sizes. Their GPU path is enabled only with FMR_EXPERIMENTAL_RATES=1 until it has passed tests/test_newrates_gpu.py."""
+sizes. GPU parity: tests/test_newrates_gpu.py (green on a B200 since round 2, profiles/pytest_newrates_r02.log)."""
 import numpy as np
 import pytest
 
@@ -19,8 +19,7 @@ def _blocks(fs):
 
 @needs_ref
 @pytest.mark.parametrize("fs", RATES)
-def test_restatement_and_schedule_match_reference(fs, monkeypatch):
-    monkeypatch.setenv("FMR_EXPERIMENTAL_RATES", "1")
+def test_restatement_and_schedule_match_reference(fs):
     blk, nblk = 2048, _blocks(fs)
     iq = siggen.fm_stereo_iq(fs, blk * nblk, 1)
     c = ref.RefChain("fm", fs, stereo=True)
@@ -40,8 +39,7 @@ def test_restatement_and_schedule_match_reference(fs, monkeypatch):
 
 @needs_ref
 @pytest.mark.parametrize("fs", AM_RATES)
-def test_am_restatement_and_schedule_match_reference(fs, monkeypatch):
-    monkeypatch.setenv("FMR_EXPERIMENTAL_RATES", "1")
+def test_am_restatement_and_schedule_match_reference(fs):
     blk = 2048
     nblk = int(np.ceil(0.4 * fs / blk)) + 4
     iq = siggen.am_iq(fs, blk * nblk, 0)
@@ -61,14 +59,14 @@ def test_am_restatement_and_schedule_match_reference(fs, monkeypatch):
     assert list(out) == list(ref_lens)
 
 
-def test_unverified_rates_are_refused_by_default(monkeypatch):
+def test_rates_without_tables_are_refused():
+    """A ratio r8brain would design a chain for but whose tables are not shipped: FMR_ERR_UNSUPPORTED, never a guess."""
     from airspy_fmradion_b200 import _capi
     L = _capi.lib()
-    monkeypatch.delenv("FMR_EXPERIMENTAL_RATES", raising=False)
     bl = np.full(4, 2048, dtype=np.uint32)
     out = np.zeros(4, dtype=np.uint32)
-    for fs in RATES:
+    for fs in (2.0e6, 1.8e6, 250000.0):
         assert L.fmr_fm_schedule(fs, 1, 0, bl.ctypes.data, 4, None, out.ctypes.data) == 2  # FMR_ERR_UNSUPPORTED
-    for fs in AM_RATES:
-        assert L.fmr_am_schedule(fs, 0, bl.ctypes.data, 4, out.ctypes.data) == 2
-    assert L.fmr_fm_schedule(1.0e7, 1, 0, bl.ctypes.data, 4, None, out.ctypes.data) == 0
+    assert L.fmr_am_schedule(100000.0, 0, bl.ctypes.data, 4, out.ctypes.data) == 2
+    for fs in RATES + [1.0e7]:
+        assert L.fmr_fm_schedule(fs, 1, 0, bl.ctypes.data, 4, None, out.ctypes.data) == 0

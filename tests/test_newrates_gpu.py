@@ -1,21 +1,28 @@
-"""GPU parity for the rate pairs added at the end of round 1 without GPU budget left (their kernels are the ones the
-2.5 MHz and 1 MHz chains use; only the tables are new). Gated: run with FMR_EXPERIMENTAL_RATES=1, and once green flip
-their `verified` flag in tools/gen_tables.py and drop the gate."""
-import os
-
+"""GPU parity for every rate pair the library serves beyond the BASELINE ones (reference: any `ifrate` the source
+reports, main.cpp:673-729, IfResampler.cpp:25-35): same bar as the 10 MHz / 1 MHz chains. First green run on a B200:
+profiles/pytest_newrates_r02.log."""
 import numpy as np
 import pytest
 
 from oracle import siggen
 from tests.oracle_select import oracle_fm_run
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FMR_EXPERIMENTAL_RATES") != "1",
-                                 reason="unverified rate pairs: set FMR_EXPERIMENTAL_RATES=1 (tools/next_round_ab.sh)")]
+pytestmark = [pytest.mark.gpu]
+
+
+@pytest.mark.parametrize("fs", [6.0e6, 2.5e6])
+def test_enabled_rate_matches_oracle(fs):
+    """6 MHz (Airspy R2 alternative rate) and 2.5 MHz chains are served to every caller (`verified=1`): same parity bar
+    as the 10 MHz / 1 MHz chains (main.cpp:673-729, IfResampler.cpp:25-35)."""
+    _fm_rate_case(fs)
 
 
 @pytest.mark.parametrize("fs", [3.0e6, 2.4e6, 2.048e6, 1.44e6, 1.2e6, 1152000.0, 960000.0, 912000.0, 768000.0])
 def test_new_rate_matches_oracle(fs):
+    _fm_rate_case(fs)
+
+
+def _fm_rate_case(fs):
     from airspy_fmradion_b200 import FmDecoder
     blk, per = 2048, 64
     nblk = (int(np.ceil(0.75 * fs / blk)) + per - 1) // per * per  # past the PLL lock at 0.5 s
