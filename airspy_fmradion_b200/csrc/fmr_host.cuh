@@ -20,6 +20,7 @@
 
 #include "fmr_fft.cuh"
 #include "fmr_fft_inplace.cuh"
+#include "fmr_fdr.cuh"
 #include "fmr_hbstream.cuh"
 #include "fmr_kernels.cuh"
 #include "fmr_tables.h"
@@ -219,6 +220,11 @@ template <typename S> struct Resampler {
   bool fft_epi = false;                      // FMR_FFT_EPI=1: k_fir_fft_ip<512, 512, 1> (polyphase bank in shared memory)
   bool fft_regcap = false;                   // FMR_FFT_REGCAP=1: k_fir_fft_ip<512, 896> (72 registers; for --handles overlap)
   bool fft_inplace32 = false;                // FMR_FFT_INPLACE=2: k_fir_fft_ip32 (host-checked, not yet measured)
+  bool use_fdr = false;                      // frequency-domain low-pass + resampling (fmr_fdr.cuh); FMR_FDR=0: off
+  float *d_fdr_Hs = nullptr;
+  float2 *d_fdr_tab = nullptr;
+  int64_t fdr_next = 0;                      // first block of the absolute grid that has not been computed yet
+  int64_t fdr_hist = 512;                    // output samples before f0 that readers of the output ring may still need
   int fft_threads = 512;               // FMR_FFT_THREADS=1024: the 32-warp form of the fused 16384-point kernel
   bool use_fft = false;
   bool use_dec2 = false; // double chains with a decimate-by-2 low-pass (audio resampler)
@@ -469,6 +475,21 @@ template <typename S> struct Resampler {
       if (const char *e = getenv("FMR_FFT_MIN_OUT")) fft_min_out = atoi(e);
       fuse_fi = !env_off("FMR_FUSE_FI");
     }
+    if constexpr (sizeof(S) == sizeof(float)) {
+      // 625:192 pairs: the low-pass and the polyphase bank as one forward + one small inverse FFT (fmr_fdr.cuh)
+      if (use_fft && d->has_fi && d->bc.down == 1 && d->fi.instep == fdr::kInStep && d->fi.outstep == fdr::kOutStep &&
+          (d->bc.klen - 1) / 2 + d->fi.flen / 2 <= fdr::kGuardIn && !env_off("FMR_FDR")) {
+        std::vector<float2> tb;
+        std::vector<float> hs;
+        fdr::fdr_make_tables(d->bc.taps, d->bc.klen, tb, hs);
+        FMR_CUDA(mem.alloc(&d_fdr_tab, tb.size(), false));
+        FMR_CUDA(cudaMemcpy(d_fdr_tab, tb.data(), sizeof(float2) * tb.size(), cudaMemcpyHostToDevice));
+        FMR_CUDA(mem.alloc(&d_fdr_Hs, hs.size(), false));
+        FMR_CUDA(cudaMemcpy(d_fdr_Hs, hs.data(), sizeof(float) * hs.size(), cudaMemcpyHostToDevice));
+        FMR_CUDA(cudaFuncSetAttribute(k_fdr, cudaFuncAttributeMaxDynamicSharedMemorySize, kFdrSmemBytes));
+        use_fdr = true;
+      }
+    }
     if (sizeof(S) == sizeof(double) && d->bc.down == 2 && (d->bc.klen + 1) / 2 <= kDecMaxTaps) {
       FMR_CUDA(cudaFuncSetAttribute(k_fir_dec2_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)dec2_smem(d->bc.klen)));
@@ -634,6 +655,17 @@ template <typename S> struct Resampler {
     }
     return launched;
   }
+  // frequency-domain form (fmr_fdr.cuh): blocks [j0, j1] of the absolute grid, whole
+  void launch_fdr(Ring<float2> in, Ring<float2> o, int64_t j0, int64_t j1, int64_t avail, cudaStream_t st) {
+    FdrParams P;
+    P.j0 = j0;
+    P.m_lo = j0 * fdr::kAdvOut;
+    P.m_hi = (j1 + 1) * fdr::kAdvOut;
+    P.avail = avail;
+    dim3 grid((unsigned)(j1 - j0 + 1), gcn);
+    k_fdr<<<grid, kFdrThreads, kFdrSmemBytes, st>>>(in, o, d_fdr_Hs, d_fdr_tab, P);
+  }
+  void launch_fdr(Ring<double2>, Ring<double2>, int64_t, int64_t, int64_t, cudaStream_t) {}
   void launch_dec2(Ring<double2> in, Ring<double2> o, int64_t q0, int n, cudaStream_t st) {
     dim3 grid((n + kDecTile - 1) / kDecTile, gcn);
     k_fir_dec2_f64<<<grid, kDecThreads, dec2_smem(d->bc.klen), st>>>(in, o, d_bc, d->bc.klen, q0, n);
@@ -750,8 +782,23 @@ template <typename S> struct Resampler {
       bc_in = sub(r_hb);
     }
     const int n_bc = (int)(b1 - b0), n_fi = (int)(f1 - f0);
-    // fused low-pass + polyphase bank: the intermediate stream stays in shared memory
-    if (d->has_fi && use_fft && fuse_fi && d->bc.down == 1 && n_bc >= fft_min_out && n_fi > 0) {
+    if (use_fdr) {
+      // Frequency-domain low-pass + resampling on the absolute block grid (fmr_fdr.cuh), for calls of any size: every
+      // block whose 10000 input samples are complete (and whose outputs fit the output ring) is computed as a whole,
+      // possibly ahead of the reference's release schedule, which lags the input by more than a block (the block
+      // convolver's latency of 15231 samples), so the released range [f0, f1) is always covered.
+      const int64_t j_in = (h1 >= fdr::kNin - fdr::kGuardIn) ? (h1 - (fdr::kNin - fdr::kGuardIn)) / fdr::kAdvIn : -1;
+      const int64_t j_cap = (f0 - fdr_hist + (int64_t)out.cap) / fdr::kAdvOut - 1;
+      const int64_t j_last = std::min(j_in, j_cap);
+      if (j_last >= fdr_next) {
+        if (prof) prof->begin(p_bc, st);
+        launch_fdr(bc_in, out, fdr_next, j_last, h1, st);
+        (*launches)++;
+        if (prof) prof->end(p_bc, st);
+      }
+      if ((j_last + 1) * fdr::kAdvOut < f1) return fail(FMR_ERR_INVALID, "internal: block grid behind the release schedule");
+      if (advance) fdr_next = std::max(fdr_next, j_last + 1);
+    } else if (d->has_fi && use_fft && fuse_fi && d->bc.down == 1 && n_bc >= fft_min_out && n_fi > 0) {
       if (prof) prof->begin(p_bc, st);
       (*launches) += launch_fft_fused(bc_in, out, f0, n_fi, h1, b1, st);
       if (prof) prof->end(p_bc, st);
