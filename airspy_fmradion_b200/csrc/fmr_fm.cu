@@ -328,6 +328,7 @@ static fmr_status fm_build(fmr_fm *h) {
   h->ifres.p_hb = h->prof.add("if_halfband_cascade");
   h->ifres.p_bc = h->prof.add("if_lowpass");
   h->ifres.p_fi = h->prof.add("if_polyphase");
+  h->ifres.p_fe = h->prof.add("if_frontend_fused");
   h->p_hist = h->prof.add("save_hist");
   h->p_fmf = h->prof.add("fm_if_filter");
   h->p_fused = h->prof.add("fm_core_fused");

@@ -6,13 +6,14 @@
 //
 // One CTA per SM, persistent over channels; a CTA takes one channel at a time through all blocks of the call.
 // Warp-specialised, register budgets moved with setmaxnreg:
-//   * 4 producer warps (208 registers): every thread runs the register-resident streaming half-band cascade
-//     (HbsCascade, fmr_hbstream.cuh) over its own stream tile = 60 consecutive 1.25 MHz samples of the current block
-//     (125 tiles x 60 = the 7500 new samples of a block). Its 10 MHz input rows are staged by the TMA unit: one
-//     5-D tensor-map copy per warp and row (box = 32 tiles x 256 bytes, SWIZZLE_128B so that the lanes' LDS.128 of
+//   * 8 producer warps (152 registers): every thread runs the register-resident streaming half-band cascade
+//     (HbsCascade, fmr_hbstream.cuh) over its own stream tile = 30 consecutive 1.25 MHz samples of the current block
+//     (250 tiles x 30 = the 7500 new samples of a block). Its 10 MHz input rows are staged by the TMA unit: one
+//     5-D tensor-map copy per warp and row (box = 32 tiles x 128 bytes, SWIZZLE_128B so that the lanes' LDS.128 of
 //     their own rows are conflict free), completion counted on an mbarrier per warp and stage. Outputs go straight
 //     into B, a 10000-sample circular buffer in shared memory indexed by the absolute 1.25 MHz sample number.
-//   * 8 consumer warps (120 registers): when B holds a whole block (7500 new + 2500 samples it shares with the
+//     (Two producer warps per scheduler: one alone runs at half the FMA pipe's packed-FP32 rate, measured.)
+//   * 8 consumer warps (104 registers): when B holds a whole block (7500 new + 2500 samples it shares with the
 //     previous block), pass 1 of the 10000-point forward FFT reads B and writes A; B is handed back to the producers,
 //     which meanwhile kept their TMA pipeline filled; passes 2 and 3, the multiplication by H0, the 3072-point inverse
 //     and the stores to the 384 kHz ring run out of A while the producers fill B with the next block.
@@ -29,6 +30,8 @@
 
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "fmr_fdr.cuh"
 #include "fmr_hbstream.cuh"
 
@@ -36,29 +39,44 @@ namespace fmr {
 namespace fe {
 
 using D = HbsDelays<4, 5, 8>;
-constexpr int kU = 4;                                              // macro-steps (16 input samples) per block step
-constexpr int kProdWarps = 4, kConsWarps = 8;
-constexpr int kProdThreads = 32 * kProdWarps, kConsThreads = 32 * kConsWarps, kThreads = kProdThreads + kConsThreads;
-constexpr int kTile = 60, kTiles = fdr::kAdvIn / kTile;            // 125 stream tiles of 60 outputs per block
-static_assert(kTiles * kTile == fdr::kAdvIn && kTiles <= kProdThreads, "tiles must cover the block's new samples");
-constexpr int kBlockSteps = (D::kWarm + kTile / 2 + kU - 1) / kU;  // 11: 3 of warm-up, 7.5 of output
-constexpr int kRows = kBlockSteps * kU / 2;                        // 22 rows of 32 input samples per tile and block
+constexpr int kConsWarps = 8, kConsThreads = 32 * kConsWarps;
 constexpr int kStages = 2;
-constexpr int kStageBytes = 2 * 32 * 128;                          // one warp's box: 2 chunks x 32 tiles x 128 bytes
-constexpr int kTileIn = 8 * kTile;                                 // 480 input samples between tiles
 constexpr int kBlockIn = 8 * fdr::kAdvIn;                          // 60000 input samples between blocks
-constexpr int kRowChunks = 2 * kRows;                              // 44 chunks of 16 samples per tile and block
 // first input sample of (block j, tile 0, row 0): 16 * (((7500 j + 1250 + A3) >> 1) - kWarm) = 60000 j + kIn0
 constexpr int kIn0 = 16 * (((fdr::kGuardIn + D::A3) >> 1) - D::kWarm);
-constexpr int kInSpan = kIn0 + (kTiles - 1) * kTileIn + kRows * 32; // input of block j ends at 60000 j + kInSpan (exclusive)
-// shared memory map (bytes)
-constexpr int kOffA = 0;
-constexpr int kOffB = fdr::kNin * 8;
-constexpr int kOffStage = ((2 * fdr::kNin * 8 + 1023) / 1024) * 1024;
-constexpr int kOffBar = kOffStage + kProdWarps * kStages * kStageBytes;
-constexpr int kSmemBytes = kOffBar + 128;
-static_assert(kSmemBytes <= 232448, "shared memory budget");
 static_assert(fdr::kZLen <= fdr::kNin, "the 3072-point buffer aliases A");
+
+// One shape of the kernel: PW producer warps, U macro-steps (16 input samples) per block step of the cascade,
+// stream tiles of TILE outputs, RS macro-steps per staged row, setmaxnreg budgets PREGS / CREGS.
+// SPLIT: a stream tile is run by TWO threads (even lane: real parts, odd lane: imaginary parts; the filters are real), i.e.
+// twice the warps for the same arithmetic, scalar FADD / FFMA instead of the packed forms, half the registers.
+template <int PW, int U_, int TILE, int RS, int PREGS, int CREGS, bool SPLIT = false> struct Cfg {
+  static constexpr int kProdWarps = PW, kU = U_, kTile = TILE, kRowSteps = RS, kProdRegs = PREGS, kConsRegs = CREGS;
+  static constexpr bool kSplit = SPLIT;
+  static constexpr int kProdThreads = 32 * PW, kThreads = kProdThreads + kConsThreads;
+  static constexpr int kTiles = fdr::kAdvIn / TILE;
+  static constexpr int kWarpTiles = SPLIT ? 16 : 32;                // stream tiles per producer warp
+  static_assert(kTiles * TILE == fdr::kAdvIn && kTiles <= PW * kWarpTiles && (TILE % 2) == 0, "tiles must cover the block's new samples");
+  static_assert(U_ % RS == 0, "a block step is a whole number of rows");
+  static constexpr int kBlockSteps = (D::kWarm + TILE / 2 + U_ - 1) / U_;
+  static constexpr int kRows = kBlockSteps * U_ / RS;               // staged rows per tile and block
+  static constexpr int kStageBytes = RS * kWarpTiles * 128;        // one warp's box: RS chunks x its tiles x 128 bytes
+  static constexpr int kTileIn = 8 * TILE;                         // input samples between tiles
+  static constexpr int kRowChunks = RS * kRows;                    // chunks of 16 samples per tile and block
+  static constexpr int kInSpan = kIn0 + (kTiles - 1) * kTileIn + kRowChunks * 16; // block j's input ends at 60000 j + kInSpan
+  // shared memory map (bytes)
+  static constexpr int kOffA = 0;
+  static constexpr int kOffB = fdr::kNin * 8;
+  static constexpr int kOffStage = ((2 * fdr::kNin * 8 + 1023) / 1024) * 1024;
+  static constexpr int kOffBar = kOffStage + PW * kStages * kStageBytes;
+  static constexpr int kSmemBytes = kOffBar + 8 * (PW * kStages + 2);
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+  static_assert(PW * 32 * PREGS + kConsThreads * CREGS <= 65536, "register file");
+};
+using CfgA = Cfg<4, 4, 60, 2, 208, 120>;  // 4 producer warps, long tiles (47 % warm-up), cascade block step of 64 samples
+using CfgB = Cfg<8, 2, 30, 1, 168, 88>;   // 8 producer warps (two per scheduler), short tiles (87 % warm-up)
+using CfgC = Cfg<8, 1, 30, 1, 152, 104>;  // the same with the smallest cascade (no spills, more register moves)
+using CfgS = Cfg<8, 4, 60, 2, 128, 128, true>; // 8 producer warps on long tiles: real and imaginary part on two lanes
 
 struct Params {
   const float2 *hb_ring; // 1.25 MHz ring (unfused path's output): samples shared with the block before the first one
@@ -94,8 +112,8 @@ __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"
 // then through the CTA's channels, so the TMA pipeline never drains at a block or channel boundary.
 struct RowIter {
   int ch, blk, row;
-  __device__ __forceinline__ void next(int n_blocks, int ch_step) {
-    if (++row == kRows) {
+  __device__ __forceinline__ void next(int n_rows, int n_blocks, int ch_step) {
+    if (++row == n_rows) {
       row = 0;
       if (++blk == n_blocks) {
         blk = 0;
@@ -105,7 +123,25 @@ struct RowIter {
   }
 };
 
-__global__ void __launch_bounds__(kThreads, 1) k_frontend_fused(const __grid_constant__ CUtensorMap tm, const Params P) {
+// wait with back-off: the consumers wait for a whole block of producer work, spinning would take issue slots from it
+__device__ __forceinline__ void mbar_wait_sleep(unsigned a, unsigned parity) {
+  unsigned done;
+  for (;;) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(256);
+  }
+}
+
+template <class CF>
+__global__ void __launch_bounds__(CF::kThreads, 1) k_frontend_fused(const __grid_constant__ CUtensorMap tm, const Params P) {
+  constexpr int kProdWarps = CF::kProdWarps, kU = CF::kU, kTile = CF::kTile, kRowSteps = CF::kRowSteps;
+  constexpr int kProdThreads = CF::kProdThreads, kTiles = CF::kTiles, kBlockSteps = CF::kBlockSteps, kRows = CF::kRows;
+  constexpr int kStageBytes = CF::kStageBytes, kOffA = CF::kOffA, kOffB = CF::kOffB, kOffStage = CF::kOffStage, kOffBar = CF::kOffBar;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem_raw);
   float2 *A = reinterpret_cast<float2 *>(smem_raw + kOffA);
@@ -125,14 +161,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_frontend_fused(const __grid_con
   const int ch_step = gridDim.x;
   if (tid < kProdThreads) {
     // =============================== producers: half-band cascade, HBM -> B ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    if constexpr (CF::kProdRegs != CF::kConsRegs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CF::kProdRegs));
+    constexpr bool kSplit = CF::kSplit;
+    constexpr int kWarpTiles = CF::kWarpTiles;
+    using V = typename std::conditional<kSplit, float, float2>::type;
     const int lane = tid & 31, warp = tid >> 5;
-    const bool live = tid < kTiles;
+    const int wl = kSplit ? (lane >> 1) : lane;  // this lane's tile within the warp's box
+    const int comp = kSplit ? (lane & 1) : 0;    // split form: 0 = real parts, 1 = imaginary parts
+    const int tile = warp * kWarpTiles + wl;
+    const bool live = tile < kTiles;
     const unsigned mbar0 = bar_full + 8 * kStages * warp;
     const unsigned stage0 = smem_s + kOffStage + warp * (kStages * kStageBytes);
-    // this lane's two 128-byte lines of a stage (chunk 0 / chunk 1 of its tile) and their swizzle terms
-    const unsigned line0 = stage0 + lane * 128, line1 = line0 + 32 * 128;
-    const unsigned sw0 = (lane & 7) << 4, sw1 = sw0; // line index = chunk * 32 + lane: (line & 7) = (lane & 7)
+    // this lane's 128-byte line of a row's macro-step ms is line (kWarpTiles ms + wl) of the stage: SWIZZLE_128B xors
+    // the 16-byte unit index with (line & 7) = (wl & 7)
+    const unsigned line0 = stage0 + wl * 128;
+    const unsigned sw = (wl & 7) << 4;
     float t1[4], t2[5], t3[8];
 #pragma unroll
     for (int k = 0; k < 4; k++) t1[k] = P.t1[k];
@@ -141,14 +184,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_frontend_fused(const __grid_con
 #pragma unroll
     for (int k = 0; k < 8; k++) t3[k] = P.t3[k];
     RowIter nx{(int)blockIdx.x, 0, 0};
-    auto issue = [&](int rseq) {
+    auto issue = [&](int rs) {
       if (nx.ch < P.n_channels) {
         if (lane == 0) {
-          const unsigned mb = mbar0 + 8 * (rseq % kStages);
+          const unsigned mb = mbar0 + 8 * (rs % kStages);
           mbar_expect_tx(mb, kStageBytes);
-          tma_load_5d(stage0 + (rseq % kStages) * kStageBytes, &tm, 0, 32 * warp, 2 * nx.row, nx.blk, nx.ch, mb);
+          tma_load_5d(stage0 + (rs % kStages) * kStageBytes, &tm, 0, kWarpTiles * warp, kRowSteps * nx.row, nx.blk, nx.ch, mb);
         }
-        nx.next(P.n_blocks, ch_step);
+        nx.next(kRows, P.n_blocks, ch_step);
       }
     };
     int rseq = 0; // rows consumed so far by this warp (all channels)
@@ -158,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_frontend_fused(const __grid_con
     for (int ch = blockIdx.x; ch < P.n_channels; ch += ch_step) {
       for (int blk = 0; blk < P.n_blocks; blk++, bseq++) {
         const int64_t j = P.j0 + blk;
-        const int64_t m_lo = j * fdr::kAdvIn + fdr::kGuardIn + (int64_t)kTile * (live ? tid : kTiles - 1);
+        const int64_t m_lo = j * fdr::kAdvIn + fdr::kGuardIn + (int64_t)kTile * (live ? tile : kTiles - 1);
         int pos = (int)(m_lo % fdr::kNin); // B is indexed by the absolute sample number modulo 10000
         if (blk == 0) {
           // first block of a channel: the 2500 samples it shares with its predecessor come from the 1.25 MHz ring
@@ -173,33 +216,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_frontend_fused(const __grid_con
             *reinterpret_cast<float4 *>(B + pb) = v;
           }
         }
-        HbsCascade<4, 5, 8, kU> cas;
+        HbsCascade<4, 5, 8, kU, V> cas;
         cas.clear();
         for (int bs = 0; bs < kBlockSteps; bs++) {
 #pragma unroll
-          for (int q = 0; q < kU / 2; q++, rseq++) {
+          for (int q = 0; q < kU / kRowSteps; q++, rseq++) {
             const int st = rseq % kStages;
             mbar_wait(mbar0 + 8 * st, (unsigned)((rseq / kStages) & 1));
-            const unsigned a0 = line0 + st * kStageBytes, a1 = line1 + st * kStageBytes;
 #pragma unroll
-            for (int ms = 0; ms < 2; ms++) {
-              float2 x[16];
-              const unsigned a = ms ? a1 : a0, sw = ms ? sw1 : sw0;
+            for (int ms = 0; ms < kRowSteps; ms++) {
+              V x[16];
+              const unsigned a = line0 + st * kStageBytes + ms * (kWarpTiles * 128);
 #pragma unroll
               for (int w = 0; w < 8; w++) {
                 float4 v;
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
                              : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                              : "r"(a + ((w << 4) ^ sw)));
-                x[2 * w] = make_float2(v.x, v.y);
-                x[2 * w + 1] = make_float2(v.z, v.w);
+                if constexpr (kSplit) {
+                  x[2 * w] = comp ? v.y : v.x;
+                  x[2 * w + 1] = comp ? v.w : v.z;
+                } else {
+                  x[2 * w] = make_float2(v.x, v.y);
+                  x[2 * w + 1] = make_float2(v.z, v.w);
+                }
               }
-              cas.feed(2 * q + ms, x, t1);
+              cas.feed(kRowSteps * q + ms, x, t1);
             }
             __syncwarp();
             issue(rseq + kStages);
           }
-          float2 y[2 * kU];
+          V y[2 * kU];
           cas.finish(t2, t3, y);
           if (bs >= D::kWarm / kU) {
             // B still holds the previous block until pass 1 of its FFT has read it
@@ -208,7 +255,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_frontend_fused(const __grid_con
 #pragma unroll
               for (int q = 0; q < 2 * kU; q += 2) {
                 if (bs < kBlockSteps - 1 || q < kTile - 2 * kU * (kBlockSteps - 1 - D::kWarm / kU)) {
-                  *reinterpret_cast<float4 *>(B + pos) = make_float4(y[q].x, y[q].y, y[q + 1].x, y[q + 1].y);
+                  if constexpr (kSplit) {
+                    float *bp = reinterpret_cast<float *>(B + pos) + comp;
+                    bp[0] = y[q];
+                    bp[2] = y[q + 1];
+                  } else {
+                    *reinterpret_cast<float4 *>(B + pos) = make_float4(y[q].x, y[q].y, y[q + 1].x, y[q + 1].y);
+                  }
                   pos += 2;
                   if (pos >= fdr::kNin) pos -= fdr::kNin;
                 }
@@ -221,14 +274,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_frontend_fused(const __grid_con
     }
   } else {
     // =============================== consumers: B -> FFT -> 384 kHz ring ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    if constexpr (CF::kProdRegs != CF::kConsRegs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CF::kConsRegs));
     const int ct = tid - kProdThreads;
     uint32_t bseq = 0;
     for (int ch = blockIdx.x; ch < P.n_channels; ch += ch_step) {
       for (int blk = 0; blk < P.n_blocks; blk++, bseq++) {
         const int64_t j = P.j0 + blk;
         const int o625 = (int)((12 * j + 14) & 15); // (7500 j - 1250) mod 10000 = 625 * o625
-        mbar_wait(bar_bfull, bseq & 1);
+        mbar_wait_sleep(bar_bfull, bseq & 1);
         for (int b = ct; b < 625; b += kConsThreads) {
           fdr::fwd1(b, [&](int bb, int a) { return B[bb + 625 * ((o625 + a) & 15)]; }, A, P.tab);
         }

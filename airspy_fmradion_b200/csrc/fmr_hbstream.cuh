@@ -46,6 +46,17 @@ FMR_HD float2 hbs_acc(float2 y, float t, float2 u, float2 v) {
 #endif
 }
 
+// real-valued form (one component of the complex stream per thread): the same two roundings per lane as FADD2 / FFMA2
+FMR_HD float hbs_acc(float y, float t, float u, float v) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(t, __fadd_rn(u, v), y);
+#else
+  return fmaf(t, u + v, y);
+#endif
+}
+FMR_HD void hbs_fill(float2 &d, float v) { d.x = d.y = v; }
+FMR_HD void hbs_fill(float &d, float v) { d = v; }
+
 constexpr int hbs_even_ceil(int v) { return (v + 1) & ~1; }
 
 // Delay bookkeeping of the streaming cascade. Macro-step i consumes input samples
@@ -80,18 +91,18 @@ template <int N1, int N2, int N3> struct HbsDelays {
 
 // One stage: NEW outputs per call. wE[q] = E[m0 + q], wO[q] = O[m0 - N + q] with m0 the first
 // output index of the call; CE even-phase and CO = CE + N odd-phase samples are carried.
-template <int N, int NEW, int CE> struct HbsStage {
+template <int N, int NEW, int CE, typename V = float2> struct HbsStage {
   static constexpr int CO = CE + N;
-  float2 wO[CO + NEW];
-  float2 wE[CE + NEW];
+  V wO[CO + NEW];
+  V wE[CE + NEW];
   FMR_HD void clear(float v = 0.f) {
 #pragma unroll
-    for (int q = 0; q < CO + NEW; q++) wO[q].x = wO[q].y = v;
+    for (int q = 0; q < CO + NEW; q++) hbs_fill(wO[q], v);
 #pragma unroll
-    for (int q = 0; q < CE + NEW; q++) wE[q].x = wE[q].y = v;
+    for (int q = 0; q < CE + NEW; q++) hbs_fill(wE[q], v);
   }
   // in[0] has an even absolute index
-  FMR_HD void run(const float2 (&in)[2 * NEW], const float *t, float2 (&out)[NEW]) {
+  FMR_HD void run(const V (&in)[2 * NEW], const float *t, V (&out)[NEW]) {
 #pragma unroll
     for (int q = 0; q < NEW; q++) {
       wE[CE + q] = in[2 * q];
@@ -99,7 +110,7 @@ template <int N, int NEW, int CE> struct HbsStage {
     }
 #pragma unroll
     for (int r = 0; r < NEW; r++) {
-      float2 y = wE[r];
+      V y = wE[r];
 #pragma unroll
       for (int k = 0; k < N; k++) y = hbs_acc(y, t[k], wO[r + N + k], wO[r + N - k - 1]);
       out[r] = y;
@@ -113,27 +124,27 @@ template <int N, int NEW, int CE> struct HbsStage {
 
 // The cascade over U macro-steps (16*U input samples -> 2*U outputs): stage 1 runs per
 // macro-step, stages 2 and 3 once per block step.
-template <int N1, int N2, int N3, int U> struct HbsCascade {
+template <int N1, int N2, int N3, int U, typename V = float2> struct HbsCascade {
   using D = HbsDelays<N1, N2, N3>;
-  HbsStage<N1, 8, D::CE1> s1;
-  HbsStage<N2, 4 * U, D::CE2> s2;
-  HbsStage<N3, 2 * U, D::CE3> s3;
-  float2 x1[8 * U];
+  HbsStage<N1, 8, D::CE1, V> s1;
+  HbsStage<N2, 4 * U, D::CE2, V> s2;
+  HbsStage<N3, 2 * U, D::CE3, V> s3;
+  V x1[8 * U];
   FMR_HD void clear(float v = 0.f) {
     s1.clear(v);
     s2.clear(v);
     s3.clear(v);
   }
   // u-th macro-step of the block: 16 input samples
-  FMR_HD void feed(int u, const float2 (&x)[16], const float *t1) {
-    float2 o[8];
+  FMR_HD void feed(int u, const V (&x)[16], const float *t1) {
+    V o[8];
     s1.run(x, t1, o);
 #pragma unroll
     for (int q = 0; q < 8; q++) x1[8 * u + q] = o[q];
   }
   // after U feeds: final outputs y[0..2U) = x3[2*i0 - A3 ...], i0 = first macro-step of the block
-  FMR_HD void finish(const float *t2, const float *t3, float2 (&y)[2 * U]) {
-    float2 x2[4 * U];
+  FMR_HD void finish(const float *t2, const float *t3, V (&y)[2 * U]) {
+    V x2[4 * U];
     s2.run(x1, t2, x2);
     s3.run(x2, t3, y);
   }

@@ -21,6 +21,7 @@
 #include "fmr_fft.cuh"
 #include "fmr_fft_inplace.cuh"
 #include "fmr_fdr.cuh"
+#include "fmr_frontend.cuh"
 #include "fmr_hbstream.cuh"
 #include "fmr_kernels.cuh"
 #include "fmr_tables.h"
@@ -223,6 +224,14 @@ template <typename S> struct Resampler {
   bool use_fdr = false;                      // frequency-domain low-pass + resampling (fmr_fdr.cuh); FMR_FDR=0: off
   float *d_fdr_Hs = nullptr;
   float2 *d_fdr_tab = nullptr;
+  bool use_fe = false;                       // fused persistent front end (fmr_frontend.cuh); FMR_FE=0: off
+  int fe_variant = 0;                        // FMR_FE_VARIANT: 0 = CfgA, 1 = CfgB, 2 = CfgC, 3 = CfgS (fmr_frontend.cuh)
+  int fe_min_blocks = 2;                     // fewer whole blocks inside the call's buffer: unfused kernels only
+  int p_fe = -1;
+  typedef CUresult (*TmEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  TmEncodeFn tm_encode = nullptr;
   int64_t fdr_next = 0;                      // first block of the absolute grid that has not been computed yet
   int64_t fdr_hist = 512;                    // output samples before f0 that readers of the output ring may still need
   int fft_threads = 512;               // FMR_FFT_THREADS=1024: the 32-warp form of the fused 16384-point kernel
@@ -488,6 +497,25 @@ template <typename S> struct Resampler {
         FMR_CUDA(cudaMemcpy(d_fdr_Hs, hs.data(), sizeof(float) * hs.size(), cudaMemcpyHostToDevice));
         FMR_CUDA(cudaFuncSetAttribute(k_fdr, cudaFuncAttributeMaxDynamicSharedMemorySize, kFdrSmemBytes));
         use_fdr = true;
+        // fused persistent front end: 10 MHz cf32 chain only (three half-band stages 4/5/8 in front)
+        if (lin && hb_stream && !env_off("FMR_FE")) {
+          cudaDriverEntryPointQueryResult qr;
+          void *fn = nullptr;
+          if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn &&
+              qr == cudaDriverEntryPointSuccess) {
+            tm_encode = reinterpret_cast<TmEncodeFn>(fn);
+            CUtensorMap probe;
+            if (const char *ev = getenv("FMR_FE_VARIANT")) fe_variant = std::min(3, std::max(0, atoi(ev)));
+            if (fe_encode(&probe, r_hb.base, 1, 1, (size_t)fe::kBlockIn)) {
+              FMR_CUDA(fe_dispatch([&](auto cf) {
+                using CF = decltype(cf);
+                return cudaFuncSetAttribute(fe::k_frontend_fused<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kSmemBytes);
+              }));
+              use_fe = true;
+              if (const char *ev = getenv("FMR_FE_MIN_BLOCKS")) fe_min_blocks = std::max(1, atoi(ev));
+            }
+          }
+        }
       }
     }
     if (sizeof(S) == sizeof(double) && d->bc.down == 2 && (d->bc.klen + 1) / 2 <= kDecMaxTaps) {
@@ -655,6 +683,58 @@ template <typename S> struct Resampler {
     }
     return launched;
   }
+  template <typename F> auto fe_dispatch(F &&f) const {
+    if (fe_variant == 1) return f(fe::CfgB{});
+    if (fe_variant == 2) return f(fe::CfgC{});
+    if (fe_variant == 3) return f(fe::CfgS{});
+    return f(fe::CfgA{});
+  }
+  int fe_in_span() const {
+    return fe_dispatch([](auto cf) { return decltype(cf)::kInSpan; });
+  }
+  // Tensor map of the fused front end's input (fmr_frontend.cuh): element (f, t, q, k, c) = float f of 128-byte chunk q
+  // of stream tile t of block k of channel c; `first` = input sample (row 0, tile 0, block 0, channel 0). Rows of
+  // neighbouring tiles overlap in memory (a tile re-reads the end of its predecessor's range as warm-up).
+  bool fe_encode(CUtensorMap *tm, const void *first, int n_blocks, int n_ch, size_t stride_samples) const {
+    if (!tm_encode) return false;
+    return fe_dispatch([&](auto cf) {
+      using CF = decltype(cf);
+      const cuuint64_t dims[5] = {32, (cuuint64_t)CF::kTiles, (cuuint64_t)CF::kRowChunks, (cuuint64_t)n_blocks, (cuuint64_t)n_ch};
+      const cuuint64_t strides[4] = {(cuuint64_t)CF::kTileIn * 8, 128, (cuuint64_t)fe::kBlockIn * 8, (cuuint64_t)stride_samples * 8};
+      const cuuint32_t box[5] = {32, (cuuint32_t)CF::kWarpTiles, (cuuint32_t)CF::kRowSteps, 1, 1}, es[5] = {1, 1, 1, 1, 1};
+      return tm_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void *>(first), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    });
+  }
+  // blocks [ja, jb] of the absolute grid, every channel, in the fused kernel
+  bool launch_fe(const InSrc<float2> &src, Ring<float2> hb, Ring<float2> o, int64_t ja, int64_t jb, cudaStream_t st) {
+    CUtensorMap tm;
+    const float2 *first = src.lin + (ja * fe::kBlockIn + fe::kIn0 - src.start);
+    if (!fe_encode(&tm, first, (int)(jb - ja + 1), gcn, src.stride)) return false;
+    fe::Params P;
+    P.hb_ring = hb.base;
+    P.hb_cap = hb.cap;
+    P.out = o.base;
+    P.out_cap = o.cap;
+    P.Hs = d_fdr_Hs;
+    P.tab = d_fdr_tab;
+    P.j0 = ja;
+    P.n_blocks = (int)(jb - ja + 1);
+    P.n_channels = gcn;
+    for (int k = 0; k < 8; k++) {
+      P.t1[k] = hbt.t[0][k];
+      P.t2[k] = hbt.t[1][k];
+      P.t3[k] = hbt.t[2][k];
+    }
+    fe_dispatch([&](auto cf) {
+      using CF = decltype(cf);
+      fe::k_frontend_fused<CF><<<std::min(sm_count, gcn), CF::kThreads, CF::kSmemBytes, st>>>(tm, P);
+      return 0;
+    });
+    return true;
+  }
+  bool launch_fe(const InSrc<double2> &, Ring<double2>, Ring<double2>, int64_t, int64_t, cudaStream_t) { return false; }
   // frequency-domain form (fmr_fdr.cuh): blocks [j0, j1] of the absolute grid, whole
   void launch_fdr(Ring<float2> in, Ring<float2> o, int64_t j0, int64_t j1, int64_t avail, cudaStream_t st) {
     FdrParams P;
@@ -758,6 +838,27 @@ template <typename S> struct Resampler {
     const int64_t b0 = bc_out(d, h0), b1 = bc_out(d, h1);
     const int64_t f0 = fi_out(d, b0), f1 = fi_out(d, b1);
     Ring<V> bc_in = src.ring;
+    // ---- which blocks of the frequency-domain resampler's grid this call computes, and which of them the fused
+    // front end takes (fmr_frontend.cuh): those whose whole 10 MHz input lies in this call's buffer
+    int64_t j_last = -1, ja = 0, jb = -1;
+    if (use_fdr) {
+      // every block whose 10000 input samples are complete (and whose outputs fit the output ring) is computed as a
+      // whole, possibly ahead of the reference's release schedule, which lags the input by more than a block (the
+      // block convolver's latency of 15231 samples), so the released range [f0, f1) is always covered
+      const int64_t j_in = (h1 >= fdr::kNin - fdr::kGuardIn) ? (h1 - (fdr::kNin - fdr::kGuardIn)) / fdr::kAdvIn : -1;
+      const int64_t j_cap = (f0 - fdr_hist + (int64_t)out.cap) / fdr::kAdvOut - 1;
+      j_last = std::min(j_in, j_cap);
+      if ((j_last + 1) * fdr::kAdvOut < f1) return fail(FMR_ERR_INVALID, "internal: block grid behind the release schedule");
+      if (use_fe && j_last >= fdr_next && src.fmt == 0 && !fs4 && !(src.start & 1) && !(src.stride & 1) &&
+          !(reinterpret_cast<uintptr_t>(src.lin) & 15)) {
+        auto cdiv = [](int64_t a, int64_t b) { return (a >= 0) ? (a + b - 1) / b : -((-a) / b); };
+        auto fdiv = [](int64_t a, int64_t b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
+        ja = std::max(fdr_next, cdiv(src.start - fe::kIn0, fe::kBlockIn));
+        jb = std::min(j_last, fdiv(src.start + src.n_new - fe_in_span(), fe::kBlockIn));
+        if (jb - ja + 1 < fe_min_blocks) jb = ja - 1;
+      }
+    }
+    const bool fused = jb >= ja;
     if (d->n_hb > 0 || linear_in) {
       const int n = (int)(h1 - h0);
       if (n > 0) {
@@ -771,32 +872,63 @@ template <typename S> struct Resampler {
           hb_dispatch([&](auto kern) { kern<<<grid, kHbThreads, sm, st>>>(src, hb_out_ring, tp, o0, cnt, fs4); });
           (*launches)++;
         };
-        int64_t sa = h0, sb = h0; // [sa, sb): outputs the streaming kernel produces
-        if constexpr (sizeof(S) == sizeof(float)) {
-          if (hb_stream && src.fmt == 0 && !fs4) sb = hbs_launch(src, hb_out_ring, h0, h1, &sa, st, launches);
+        auto hb_range = [&](int64_t lo, int64_t hi) {
+          if (hi <= lo) return;
+          int64_t sa = lo, sb = lo; // [sa, sb): outputs the streaming kernel produces
+          if constexpr (sizeof(S) == sizeof(float)) {
+            if (hb_stream && src.fmt == 0 && !fs4) sb = hbs_launch(src, hb_out_ring, lo, hi, &sa, st, launches);
+          }
+          tiled(lo, (int)(sa - lo));
+          tiled(sb, (int)(hi - sb));
+        };
+        // With fused blocks [ja, jb] only the ends of the 1.25 MHz stream go to the ring: what the unfused blocks before
+        // ja read (which includes the 2500 samples block ja shares with its predecessor), and everything from the first
+        // sample of block jb + 1 on (history of the next call).
+        const int64_t head_hi = fused ? std::min(h1, ja * fdr::kAdvIn + fdr::kGuardIn) : h1;
+        const int64_t tail_lo = fused ? std::max(h0, (jb + 1) * fdr::kAdvIn - fdr::kGuardIn) : h1;
+        if (fused && head_hi < tail_lo) {
+          hb_range(h0, head_hi);
+          hb_range(tail_lo, h1);
+        } else {
+          hb_range(h0, h1);
         }
-        tiled(h0, (int)(sa - h0));
-        tiled(sb, (int)(h1 - sb));
         if (prof) prof->end(p_hb, st);
       }
       bc_in = sub(r_hb);
     }
     const int n_bc = (int)(b1 - b0), n_fi = (int)(f1 - f0);
     if (use_fdr) {
-      // Frequency-domain low-pass + resampling on the absolute block grid (fmr_fdr.cuh), for calls of any size: every
-      // block whose 10000 input samples are complete (and whose outputs fit the output ring) is computed as a whole,
-      // possibly ahead of the reference's release schedule, which lags the input by more than a block (the block
-      // convolver's latency of 15231 samples), so the released range [f0, f1) is always covered.
-      const int64_t j_in = (h1 >= fdr::kNin - fdr::kGuardIn) ? (h1 - (fdr::kNin - fdr::kGuardIn)) / fdr::kAdvIn : -1;
-      const int64_t j_cap = (f0 - fdr_hist + (int64_t)out.cap) / fdr::kAdvOut - 1;
-      const int64_t j_last = std::min(j_in, j_cap);
+      // Frequency-domain low-pass + resampling on the absolute block grid (fmr_fdr.cuh), for calls of any size
+      auto unfused = [&](int64_t j0, int64_t j1) {
+        if (j1 < j0) return;
+        launch_fdr(bc_in, out, j0, j1, h1, st);
+        (*launches)++;
+      };
       if (j_last >= fdr_next) {
         if (prof) prof->begin(p_bc, st);
-        launch_fdr(bc_in, out, fdr_next, j_last, h1, st);
-        (*launches)++;
+        unfused(fdr_next, fused ? ja - 1 : j_last);
+        if (fused) unfused(jb + 1, j_last);
         if (prof) prof->end(p_bc, st);
+        if (fused) {
+          if (prof) prof->begin(p_fe, st);
+          if (!launch_fe(src, bc_in, out, ja, jb, st)) return fail(FMR_ERR_CUDA, "tensor map of the fused front end rejected");
+          (*launches)++;
+          if (prof) prof->end(p_fe, st);
+        }
+        if (fdr_next == 0) { // (after the block kernels: it overwrites their first outputs)
+          // Stream start: the reference's bank starts on a zero-initialised delay line, i.e. it sees zeros instead of the
+          // zero-phase filter's pre-ringing in front of filter output 0 (CDSPFracInterpolator.h:861-925). That only
+          // shows in the outputs whose window begins before it: redo those few with the time-domain kernels.
+          const int half = d->fi.flen / 2 - 1;
+          const int n_m = (half * d->fi.outstep + d->fi.instep - 1) / d->fi.instep; // first m with floor(m I / O) >= half
+          const int n_y = (int)(((int64_t)(n_m - 1) * d->fi.instep) / d->fi.outstep) - half + d->fi.flen + 1;
+          dim3 g1((n_y + kFirTile - 1) / kFirTile, gcn);
+          k_fir_long<S><<<g1, kFirThreads, smem_fir, st>>>(bc_in, sub(r_bc), d_bc, d->bc.klen, d->bc.down, 0, n_y);
+          dim3 g2((n_m + kFiTile - 1) / kFiTile, gcn);
+          k_frac_interp<S><<<g2, kFiThreads, smem_fi, st>>>(sub(r_bc), out, d_fi, d->fi.instep, d->fi.outstep, d->fi.flen, 0, n_m);
+          (*launches) += 2;
+        }
       }
-      if ((j_last + 1) * fdr::kAdvOut < f1) return fail(FMR_ERR_INVALID, "internal: block grid behind the release schedule");
       if (advance) fdr_next = std::max(fdr_next, j_last + 1);
     } else if (d->has_fi && use_fft && fuse_fi && d->bc.down == 1 && n_bc >= fft_min_out && n_fi > 0) {
       if (prof) prof->begin(p_bc, st);

@@ -48,7 +48,7 @@ int main() {
   cudaMalloc(&d, h.size() * 4);
   cudaMalloc(&dout, 8192);
   cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
-  const size_t off = 7 * 2; // base offset in floats (16-byte aligned: even sample index)
+  const size_t off = 6 * 2; // base offset in floats (16-byte aligned: even sample index)
   for (int order = 0; order < 2; order++) {
     CUtensorMap tm;
     cuuint64_t dims[5], strides[4];

@@ -36,6 +36,12 @@ VARIANTS = [
     ("fft_inplace_r32_epi", {"FMR_FFT_INPLACE": "2", "FMR_FFT_EPI": "1"}, 329, 8192),
     ("fft_inplace_8k", {"FMR_FFT_INPLACE8K": "1"}, 329, 8192),
     ("fdr_off", {"FMR_FDR": "0"}, 329, 8192),
+    ("fe_off", {"FMR_FE": "0"}, 329, 8192),
+    ("fe_a", {"FMR_FE_VARIANT": "0"}, 329, 8192),
+    ("fe_b", {"FMR_FE_VARIANT": "1"}, 329, 8192),
+    ("fe_c", {"FMR_FE_VARIANT": "2"}, 329, 8192),
+    ("fe_s", {"FMR_FE_VARIANT": "3"}, 329, 8192),
+    ("fe_a_658", {"FMR_FE_VARIANT": "0"}, 658, 8192),
     ("all_on_329_c16384", {}, 329, 16384),
     ("fft_inplace_r32_8k", {"FMR_FFT_INPLACE": "2", "FMR_FFT_INPLACE8K": "1"}, 329, 8192),
 ]
@@ -58,7 +64,7 @@ def main():
     iq = bench.gen_iq_device(torch, dev, fs, Cgen, Tmax, mode)
     stream = torch.cuda.current_stream()
     for name, env, nblk, C in variants:
-        for k in ("FMR_HB_STREAM", "FMR_FUSE_FI", "FMR_FFT_F64", "FMR_HBS_TILE", "FMR_FFT", "FMR_SERIAL_V2", "FMR_TIME_CHUNKS", "FMR_SERIAL_SMS", "FMR_CORE_FUSED", "FMR_HBS_STAGES", "FMR_HBS_L2PF", "FMR_HBS_TMA", "FMR_FFT_N", "FMR_CORE_ROT", "FMR_FUSED_CHUNKS", "FMR_CHUNK_MIN_BLOCKS", "FMR_FFT_TW", "FMR_FFT_THREADS", "FMR_FFT_INPLACE", "FMR_FFT_INPLACE8K", "FMR_FFT_REGCAP", "FMR_FFT_EPI", "FMR_FDR"):
+        for k in ("FMR_HB_STREAM", "FMR_FUSE_FI", "FMR_FFT_F64", "FMR_HBS_TILE", "FMR_FFT", "FMR_SERIAL_V2", "FMR_TIME_CHUNKS", "FMR_SERIAL_SMS", "FMR_CORE_FUSED", "FMR_HBS_STAGES", "FMR_HBS_L2PF", "FMR_HBS_TMA", "FMR_FFT_N", "FMR_CORE_ROT", "FMR_FUSED_CHUNKS", "FMR_CHUNK_MIN_BLOCKS", "FMR_FFT_TW", "FMR_FFT_THREADS", "FMR_FFT_INPLACE", "FMR_FFT_INPLACE8K", "FMR_FFT_REGCAP", "FMR_FFT_EPI", "FMR_FDR", "FMR_FE", "FMR_FE_VARIANT"):
             os.environ.pop(k, None)
         os.environ.update(env)
         C = min(C, Cgen)
