@@ -1104,6 +1104,12 @@ extern "C" fmr_status fmr_fm_tap_if(fmr_fm *h, uint32_t channel, float *re_im, s
 
 extern "C" uint32_t fmr_fm_last_launches(fmr_fm *h) { return h ? h->last_launches : 0; }
 
+extern "C" fmr_status fmr_fm_last_plan(fmr_fm *h, uint64_t plan[5]) {
+  if (!h || !plan) return fail(FMR_ERR_INVALID, "null argument");
+  for (int i = 0; i < 5; i++) plan[i] = h->ifc ? h->ifres.last_plan[i] : 0;
+  return FMR_OK;
+}
+
 extern "C" fmr_status fmr_fm_set_profiling(fmr_fm *h, int enable) {
   if (!h) return fail(FMR_ERR_INVALID, "null handle");
   FMR_CUDA(cudaSetDevice(h->cfg.device));

@@ -232,6 +232,7 @@ template <typename S> struct Resampler {
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   TmEncodeFn tm_encode = nullptr;
+  uint64_t last_plan[5] = {0, 0, 0, 0, 0};   // fmr_fm_last_plan
   int64_t fdr_next = 0;                      // first block of the absolute grid that has not been computed yet
   int64_t fdr_hist = 512;                    // output samples before f0 that readers of the output ring may still need
   int fft_threads = 512;               // FMR_FFT_THREADS=1024: the 32-warp form of the fused 16384-point kernel
@@ -859,6 +860,14 @@ template <typename S> struct Resampler {
       }
     }
     const bool fused = jb >= ja;
+    if (use_fdr) {
+      const int64_t n_all = std::max<int64_t>(0, j_last - fdr_next + 1), n_fe = fused ? jb - ja + 1 : 0;
+      last_plan[0] = (uint64_t)n_fe;
+      last_plan[1] = (uint64_t)(n_all - n_fe);
+      last_plan[2] = 0;
+      last_plan[3] = (uint64_t)fdr::kAdvIn << d->n_hb;
+      last_plan[4] = (uint64_t)fdr::kAdvOut;
+    }
     if (d->n_hb > 0 || linear_in) {
       const int n = (int)(h1 - h0);
       if (n > 0) {
@@ -874,6 +883,7 @@ template <typename S> struct Resampler {
         };
         auto hb_range = [&](int64_t lo, int64_t hi) {
           if (hi <= lo) return;
+          last_plan[2] += (uint64_t)(hi - lo);
           int64_t sa = lo, sb = lo; // [sa, sb): outputs the streaming kernel produces
           if constexpr (sizeof(S) == sizeof(float)) {
             if (hb_stream && src.fmt == 0 && !fs4) sb = hbs_launch(src, hb_out_ring, lo, hi, &sa, st, launches);

@@ -246,6 +246,13 @@ class FmDecoder(_Base):
     def last_launches(self):
         return int(_capi.lib().fmr_fm_last_launches(self._h))
 
+    def last_plan(self):
+        """How the last call's IF front end ran, per channel (fmr_fm_last_plan)."""
+        p = (C.c_uint64 * 5)()
+        check(_capi.lib().fmr_fm_last_plan(self._h, p))
+        return {"fused_blocks": int(p[0]), "unfused_blocks": int(p[1]), "unfused_halfband_outputs": int(p[2]),
+                "block_in": int(p[3]), "block_out": int(p[4])}
+
 
 class AmDecoder(_Base):
     # Static constants (include/AmDecode.h:35-40)

@@ -155,6 +155,73 @@ def cpu_reference(wl, seconds, threads):
                       "/root/reference with a generic-C VOLK shim, unthrottled" % (threads, blocks, BLK, wl),
             "seconds": tn}
 
+def rooflines(wl, dec, stage, C, T, n_audio, width, step_ms, peak, peak_src, fs):
+    """The `roofline` object of the bench line. Headline = the kernel that streams the IQ input from HBM, on ITS OWN
+    algorithmic bytes and its own device time (CUDA events recorded by the library around its launch, on the launching
+    stream); `whole_step` = the step's algorithmic bytes (IQ in + audio out) over the step time; `stages` lists every
+    stage with the bytes it moves algorithmically, what bounds it, and (HBM-bound stages only) a fraction of the peak."""
+    if not stage:
+        return None
+    fs_mode = WORKLOADS[wl][3]
+    plan = dec.last_plan() if hasattr(dec, "last_plan") else {"fused_blocks": 0, "unfused_blocks": 0,
+                                                              "unfused_halfband_outputs": 0, "block_in": 0, "block_out": 0}
+    n_if = int(T * (384000.0 if fs_mode == "fm" else 48000.0) / fs)  # IF-rate samples per channel per step
+    n48 = n_audio // width
+    dec_hb = plan["block_in"] // 7500 if plan["block_in"] else 8       # input samples per half-band output
+    own = {  # stage -> (bytes per step, bound)
+        "if_frontend_fused": (C * plan["fused_blocks"] * (plan["block_in"] + plan["block_out"]) * 8, "hbm"),
+        "if_halfband_cascade": (C * (plan["unfused_halfband_outputs"] * (dec_hb + 1) * 8 if plan["block_in"] else T * 9), "hbm"),
+        "if_lowpass": (C * (plan["unfused_blocks"] * (10000 + plan["block_out"]) * 8 if plan["block_in"] else (T // 8 + n_if) * 8),
+                       "shared memory / FP32 issue (FFT)"),
+        "fm_core_fused": (C * n_if * (8 + 16), "latency (serial AGC / PLL recurrences, one lane per channel)"),
+        "fm_multipath": (C * n_if * 16, "FP32 issue (sample-serial NLMS)"),
+        "audio_halfband_cascade": (C * (n_if * 16 + n_if // 4 * 16), "shared memory / FP64"),
+        "audio_lowpass": (C * (n_if // 4 + n48) * 16, "shared memory / FP64 (FFT)"),
+        "pilot_cut_fir": (C * n48 * 32, "FP64"),
+        "dcblock_matrix": (C * n48 * (16 + 8 * width), "latency (serial IIR, one lane per channel)"),
+    }
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
+    except Exception:
+        pass
+    stages = {}
+    for k, v in stage.items():
+        b, bound = own.get(k, (None, "-"))
+        e = {"ms": round(v, 4), "bound": bound}
+        if b:
+            e["algorithmic_bytes"] = int(b)
+            e["gb_per_s"] = round(b / (v * 1e-3) / 1e9, 1)
+            if bound == "hbm":
+                e["frac"] = round(e["gb_per_s"] / peak, 4)
+        stages[k] = e
+    head = "if_frontend_fused" if stage.get("if_frontend_fused") else "if_halfband_cascade"
+    hb, _ = own[head]
+    ach = hb / (stage[head] * 1e-3) / 1e9
+    tr = traffic.get(head, {})
+    alg_step = C * T * 8 + C * n_audio * 8
+    whole = alg_step / (step_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": head, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": (hb * tr["dram_bytes_per_algorithmic_byte"]) if "dram_bytes_per_algorithmic_byte" in tr else None,
+            "traffic_source": tr.get("source"),
+            "algorithmic_bytes": int(hb), "kernel_ms": stage[head], "peak_source": peak_src,
+            "whole_step": {"algorithmic_bytes": int(alg_step), "achieved": whole, "frac": whole / peak, "ms": step_ms},
+            "whole_step_frac": whole / peak,
+            "front_end_plan": plan, "stages": stages}
+    mpf = WORKLOADS[wl][2]
+    if mpf > 0 and stage.get("fm_multipath"):
+        # SURVEY 8(d): the multipath configuration is compute bound, report it against the FP32 roofline too.
+        # MultipathFilter.cpp:108-161: 4 * stages + 1 complex taps; per 384 kHz sample one complex FIR (8 flop per tap),
+        # every 4th in-call sample the NLMS update (another ~10 flop per tap)
+        ntaps = 4 * mpf + 1
+        flop = C * n_if * (8 * ntaps + 10 * ntaps / 4.0)
+        pk = 148 * 128 * 2 * 1.965e9 / 1e12
+        a = flop / (stage["fm_multipath"] * 1e-3) / 1e12
+        roof["fp32"] = {"bound": "fp32", "kernel": "fm_multipath (k_mpf)", "achieved": a, "peak": pk, "unit": "TFLOP/s",
+                        "frac": a / pk, "flop_per_if_sample": 8 * ntaps + 10 * ntaps / 4.0,
+                        "peak_source": "nominal: 148 SMs x 128 FP32 lanes x 2 x 1.965 GHz (no measured FP32 figure in MEASURED_PEAKS.json)"}
+    return roof
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -184,25 +251,49 @@ def main():
     fs, stereo, mpf, mode = WORKLOADS[wl]
     metric = "IQ Msamples/s (%s)" % wl
 
+    nblk = args.blocks
+    T = nblk * BLK
+    # channels per GPU: as many as fit comfortably in 180 GB with their rings (the serial recurrences cost the same for
+    # 1 or 16384 channels, so throughput grows with the channel count); cfg4's 384 kHz rings are 10x larger per input
+    # sample; cfg3: 592 CTAs of 3 channels = one wave of the multipath kernel (4 CTAs/SM)
+    C = args.channels or {"cfg2_fm_stereo_10Msps": 16384, "cfg3_fm_stereo_10Msps_E200": 1776,
+                          "cfg4_fm_stereo_1Msps": 8192, "cfg5_am_384ksps": 8192}[wl]
+    Ce = min(C, 1024)  # channels of the end-to-end (host buffer) measurement: 16384 would need 88 GB of pinned memory
+    config = {"workload": wl, "channels_per_gpu": C, "samples_per_channel_per_step": T,
+              "block": BLK, "blocks_per_step": nblk, "input_bytes_per_step": C * T * 8,
+              "l2": "input per step (%.0f MB) exceeds the 126 MB L2" % (C * T * 8 / 1e6),
+              "parallelism": "channels sharded %d per GPU, no data-path collective" % C,
+              "e2e_channels_per_gpu": Ce}
+
     if args.impl == "reference":
+        # The reference's own CPU implementation of the path (oracle/_ref) on all host threads. One step = one bounded
+        # sample of the same workload (every thread decodes its own stream); W warm-up samples, then K timed ones.
         if rank != 0:
             return 0
+        from oracle import ref, siggen
+        if not ref.available():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfmref.so was not built"}))
+            return 0
         threads = os.cpu_count() or 1
-        vals, secs = [], 0.0
-        res = None
-        for _ in range(max(1, min(args.steps, 3))):
-            res = cpu_reference(wl, max(1.0, args.cpu_seconds / 2), threads)
-            if res is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfmref.so was not built"}))
-                return 0
-            vals.append(res["value"])
-            secs += res["seconds"]
-        v = float(np.median(vals))
-        res["value"] = v
+        m = 0 if mode == "fm" else 1
+        n_iq = BLK * 2048
+        iq = siggen.fm_stereo_iq(fs, n_iq, 0) if mode == "fm" else siggen.am_iq(fs, n_iq, 0)
+        probe = 400 if mpf == 0 else 100
+        t = ref.bench(m, fs, stereo, mpf, threads, probe, BLK, iq)
+        blocks = max(200, int(probe / t * max(0.5, args.cpu_seconds / 4)))  # ~1.5 s of wall time per step
+        for _ in range(max(0, args.warmup - 1)):
+            ref.bench(m, fs, stereo, mpf, threads, blocks, BLK, iq)
+        secs = [ref.bench(m, fs, stereo, mpf, threads, blocks, BLK, iq) for _ in range(max(1, args.steps))]
+        tot = float(np.sum(secs))
+        v = threads * blocks * BLK * len(secs) / tot / 1e6
+        res = {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "reference",
+               "sample": "%d steps, each %d threads x %d blocks of %d IQ samples (%s), the reference's own classes compiled from "
+                         "/root/reference with a generic-C VOLK shim, unthrottled" % (len(secs), threads, blocks, BLK, wl),
+               "seconds": tot}
         line = {"impl": "reference", "metric": metric, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs / len(vals),
+                "steps": len(secs), "warmup": max(1, args.warmup), "ms_per_step": 1000.0 * tot / len(secs),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32",
-                "data": "synthetic", "config": {"workload": wl, "block": BLK},
+                "data": "synthetic", "config": config,
                 "cpu_baseline": res,
                 "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -219,14 +310,6 @@ def main():
     torch.cuda.set_device(dev_index)
     dev = torch.device("cuda", dev_index)
 
-    nblk = args.blocks
-    T = nblk * BLK
-    # channels per GPU: as many as fit comfortably in 180 GB with their rings (the serial recurrences cost
-    # the same for 1 or 16384 channels, so throughput grows with the channel count); cfg4's 384 kHz
-    # rings are 10x larger per input sample; cfg3: 592 CTAs of 3 channels = one wave of the multipath
-    # kernel (4 CTAs/SM)
-    C = args.channels or {"cfg2_fm_stereo_10Msps": 16384, "cfg3_fm_stereo_10Msps_E200": 1776,
-                          "cfg4_fm_stereo_1Msps": 8192, "cfg5_am_384ksps": 8192}[wl]
     dec = make_decoder(wl, C, T, nblk, dev_index)
     iq = gen_iq_device(torch, dev, fs, C, T, mode)
     width = 2 if (mode == "fm" and stereo) else 1
@@ -276,38 +359,10 @@ def main():
         for k, v in dec.stage_times().items():
             stage[k] = stage.get(k, 0.0) + v / reps
     dec.set_profiling(False)
-    dom = max(stage, key=stage.get) if stage else None
     peak, peak_src = peaks()
-    alg_bytes = C * T * 8 + C * int(lens.sum()) * 8  # IQ read + audio written, per launch/step
-    roof = None
-    tj = {}
-    try:  # DRAM bytes per input sample of the profiled kernels from the committed ncu captures
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
-    except Exception:
-        tj = {}
-
-    def traffic_of(name):
-        e = tj.get(name)
-        return e["bytes_per_input_sample"] * C * T if isinstance(e, dict) and "bytes_per_input_sample" in e else None
-
-    if dom:
-        ach = alg_bytes / (stage[dom] * 1e-3) / 1e9
-        # the same arithmetic for every stage that takes more than 10 % of the step, so that the kernel
-        # that actually streams the input from HBM (if_halfband_cascade) is always listed
-        per_stage = {}
-        tot = sum(stage.values())
-        for k, v in stage.items():
-            if v >= 0.1 * tot:
-                a = alg_bytes / (v * 1e-3) / 1e9
-                per_stage[k] = {"ms": round(v, 4), "achieved": round(a, 1), "frac": round(a / peak, 4),
-                                "traffic": traffic_of(k)}
-        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic_of(dom), "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                "kernel_ms": stage[dom],
-                "whole_step_frac": (alg_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
-                "stages": per_stage,
-                "stage_ms": {k: round(v, 4) for k, v in stage.items()}}
-
+    n_audio = int(lens.sum())  # audio values per channel per step (interleaved L, R when stereo)
+    alg_bytes = C * T * 8 + C * n_audio * 8  # IQ read + audio written, per step
+    roof = rooflines(wl, dec, stage, C, T, n_audio, width, ms / args.steps, peak, peak_src, fs)
     # opt-in: the same channels as G independent handles on G streams. Channels are independent, so this is only a
     # different schedule: the HBM-bound, shared-memory-bound and latency-bound kernels of different handles overlap.
     multi = None
@@ -353,7 +408,6 @@ def main():
     # end to end through the host-buffer entry point (pinned host memory, H2D + D2H inside)
     e2e = None
     if not args.no_e2e:
-        Ce = min(C, 1024)
         dec2 = make_decoder(wl, Ce, T, nblk, dev_index)
         h_iq = torch.empty((Ce, T), dtype=torch.complex64, pin_memory=True)
         h_iq.copy_(iq[:Ce])
@@ -465,11 +519,10 @@ def main():
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (IF) / f64 (PLL, audio)",
                 "data": "synthetic",
-                "config": {"workload": wl, "channels_per_gpu": C, "samples_per_channel_per_step": T,
-                           "block": BLK, "blocks_per_step": nblk, "input_bytes_per_step": C * T * 8,
-                           "l2": "input per step (%.0f MB) exceeds the 126 MB L2" % (C * T * 8 / 1e6),
-                           "parallelism": "channels sharded %d per GPU, no data-path collective" % C},
+                "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+        if isinstance(roof, dict) and "fp32" in roof:
+            line["roofline_fp32"] = roof.pop("fp32")
         if single_homed is not None:
             line["single_homed"] = single_homed
         if multi is not None:

@@ -157,6 +157,11 @@ fmr_status fmr_fm_tap_if(fmr_fm *h, uint32_t channel, float *re_im, size_t cap_c
                          uint64_t *n_complex);
 /* Kernel launches issued by the last process call (for bench accounting). */
 uint32_t fmr_fm_last_launches(fmr_fm *h);
+/* How the last process call's IF front end was executed, per channel (for bench accounting of each kernel's own
+ * bytes): plan[0] = blocks of the frequency-domain resampler's grid taken by the fused front-end kernel, plan[1] = blocks
+ * taken by the unfused kernel, plan[2] = 1.25 MHz samples the unfused half-band kernels produced, plan[3] = input
+ * samples per block (60000 at 10 Msps), plan[4] = output samples per block (2304). All zero for chains without it. */
+fmr_status fmr_fm_last_plan(fmr_fm *h, uint64_t plan[5]);
 /* Per-stage device timing (CUDA events on the launching stream). Enable, run a process
  * call, synchronise, then read: ms[i] is the duration of stage names[i] in the last call. */
 fmr_status fmr_fm_set_profiling(fmr_fm *h, int enable);
