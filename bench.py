@@ -265,6 +265,7 @@ def main():
               "parallelism": "channels sharded %d per GPU, no data-path collective" % C,
               "e2e_channels_per_gpu": Ce}
 
+
     if args.impl == "reference":
         # The reference's own CPU implementation of the path (oracle/_ref) on all host threads. One step = one bounded
         # sample of the same workload (every thread decodes its own stream); W warm-up samples, then K timed ones.
@@ -309,6 +310,15 @@ def main():
     dev_index = local_rank if world > 1 else 0
     torch.cuda.set_device(dev_index)
     dev = torch.device("cuda", dev_index)
+    affinity = None
+    try:  # run this rank (and first-touch its pinned staging buffers) on the CPUs next to its GPU
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(dev_index)
+        pynvml.nvmlDeviceSetCpuAffinity(hnd)
+        affinity = len(os.sched_getaffinity(0))
+    except Exception:
+        affinity = None
 
     dec = make_decoder(wl, C, T, nblk, dev_index)
     iq = gen_iq_device(torch, dev, fs, C, T, mode)
@@ -428,6 +438,25 @@ def main():
         e2e = {"value": world * Ce * T * args.e2e_steps / dt / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": Ce * T * 8, "d2h_bytes_per_step": int(a.shape[1]) * 8 * Ce,
                "channels": Ce, "note": "fmr_fm_process_host: pinned host IQ -> device -> audio back to host"}
+        # The ceiling of this number on this box: the same pinned buffer copied to the device by every rank at the same
+        # time, nothing else (PCIe + host memory; on the 8-GPU node all GPUs hang off one NUMA node).
+        d_sink = torch.empty((Ce, T), dtype=torch.complex64, device=dev)
+        d_sink.copy_(h_iq, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            d_sink.copy_(h_iq, non_blocking=True)
+        torch.cuda.synchronize()
+        dtc = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([dtc], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dtc = float(tt.item())
+        del d_sink
+        e2e["h2d_ceiling"] = {"gb_per_s": world * Ce * T * 8 * args.e2e_steps / dtc / 1e9,
+                              "value": world * Ce * T * args.e2e_steps / dtc / 1e6, "unit": "Msamples/s",
+                              "note": "plain pinned-host -> device copy of the same cf32 buffer on all %d ranks at once" % world}
+        e2e["frac_of_h2d_ceiling"] = e2e["value"] / e2e["h2d_ceiling"]["value"]
         if mode == "fm" and fs != 384000.0:
             # same call with the IQ as int16 pairs (16-bit WAV as FileSource reads it): half the PCIe bytes
             h_i16 = torch.empty((Ce, T, 2), dtype=torch.int16, pin_memory=True)
@@ -509,6 +538,10 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))  # the CPU baseline gets every host core
+        except Exception:
+            pass
         try:
             cpu = cpu_reference(wl, args.cpu_seconds, os.cpu_count() or 1)
         except Exception as ex:  # the bench line must still print
