@@ -455,7 +455,10 @@ static fmr_status am_build(fmr_am *h) {
   }
   FMR_CUDA(h->mem.alloc(&h->hist[0], (size_t)C * kHist));
   FMR_CUDA(h->mem.alloc(&h->hist[1], (size_t)C * kHist));
-  h->r_if.cap = pow2ceil((uint64_t)max48 + 1024);
+  // + what the frequency-domain resampler (1 MHz -> 48 kHz chain) may produce ahead of the release schedule, and the
+  // history the longest channel filter (2049 taps) reads behind it
+  h->r_if.cap = pow2ceil((uint64_t)max48 + 2560 + fdr::kMaxAdvOut);
+  h->ifres.fdr_hist = 2560;
   FMR_CUDA(h->mem.alloc(&h->r_if.base, (size_t)C * h->r_if.cap));
   h->r_flt.cap = h->r_if.cap;
   FMR_CUDA(h->mem.alloc(&h->r_flt.base, (size_t)C * h->r_flt.cap));

@@ -44,27 +44,42 @@ using ipfft::mk;
 using ipfft::nat;
 using ipfft::powers16;
 
-constexpr int kNin = 10000;            // 16 * 625
-constexpr int kNout = 3072;            // 16 * 192
+constexpr int kNin = 10000;            // forward transform, 16 x 25 x 25, for every rate pair
+// Geometry of one rate pair: the inverse transform has kNout = 256 * RL points (RL = its last radix):
+//   625:192 (10 MHz, 2.5 MHz -> 384 kHz; 1.25 MHz in front of the low-pass):  RL = 12, 3072 points
+//   125:48  (1 MHz -> 384 kHz; 1 MHz -> 48 kHz behind three half-bands):      RL = 15, 3840 points
+//   125:32  (6 MHz, 3 MHz -> 384 kHz; 1.5 MHz in front of the low-pass):      RL = 10, 2560 points
+template <int RL> struct Geo {
+  static constexpr int kNout = 256 * RL;
+  static constexpr int kChunk = 16 * RL;                     // slots per chunk of the inverse's first pass
+  static constexpr int kZLen = kNout + 16;                   // one pad word per chunk
+  static constexpr int kHalf = kNout / 2;                    // bins |k| < kHalf are kept (k = -kHalf too)
+  static constexpr int kL = (kHalf - 1) / 400;               // band outputs of a last-pass butterfly: k3 in [0, kL] and [24 - kL, 24]
+  static constexpr int kKeep = 2 * (kL + 1);
+  static constexpr int kTi1 = 625 + 200;                     // [kChunk] W_kNout^b
+  static constexpr int kTi2 = kTi1 + kChunk;                 // [RL]     W_kChunk^k3
+  static constexpr int kTabLen = kTi2 + RL;
+  static constexpr int kHsLen = kKeep * 400;
+};
+// twiddle table (float2), built in double by the host (fdr_make_tables):
+constexpr int kTw1 = 0;                // [625]    W_10000^b
+constexpr int kTw2 = kTw1 + 625;       // [25][8]  W_625^(n3 * {1,2,3,4,5,10,15,20})
+// spectrum table (float, H0 is real: the low-pass is symmetric): Hs[e * 400 + r] = H0[freq(r, e)] / N_in,
+// r = k1 + 16 k2 in [0, 400), e in [0, kKeep) <-> k3 = e (e <= kL) or 25 - kKeep + e; 0 where the bin is outside the band.
+
+constexpr int kMaxAdvOut = 3072;       // most outputs per block over the pairs (125:48 with its guard of 1000)
+// The 625:192 pair (what the fused front end, fmr_frontend.cuh, is built for)
+using G12 = Geo<12>;
+constexpr int kNout = G12::kNout;
 constexpr int kInStep = 625, kOutStep = 192;
 constexpr int kGuardIn = 1250;         // input samples dropped at either end of a block (2 * 625 >= 1153 + 9)
 constexpr int kAdvIn = kNin - 2 * kGuardIn;                  // 7500 new input samples per block
 constexpr int kGuardOut = kGuardIn / kInStep * kOutStep;     // 384
 constexpr int kAdvOut = kAdvIn / kInStep * kOutStep;         // 2304 outputs per block
-constexpr int kZLen = kNout + kNout / 192;                   // 3072-point buffer, one pad word per 192
-constexpr int kHalf = kNout / 2;                             // 1536: bins |k| < kHalf are kept (k = -1536 too)
-constexpr int kKeep = 8;                                     // outputs of a last-pass forward butterfly inside the band
-// twiddle table (float2), built in double by the host (fdr_make_tables):
-constexpr int kTw1 = 0;                // [625]    W_10000^b
-constexpr int kTw2 = kTw1 + 625;       // [25][8]  W_625^(n3 * {1,2,3,4,5,10,15,20})
-constexpr int kTi1 = kTw2 + 200;       // [192]    W_3072^b
-constexpr int kTi2 = kTi1 + 192;       // [12]     W_192^k3
-constexpr int kTabLen = kTi2 + 12;     // 1029
-// spectrum table (float, H0 is real: the low-pass is symmetric): Hs[e * 400 + r] = H0[freq(r, e)] / N_in,
-// r = k1 + 16 k2 in [0, 400), e in [0, 8) <-> k3 = e (e < 4) or 17 + e (e >= 4); 0 where the bin is outside the band.
-constexpr int kHsLen = kKeep * 400;
+constexpr int kZLen = G12::kZLen;
+constexpr int kKeep = G12::kKeep;
 
-FMR_IP_HD int zpos(int k) { return k + k / 192; }
+template <int RL> FMR_IP_HD int zpos(int k) { return k + k / (16 * RL); }
 FMR_IP_HD float2 smul(float s, float2 a) { return mk(s * a.x, s * a.y); }
 FMR_IP_HD float2 sfma(float s, float2 a, float2 b) { // s * a + b
 #ifdef __CUDA_ARCH__
@@ -131,19 +146,23 @@ FMR_IP_HD void dft25(float2 (&v)[25]) {
   for (int k1 = 0; k1 < 5; k1++) dft5(v[5 * k1], v[5 * k1 + 1], v[5 * k1 + 2], v[5 * k1 + 3], v[5 * k1 + 4]);
 }
 FMR_IP_HD int nat25(int k) { return 5 * (k % 5) + k / 5; }
-// the 8 outputs inside the band: o[e] = X[k3], k3 = e (e < 4), 17 + e (e >= 4)
-FMR_IP_HD void dft25_band(float2 (&v)[25], float2 (&o)[kKeep]) {
+// the 2 (L + 1) outputs inside the band: o[e] = X[k3], k3 = e (e <= L), 25 - 2 (L + 1) + e (e > L); L = 3 or 4.
+// X[k1 + 5 k2] is output k2 of the k1-th second-step DFT: the band needs k2 = 0 (k3 = k1 <= L) and k2 = 4 (k3 = 20 + k1).
+template <int L> FMR_IP_HD void dft25_band(float2 (&v)[25], float2 (&o)[2 * (L + 1)]) {
+  static_assert(L == 3 || L == 4, "band width");
   dft25_head(v);
-  o[0] = cadd(cadd(v[0], cadd(v[1], v[4])), cadd(v[2], v[3])); // k1 = 0, k2 = 0
 #pragma unroll
-  for (int k1 = 1; k1 < 4; k1++) {
-    dft5_04(v[5 * k1], v[5 * k1 + 1], v[5 * k1 + 2], v[5 * k1 + 3], v[5 * k1 + 4]);
-    o[k1] = v[5 * k1];         // X[k1]
-    o[3 + k1] = v[5 * k1 + 4]; // X[k1 + 20]
+  for (int k1 = 0; k1 < 5; k1++) {
+    const bool lo = k1 <= L, hi = 20 + k1 >= 24 - L;
+    if (lo && !hi) {
+      o[k1] = cadd(cadd(v[5 * k1], cadd(v[5 * k1 + 1], v[5 * k1 + 4])), cadd(v[5 * k1 + 2], v[5 * k1 + 3]));
+    } else {
+      float2 t0 = v[5 * k1];
+      dft5_04(t0, v[5 * k1 + 1], v[5 * k1 + 2], v[5 * k1 + 3], v[5 * k1 + 4]);
+      if (lo) o[k1] = t0;
+      if (hi) o[(L + 1) + (20 + k1) - (24 - L)] = v[5 * k1 + 4];
+    }
   }
-  float2 t0 = v[20];
-  dft5_04(t0, v[21], v[22], v[23], v[24]);
-  o[7] = v[24]; // X[24]
 }
 
 // ---- 12-point forward DFT in registers (n = 3 n1 + n2, k = k1 + 4 k2); X[k] is left in v[3 (k & 3) + (k >> 2)]
@@ -167,6 +186,57 @@ FMR_IP_HD void dft12(float2 (&v)[12]) {
   }
 }
 FMR_IP_HD int nat12(int k) { return 3 * (k & 3) + (k >> 2); }
+
+// ---- 3-point forward DFT
+FMR_IP_HD void dft3(float2 &x0, float2 &x1, float2 &x2) {
+  const float c = 0.86602540378443864676f;
+  const float2 s = cadd(x1, x2), d = csub(x1, x2);
+  const float2 m = sfma(-0.5f, s, x0), jd = smul(c, d);
+  x0 = cadd(x0, s);
+  x1 = cadd(m, mulmj(jd));
+  x2 = cadd(m, mulpj(jd));
+}
+// ---- 15-point forward DFT in registers (n = 3 n1 + n2, k = k1 + 5 k2); X[k] is left in v[3 (k % 5) + k / 5]
+FMR_IP_HD void dft15(float2 (&v)[15]) {
+#pragma unroll
+  for (int n2 = 0; n2 < 3; n2++) dft5(v[n2], v[3 + n2], v[6 + n2], v[9 + n2], v[12 + n2]);
+  // W_15^(n2 k1)
+  v[3 + 1] = cmul(v[3 + 1], mk(0.9135454576426008666f, -0.40673664307580015276f));   // 1
+  v[6 + 1] = cmul(v[6 + 1], mk(0.66913060635885823757f, -0.7431448254773941331f));   // 2
+  v[9 + 1] = cmul(v[9 + 1], mk(0.30901699437494745126f, -0.95105651629515353118f));  // 3
+  v[12 + 1] = cmul(v[12 + 1], mk(-0.10452846326765333207f, -0.99452189536827340088f)); // 4
+  v[3 + 2] = cmul(v[3 + 2], mk(0.66913060635885823757f, -0.7431448254773941331f));   // 2
+  v[6 + 2] = cmul(v[6 + 2], mk(-0.10452846326765333207f, -0.99452189536827340088f)); // 4
+  v[9 + 2] = cmul(v[9 + 2], mk(-0.80901699437494734024f, -0.58778525229247324813f)); // 6
+  v[12 + 2] = cmul(v[12 + 2], mk(-0.97814760073380568883f, 0.20791169081775906502f)); // 8
+#pragma unroll
+  for (int k1 = 0; k1 < 5; k1++) dft3(v[3 * k1], v[3 * k1 + 1], v[3 * k1 + 2]);
+}
+// ---- 10-point forward DFT in registers (n = 2 n1 + n2, k = k1 + 5 k2); X[k] is left in v[2 (k % 5) + k / 5]
+FMR_IP_HD void dft10(float2 (&v)[10]) {
+#pragma unroll
+  for (int n2 = 0; n2 < 2; n2++) dft5(v[n2], v[2 + n2], v[4 + n2], v[6 + n2], v[8 + n2]);
+  v[2 + 1] = cmul(v[2 + 1], mk(0.80901699437494745126f, -0.5877852522924731371f));   // W_10^1
+  v[4 + 1] = cmul(v[4 + 1], mk(0.30901699437494745126f, -0.95105651629515353118f));  // 2
+  v[6 + 1] = cmul(v[6 + 1], mk(-0.30901699437494734024f, -0.9510565162951536422f));  // 3
+  v[8 + 1] = cmul(v[8 + 1], mk(-0.80901699437494734024f, -0.58778525229247324813f)); // 4
+#pragma unroll
+  for (int k1 = 0; k1 < 5; k1++) {
+    const float2 a = v[2 * k1], b = v[2 * k1 + 1];
+    v[2 * k1] = cadd(a, b);
+    v[2 * k1 + 1] = csub(a, b);
+  }
+}
+// last pass of the inverse: RL-point DFT in registers, X[k] is left in v[nat_last<RL>(k)]
+template <int RL> FMR_IP_HD void dft_last(float2 (&v)[RL]) {
+  static_assert(RL == 12 || RL == 15 || RL == 10, "inverse size");
+  if constexpr (RL == 12) dft12(v);
+  if constexpr (RL == 15) dft15(v);
+  if constexpr (RL == 10) dft10(v);
+}
+template <int RL> FMR_IP_HD int nat_last(int k) {
+  return (RL == 12) ? 3 * (k & 3) + (k >> 2) : (RL == 15) ? 3 * (k % 5) + k / 5 : 2 * (k % 5) + k / 5;
+}
 
 // ---- forward pass 1: radix 16, stride 625. b in [0, 625); x[b + 625 a] comes from ld(b, a)
 template <typename LD> FMR_IP_HD void fwd1(int b, LD ld, float2 *A, const float2 *__restrict__ tab) {
@@ -202,75 +272,76 @@ FMR_IP_HD void fwd2(int i, float2 *A, const float2 *__restrict__ tab) {
     p[25 * k2] = cmul(v[nat25(k2)], w);
   }
 }
-// ---- forward pass 3: the 8 band outputs of the radix-25 butterfly over 25 contiguous slots, times H0, conjugated.
+// ---- forward pass 3: the band outputs of the radix-25 butterfly over 25 contiguous slots, times H0, conjugated.
 // i in [0, 400): k1 = i & 15, k2 = i >> 4, and r = k1 + 16 k2 = i.
-FMR_IP_HD void fwd3_compute(int i, const float2 *A, const float *__restrict__ Hs, float2 (&o)[kKeep]) {
+template <int RL> FMR_IP_HD void fwd3_compute(int i, const float2 *A, const float *__restrict__ Hs, float2 (&o)[Geo<RL>::kKeep]) {
   const float2 *p = A + 625 * (i & 15) + 25 * (i >> 4);
   float2 v[25];
 #pragma unroll
   for (int a = 0; a < 25; a++) v[a] = p[a];
-  dft25_band(v, o);
+  dft25_band<Geo<RL>::kL>(v, o);
 #pragma unroll
-  for (int e = 0; e < kKeep; e++) {
+  for (int e = 0; e < Geo<RL>::kKeep; e++) {
     const float h = Hs[400 * e + i];
     o[e] = mk(h * o[e].x, -h * o[e].y);
   }
 }
 // natural-order bin of band output e of butterfly r, or -1 if it lies outside the band
-FMR_IP_HD int band_bin(int r, int e) {
-  if (e < 4) {
+template <int RL> FMR_IP_HD int band_bin(int r, int e) {
+  using G = Geo<RL>;
+  if (e <= G::kL) {
     const int k = r + 400 * e;
-    return (k < kHalf) ? k : -1;
+    return (k < G::kHalf) ? k : -1;
   }
-  const int k = r + 400 * (17 + e) - kNin; // negative frequency
-  return (k >= -kHalf) ? k + kNout : -1;
+  const int k = r + 400 * (25 - G::kKeep + e) - kNin; // negative frequency
+  return (k >= -G::kHalf) ? k + G::kNout : -1;
 }
-FMR_IP_HD void fwd3_store(int i, float2 *Z, const float2 (&o)[kKeep]) {
+template <int RL> FMR_IP_HD void fwd3_store(int i, float2 *Z, const float2 (&o)[Geo<RL>::kKeep]) {
 #pragma unroll
-  for (int e = 0; e < kKeep; e++) {
-    const int k = band_bin(i, e);
-    if (k >= 0) Z[zpos(k)] = o[e];
+  for (int e = 0; e < Geo<RL>::kKeep; e++) {
+    const int k = band_bin<RL>(i, e);
+    if (k >= 0) Z[zpos<RL>(k)] = o[e];
   }
 }
-// ---- inverse (run as a forward transform of the conjugated spectrum), pass 1: radix 16, stride 192. b in [0, 192)
-FMR_IP_HD void inv1(int b, float2 *Z, const float2 *__restrict__ tab) {
-  float2 *p = Z + b; // zpos(b + 192 a) = b + 193 a
+// ---- inverse (run as a forward transform of the conjugated spectrum), pass 1: radix 16, stride kChunk. b in [0, kChunk)
+template <int RL> FMR_IP_HD void inv1(int b, float2 *Z, const float2 *__restrict__ tab) {
+  constexpr int S = Geo<RL>::kChunk + 1; // zpos(b + kChunk a) = b + (kChunk + 1) a
+  float2 *p = Z + b;
   float2 v[16];
 #pragma unroll
-  for (int a = 0; a < 16; a++) v[a] = p[193 * a];
+  for (int a = 0; a < 16; a++) v[a] = p[S * a];
   fft16(v);
   float2 w[16];
-  powers16(tab[kTi1 + b], w);
+  powers16(tab[Geo<RL>::kTi1 + b], w);
   p[0] = v[nat(0)];
 #pragma unroll
-  for (int d = 1; d < 16; d++) p[193 * d] = cmul(v[nat(d)], w[d]);
+  for (int d = 1; d < 16; d++) p[S * d] = cmul(v[nat(d)], w[d]);
 }
-// ---- pass 2: radix 16 inside chunk i1, stride 12. u in [0, 192): i1 = u & 15, k3 = u >> 4 (193 = 1 mod 16)
-FMR_IP_HD void inv2(int u, float2 *Z, const float2 *__restrict__ tab) {
+// ---- pass 2: radix 16 inside chunk i1, stride RL. u in [0, kChunk): i1 = u & 15, k3 = u >> 4 (kChunk + 1 = 1 mod 16)
+template <int RL> FMR_IP_HD void inv2(int u, float2 *Z, const float2 *__restrict__ tab) {
   const int i1 = u & 15, k3 = u >> 4;
-  float2 *p = Z + 193 * i1 + k3;
+  float2 *p = Z + (Geo<RL>::kChunk + 1) * i1 + k3;
   float2 v[16];
 #pragma unroll
-  for (int a = 0; a < 16; a++) v[a] = p[12 * a];
+  for (int a = 0; a < 16; a++) v[a] = p[RL * a];
   fft16(v);
   float2 w[16];
-  powers16(tab[kTi2 + k3], w);
+  powers16(tab[Geo<RL>::kTi2 + k3], w);
   p[0] = v[nat(0)];
 #pragma unroll
-  for (int d = 1; d < 16; d++) p[12 * d] = cmul(v[nat(d)], w[d]);
+  for (int d = 1; d < 16; d++) p[RL * d] = cmul(v[nat(d)], w[d]);
 }
-// ---- pass 3: radix 12 over 12 contiguous slots; t in [0, 256): i1 = t & 15, i2 = t >> 4; output sample
-// i = t + 256 i3 of the block (i3 in [0, 12)) goes to st(i, value). Lanes = consecutive output samples.
-template <typename ST> FMR_IP_HD void inv3(int t, const float2 *Z, ST st) {
-  const float2 *p = Z + 193 * (t & 15) + 12 * (t >> 4);
-  float2 v[12];
+// ---- pass 3: radix RL over RL contiguous slots; t in [0, 256): i1 = t & 15, i2 = t >> 4; output sample
+// i = t + 256 i3 of the block (i3 in [0, RL)) goes to st(i, value). Lanes = consecutive output samples.
+template <int RL, typename ST> FMR_IP_HD void inv3(int t, const float2 *Z, ST st) {
+  const float2 *p = Z + (Geo<RL>::kChunk + 1) * (t & 15) + RL * (t >> 4);
+  float2 v[RL];
 #pragma unroll
-  for (int a = 0; a < 12; a++) v[a] = p[a];
-  dft12(v);
+  for (int a = 0; a < RL; a++) v[a] = p[a];
+  dft_last<RL>(v);
 #pragma unroll
-  for (int i3 = 0; i3 < 12; i3++) st(t + 256 * i3, cconj(v[nat12(i3)]));
+  for (int i3 = 0; i3 < RL; i3++) st(t + 256 * i3, cconj(v[nat_last<RL>(i3)]));
 }
-
 
 } // namespace fdr
 } // namespace fmr
@@ -278,27 +349,30 @@ template <typename ST> FMR_IP_HD void inv3(int t, const float2 *Z, ST st) {
 #if defined(__CUDACC__) && defined(FMR_KERNELS_CUH)
 namespace fmr {
 // k_fdr: one CTA = one block of the absolute block grid of one channel. Block j holds input samples
-// [7500 j - 1250, 7500 j + 8750) of the 1.25 MHz ring and yields outputs [2304 j, 2304 (j + 1)) of the 384 kHz stream;
-// only outputs in [m_lo, m_hi) are stored (a process call covers an arbitrary output range, so its first and last
-// block are partial). Input samples at negative indices or at indices >= avail read as zero, as in k_fir_fft.
+// [adv_in j - guard_in, adv_in j - guard_in + 10000) of the ring in front of the low-pass and yields outputs
+// [adv_out j, adv_out (j + 1)) of the resampled stream (625:192: 7500 / 1250 / 2304); only outputs in [m_lo, m_hi) are
+// stored. Input samples at negative indices or at indices >= avail read as zero, as in k_fir_fft.
 // The grid is absolute, so the result does not depend on how the stream was cut into calls.
 struct FdrParams {
   int64_t j0;         // block index of blockIdx.x == 0
   int64_t m_lo, m_hi; // outputs this launch stores
   int64_t avail;      // valid input samples in the ring
+  int adv_in, guard_in, adv_out, guard_out;
 };
 constexpr int kFdrThreads = 256;
-constexpr int kFdrSmemBytes = (fdr::kNin + fdr::kZLen) * (int)sizeof(float2);
+template <int RL> constexpr int fdr_smem_bytes() { return (fdr::kNin + fdr::Geo<RL>::kZLen) * (int)sizeof(float2); }
 
-static __global__ void __launch_bounds__(kFdrThreads, 2)
+template <int RL>
+__global__ void __launch_bounds__(kFdrThreads, 2)
     k_fdr(Ring<float2> in, Ring<float2> out, const float *__restrict__ Hs, const float2 *__restrict__ tab, FdrParams P) {
   using namespace fdr;
+  using G = Geo<RL>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *A = reinterpret_cast<float2 *>(smem_raw);
   float2 *Z = A + kNin;
   const uint32_t c = blockIdx.y;
   const int64_t j = P.j0 + blockIdx.x;
-  const int64_t base = j * kAdvIn - kGuardIn;
+  const int64_t base = j * P.adv_in - P.guard_in;
   const int tid = threadIdx.x;
   {
     const uint32_t pos0 = (uint32_t)base & (in.cap - 1);
@@ -320,18 +394,18 @@ static __global__ void __launch_bounds__(kFdrThreads, 2)
   for (int i = tid; i < 400; i += kFdrThreads) fwd2(i, A, tab);
   __syncthreads();
   for (int i = tid; i < 400; i += kFdrThreads) {
-    float2 o[kKeep];
-    fwd3_compute(i, A, Hs, o);
-    fwd3_store(i, Z, o);
+    float2 o[G::kKeep];
+    fwd3_compute<RL>(i, A, Hs, o);
+    fwd3_store<RL>(i, Z, o);
   }
   __syncthreads();
-  if (tid < 192) inv1(tid, Z, tab);
+  if (tid < G::kChunk) inv1<RL>(tid, Z, tab);
   __syncthreads();
-  if (tid < 192) inv2(tid, Z, tab);
+  if (tid < G::kChunk) inv2<RL>(tid, Z, tab);
   __syncthreads();
-  const int64_t mb = j * kAdvOut - kGuardOut; // output index of block sample 0
-  const int64_t lo = max(P.m_lo, j * kAdvOut), hi = min(P.m_hi, (j + 1) * kAdvOut);
-  inv3(tid, Z, [&](int i, float2 v) {
+  const int64_t mb = j * P.adv_out - P.guard_out; // output index of block sample 0
+  const int64_t lo = max(P.m_lo, j * P.adv_out), hi = min(P.m_hi, (j + 1) * P.adv_out);
+  inv3<RL>(tid, Z, [&](int i, float2 v) {
     const int64_t m = mb + i;
     if (m >= lo && m < hi) out.st(c, m, v);
   });
@@ -348,22 +422,24 @@ inline float2 fdr_w(double num, double den) { // W_den^num
   const double a = -2.0 * 3.14159265358979323846264338327950288 * std::fmod(num, den) / den;
   return mk((float)std::cos(a), (float)std::sin(a));
 }
+template <int RL>
 inline void fdr_make_tables(const double *taps, int klen, std::vector<float2> &tab, std::vector<float> &Hs) {
-  tab.assign(kTabLen, mk(0.f, 0.f));
+  using G = Geo<RL>;
+  tab.assign(G::kTabLen, mk(0.f, 0.f));
   for (int b = 0; b < 625; b++) tab[kTw1 + b] = fdr_w(b, kNin);
   const int mult[8] = {1, 2, 3, 4, 5, 10, 15, 20};
   for (int n3 = 0; n3 < 25; n3++) {
     for (int q = 0; q < 8; q++) tab[kTw2 + 8 * n3 + q] = fdr_w((double)n3 * mult[q], 625.0);
   }
-  for (int b = 0; b < 192; b++) tab[kTi1 + b] = fdr_w(b, kNout);
-  for (int k3 = 0; k3 < 12; k3++) tab[kTi2 + k3] = fdr_w(k3, 192.0);
+  for (int b = 0; b < G::kChunk; b++) tab[G::kTi1 + b] = fdr_w(b, G::kNout);
+  for (int k3 = 0; k3 < RL; k3++) tab[G::kTi2 + k3] = fdr_w(k3, G::kChunk);
   // H0[k] = sum_i h[i] cos(2 pi k (i - fl2) / N) (zero phase, real for the symmetric low-pass), with 1/N folded in
-  Hs.assign(kHsLen, 0.f);
+  Hs.assign(G::kHsLen, 0.f);
   const int fl2 = (klen - 1) / 2;
-  for (int e = 0; e < kKeep; e++) {
+  for (int e = 0; e < G::kKeep; e++) {
     for (int r = 0; r < 400; r++) {
-      if (band_bin(r, e) < 0) continue;
-      const int k = (e < 4) ? r + 400 * e : r + 400 * (17 + e) - kNin; // signed frequency
+      if (band_bin<RL>(r, e) < 0) continue;
+      const int k = (e <= G::kL) ? r + 400 * e : r + 400 * (25 - G::kKeep + e) - kNin; // signed frequency
       double acc = 0.0;
       for (int i = 0; i < klen; i++) {
         const long long ph = ((long long)k * (i - fl2)) % kNin;

@@ -219,8 +219,8 @@ static fmr_status fm_build(fmr_fm *h) {
   FMR_CUDA(h->mem.alloc(&h->hist[0], (size_t)C * kHist));
   FMR_CUDA(h->mem.alloc(&h->hist[1], (size_t)C * kHist));
   // + one block of the frequency-domain resampler's grid: it produces whole blocks, up to 2303 samples ahead of the
-  // reference's release schedule (Resampler::run, fmr_fdr.cuh)
-  h->r_if.cap = pow2ceil((uint64_t)max384 + 512 + fdr::kAdvOut);
+  // reference's release schedule (Resampler::run, fmr_fdr.cuh); up to 3071 for the 125:48 pairs
+  h->r_if.cap = pow2ceil((uint64_t)max384 + 512 + fdr::kMaxAdvOut);
   FMR_CUDA(h->mem.alloc(&h->r_if.base, (size_t)C * h->r_if.cap));
   h->r_iff = h->r_if;
   if (cfg.fmfilter) {

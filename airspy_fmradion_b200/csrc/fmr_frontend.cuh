@@ -291,22 +291,22 @@ __global__ void __launch_bounds__(CF::kThreads, 1) k_frontend_fused(const __grid
         cons_sync();
         {
           float2 o0[fdr::kKeep], o1[fdr::kKeep];
-          fdr::fwd3_compute(ct, A, P.Hs, o0);
-          if (ct + kConsThreads < 400) fdr::fwd3_compute(ct + kConsThreads, A, P.Hs, o1);
+          fdr::fwd3_compute<12>(ct, A, P.Hs, o0);
+          if (ct + kConsThreads < 400) fdr::fwd3_compute<12>(ct + kConsThreads, A, P.Hs, o1);
           cons_sync(); // the 3072-point buffer aliases A: every butterfly has loaded before anyone stores
-          fdr::fwd3_store(ct, A, o0);
-          if (ct + kConsThreads < 400) fdr::fwd3_store(ct + kConsThreads, A, o1);
+          fdr::fwd3_store<12>(ct, A, o0);
+          if (ct + kConsThreads < 400) fdr::fwd3_store<12>(ct + kConsThreads, A, o1);
         }
         cons_sync();
-        if (ct < 192) fdr::inv1(ct, A, P.tab);
+        if (ct < 192) fdr::inv1<12>(ct, A, P.tab);
         cons_sync();
-        if (ct < 192) fdr::inv2(ct, A, P.tab);
+        if (ct < 192) fdr::inv2<12>(ct, A, P.tab);
         cons_sync();
         {
           const int64_t mb = j * fdr::kAdvOut - fdr::kGuardOut;
           float2 *__restrict__ orow = P.out + (size_t)ch * P.out_cap;
           const uint32_t omask = P.out_cap - 1;
-          fdr::inv3(ct, A, [&](int i, float2 v) {
+          fdr::inv3<12>(ct, A, [&](int i, float2 v) {
             if (i >= fdr::kGuardOut && i < fdr::kGuardOut + fdr::kAdvOut) orow[(uint32_t)(mb + i) & omask] = v;
           });
         }

@@ -222,6 +222,8 @@ template <typename S> struct Resampler {
   bool fft_regcap = false;                   // FMR_FFT_REGCAP=1: k_fir_fft_ip<512, 896> (72 registers; for --handles overlap)
   bool fft_inplace32 = false;                // FMR_FFT_INPLACE=2: k_fir_fft_ip32 (host-checked, not yet measured)
   bool use_fdr = false;                      // frequency-domain low-pass + resampling (fmr_fdr.cuh); FMR_FDR=0: off
+  int fdr_rl = 0;                            // last radix of its inverse transform: 12 (625:192), 15 (125:48), 10 (125:32)
+  int fdr_adv_in = 0, fdr_guard_in = 0, fdr_adv_out = 0, fdr_guard_out = 0; // block grid of this chain
   float *d_fdr_Hs = nullptr;
   float2 *d_fdr_tab = nullptr;
   bool use_fe = false;                       // fused persistent front end (fmr_frontend.cuh); FMR_FE=0: off
@@ -234,6 +236,7 @@ template <typename S> struct Resampler {
   TmEncodeFn tm_encode = nullptr;
   uint64_t last_plan[5] = {0, 0, 0, 0, 0};   // fmr_fm_last_plan
   int64_t fdr_next = 0;                      // first block of the absolute grid that has not been computed yet
+  int64_t fdr_out_done = 0;                  // outputs stored so far (beyond fdr_next's blocks: a partial block's head)
   int64_t fdr_hist = 512;                    // output samples before f0 that readers of the output ring may still need
   int fft_threads = 512;               // FMR_FFT_THREADS=1024: the 32-warp form of the fused 16384-point kernel
   bool use_fft = false;
@@ -486,20 +489,34 @@ template <typename S> struct Resampler {
       fuse_fi = !env_off("FMR_FUSE_FI");
     }
     if constexpr (sizeof(S) == sizeof(float)) {
-      // 625:192 pairs: the low-pass and the polyphase bank as one forward + one small inverse FFT (fmr_fdr.cuh)
-      if (use_fft && d->has_fi && d->bc.down == 1 && d->fi.instep == fdr::kInStep && d->fi.outstep == fdr::kOutStep &&
-          (d->bc.klen - 1) / 2 + d->fi.flen / 2 <= fdr::kGuardIn && !env_off("FMR_FDR")) {
+      // 625:192, 125:48 and 125:32 pairs: the low-pass and the polyphase bank as one forward + one small inverse FFT
+      // (fmr_fdr.cuh). Blocks of 10000 input samples; guard = the filter's half length + the bank's, rounded up to a
+      // whole number of input steps so that every block starts on an output sample.
+      const int fdr_j = d->has_fi && d->fi.instep > 0 ? fdr::kNin / d->fi.instep : 0;
+      const int fdr_nout = fdr_j * (d->has_fi ? d->fi.outstep : 0);
+      const int rl = (fdr_j * d->fi.instep == fdr::kNin && fdr_nout % 256 == 0) ? fdr_nout / 256 : 0;
+      if (use_fft && d->has_fi && d->bc.down == 1 && (rl == 12 || rl == 15 || rl == 10) && !env_off("FMR_FDR")) {
+        const int need = (d->bc.klen - 1) / 2 + d->fi.flen / 2 + 1;
+        fdr_guard_in = (need + d->fi.instep - 1) / d->fi.instep * d->fi.instep;
+        fdr_adv_in = fdr::kNin - 2 * fdr_guard_in;
+        fdr_guard_out = fdr_guard_in / d->fi.instep * d->fi.outstep;
+        fdr_adv_out = fdr_adv_in / d->fi.instep * d->fi.outstep;
+        fdr_rl = rl;
         std::vector<float2> tb;
         std::vector<float> hs;
-        fdr::fdr_make_tables(d->bc.taps, d->bc.klen, tb, hs);
+        if (rl == 12) fdr::fdr_make_tables<12>(d->bc.taps, d->bc.klen, tb, hs);
+        if (rl == 15) fdr::fdr_make_tables<15>(d->bc.taps, d->bc.klen, tb, hs);
+        if (rl == 10) fdr::fdr_make_tables<10>(d->bc.taps, d->bc.klen, tb, hs);
         FMR_CUDA(mem.alloc(&d_fdr_tab, tb.size(), false));
         FMR_CUDA(cudaMemcpy(d_fdr_tab, tb.data(), sizeof(float2) * tb.size(), cudaMemcpyHostToDevice));
         FMR_CUDA(mem.alloc(&d_fdr_Hs, hs.size(), false));
         FMR_CUDA(cudaMemcpy(d_fdr_Hs, hs.data(), sizeof(float) * hs.size(), cudaMemcpyHostToDevice));
-        FMR_CUDA(cudaFuncSetAttribute(k_fdr, cudaFuncAttributeMaxDynamicSharedMemorySize, kFdrSmemBytes));
+        FMR_CUDA(cudaFuncSetAttribute(k_fdr<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, fdr_smem_bytes<12>()));
+        FMR_CUDA(cudaFuncSetAttribute(k_fdr<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, fdr_smem_bytes<15>()));
+        FMR_CUDA(cudaFuncSetAttribute(k_fdr<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, fdr_smem_bytes<10>()));
         use_fdr = true;
         // fused persistent front end: 10 MHz cf32 chain only (three half-band stages 4/5/8 in front)
-        if (lin && hb_stream && !env_off("FMR_FE")) {
+        if (lin && hb_stream && rl == 12 && fdr_guard_in == fdr::kGuardIn && !env_off("FMR_FE")) {
           cudaDriverEntryPointQueryResult qr;
           void *fn = nullptr;
           if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn &&
@@ -737,16 +754,23 @@ template <typename S> struct Resampler {
   }
   bool launch_fe(const InSrc<double2> &, Ring<double2>, Ring<double2>, int64_t, int64_t, cudaStream_t) { return false; }
   // frequency-domain form (fmr_fdr.cuh): blocks [j0, j1] of the absolute grid, whole
-  void launch_fdr(Ring<float2> in, Ring<float2> o, int64_t j0, int64_t j1, int64_t avail, cudaStream_t st) {
+  void launch_fdr(Ring<float2> in, Ring<float2> o, int64_t j0, int64_t j1, int64_t avail, cudaStream_t st, int64_t m_lo = -1,
+                  int64_t m_hi = -1) {
     FdrParams P;
     P.j0 = j0;
-    P.m_lo = j0 * fdr::kAdvOut;
-    P.m_hi = (j1 + 1) * fdr::kAdvOut;
+    P.m_lo = (m_lo >= 0) ? m_lo : j0 * fdr_adv_out;
+    P.m_hi = (m_hi >= 0) ? m_hi : (j1 + 1) * fdr_adv_out;
     P.avail = avail;
+    P.adv_in = fdr_adv_in;
+    P.guard_in = fdr_guard_in;
+    P.adv_out = fdr_adv_out;
+    P.guard_out = fdr_guard_out;
     dim3 grid((unsigned)(j1 - j0 + 1), gcn);
-    k_fdr<<<grid, kFdrThreads, kFdrSmemBytes, st>>>(in, o, d_fdr_Hs, d_fdr_tab, P);
+    if (fdr_rl == 12) k_fdr<12><<<grid, kFdrThreads, fdr_smem_bytes<12>(), st>>>(in, o, d_fdr_Hs, d_fdr_tab, P);
+    if (fdr_rl == 15) k_fdr<15><<<grid, kFdrThreads, fdr_smem_bytes<15>(), st>>>(in, o, d_fdr_Hs, d_fdr_tab, P);
+    if (fdr_rl == 10) k_fdr<10><<<grid, kFdrThreads, fdr_smem_bytes<10>(), st>>>(in, o, d_fdr_Hs, d_fdr_tab, P);
   }
-  void launch_fdr(Ring<double2>, Ring<double2>, int64_t, int64_t, int64_t, cudaStream_t) {}
+  void launch_fdr(Ring<double2>, Ring<double2>, int64_t, int64_t, int64_t, cudaStream_t, int64_t = -1, int64_t = -1) {}
   void launch_dec2(Ring<double2> in, Ring<double2> o, int64_t q0, int n, cudaStream_t st) {
     dim3 grid((n + kDecTile - 1) / kDecTile, gcn);
     k_fir_dec2_f64<<<grid, kDecThreads, dec2_smem(d->bc.klen), st>>>(in, o, d_bc, d->bc.klen, q0, n);
@@ -841,15 +865,23 @@ template <typename S> struct Resampler {
     Ring<V> bc_in = src.ring;
     // ---- which blocks of the frequency-domain resampler's grid this call computes, and which of them the fused
     // front end takes (fmr_frontend.cuh): those whose whole 10 MHz input lies in this call's buffer
-    int64_t j_last = -1, ja = 0, jb = -1;
+    int64_t j_last = -1, ja = 0, jb = -1, j_part = -1;
     if (use_fdr) {
       // every block whose 10000 input samples are complete (and whose outputs fit the output ring) is computed as a
       // whole, possibly ahead of the reference's release schedule, which lags the input by more than a block (the
       // block convolver's latency of 15231 samples), so the released range [f0, f1) is always covered
-      const int64_t j_in = (h1 >= fdr::kNin - fdr::kGuardIn) ? (h1 - (fdr::kNin - fdr::kGuardIn)) / fdr::kAdvIn : -1;
-      const int64_t j_cap = (f0 - fdr_hist + (int64_t)out.cap) / fdr::kAdvOut - 1;
+      const int64_t j_in = (h1 >= fdr::kNin - fdr_guard_in) ? (h1 - (fdr::kNin - fdr_guard_in)) / fdr_adv_in : -1;
+      const int64_t j_cap = (f0 - fdr_hist + (int64_t)out.cap) / fdr_adv_out - 1;
       j_last = std::min(j_in, j_cap);
-      if ((j_last + 1) * fdr::kAdvOut < f1) return fail(FMR_ERR_INVALID, "internal: block grid behind the release schedule");
+      // Chains whose block convolver withholds less than a block (1 MHz: 7269 samples) release outputs of the block that
+      // is still filling: that block is then evaluated on what has arrived (zeros behind it, which only its not yet
+      // released outputs can see) and only [.., f1) is stored; it is evaluated again, whole, when it is complete.
+      if ((j_last + 1) * fdr_adv_out < f1) {
+        j_part = j_last + 1;
+        if ((j_part + 1) * fdr_adv_out < f1 || j_part > j_cap) {
+          return fail(FMR_ERR_INVALID, "internal: block grid behind the release schedule");
+        }
+      }
       if (use_fe && j_last >= fdr_next && src.fmt == 0 && !fs4 && !(src.start & 1) && !(src.stride & 1) &&
           !(reinterpret_cast<uintptr_t>(src.lin) & 15)) {
         auto cdiv = [](int64_t a, int64_t b) { return (a >= 0) ? (a + b - 1) / b : -((-a) / b); };
@@ -865,8 +897,8 @@ template <typename S> struct Resampler {
       last_plan[0] = (uint64_t)n_fe;
       last_plan[1] = (uint64_t)(n_all - n_fe);
       last_plan[2] = 0;
-      last_plan[3] = (uint64_t)fdr::kAdvIn << d->n_hb;
-      last_plan[4] = (uint64_t)fdr::kAdvOut;
+      last_plan[3] = (uint64_t)fdr_adv_in << d->n_hb;
+      last_plan[4] = (uint64_t)fdr_adv_out;
     }
     if (d->n_hb > 0 || linear_in) {
       const int n = (int)(h1 - h0);
@@ -911,13 +943,18 @@ template <typename S> struct Resampler {
       // Frequency-domain low-pass + resampling on the absolute block grid (fmr_fdr.cuh), for calls of any size
       auto unfused = [&](int64_t j0, int64_t j1) {
         if (j1 < j0) return;
-        launch_fdr(bc_in, out, j0, j1, h1, st);
+        // (outputs below fdr_out_done were stored from the block's partial evaluation and have been consumed: keep them)
+        launch_fdr(bc_in, out, j0, j1, h1, st, std::max(j0 * (int64_t)fdr_adv_out, fdr_out_done), -1);
         (*launches)++;
       };
-      if (j_last >= fdr_next) {
+      if (j_last >= fdr_next || j_part >= 0) {
         if (prof) prof->begin(p_bc, st);
         unfused(fdr_next, fused ? ja - 1 : j_last);
         if (fused) unfused(jb + 1, j_last);
+        if (j_part >= 0) {
+          launch_fdr(bc_in, out, j_part, j_part, h1, st, std::max(j_part * (int64_t)fdr_adv_out, fdr_out_done), f1);
+          (*launches)++;
+        }
         if (prof) prof->end(p_bc, st);
         if (fused) {
           if (prof) prof->begin(p_fe, st);
@@ -939,7 +976,12 @@ template <typename S> struct Resampler {
           (*launches) += 2;
         }
       }
-      if (advance) fdr_next = std::max(fdr_next, j_last + 1);
+      if (advance) {
+        const bool first = (fdr_next == 0);
+        fdr_next = std::max(fdr_next, j_last + 1);
+        fdr_out_done = std::max(fdr_out_done, (j_part >= 0) ? f1 : fdr_next * (int64_t)fdr_adv_out);
+        (void)first;
+      }
     } else if (d->has_fi && use_fft && fuse_fi && d->bc.down == 1 && n_bc >= fft_min_out && n_fi > 0) {
       if (prof) prof->begin(p_bc, st);
       (*launches) += launch_fft_fused(bc_in, out, f0, n_fi, h1, b1, st);

@@ -10,9 +10,15 @@
 // ring, the dot product is reduced with warp shuffles, so a sample costs no block barrier.
 // The ring is stored twice back to back so that the N-tap window is always contiguous (tap
 // loads with immediate offsets, no per-tap wrap arithmetic); a lane's partial dot product runs
-// as four independent accumulator chains (the summation order differs from VOLK's SIMD order
+// as two independent accumulator chains (the summation order differs from VOLK's SIMD order
 // either way); the window stays in registers for the coefficient update; input samples are
 // prefetched one batch of eight ahead.
+//
+// Batching: the coefficients only change after the samples i = 0, 4, 8, ... of a call, so the four outputs i = 4q+1 ..
+// 4q+4 all use the coefficients left by update q and are evaluated TOGETHER (four windows one sample apart, sixteen
+// independent accumulator chains, eight interleaved warp reductions), then update q+1 runs on the window and output of
+// i = 4q+4. Every output and update is the same expression on the same operands as in the sample-by-sample order
+// (MultipathFilter.cpp:176-186); only the latency of one sample's dependent chain is no longer paid four times.
 #ifndef FMR_MPF_CUH
 #define FMR_MPF_CUH
 
@@ -69,85 +75,120 @@ __global__ void __launch_bounds__(32 * kMpfWarps, 4)
       continue;
     }
     bool ok = true;
-    // samples are fetched 8 at a time, one batch ahead, so their latency is not paid per sample
-    float2 xbuf[8], xnext[8];
+    const uint32_t mask = kMpfRing - 1;
+    // MultipathFilter::update_coeff (MultipathFilter.cpp:108-161) on the window `sv` and the output (yr, yi)
+    auto update = [&](const float2 (&sv)[J], float yr, float yi) -> bool {
+      float m4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int u = 0; u < 8; u++) xnext[u] = (u < n) ? in.ld(c, tb + u) : make_float2(0.f, 0.f);
-    for (int i = 0; i < n; i++) {
-      if ((i & 7) == 0) {
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          xbuf[u] = xnext[u];
-          xnext[u] = (i + 8 + u < n) ? in.ld(c, tb + i + 8 + u) : make_float2(0.f, 0.f);
-        }
-      }
-      float2 x = xbuf[0];
-#pragma unroll
-      for (int u = 1; u < 8; u++) {
-        if ((i & 7) == u) x = xbuf[u];
-      }
-      cnt++;
-      if (lane == 0) {
-        ring[cnt & (kMpfRing - 1)] = x;
-        ring[(cnt & (kMpfRing - 1)) + kMpfRing] = x;
-      }
-      __syncwarp();
-      const bool upd = ((i & 3) == 0);
-      // tap k = lane + 32 j reads the sample N-1-k steps behind the newest: contiguous from `wbase`
-      const float2 *__restrict__ w = ring + ((cnt - (uint32_t)(N - 1)) & (kMpfRing - 1)) + lane;
-      // rows j < N/32 are full for every lane; only the rows behind them need the per-lane k < N
-      // test. Explicit FMAs: two per tap and component, no separate add.
-      float2 sv[J];
-      float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < J; j++) m4[j & 3] = fmaf(sv[j].y, sv[j].y, fmaf(sv[j].x, sv[j].x, m4[j & 3]));
+      const float ms = warp_sum((m4[0] + m4[1]) + (m4[2] + m4[3]));
+      const double env = (double)(yr * yr + yi * yi);
+      const double err = 1.0 - env;
+      const float mu = (float)(0.1 / ((double)ms + 1e-10));
+      const float factor = (float)(err * (double)mu);
+      const float fr = factor * yr, fi = factor * yi;
+      // taps beyond N keep a zero coefficient because their window sample was read as zero
 #pragma unroll
       for (int j = 0; j < J; j++) {
-        if (j < jf || lane + 32 * j < N) {
-          sv[j] = w[32 * j];
-        } else {
-          sv[j] = make_float2(0.f, 0.f);
-        }
-        ar[j & 3] = fmaf(-sv[j].y, cf[j].y, fmaf(sv[j].x, cf[j].x, ar[j & 3]));
-        ai[j & 3] = fmaf(sv[j].y, cf[j].x, fmaf(sv[j].x, cf[j].y, ai[j & 3]));
+        cf[j].x = fmaf(fi, sv[j].y, fmaf(fr, sv[j].x, cf[j].x));
+        cf[j].y = fmaf(-fr, sv[j].y, fmaf(fi, sv[j].x, cf[j].y));
       }
-      float yr = (ar[0] + ar[1]) + (ar[2] + ar[3]), yi = (ai[0] + ai[1]) + (ai[2] + ai[3]);
-      yr = warp_sum(yr);
-      yi = warp_sum(yi);
-      if (!isfinite(yr) || !isfinite(yi)) {
-        ok = false;
-        break;
-      }
-      if (lane == 0) out.st(c, tb + i, make_float2(yr, yi));
-      if (upd) {
-        // MultipathFilter::update_coeff (MultipathFilter.cpp:108-161)
-        float m4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < J; j++) m4[j & 3] = fmaf(sv[j].y, sv[j].y, fmaf(sv[j].x, sv[j].x, m4[j & 3]));
-        const float ms = warp_sum((m4[0] + m4[1]) + (m4[2] + m4[3]));
-        const double env = (double)(yr * yr + yi * yi);
-        const double err = 1.0 - env;
-        const float mu = (float)(0.1 / ((double)ms + 1e-10));
-        const float factor = (float)(err * (double)mu);
-        const float fr = factor * yr, fi = factor * yi;
-        // taps beyond N keep a zero coefficient because their window sample was read as zero
+      // the reference tap is pinned to 1+0j (MultipathFilter.cpp:158-160)
+      if (lane == (ref_idx & 31)) {
 #pragma unroll
         for (int j = 0; j < J; j++) {
-          cf[j].x = fmaf(fi, sv[j].y, fmaf(fr, sv[j].x, cf[j].x));
-          cf[j].y = fmaf(-fr, sv[j].y, fmaf(fi, sv[j].x, cf[j].y));
-        }
-        // the reference tap is pinned to 1+0j (MultipathFilter.cpp:158-160)
-        if (lane == (ref_idx & 31)) {
-#pragma unroll
-          for (int j = 0; j < J; j++) {
-            if (j == (ref_idx >> 5)) cf[j] = make_float2(1.f, 0.f);
-          }
-        }
-        err_keep = err;
-        if (!isfinite(err)) {
-          ok = false;
-          break;
+          if (j == (ref_idx >> 5)) cf[j] = make_float2(1.f, 0.f);
         }
       }
+      err_keep = err;
+      return isfinite(err);
+    };
+    // one sample: output (and update when `upd`); false = the reference's failure path
+    auto step1 = [&](float2 x, int i, bool upd) -> bool {
+      cnt++;
+      if (lane == 0) {
+        ring[cnt & mask] = x;
+        ring[(cnt & mask) + kMpfRing] = x;
+      }
+      __syncwarp();
+      // tap k = lane + 32 j reads the sample N-1-k steps behind the newest: contiguous from `w`
+      const float2 *__restrict__ w = ring + ((cnt - (uint32_t)(N - 1)) & mask) + lane;
+      float2 sv[J];
+      // (the same two accumulator chains per output as in the batch below: a sample's value does not depend on which
+      // of the two paths the call partition sends it through)
+      float ar[2] = {0.f, 0.f}, ai[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < J; j++) {
+        sv[j] = (j < jf || lane + 32 * j < N) ? w[32 * j] : make_float2(0.f, 0.f);
+        ar[j & 1] = fmaf(-sv[j].y, cf[j].y, fmaf(sv[j].x, cf[j].x, ar[j & 1]));
+        ai[j & 1] = fmaf(sv[j].y, cf[j].x, fmaf(sv[j].x, cf[j].y, ai[j & 1]));
+      }
+      const float yr = warp_sum(ar[0] + ar[1]), yi = warp_sum(ai[0] + ai[1]);
+      if (!isfinite(yr) || !isfinite(yi)) return false;
+      if (lane == 0) out.st(c, tb + i, make_float2(yr, yi));
+      return upd ? update(sv, yr, yi) : true;
+    };
+    // sample 0 of the call: output with the carried coefficients, then the first update
+    ok = step1(in.ld(c, tb), 0, true);
+    int i = 1;
+    // batches of four: outputs i .. i+3 with the same coefficients, update after i+3 (i = 1 mod 4)
+    for (; ok && i + 3 < n; i += 4) {
+      const float2 xq = (lane < 4) ? in.ld(c, tb + i + lane) : make_float2(0.f, 0.f);
+      if (lane < 4) {
+        const uint32_t pz = (cnt + 1 + lane) & mask;
+        ring[pz] = xq;
+        ring[pz + kMpfRing] = xq;
+      }
+      cnt += 4;
+      __syncwarp();
+      // window of output d (d = 0..3): newest sample cnt - 3 + d; tap k reads slot w[32 j + d]
+      const float2 *__restrict__ w = ring + ((cnt - 3 - (uint32_t)(N - 1)) & mask) + lane;
+      float2 sv[J]; // window of the fourth output (the one the update uses)
+      float ar[4][2], ai[4][2];
+#pragma unroll
+      for (int d = 0; d < 4; d++) ar[d][0] = ar[d][1] = ai[d][0] = ai[d][1] = 0.f;
+#pragma unroll
+      for (int j = 0; j < J; j++) {
+        const bool on = (j < jf || lane + 32 * j < N);
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+          const float2 v = on ? w[32 * j + d] : make_float2(0.f, 0.f);
+          if (d == 3) sv[j] = v;
+          ar[d][j & 1] = fmaf(-v.y, cf[j].y, fmaf(v.x, cf[j].x, ar[d][j & 1]));
+          ai[d][j & 1] = fmaf(v.y, cf[j].x, fmaf(v.x, cf[j].y, ai[d][j & 1]));
+        }
+      }
+      float yr[4], yi[4];
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        yr[d] = ar[d][0] + ar[d][1];
+        yi[d] = ai[d][0] + ai[d][1];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+          yr[d] += __shfl_xor_sync(0xffffffffu, yr[d], o);
+          yi[d] += __shfl_xor_sync(0xffffffffu, yi[d], o);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        if (ok && (!isfinite(yr[d]) || !isfinite(yi[d]))) ok = false;
+      }
+      if (!ok) break;
+      if (lane < 4) {
+        float2 y = make_float2(yr[0], yi[0]);
+#pragma unroll
+        for (int d = 1; d < 4; d++) {
+          if (lane == d) y = make_float2(yr[d], yi[d]);
+        }
+        out.st(c, tb + i + lane, y);
+      }
+      ok = update(sv, yr[3], yi[3]);
     }
+    // the last (n - 1) mod 4 samples of the call: outputs only
+    for (; ok && i < n; i++) ok = step1(in.ld(c, tb + i), i, false);
     if (!ok) {
       // FmDecode.cpp:114-123: reset coefficients, pass the call through unfiltered
 #pragma unroll

@@ -23,20 +23,31 @@ def _arr(text, name):
 
 def test_tables_allow_band_limited_resampling():
     text = open(INC).read()
-    for chain in ("chain0", "chain2"):  # 10 MHz and 2.5 MHz -> 384 kHz: 1.25 MHz in front of the low-pass
-        bc, fi = _arr(text, chain + "_bc"), _arr(text, chain + "_fi").reshape(192, 18)
-        assert len(bc) == 2307 and np.array_equal(bc, bc[::-1])
+    # chain index in fmr_tables_generated.inc -> (instep, outstep, flen): every chain the frequency-domain form serves
+    chains = {"chain0": (625, 192, 18), "chain2": (625, 192, 18),   # 10 MHz, 2.5 MHz -> 384 kHz
+              "chain1": (125, 32, 18), "chain6": (125, 32, 18),     # 6 MHz, 3 MHz -> 384 kHz
+              "chain3": (125, 48, 24), "chain18": (125, 48, 24)}    # 1 MHz -> 384 kHz, 1 MHz -> 48 kHz
+    for chain, (instep, outstep, flen) in chains.items():
+        bc, fi = _arr(text, chain + "_bc"), _arr(text, chain + "_fi").reshape(outstep, flen)
+        assert np.array_equal(bc, bc[::-1]), chain
+        assert (len(bc) - 1) // 2 + flen // 2 + 1 <= 1500  # guard of a 10000-sample block
         n = 1 << 18
         mag = np.abs(np.fft.rfft(np.concatenate([bc, np.zeros(n - len(bc))]))) / bc.sum()
-        edge = int(np.ceil(192.0 / 1250.0 * n))  # output Nyquist (192 kHz) on the 1.25 MHz axis
-        assert mag[edge:].max() < 2e-9
-        f = np.linspace(0.0, 0.16, 321)
-        e = np.exp(-2j * np.pi * np.outer(f, np.arange(18)))
+        nyq = 0.5 * outstep / instep  # output Nyquist on the input axis = the edge of the kept band
+        edge = int(np.ceil(nyq * n))
+        assert mag[edge:].max() < 2e-9, (chain, mag[edge:].max())
+        f = np.linspace(0.0, nyq * 1.04, 321)
+        e = np.exp(-2j * np.pi * np.outer(f, np.arange(flen)))
         worst = 0.0
-        for p in range(192):
+        for p in range(outstep):
+            # row p evaluates the stream (flen / 2 - 1) + frac(p * instep / outstep) samples into its window
+            delay = (flen // 2 - 1) + ((p * instep) % outstep) / outstep if chain in ("", ) else None
             h = e @ fi[p]
-            worst = max(worst, np.abs(h * np.exp(2j * np.pi * f * (8 + p / 192.0)) - 1.0).max())
-        assert worst < 2e-8, worst
+            ph = np.unwrap(np.angle(h))
+            d = -(ph[8] - ph[0]) / (2 * np.pi * (f[8] - f[0]))
+            assert abs(d - (flen // 2 - 1) - p / outstep) < 1e-6, (chain, p, d)  # bank row p <-> fraction p / outstep
+            worst = max(worst, np.abs(h * np.exp(2j * np.pi * f * ((flen // 2 - 1) + p / outstep)) - 1.0).max())
+        assert worst < 3e-8, (chain, worst)
 
 
 def test_fdr_host_emulation(tmp_path):
