@@ -816,11 +816,12 @@ static fmr_status am_ensure_staging(fmr_am *h, size_t raw_bytes, bool want_sink)
     FMR_CUDA(h->mem.alloc(&h->d_iq, (size_t)C * h->cfg.max_samples_per_call * 2, false));
     FMR_CUDA(h->mem.alloc(&h->d_audio, (size_t)C * h->audio_cap, false));
   }
-  if (raw_bytes > h->raw_cap) {
-    FMR_CUDA(cudaDeviceSynchronize());
-    FMR_CUDA(h->mem.alloc(&h->d_raw, raw_bytes, false));
-    h->raw_cap = raw_bytes;
+  if (raw_bytes > 0 && !h->d_raw) {
+    // once, for the widest file format (cf32: 8 bytes per IQ sample): a handle that alternates formats never reallocates
+    h->raw_cap = (size_t)C * h->cfg.max_samples_per_call * 8;
+    FMR_CUDA(h->mem.alloc(&h->d_raw, h->raw_cap, false));
   }
+  if (raw_bytes > h->raw_cap) return fail(FMR_ERR_CAPACITY, "raw staging buffer too small for this call");
   if (want_sink && !h->d_levels) {
     FMR_CUDA(h->mem.alloc(&h->d_out, (size_t)C * h->audio_cap * 8, false));
     FMR_CUDA(h->mem.alloc(&h->d_levels, (size_t)C * h->cfg.max_blocks_per_call));

@@ -10,7 +10,6 @@
 #include "fmr_host.cuh"
 #include "fmr_io.cuh"
 #include "fmr_mpf.cuh"
-#include "fmr_partition.cuh"
 
 namespace fmr {
 thread_local std::string g_err;
@@ -20,61 +19,11 @@ using namespace fmr;
 
 constexpr int kMaxHostChunks = 8;       // time chunks of fmr_fm_process_host's copy/compute pipeline
 constexpr int kHostChunkMinBlocks = 16; // a chunk is at least this many source blocks
-#define kMaxTimeChunks 8                // time chunks of the pipeline inside process_device
-constexpr int kTimeChunkMinBlocks = 32; // a time chunk is at least this many source blocks
-constexpr int kMaxGroups = 4;  // streams owned by the handle
-constexpr int kGroupMin = 1 << 28; // channel groups are disabled: measured slower (all groups hit their serial phase together)
-
-// Debug timeline (FMR_TRACE=1): start/stop events around every launch group of the time-chunk
-// pipeline, printed relative to the fork event after the call has drained.
-struct Trace {
-  struct Item {
-    const char *name;
-    int chunk;
-    cudaEvent_t a, b;
-  };
-  bool on = false;
-  std::vector<Item> items;
-  cudaEvent_t origin = nullptr;
-  void begin(const char *name, int chunk, cudaStream_t st) {
-    if (!on) return;
-    Item it{name, chunk, nullptr, nullptr};
-    cudaEventCreate(&it.a);
-    cudaEventCreate(&it.b);
-    cudaEventRecord(it.a, st);
-    items.push_back(it);
-  }
-  void end(cudaStream_t st) {
-    if (!on) return;
-    cudaEventRecord(items.back().b, st);
-  }
-  void dump() {
-    if (!on) return;
-    for (auto &it : items) {
-      float t0 = 0, t1 = 0;
-      cudaEventSynchronize(it.b);
-      cudaEventElapsedTime(&t0, origin, it.a);
-      cudaEventElapsedTime(&t1, origin, it.b);
-      fprintf(stderr, "[fmr trace] chunk %d %-10s %8.3f -> %8.3f ms\n", it.chunk, it.name, t0, t1);
-      cudaEventDestroy(it.a);
-      cudaEventDestroy(it.b);
-    }
-    items.clear();
-  }
-};
 
 struct fmr_fm {
   fmr_fm_config cfg;
-  Trace trace;
-  SmPartition part;       // FMR_SERIAL_SMS > 0: private SMs for the serial kernels (green contexts)
-  cudaEvent_t ev_p[kMaxTimeChunks][5] = {{nullptr}};
-  int max_time_chunks = 1; // FMR_TIME_CHUNKS: the two-stream pipeline is off by default
-  int chunk_min_blocks = 32;
-  int want_serial_sms = 0;
-  bool serial_v2 = true;  // FMR_SERIAL_V2=0: the first-generation AGC / PLL kernels
   bool core_fused = true; // FMR_CORE_FUSED=0: AGC / discriminator / PLL as separate launches
-  bool fused_chunks = false; // FMR_FUSED_CHUNKS=1: keep the fused core inside the time-chunk pipeline
-  int rot_sms = 148;      // FMR_CORE_ROT=0 disables the per-CTA rotation of warp roles in the fused core
+  int rot_sms = 148;      // SM count: CTAs that share an SM rotate the warp roles of the fused core
   int C = 0;
   const ChainDesc *ifc = nullptr; // null when input_rate == 384000 (no IfResampler, main.cpp:778)
   const ChainDesc *auc = nullptr;
@@ -104,8 +53,6 @@ struct fmr_fm {
   double *d_pilotcut = nullptr;
   float *d_atan = nullptr;
   MpfDev mpf;
-  cudaStream_t gstream[kMaxGroups] = {nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[kMaxGroups] = {nullptr}, ev_chunk[kMaxTimeChunks] = {nullptr};
   Prof prof;
   int p_hist = -1, p_fmf = -1, p_core = -1, p_agc = -1, p_mpf = -1, p_core2 = -1, p_pcut = -1, p_tail = -1, p_fused = -1;
   FmCoreParams core;
@@ -182,27 +129,6 @@ static fmr_status fm_build(fmr_fm *h) {
   if (!h->auc) return fail(FMR_ERR_UNSUPPORTED, "audio resampler tables missing");
   FMR_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   FMR_CUDA(h->slots.init(4 * sizeof(uint32_t) * (size_t)max_blocks));
-  int prio_least = 0, prio_greatest = 0;
-  FMR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-  for (int g = 0; g < kMaxGroups; g++) {
-    // gstream[1] carries the latency-bound serial kernels of the time-chunk pipeline: it gets the
-    // highest priority so that its few small CTAs are placed as soon as resources free up instead
-    // of queueing behind the tens of thousands of CTAs of the front-end kernels on gstream[0].
-    FMR_CUDA(cudaStreamCreateWithPriority(&h->gstream[g], cudaStreamNonBlocking,
-                                          (g == 1) ? prio_greatest : prio_least));
-    FMR_CUDA(cudaEventCreateWithFlags(&h->ev_join[g], cudaEventDisableTiming));
-  }
-  FMR_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-  FMR_CUDA(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
-  for (int k = 0; k < kMaxTimeChunks; k++) {
-    FMR_CUDA(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
-    for (int q = 0; q < 5; q++) FMR_CUDA(cudaEventCreateWithFlags(&h->ev_p[k][q], cudaEventDisableTiming));
-  }
-  if (h->want_serial_sms > 0 && h->max_time_chunks > 1) {
-    FMR_CUDA(cudaFree(0));
-    h->part.init(cfg.device, h->want_serial_sms, h->trace.on);
-  }
-
   int64_t max384 = max_in + 8;
   if (h->ifc) {
     fmr_status s = h->ifres.init(h->ifc, C, max_in, true, h->mem);
@@ -356,25 +282,10 @@ extern "C" fmr_status fmr_fm_create(const fmr_fm_config *cfg, fmr_fm **out) {
   }
   fmr_fm *h = new fmr_fm();
   h->cfg = *cfg;
-  if (const char *e = getenv("FMR_TRACE")) h->trace.on = atoi(e) != 0;
-  if (const char *e = getenv("FMR_TIME_CHUNKS")) h->max_time_chunks = std::max(1, std::min(atoi(e), kMaxTimeChunks));
-  if (const char *e = getenv("FMR_CHUNK_MIN_BLOCKS")) h->chunk_min_blocks = std::max(1, atoi(e));
-  h->want_serial_sms = 0;
-  if (const char *e = getenv("FMR_SERIAL_SMS")) h->want_serial_sms = std::max(0, atoi(e));
-  if (const char *e = getenv("FMR_SERIAL_V2")) h->serial_v2 = atoi(e) != 0;
   if (const char *e = getenv("FMR_CORE_FUSED")) h->core_fused = atoi(e) != 0;
-  if (const char *e = getenv("FMR_FUSED_CHUNKS")) h->fused_chunks = atoi(e) != 0;
-  if (h->fused_chunks && !Resampler<float>::env_off("FMR_CORE_CARVEOUT")) {
-    // Kernels that want different shared-memory carve-outs do not share an SM: ask for the same (maximum)
-    // carve-out the front-end kernels need, so that core CTAs can be placed beside them.
-    cudaFuncSetAttribute(k_fm_core_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  }
   {
     int sms = fmr_device_sm_count(cfg->device);
     h->rot_sms = sms > 0 ? sms : 148;
-    if (const char *e = getenv("FMR_CORE_ROT")) {
-      if (atoi(e) == 0) h->rot_sms = 1 << 30;
-    }
   }
   fmr_status s = fm_build(h);
   if (s != FMR_OK) {
@@ -394,14 +305,6 @@ extern "C" void fmr_fm_destroy(fmr_fm *h) {
   h->mem.release();
   h->slots.release();
   h->prof.release();
-  for (int g = 0; g < kMaxGroups; g++) {
-    if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
-    if (h->ev_join[g]) cudaEventDestroy(h->ev_join[g]);
-  }
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  for (int k = 0; k < kMaxTimeChunks; k++) {
-    if (h->ev_chunk[k]) cudaEventDestroy(h->ev_chunk[k]);
-  }
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
   for (int k = 0; k < kMaxHostChunks; k++) {
@@ -522,193 +425,104 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
   }
   int launches = 0;
   Prof &pf = h->prof;
-  pf.reset();
+  // one profile per public call: a host call's chunks accumulate into it (fmr_fm_stage_times)
+  if (!h->in_host_call || h->host_b0 == 0) pf.reset();
   const int64_t t0 = h->cum384, t1 = h->cum384 + n384;
   const int64_t j0 = h->cum48;
-  // ---- time chunks. The serial recurrences (AGC, PLL, DC block) are latency bound and take the
-  // same time for 1 or 4096 channels; to hide them the call is cut into a few chunks of blocks and
-  // run as a two-stream pipeline: stream A does the front end (half-band cascade, FFT low-pass,
-  // polyphase bank) of chunk k+1 while stream B does the 384 kHz core and the audio tail of chunk k.
-  int n_chunks = 1;
-  if (!pf.on && !h->sink_on && n_blocks >= 2 * (uint32_t)h->chunk_min_blocks) {
-    n_chunks = (int)(n_blocks / h->chunk_min_blocks);
-    if (n_chunks > h->max_time_chunks) n_chunks = h->max_time_chunks;
-    if (n_chunks < 1) n_chunks = 1;
-  }
-  Trace &tr = h->trace;
-  std::vector<uint32_t> cb(n_chunks + 1);
-  for (int k = 0; k <= n_chunks; k++) cb[k] = (uint32_t)((uint64_t)n_blocks * k / n_chunks);
-  // chunk-relative call tables (what the kernels walk); e384/e48 themselves stay absolute on the host
-  uint32_t *rel384 = tab + 2 * (size_t)h->cfg.max_blocks_per_call;
-  uint32_t *rel48 = rel384 + h->cfg.max_blocks_per_call;
-  for (int k = 0; k < n_chunks; k++) {
-    const uint32_t base384 = cb[k] ? e384[cb[k] - 1] : 0, base48 = cb[k] ? e48[cb[k] - 1] : 0;
-    for (uint32_t b = cb[k]; b < cb[k + 1]; b++) {
-      rel384[b] = e384[b] - base384;
-      rel48[b] = e48[b] - base48;
-    }
-  }
-  FMR_CUDA(cudaMemcpyAsync(h->d_e384, rel384, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
-  FMR_CUDA(cudaMemcpyAsync(h->d_e48, rel48, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
+  // The call is one straight pipeline on the caller's stream: front end -> [IF filter] -> 384 kHz core -> audio
+  // resamplers -> pilot cut -> DC block + matrix. (Two-stream pipelines over time chunks or channel groups were measured in
+  // rounds 1 and 2 and are slower: chunking inflates every stage by more than the overlap hides, profiles/README.md.)
+  FMR_CUDA(cudaMemcpyAsync(h->d_e384, e384, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
+  FMR_CUDA(cudaMemcpyAsync(h->d_e48, e48, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
   h->slots.commit(slot, st);
-  // sA: front end; sB: parallel kernels after it; sS: the serial recurrences. Without an SM
-  // partition sS == sB (one in-order stream, no extra events needed).
-  // sG / sL / sT: AGC, PLL and tail each get their own in-order stream on the serial partition, so
-  // that AGC of chunk k+1, PLL of chunk k and the tail of chunk k-1 form a pipeline.
-  cudaStream_t sA = st, sB = st, sU = st, sG = st, sL = st, sT = st;
-  const bool parted = (n_chunks > 1 && h->part.ok);
-  if (n_chunks > 1) {
-    sA = parted ? h->part.s_front : h->gstream[0];
-    sB = parted ? h->part.s_post : h->gstream[1];
-    sU = parted ? h->part.s_post2 : sB;
-    sG = parted ? h->part.s_serial : sB;
-    sL = parted ? h->part.s_serial2 : sB;
-    sT = parted ? h->part.s_serial3 : sB;
-    FMR_CUDA(cudaEventRecord(h->ev_fork, st));
-    FMR_CUDA(cudaStreamWaitEvent(sA, h->ev_fork, 0));
-    FMR_CUDA(cudaStreamWaitEvent(sB, h->ev_fork, 0));
-    if (parted) {
-      FMR_CUDA(cudaStreamWaitEvent(sU, h->ev_fork, 0));
-      FMR_CUDA(cudaStreamWaitEvent(sG, h->ev_fork, 0));
-      FMR_CUDA(cudaStreamWaitEvent(sL, h->ev_fork, 0));
-      FMR_CUDA(cudaStreamWaitEvent(sT, h->ev_fork, 0));
-    }
-  }
-  // hand-over between sB and sS (only when they differ)
-  auto hop = [&](cudaStream_t from, cudaStream_t to, cudaEvent_t ev) -> cudaError_t {
-    if (from == to) return cudaSuccess;
-    cudaError_t e = cudaEventRecord(ev, from);
-    if (e != cudaSuccess) return e;
-    return cudaStreamWaitEvent(to, ev, 0);
-  };
-  if (tr.on) {
-    if (!tr.origin) cudaEventCreate(&tr.origin);
-    cudaEventRecord(tr.origin, st);
-  }
   h->ifres.gc0 = 0;
   h->ifres.gcn = C;
   h->aures.gc0 = 0;
   h->aures.gcn = C;
   const uint32_t flag_b0 = h->in_host_call ? h->host_b0 : 0;
   if (!h->in_host_call) h->last_chunks.clear();
-  int64_t in_off = 0;
-  for (int k = 0; k < n_chunks; k++) {
-    const uint32_t b0 = cb[k], nb = cb[k + 1] - cb[k];
-    int64_t n_in = 0;
-    for (uint32_t b = b0; b < b0 + nb; b++) n_in += block_len[b];
-    const uint32_t s384 = b0 ? e384[b0 - 1] : 0, s48 = b0 ? e48[b0 - 1] : 0;
-    const uint32_t n384k = e384[b0 + nb - 1] - s384, n48k = e48[b0 + nb - 1] - s48;
-    const int64_t t0k = t0 + s384, j0k = j0 + s48;
-    const uint32_t *d_e384 = h->d_e384 + b0, *d_e48 = h->d_e48 + b0;
-    uint8_t *d_flags = h->d_flags + (size_t)C * (flag_b0 + b0);
-    float *d_stats = h->d_stats + (size_t)C * b0 * 3;
-    h->last_chunks.push_back(std::make_pair(flag_b0 + b0, nb));
-    // ---- stream A: Fs/4 shift + IF resampler -> r_if[t0k, t0k + n384k)
-    InSrc<float2> src;
-    src.lin = reinterpret_cast<const float2 *>(d_iq);
-    src.stride = iq_stride;
-    src.fmt = h->iq_fmt;
-    src.hist = h->hist[h->hist_cur];
-    src.start = h->cum_in;
-    src.n_new = in_off + n_in; // samples of this call readable so far
-    src.ring = Ring<float2>{nullptr, 0};
-    if (h->ifc) {
-      int64_t o0, o1;
-      tr.begin("frontend", k, sA);
-      s = h->ifres.run(src, n_in, h->r_if, h->cfg.fs4_shift, sA, &o0, &o1, &launches, true);
-      tr.end(sA);
-      if (s != FMR_OK) return s;
-      if (o0 != t0k || o1 != t0k + n384k) return fail(FMR_ERR_INVALID, "internal: IF schedule mismatch");
-    } else if (n_in > 0) {
-      HbTaps<float> t;
-      memset(&t, 0, sizeof(t));
-      InSrc<float2> s2 = src;
-      dim3 grid((unsigned)((n_in + kHbTile - 1) / kHbTile), C);
-      pf.begin(h->ifres.p_hb, sA);
-      k_hb_cascade<float, 0, true, 0, 0, 0><<<grid, kHbThreads, Resampler<float>::hb_smem(t, 0), sA>>>(
-          s2, h->r_if, t, t0k, (int)n_in, h->cfg.fs4_shift);
-      pf.end(h->ifres.p_hb, sA);
-      launches++;
-    }
-    in_off += n_in;
-    if (k == n_chunks - 1 && h->ifc && total_in > 0) {
-      pf.begin(h->p_hist, sA);
-      k_save_hist<float2><<<C, 128, 0, sA>>>(src.lin, iq_stride, (int64_t)total_in, h->hist[h->hist_cur],
-                                             h->hist[h->hist_cur ^ 1], h->iq_fmt);
-      pf.end(h->p_hist, sA);
-      launches++;
-    }
-    if (n_chunks > 1) {
-      FMR_CUDA(cudaEventRecord(h->ev_chunk[k], sA));
-      FMR_CUDA(cudaStreamWaitEvent(sB, h->ev_chunk[k], 0));
-      if (parted) FMR_CUDA(cudaStreamWaitEvent(sG, h->ev_chunk[k], 0));
-    }
-    if (n384k == 0) continue;
-    // ---- stream B: optional IF filter (FmDecode.cpp:98-102)
+  h->last_chunks.push_back(std::make_pair(flag_b0, n_blocks));
+  const uint32_t nb = n_blocks;
+  const uint32_t *d_e384 = h->d_e384, *d_e48 = h->d_e48;
+  uint8_t *d_flags = h->d_flags + (size_t)C * flag_b0;
+  float *d_stats = h->d_stats;
+  // ---- Fs/4 shift + IF resampler -> r_if[t0, t1)
+  InSrc<float2> src;
+  src.lin = reinterpret_cast<const float2 *>(d_iq);
+  src.stride = iq_stride;
+  src.fmt = h->iq_fmt;
+  src.hist = h->hist[h->hist_cur];
+  src.start = h->cum_in;
+  src.n_new = (int64_t)total_in;
+  src.ring = Ring<float2>{nullptr, 0};
+  if (h->ifc) {
+    int64_t o0, o1;
+    s = h->ifres.run(src, (int64_t)total_in, h->r_if, h->cfg.fs4_shift, st, &o0, &o1, &launches, true);
+    if (s != FMR_OK) return s;
+    if (o0 != t0 || o1 != t1) return fail(FMR_ERR_INVALID, "internal: IF schedule mismatch");
+  } else if (total_in > 0) {
+    HbTaps<float> t;
+    memset(&t, 0, sizeof(t));
+    dim3 grid((unsigned)((total_in + kHbTile - 1) / kHbTile), C);
+    pf.begin(h->ifres.p_hb, st);
+    k_hb_cascade<float, 0, true, 0, 0, 0><<<grid, kHbThreads, Resampler<float>::hb_smem(t, 0), st>>>(
+        src, h->r_if, t, t0, (int)total_in, h->cfg.fs4_shift);
+    pf.end(h->ifres.p_hb, st);
+    launches++;
+  }
+  if (h->ifc && total_in > 0) {
+    pf.begin(h->p_hist, st);
+    k_save_hist<float2><<<C, 128, 0, st>>>(src.lin, iq_stride, (int64_t)total_in, h->hist[h->hist_cur],
+                                           h->hist[h->hist_cur ^ 1], h->iq_fmt);
+    pf.end(h->p_hist, st);
+    launches++;
+  }
+  if (n384 > 0) {
+    // ---- optional IF filter (FmDecode.cpp:98-102)
     if (h->cfg.fmfilter) {
-      dim3 grid((n384k + kQTile - 1) / kQTile, C);
-      pf.begin(h->p_fmf, sB);
-      k_fir_quirk<float><<<grid, kQThreads, fq_smem(h->fmfilter_taps, sizeof(float2), sizeof(float)), sB>>>(h->r_if, h->r_iff, h->d_fmfilter, h->fmfilter_taps, t0k, (int)n384k,
-                                               d_e384, (int)nb);
-      pf.end(h->p_fmf, sB);
+      dim3 grid((n384 + kQTile - 1) / kQTile, C);
+      pf.begin(h->p_fmf, st);
+      k_fir_quirk<float><<<grid, kQThreads, fq_smem(h->fmfilter_taps, sizeof(float2), sizeof(float)), st>>>(
+          h->r_if, h->r_iff, h->d_fmfilter, h->fmfilter_taps, t0, (int)n384, d_e384, (int)nb);
+      pf.end(h->p_fmf, st);
       launches++;
     }
     // ---- 384 kHz core. Stereo without the multipath filter: one warp-specialised kernel (fmr_core.cuh);
     // otherwise AGC (serial) -> [multipath] -> discriminator + statistics (parallel) -> PLL (serial).
-    const bool fused = h->core_fused && h->cfg.stereo && h->cfg.multipath_stages == 0 && (h->max_time_chunks == 1 || h->fused_chunks);
+    const bool fused = h->core_fused && h->cfg.stereo && h->cfg.multipath_stages == 0;
     dim3 cgrid((C + 31) / 32);
+    const int first = (flag_b0 == 0) ? 1 : 0;
     if (fused) {
-      dim3 fgrid((C + 31) / 32);
-      pf.begin(h->p_fused, sB);
-      tr.begin("core", k, sB);
-      k_fm_core_fused<<<fgrid, kCfThreads, 0, sB>>>(h->r_if, h->r_iff, h->r_384, h->d_state, d_flags, h->d_pps, d_e384,
-                                                   (int)nb, t0k, h->core, h->d_atan, (int)(flag_b0 + b0),
-                                                   (k == 0 && flag_b0 == 0) ? 1 : 0, h->rot_sms);
-      tr.end(sB);
-      pf.end(h->p_fused, sB);
+      pf.begin(h->p_fused, st);
+      k_fm_core_fused<<<cgrid, kCfThreads, 0, st>>>(h->r_if, h->r_iff, h->r_384, h->d_state, d_flags, h->d_pps, d_e384, (int)nb, t0,
+                                                   h->core, h->d_atan, (int)flag_b0, first, h->rot_sms);
+      pf.end(h->p_fused, st);
       launches++;
     } else {
-      if (h->cfg.fmfilter) FMR_CUDA(hop(sB, sG, h->ev_p[k][0]));
-      pf.begin(h->p_agc, sG);
-      tr.begin("agc", k, sG);
-      if (h->serial_v2) {
-        k_fm_agc2<<<cgrid, 32, 0, sG>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
-      } else {
-        k_fm_agc<<<cgrid, 32, 0, sG>>>(h->r_iff, h->r_agc, h->d_state, (int)n384k, t0k, h->core);
-      }
-      tr.end(sG);
-      pf.end(h->p_agc, sG);
+      pf.begin(h->p_agc, st);
+      k_fm_agc2<<<cgrid, 32, 0, st>>>(h->r_iff, h->r_agc, h->d_state, (int)n384, t0, h->core);
+      pf.end(h->p_agc, st);
       launches++;
-      FMR_CUDA(hop(sG, sB, h->ev_p[k][1]));
       Ring<float2> disc_in = h->r_agc;
       if (h->cfg.multipath_stages > 0) {
-        pf.begin(h->p_mpf, sB);
-        h->mpf.run(h->r_agc, h->r_mpf, h->d_state, d_e384, (int)nb, t0k, sB, 0, C);
-        pf.end(h->p_mpf, sB);
+        pf.begin(h->p_mpf, st);
+        h->mpf.run(h->r_agc, h->r_mpf, h->d_state, d_e384, (int)nb, t0, st, 0, C);
+        pf.end(h->p_mpf, st);
         launches++;
         disc_in = h->r_mpf;
       }
-      pf.begin(h->p_core, sB);
+      pf.begin(h->p_core, st);
       {
-        dim3 g1((n384k + 255) / 256, C);
-        k_fm_disc<<<g1, 256, 0, sB>>>(disc_in, h->r_mpx, (int)n384k, t0k, h->core);
+        dim3 g1((n384 + 255) / 256, C);
+        k_fm_disc<<<g1, 256, 0, st>>>(disc_in, h->r_mpx, (int)n384, t0, h->core);
         dim3 g2((nb + 3) / 4, C);
-        k_fm_call_stats<<<g2, 128, 0, sB>>>(h->r_if, h->r_mpx, d_stats, d_e384, (int)nb, t0k);
+        k_fm_call_stats<<<g2, 128, 0, st>>>(h->r_if, h->r_mpx, d_stats, d_e384, (int)nb, t0);
       }
-      pf.end(h->p_core, sB);
-      FMR_CUDA(hop(sB, sL, h->ev_p[k][2]));
-      pf.begin(h->p_core2, sL);
-      tr.begin("pll", k, sL);
-      if (h->serial_v2) {
-        k_fm_pll2<<<cgrid, 32, 0, sL>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
-                                        h->core, h->d_atan, (int)(flag_b0 + b0), (k == 0 && flag_b0 == 0) ? 1 : 0);
-      } else {
-        k_fm_pll<<<cgrid, 32, 0, sL>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0k,
-                                       h->core, h->d_atan, (int)(flag_b0 + b0), (k == 0 && flag_b0 == 0) ? 1 : 0);
-      }
-      tr.end(sL);
-      pf.end(h->p_core2, sL);
-      FMR_CUDA(hop(sL, sU, h->ev_p[k][3]));
+      pf.end(h->p_core, st);
+      pf.begin(h->p_core2, st);
+      k_fm_pll2<<<cgrid, 32, 0, st>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0, h->core,
+                                     h->d_atan, (int)flag_b0, first);
+      pf.end(h->p_core2, st);
       launches += 3;
     }
     // ---- audio resamplers (mono and L-R in lock step, FmDecode.cpp:172-183)
@@ -716,54 +530,30 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
     memset(&asrc, 0, sizeof(asrc));
     asrc.ring = h->r_384;
     int64_t a0, a1;
-    tr.begin("audio", k, sU);
-    s = h->aures.run(asrc, (int64_t)n384k, h->r_48a, 0, sU, &a0, &a1, &launches, true);
-    tr.end(sU);
+    s = h->aures.run(asrc, (int64_t)n384, h->r_48a, 0, st, &a0, &a1, &launches, true);
     if (s != FMR_OK) return s;
-    if (a0 != j0k || a1 != j0k + n48k) return fail(FMR_ERR_INVALID, "internal: audio schedule mismatch");
-    if (n48k > 0) {
+    if (a0 != j0 || a1 != j0 + n48) return fail(FMR_ERR_INVALID, "internal: audio schedule mismatch");
+    if (n48 > 0) {
       // ---- pilot-cut FIR (FmDecode.cpp:190,196) then DC block + matrix
-      dim3 grid((n48k + kQTile - 1) / kQTile, C);
-      pf.begin(h->p_pcut, sU);
-      k_fir_quirk<double><<<grid, kQThreads, fq_smem(127, sizeof(double2), sizeof(double)), sU>>>(h->r_48a, h->r_48b, h->d_pilotcut, 127, j0k, (int)n48k, d_e48, (int)nb);
-      pf.end(h->p_pcut, sU);
-      FMR_CUDA(hop(sU, sT, h->ev_p[k][4]));
-      pf.begin(h->p_tail, sT);
-      k_fm_tail<<<cgrid, 32, 0, sT>>>(h->r_48b, d_audio + (size_t)s48 * w, audio_stride, h->d_state, d_flags, d_e48,
-                                      (int)nb, j0k, h->tail);
-      pf.end(h->p_tail, sT);
+      dim3 grid((n48 + kQTile - 1) / kQTile, C);
+      pf.begin(h->p_pcut, st);
+      k_fir_quirk<double><<<grid, kQThreads, fq_smem(127, sizeof(double2), sizeof(double)), st>>>(h->r_48a, h->r_48b, h->d_pilotcut,
+                                                                                                 127, j0, (int)n48, d_e48, (int)nb);
+      pf.end(h->p_pcut, st);
+      pf.begin(h->p_tail, st);
+      k_fm_tail<<<cgrid, 32, 0, st>>>(h->r_48b, d_audio, audio_stride, h->d_state, d_flags, d_e48, (int)nb, j0, h->tail);
+      pf.end(h->p_tail, st);
       launches += 2;
     }
-    if (h->sink_on && nb > 0) {
+    if (h->sink_on) {
       // ---- output stage of the block loop (main.cpp:977-1002): levels, squelch gain, sink format
       dim3 sg(nb, C);
-      k_audio_sink<<<sg, kSinkThreads, 0, sT>>>(h->r_if, t0k, d_e384, d_audio + (size_t)s48 * w, audio_stride, d_e48, (int)nb,
-                                                h->sink_out + (size_t)s48 * w * out_format_bytes(h->sink.out_fmt),
-                                                h->sink_out_stride, h->d_levels + (size_t)C * (flag_b0 + b0), h->sink);
+      k_audio_sink<<<sg, kSinkThreads, 0, st>>>(h->r_if, t0, d_e384, d_audio, audio_stride, d_e48, (int)nb, h->sink_out,
+                                                h->sink_out_stride, h->d_levels + (size_t)C * flag_b0, h->sink);
       launches++;
     }
   }
-  if (n_chunks > 1) {
-    FMR_CUDA(cudaEventRecord(h->ev_join[0], sA));
-    FMR_CUDA(cudaEventRecord(h->ev_join[1], sB));
-    FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[0], 0));
-    FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[1], 0));
-    if (parted) {
-      FMR_CUDA(cudaEventRecord(h->ev_chunk[0], sU));
-      FMR_CUDA(cudaStreamWaitEvent(st, h->ev_chunk[0], 0));
-      FMR_CUDA(cudaEventRecord(h->ev_join[2], sG));
-      FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[2], 0));
-      FMR_CUDA(cudaEventRecord(h->ev_join[3], sL));
-      FMR_CUDA(cudaStreamWaitEvent(st, h->ev_join[3], 0));
-      FMR_CUDA(cudaEventRecord(h->ev_fork2, sT));
-      FMR_CUDA(cudaStreamWaitEvent(st, h->ev_fork2, 0));
-    }
-  }
   if (h->ifc && total_in > 0) h->hist_cur ^= 1;
-  if (tr.on) {
-    cudaStreamSynchronize(st);
-    tr.dump();
-  }
   FMR_CUDA(cudaGetLastError());
   h->cum_in += (int64_t)total_in;
   h->cum384 += n384;
@@ -792,11 +582,12 @@ static fmr_status fm_ensure_staging(fmr_fm *h, size_t raw_bytes, bool want_sink)
       FMR_CUDA(cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
     }
   }
-  if (raw_bytes > h->raw_cap) {
-    FMR_CUDA(cudaDeviceSynchronize());
-    FMR_CUDA(h->mem.alloc(&h->d_raw, raw_bytes, false));
-    h->raw_cap = raw_bytes;
+  if (raw_bytes > 0 && !h->d_raw) {
+    // once, for the widest file format (S24: 6 bytes per IQ sample): a handle that alternates formats never reallocates
+    h->raw_cap = (size_t)C * h->cfg.max_samples_per_call * 6;
+    FMR_CUDA(h->mem.alloc(&h->d_raw, h->raw_cap, false));
   }
+  if (raw_bytes > h->raw_cap) return fail(FMR_ERR_CAPACITY, "raw staging buffer too small for this call");
   if (want_sink && !h->d_levels) {
     FMR_CUDA(h->mem.alloc(&h->d_out, (size_t)C * h->audio_cap * 8, false));
     FMR_CUDA(h->mem.alloc(&h->d_levels, (size_t)C * h->cfg.max_blocks_per_call));
@@ -888,14 +679,23 @@ static fmr_status fm_process_host_impl(fmr_fm *h, const void *iq_v, size_t iq_st
     h->sink.squelch = oc->squelch_level;
     h->sink_out_stride = h->audio_cap;
   }
+  // On any early return the copies already queued still read `iq` and write `audio`: drain them before the caller gets
+  // its buffers back. (The stream position has then advanced by the chunks that completed; fmr_last_error says why.)
   struct Guard {
     fmr_fm *h;
+    cudaStream_t st;
+    bool drain;
     ~Guard() {
+      if (drain) {
+        cudaStreamSynchronize(h->s_h2d);
+        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(h->s_d2h);
+      }
       h->in_host_call = false;
       h->iq_fmt = 0;
       h->sink_on = false;
     }
-  } guard{h};
+  } guard{h, st, true};
   uint8_t *d_in = direct ? reinterpret_cast<uint8_t *>(h->d_iq) : h->d_raw;
   for (int k = 0; k < n_chunks; k++) {
     const uint32_t b0 = (uint32_t)((uint64_t)n_blocks * k / n_chunks), b1 = (uint32_t)((uint64_t)n_blocks * (k + 1) / n_chunks);
@@ -938,6 +738,7 @@ static fmr_status fm_process_host_impl(fmr_fm *h, const void *iq_v, size_t iq_st
   }
   FMR_CUDA(cudaStreamSynchronize(st));
   FMR_CUDA(cudaStreamSynchronize(h->s_d2h));
+  guard.drain = false;
   h->have_levels = (oc != nullptr);
   return FMR_OK;
 }

@@ -73,9 +73,9 @@ template <int PW, int U_, int TILE, int RS, int PREGS, int CREGS, bool SPLIT = f
   static_assert(kSmemBytes <= 232448, "shared memory budget");
   static_assert(PW * 32 * PREGS + kConsThreads * CREGS <= 65536, "register file");
 };
+// (measured and dropped, profiles/sweep_frontend_variants_r02.jsonl: 8 packed producer warps on tiles of 30 outputs with
+// block steps of 32 or 16 samples - 87 % warm-up, register spills or twice the register moves - 13 % / 21 % slower)
 using CfgA = Cfg<4, 4, 60, 2, 208, 120>;  // 4 producer warps, long tiles (47 % warm-up), cascade block step of 64 samples
-using CfgB = Cfg<8, 2, 30, 1, 168, 88>;   // 8 producer warps (two per scheduler), short tiles (87 % warm-up)
-using CfgC = Cfg<8, 1, 30, 1, 152, 104>;  // the same with the smallest cascade (no spills, more register moves)
 using CfgS = Cfg<8, 4, 60, 2, 128, 128, true>; // 8 producer warps on long tiles: real and imaginary part on two lanes
 
 struct Params {

@@ -130,11 +130,20 @@ struct Prof {
     }
     on = true;
   }
+  float acc[kMax] = {0.f}; // time of earlier launches of the stage within the same public call (host calls run in chunks)
   void reset() {
-    for (int i = 0; i < n; i++) ran[i] = false;
+    for (int i = 0; i < n; i++) {
+      ran[i] = false;
+      acc[i] = 0.f;
+    }
   }
   void begin(int i, cudaStream_t st) {
-    if (on && i >= 0) cudaEventRecord(a[i], st);
+    if (!on || i < 0) return;
+    if (ran[i]) { // the stage already ran in this call: bank its time before the event pair is reused
+      float t = 0.f;
+      if (cudaEventSynchronize(b[i]) == cudaSuccess && cudaEventElapsedTime(&t, a[i], b[i]) == cudaSuccess) acc[i] += t;
+    }
+    cudaEventRecord(a[i], st);
   }
   void end(int i, cudaStream_t st) {
     if (on && i >= 0) {
@@ -150,7 +159,7 @@ struct Prof {
       if (cudaEventSynchronize(b[i]) != cudaSuccess || cudaEventElapsedTime(&t, a[i], b[i]) != cudaSuccess) {
         return fail(FMR_ERR_CUDA, "event timing failed");
       }
-      ms[k] = t;
+      ms[k] = acc[i] + t;
       nm[k] = names[i];
       k++;
     }
@@ -215,19 +224,13 @@ template <typename S> struct Resampler {
   bool fft_tw = false;
   V *d_H16rev = nullptr, *d_iptab = nullptr; // in-place form (fmr_fft_inplace.cuh)
   bool fft_inplace = true;                   // FMR_FFT_INPLACE=0: the Stockham form (k_fir_fft)
-  V *d_H16rev32 = nullptr;                   // spectrum in the digit-reversed order of the radix 32 x 32 x 16 form
-  V *d_H8rev = nullptr, *d_iptab8 = nullptr; // 8192-point in-place form
-  bool fft_inplace8k = false;                // FMR_FFT_INPLACE8K=1: k_fir_fft_ip8k for the fused 8192-point blocks
-  bool fft_epi = false;                      // FMR_FFT_EPI=1: k_fir_fft_ip<512, 512, 1> (polyphase bank in shared memory)
-  bool fft_regcap = false;                   // FMR_FFT_REGCAP=1: k_fir_fft_ip<512, 896> (72 registers; for --handles overlap)
-  bool fft_inplace32 = false;                // FMR_FFT_INPLACE=2: k_fir_fft_ip32 (host-checked, not yet measured)
   bool use_fdr = false;                      // frequency-domain low-pass + resampling (fmr_fdr.cuh); FMR_FDR=0: off
   int fdr_rl = 0;                            // last radix of its inverse transform: 12 (625:192), 15 (125:48), 10 (125:32)
   int fdr_adv_in = 0, fdr_guard_in = 0, fdr_adv_out = 0, fdr_guard_out = 0; // block grid of this chain
   float *d_fdr_Hs = nullptr;
   float2 *d_fdr_tab = nullptr;
   bool use_fe = false;                       // fused persistent front end (fmr_frontend.cuh); FMR_FE=0: off
-  int fe_variant = 0;                        // FMR_FE_VARIANT: 0 = CfgA, 1 = CfgB, 2 = CfgC, 3 = CfgS (fmr_frontend.cuh)
+  int fe_variant = 0;                        // FMR_FE_VARIANT: 0 = CfgA, 1 = CfgS (fmr_frontend.cuh)
   int fe_min_blocks = 2;                     // fewer whole blocks inside the call's buffer: unfused kernels only
   int p_fe = -1;
   typedef CUresult (*TmEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -238,15 +241,11 @@ template <typename S> struct Resampler {
   int64_t fdr_next = 0;                      // first block of the absolute grid that has not been computed yet
   int64_t fdr_out_done = 0;                  // outputs stored so far (beyond fdr_next's blocks: a partial block's head)
   int64_t fdr_hist = 512;                    // output samples before f0 that readers of the output ring may still need
-  int fft_threads = 512;               // FMR_FFT_THREADS=1024: the 32-warp form of the fused 16384-point kernel
   bool use_fft = false;
   bool use_dec2 = false; // double chains with a decimate-by-2 low-pass (audio resampler)
   bool fuse_fi = true;   // FMR_FUSE_FI=0: keep the polyphase bank as its own launch
   bool hb_stream = false; // streaming register-resident half-band cascade (10 MHz chain, cf32 input)
-  int hbs_tile = 0;       // FMR_HBS_TILE: outputs per stream tile (0 = choose by problem size)
-  int hbs_stages = 4;     // FMR_HBS_STAGES: cp.async ring depth (2, 4 or 6)
-  int hbs_l2pf = 0;       // FMR_HBS_L2PF: L2 read-ahead distance in 128-byte chunks (0 = off)
-  int hbs_tma = 1;        // FMR_HBS_TMA: 0 = cp.async (LDGSTS) staging; 1..7 = TMA bulk-copy staging configurations
+  bool hbs_tma = true;    // FMR_HBS_TMA=0: cp.async (LDGSTS) staging instead of TMA bulk copies
   int sm_count = 148;
   int fft_min_out = 0;
 
@@ -307,31 +306,12 @@ template <typename S> struct Resampler {
     FMR_CUDA(e);
     if constexpr (sizeof(S) == sizeof(float)) {
       if (lin && d->n_hb == 3 && hbt.n[0] == 4 && hbt.n[1] == 5 && hbt.n[2] == 8 && !env_off("FMR_HB_STREAM")) {
-        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream<4, 5, 8, kHbsU, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       hbs_smem_bytes(2))));
         FMR_CUDA((cudaFuncSetAttribute(k_hb_stream<4, 5, 8, kHbsU, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        hbs_smem_bytes(4))));
-        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream<4, 5, 8, kHbsU, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       hbs_smem_bytes(6))));
         hb_stream = true;
-        if (const char *ev = getenv("FMR_HBS_TILE")) hbs_tile = atoi(ev);
-        if (const char *ev = getenv("FMR_HBS_STAGES")) hbs_stages = atoi(ev);
-        if (const char *ev = getenv("FMR_HBS_L2PF")) hbs_l2pf = atoi(ev);
-        if (const char *ev = getenv("FMR_HBS_TMA")) hbs_tma = atoi(ev);
+        hbs_tma = !env_off("FMR_HBS_TMA");
         FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 2, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        HbsTma<2>::smem_bytes(3, 4))));
-        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 4, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       HbsTma<4>::smem_bytes(3, 2))));
-        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 2, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       HbsTma<2>::smem_bytes(6, 2))));
-        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 1, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       HbsTma<1>::smem_bytes(6, 4))));
-        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       HbsTma<2>::smem_bytes(2, 4))));
-        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       HbsTma<2>::smem_bytes(4, 3))));
-        FMR_CUDA((cudaFuncSetAttribute(k_hb_stream_tma<4, 5, 8, kHbsU, 2, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       HbsTma<2>::smem_bytes(3, 2))));
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -426,66 +406,11 @@ template <typename S> struct Resampler {
           FMR_CUDA(mem.alloc(&d_iptab, tb.size(), false));
           FMR_CUDA(cudaMemcpy(d_iptab, tb.data(), sizeof(V) * tb.size(), cudaMemcpyHostToDevice));
           FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
-          FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
-          if (const char *ev = getenv("FMR_FFT_REGCAP")) fft_regcap = atoi(ev) != 0;
-          if (fft_regcap) { // set up only on request (not measured yet)
-            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<512, 896>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpSmemBytes)));
-          }
-          if (const char *ev = getenv("FMR_FFT_INPLACE")) {
-            fft_inplace = atoi(ev) != 0;
-            fft_inplace32 = atoi(ev) == 2;
-          }
-          if (const char *ev = getenv("FMR_FFT_EPI")) fft_epi = atoi(ev) != 0;
-          if (fft_epi && d->has_fi && d->fi.outstep <= kEpiMaxRows && (d->fi.flen == 18 || d->fi.flen == 24)) {
-            // polyphase epilogue with the bank in shared memory (set up only on request: not measured yet)
-            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip<512, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIpEpiSmemBytes)));
-          } else {
-            fft_epi = false;
-          }
-          if (const char *ev = getenv("FMR_FFT_INPLACE8K")) fft_inplace8k = atoi(ev) != 0;
-          if (fft_inplace8k) {
-            // 8192-point in-place form for the remainder / short-filter blocks (set up only on request: not measured yet)
-            std::vector<std::complex<double>> h8(8192, std::complex<double>(0.0, 0.0));
-            for (int i = 0; i < d->bc.klen; i++) h8[i] = d->bc.taps[i];
-            host_fft(h8);
-            std::vector<V> hr8(8192), tb8(ipfft8k::kTabLen);
-            for (int pz = 0; pz < 8192; pz++) {
-              const std::complex<double> hv = h8[ipfft8k::freq_of_pos(pz)] / 8192.0;
-              hr8[pz].x = (S)hv.real();
-              hr8[pz].y = (S)hv.imag();
-            }
-            for (int q = 0; q < 128; q++) {
-              tb8[q] = wv(128.0 * q, 8192.0);
-              tb8[128 + q] = wv((double)q, 8192.0);
-            }
-            FMR_CUDA(mem.alloc(&d_H8rev, hr8.size(), false));
-            FMR_CUDA(cudaMemcpy(d_H8rev, hr8.data(), sizeof(V) * hr8.size(), cudaMemcpyHostToDevice));
-            FMR_CUDA(mem.alloc(&d_iptab8, tb8.size(), false));
-            FMR_CUDA(cudaMemcpy(d_iptab8, tb8.data(), sizeof(V) * tb8.size(), cudaMemcpyHostToDevice));
-            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip8k, cudaFuncAttributeMaxDynamicSharedMemorySize, kIp8kSmemBytes)));
-          }
-          if (fft_inplace32) {
-            // radix 32 x 32 x 16 form: its own digit-reversed order, the two-level table only. Set up only on request:
-            // the kernel has not run on a GPU yet, nothing of it may touch the default path
-            std::vector<V> hr32(kN);
-            for (int pz = 0; pz < kN; pz++) {
-              const std::complex<double> hv = hc[ipfft32::freq_of_pos(pz)] / (double)kN;
-              hr32[pz].x = (S)hv.real();
-              hr32[pz].y = (S)hv.imag();
-            }
-            FMR_CUDA(mem.alloc(&d_H16rev32, hr32.size(), false));
-            FMR_CUDA(cudaMemcpy(d_H16rev32, hr32.data(), sizeof(V) * hr32.size(), cudaMemcpyHostToDevice));
-            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip32<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIp32SmemBytes)));
-            FMR_CUDA((cudaFuncSetAttribute(k_fir_fft_ip32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIp32EpiSmemBytes)));
-          }
+          fft_inplace = !env_off("FMR_FFT_INPLACE");
         }
-        FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<S, 16384, true, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       FftCfg<S, 16384>::kSmemBytesTw)));
-        if (const char *ev = getenv("FMR_FFT_THREADS")) fft_threads = atoi(ev);
       }
       use_fft = true;
       fft_min_out = (sizeof(S) == sizeof(float)) ? kFftMinOutF32 : kFftMinOutF64;
-      if (const char *e = getenv("FMR_FFT_MIN_OUT")) fft_min_out = atoi(e);
       fuse_fi = !env_off("FMR_FUSE_FI");
     }
     if constexpr (sizeof(S) == sizeof(float)) {
@@ -523,7 +448,7 @@ template <typename S> struct Resampler {
               qr == cudaDriverEntryPointSuccess) {
             tm_encode = reinterpret_cast<TmEncodeFn>(fn);
             CUtensorMap probe;
-            if (const char *ev = getenv("FMR_FE_VARIANT")) fe_variant = std::min(3, std::max(0, atoi(ev)));
+            if (const char *ev = getenv("FMR_FE_VARIANT")) fe_variant = (atoi(ev) == 1) ? 1 : 0;
             if (fe_encode(&probe, r_hb.base, 1, 1, (size_t)fe::kBlockIn)) {
               FMR_CUDA(fe_dispatch([&](auto cf) {
                 using CF = decltype(cf);
@@ -574,9 +499,7 @@ template <typename S> struct Resampler {
   static void fft_plan(int n, int per16, int per8, bool have16, int *nb16, int *nb8) {
     *nb16 = 0;
     *nb8 = 0;
-    const char *fn = getenv("FMR_FFT_N");
-    const bool force8 = fn && atoi(fn) == 8192;
-    if (!have16 || per16 <= 0 || force8) {
+    if (!have16 || per16 <= 0) {
       *nb8 = (n + per8 - 1) / per8;
       return;
     }
@@ -645,29 +568,9 @@ template <typename S> struct Resampler {
         fz.tail_hi = last ? b1 : 0;
         fz.tail_lo = last ? b1 - (2 * d->fi.flen + 16) : 0;
         dim3 grid(nb16, gcn);
-        if (fft_inplace && fft_inplace32) {
-          fz.twtab = d_iptab; // its first 256 entries are the two-level table of W_N
-          if (fft_epi) {
-            k_fir_fft_ip32<1><<<grid, 512, kIp32EpiSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev32), klen, avail, fz);
-          } else {
-            k_fir_fft_ip32<0><<<grid, 512, kIp32SmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev32), klen, avail, fz);
-          }
-        } else if (fft_inplace) {
+        if (fft_inplace) {
           fz.twtab = d_iptab;
-          if (fft_epi) {
-            k_fir_fft_ip<512, 512, 1><<<grid, 512, kIpEpiSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
-          } else if (fft_regcap) {
-            k_fir_fft_ip<512, 896><<<grid, 512, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
-          } else if (fft_threads == 1024) {
-            k_fir_fft_ip<1024><<<grid, 1024, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
-          } else {
-            k_fir_fft_ip<512><<<grid, 512, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
-          }
-        } else if (fft_tw && fft_threads == 1024) {
-          // 32 warps per SM on the same 16384-point block: one butterfly set per thread, 64 registers
-          fz.twtab = d_twtab;
-          k_fir_fft<S, 16384, true, true, 1024><<<grid, 1024, FftCfg<S, 16384>::kSmemBytesTw, st>>>(in, o, d_H16, klen, 1, 0,
-                                                                                                  0, avail, lq16, fz);
+          k_fir_fft_ip<512><<<grid, 512, kIpSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H16rev), klen, avail, fz);
         } else if (fft_tw) {
           fz.twtab = d_twtab;
           k_fir_fft<S, 16384, true, true><<<grid, kFftThreads, FftCfg<S, 16384>::kSmemBytesTw, st>>>(in, o, d_H16, klen, 1,
@@ -687,14 +590,6 @@ template <typename S> struct Resampler {
       fz.tail_hi = b1;
       fz.tail_lo = b1 - (2 * d->fi.flen + 16);
       dim3 grid(nb8, gcn);
-      if constexpr (sizeof(S) == sizeof(float)) {
-        if (fft_inplace8k) {
-          fz.twtab = d_iptab8;
-          k_fir_fft_ip8k<<<grid, 256, kIp8kSmemBytes, st>>>(in, o, reinterpret_cast<const float2 *>(d_H8rev), klen, avail, fz);
-          launched++;
-          return launched;
-        }
-      }
       k_fir_fft<S, 8192, true><<<grid, kFftThreads, FftCfg<S, 8192>::kSmemBytes, st>>>(in, o, d_H8, klen, 1, 0, 0, avail,
                                                                                      lq8, fz);
       launched++;
@@ -702,9 +597,7 @@ template <typename S> struct Resampler {
     return launched;
   }
   template <typename F> auto fe_dispatch(F &&f) const {
-    if (fe_variant == 1) return f(fe::CfgB{});
-    if (fe_variant == 2) return f(fe::CfgC{});
-    if (fe_variant == 3) return f(fe::CfgS{});
+    if (fe_variant == 1) return f(fe::CfgS{});
     return f(fe::CfgA{});
   }
   int fe_in_span() const {
@@ -792,12 +685,9 @@ template <typename S> struct Resampler {
     a += (a & 1);
     const int64_t avail = h1 - a;
     if (avail < 64) return h0;
-    int tile = hbs_tile;
-    if (tile <= 0) {
-      // largest tile that still fills every SM three CTAs deep; warm-up costs 2*kWarm outputs per tile
-      tile = 512;
-      while (tile > 128 && (int64_t)gcn * (avail / tile) < (int64_t)sm_count * 3 * kHbsThreads) tile >>= 1;
-    }
+    // largest tile that still fills every SM three CTAs deep; warm-up costs 2*kWarm outputs per tile
+    int tile = 512;
+    while (tile > 128 && (int64_t)gcn * (avail / tile) < (int64_t)sm_count * 3 * kHbsThreads) tile >>= 1;
     tile = std::max(2 * kHbsU, tile / (2 * kHbsU) * (2 * kHbsU));
     const int nbs = (D::kWarm + tile / 2 + kHbsU - 1) / kHbsU;
     // last chunk (exclusive) a tile starting at output m touches: (m + A3)/2 - kWarm + nbs*U
@@ -823,26 +713,9 @@ template <typename S> struct Resampler {
       P.t3[k] = hbt.t[2][k];
     }
     const int grid = (P.n_streams + kHbsThreads - 1) / kHbsThreads;
-    P.l2_prefetch = hbs_l2pf;
-    auto blocks = [&](int threads) { return (P.n_streams + threads - 1) / threads; };
-    if (hbs_tma == 1) {
-      k_hb_stream_tma<4, 5, 8, kHbsU, 2, 3, 4><<<blocks(128), 128, HbsTma<2>::smem_bytes(3, 4), st>>>(P, o);
-    } else if (hbs_tma == 2) {
-      k_hb_stream_tma<4, 5, 8, kHbsU, 4, 3, 2><<<blocks(64), 64, HbsTma<4>::smem_bytes(3, 2), st>>>(P, o);
-    } else if (hbs_tma == 3) {
-      k_hb_stream_tma<4, 5, 8, kHbsU, 2, 6, 2><<<blocks(64), 64, HbsTma<2>::smem_bytes(6, 2), st>>>(P, o);
-    } else if (hbs_tma == 4) {
-      k_hb_stream_tma<4, 5, 8, kHbsU, 1, 6, 4><<<blocks(128), 128, HbsTma<1>::smem_bytes(6, 4), st>>>(P, o);
-    } else if (hbs_tma == 5) {
-      k_hb_stream_tma<4, 5, 8, kHbsU, 2, 2, 4><<<blocks(128), 128, HbsTma<2>::smem_bytes(2, 4), st>>>(P, o);
-    } else if (hbs_tma == 6) {
-      k_hb_stream_tma<4, 5, 8, kHbsU, 2, 4, 3><<<blocks(96), 96, HbsTma<2>::smem_bytes(4, 3), st>>>(P, o);
-    } else if (hbs_tma == 7) {
-      k_hb_stream_tma<4, 5, 8, kHbsU, 2, 3, 2><<<blocks(64), 64, HbsTma<2>::smem_bytes(3, 2), st>>>(P, o);
-    } else if (hbs_stages <= 2) {
-      k_hb_stream<4, 5, 8, kHbsU, 2><<<grid, kHbsThreads, hbs_smem_bytes(2), st>>>(P, o);
-    } else if (hbs_stages >= 6) {
-      k_hb_stream<4, 5, 8, kHbsU, 6><<<grid, kHbsThreads, hbs_smem_bytes(6), st>>>(P, o);
+    P.l2_prefetch = 0;
+    if (hbs_tma) {
+      k_hb_stream_tma<4, 5, 8, kHbsU, 2, 3, 4><<<(P.n_streams + 127) / 128, 128, HbsTma<2>::smem_bytes(3, 4), st>>>(P, o);
     } else {
       k_hb_stream<4, 5, 8, kHbsU, 4><<<grid, kHbsThreads, hbs_smem_bytes(4), st>>>(P, o);
     }

@@ -675,64 +675,6 @@ __global__ void __launch_bounds__(kQThreads)
 }
 
 // ---------------------------------------------------------------------------------------
-// fast_atan2f of the reference (include/Utility.h:236-304; GNU Radio table method). It sits
-// inside the PLL feedback loop, so it is replicated operation for operation.
-__device__ __forceinline__ float fast_atan2f_dev(float y, float x, const float *__restrict__ tbl) {
-  const float y_abs = fabsf(y);
-  const float x_abs = fabsf(x);
-  if (!((y_abs > 0.0f) || (x_abs > 0.0f))) return 0.0f;
-  float z;
-  if (y_abs < x_abs) {
-    z = y_abs / x_abs;
-  } else {
-    z = x_abs / y_abs;
-  }
-  float base_angle;
-  // reference: `z < TAN_MAP_RES` with the double literal 0.003921569, i.e. (double)z < T. For a float
-  // z that is equivalent to z < Tf with Tf the smallest float >= T (0x3b808082 = 0.00392156932...),
-  // which avoids a float->double conversion on the PLL's critical path.
-  if (z < __int_as_float(0x3b808082)) {
-    base_angle = z;
-  } else {
-    float alpha = z * 255.0f;
-    const int index = ((int)alpha) & 0xff;
-    alpha -= (float)index;
-    base_angle = tbl[index];
-    base_angle += (tbl[index + 1] - tbl[index]) * alpha;
-  }
-  float angle;
-  if (x_abs > y_abs) {
-    if (x >= 0.0f) {
-      angle = (y >= 0.0f) ? base_angle : -base_angle;
-    } else {
-      angle = 3.14159265358979323846f;
-      if (y >= 0.0f) {
-        angle -= base_angle;
-      } else {
-        angle = base_angle - angle;
-      }
-    }
-  } else {
-    if (y >= 0.0f) {
-      angle = 1.57079632679489661923f;
-      if (x >= 0.0f) {
-        angle -= base_angle;
-      } else {
-        angle += base_angle;
-      }
-    } else {
-      angle = -1.57079632679489661923f;
-      if (x >= 0.0f) {
-        angle += base_angle;
-      } else {
-        angle -= base_angle;
-      }
-    }
-  }
-  return angle;
-}
-
-// ---------------------------------------------------------------------------------------
 // Per-channel persistent state of the FM decoder (reference: FmDecoder members,
 // include/FmDecode.h:127-163, and the members of the blocks it owns).
 struct FmChanState {
@@ -787,52 +729,13 @@ struct FmCoreParams {
 
 // The 384 kHz core (reference: FmDecoder::process FmDecode.cpp:85-183 up to the audio
 // resamplers) is split by data dependence into three launches:
-//   k_fm_agc  — IfSimpleAgc, a float recurrence of a handful of instructions per sample,
+//   k_fm_agc2 — IfSimpleAgc, a float recurrence of a handful of instructions per sample,
 //               one lane per channel;
 //   k_fm_disc — everything between the recurrences that is parallel in time: phase
 //               discriminator, and the per-call statistics (IF RMS, baseband mean/RMS);
-//   k_fm_pll  — PilotPhaseLock + L-R mix + both deemphasis filters, one lane per channel.
-// With the multipath filter enabled k_mpf runs between k_fm_agc and k_fm_disc.
+//   k_fm_pll2 — PilotPhaseLock + L-R mix + both deemphasis filters, one lane per channel.
+// With the multipath filter enabled k_mpf runs between k_fm_agc2 and k_fm_disc.
 constexpr int kCoreChunk = 8;
-
-static __global__ void k_fm_agc(Ring<float2> iq_in, Ring<float2> iq_out, FmChanState *__restrict__ st, int n_total,
-                         int64_t t0, FmCoreParams P) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= P.n_channels) return;
-  float g = st[c].agc_gain;
-  // register double-buffer: the loads of chunk k+1 are in flight while chunk k runs the recurrence
-  float2 nxt[kCoreChunk];
-#pragma unroll
-  for (int u = 0; u < kCoreChunk; u++) nxt[u] = (u < n_total) ? iq_in.ld(c, t0 + u) : make_float2(0.f, 0.f);
-  for (int i0 = 0; i0 < n_total; i0 += kCoreChunk) {
-    float2 xin[kCoreChunk];
-#pragma unroll
-    for (int u = 0; u < kCoreChunk; u++) xin[u] = nxt[u];
-#pragma unroll
-    for (int u = 0; u < kCoreChunk; u++) {
-      const int i = i0 + kCoreChunk + u;
-      nxt[u] = (i < n_total) ? iq_in.ld(c, t0 + i) : make_float2(0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < kCoreChunk; u++) {
-      if (i0 + u >= n_total) break;
-      // IfSimpleAgc::process (IfSimpleAgc.cpp:37-57)
-      float2 x2;
-      x2.x = xin[u].x * g;
-      x2.y = xin[u].y * g;
-      const float nrm = x2.x * x2.x + x2.y * x2.y;
-      const float z = (float)(1.0 + ((double)P.agc_rate * (1.0 - (double)nrm)));
-      g *= z;
-      if (!isfinite(g)) {
-        g = 1.0f;
-      } else if (g > P.agc_max) {
-        g = P.agc_max;
-      }
-      iq_out.st(c, t0 + i0 + u, x2);
-    }
-  }
-  st[c].agc_gain = g;
-}
 
 // Branch-free atan2f for the phase discriminator of the fused core (volk_32fc_s32f_atan2_32f in the
 // reference, whose accuracy depends on the VOLK version and machine: generic = libm atan2f, newer
@@ -867,7 +770,7 @@ __device__ __forceinline__ float fmr_atan2f(float y, float x) {
   return copysignf(r, y);
 }
 
-// k_fm_agc2 — the same recurrence as k_fm_agc with the bookkeeping taken out of the loop (row
+// k_fm_agc2 — IfSimpleAgc (IfSimpleAgc.cpp:33-60) with the bookkeeping taken out of the loop (row
 // pointers and ring masks hoisted, no sign checks on the absolute index): the kernel is bound by
 // dependent-issue latency of ONE warp per SM sub-partition, so every instruction that is not the
 // recurrence costs as much as one that is.
@@ -990,201 +893,13 @@ static __global__ void k_fm_call_stats(Ring<float2> if_raw, Ring<float> mpx, flo
 // three-term series with error < 3e-19 — and re-anchored with an exact sincos(m_phase) at
 // the start of every reference call, so rounding cannot accumulate beyond one call. m_phase
 // itself is accumulated and wrapped exactly as the reference does.
-static __global__ void k_fm_pll(Ring<float> mpx, Ring<double2> out384, FmChanState *__restrict__ st,
-                         uint8_t *__restrict__ flags, PpsEventDev *__restrict__ pps,
-                         const float *__restrict__ stats, const uint32_t *__restrict__ call_end, int n_calls,
-                         int64_t t0, FmCoreParams P, const float *__restrict__ atan_tbl, int block_off,
-                         int reset_pps) {
-  // block_off / reset_pps: a process call may be cut into several launches (time chunks); PPS
-  // events are numbered by the block index within the whole call and accumulate across them.
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= P.n_channels) return;
-  FmChanState s = st[c];
-  if (reset_pps) s.n_pps = 0;
-  const double f0 = (19000.0 / 384000.0) * 2.0 * 3.14159265358979323846;
-  double sf0, cf0;
-  sincos(f0, &sf0, &cf0);
-  const int n_total = n_calls ? (int)call_end[n_calls - 1] : 0;
-  const float *__restrict__ mrow = mpx.base + (size_t)c * mpx.cap;
-  double2 *__restrict__ orow = out384.base + (size_t)c * out384.cap;
-  const uint32_t mmask = mpx.cap - 1, omask = out384.cap - 1, t0lo = (uint32_t)t0;
-  // register double-buffer over the flat sample stream of this launch: `nxt` always holds
-  // the kCoreChunk samples starting at flat index `pos_nxt`
-  float nxt[kCoreChunk];
-#pragma unroll
-  for (int u = 0; u < kCoreChunk; u++) nxt[u] = (u < n_total) ? mrow[(t0lo + (uint32_t)u) & mmask] : 0.f;
-  uint32_t prev_end = 0;
-  for (int b = 0; b < n_calls; b++) {
-    const uint32_t end = call_end[b];
-    const int n = (int)(end - prev_end);
-    if (n == 0) { // main.cpp:933-936: the decoder is not called
-      flags[(size_t)c * n_calls + b] = (uint8_t)s.stereo_detected;
-      continue;
-    }
-    const uint32_t beg = prev_end;
-    prev_end = end;
-    s.decoder_calls++;
-    const bool was_locked = (s.lock_cnt >= P.lock_delay);
-    double last_i = 0.0, last_q = 0.0;
-    double psin = 0.0, pcos = 1.0;
-    if (P.stereo) sincos(s.pll_phase, &psin, &pcos); // exact re-anchor once per reference call
-    for (int i0 = 0; i0 < n; i0 += kCoreChunk) {
-      const int valid = (n - i0 < kCoreChunk) ? (n - i0) : kCoreChunk;
-      float din[kCoreChunk];
-#pragma unroll
-      for (int u = 0; u < kCoreChunk; u++) din[u] = nxt[u];
-      {
-        const int pos = (int)beg + i0 + valid; // flat index the next chunk (of this or the next call) starts at
-#pragma unroll
-        for (int u = 0; u < kCoreChunk; u++) {
-          nxt[u] = (pos + u < n_total) ? mrow[(t0lo + (uint32_t)(pos + u)) & mmask] : 0.f;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kCoreChunk; u++) {
-        if (u >= valid) break;
-        const int i = i0 + u; // index within the reference call
-        const double xd = (double)din[u];
-        double stereo = 0.0;
-        if (P.stereo) {
-          const double tone = P.pilot_shift ? (2 * pcos * pcos - 1) : (2 * psin * pcos);
-          const double i0v = psin * xd - (P.bq_a1 * s.bi_x1 + P.bq_a2 * s.bi_x2);
-          const double q0v = pcos * xd - (P.bq_a1 * s.bq_x1 + P.bq_a2 * s.bq_x2);
-          const double new_i = P.bq_b0 * i0v;
-          const double new_q = P.bq_b0 * q0v;
-          s.bi_x2 = s.bi_x1;
-          s.bi_x1 = i0v;
-          s.bq_x2 = s.bq_x1;
-          s.bq_x1 = q0v;
-          const double perr = (double)fast_atan2f_dev((float)new_q, (float)new_i, atan_tbl);
-          last_i = new_i;
-          last_q = new_q;
-          const double ferr = P.lf_b0 * perr + P.lf_b1 * s.lf_x1;
-          s.lf_x1 = perr;
-          s.freq_err = ferr;
-          s.pll_freq += ferr;
-          // std::max(m_minfreq, std::min(m_maxfreq, m_freq)) with std::min/max's own comparisons
-        // (PilotPhaseLock.cpp:119); plain selects are far cheaper than IEEE fmin/fmax on FP64
-        {
-          const double fq = (s.pll_freq < P.pll_maxfreq) ? s.pll_freq : P.pll_maxfreq;
-          s.pll_freq = (P.pll_minfreq < fq) ? fq : P.pll_minfreq;
-        }
-          s.pll_phase += s.pll_freq;
-          // advance the phasor by m_freq = f0 + dl
-          {
-            const double dl = s.pll_freq - f0;
-            const double d2 = dl * dl;
-            const double sd = dl * (1.0 - d2 * (1.0 / 6.0) * (1.0 - d2 * (1.0 / 20.0)));
-            const double cd = 1.0 - d2 * 0.5 * (1.0 - d2 * (1.0 / 12.0));
-            const double sr = sf0 * cd + cf0 * sd; // sin(f0 + dl)
-            const double cr = cf0 * cd - sf0 * sd; // cos(f0 + dl)
-            const double ns = psin * cr + pcos * sr;
-            const double nc = pcos * cr - psin * sr;
-            psin = ns;
-            pcos = nc;
-          }
-          if (s.pll_phase > 2.0 * 3.14159265358979323846) {
-            s.pll_phase -= 2.0 * 3.14159265358979323846;
-            s.pilot_periods++;
-            if (s.pilot_periods == 19000) {
-              s.pilot_periods = 0;
-              if (was_locked) {
-                if (s.n_pps < (uint32_t)kMaxPps) {
-                  PpsEventDev ev;
-                  ev.pps_index = s.pps_cnt;
-                  ev.sample_index = s.sample_cnt + (unsigned long long)i;
-                  ev.block_position = (double)i / (double)n;
-                  ev.block = (uint32_t)(b + block_off);
-                  ev.pad = 0;
-                  pps[(size_t)c * kMaxPps + s.n_pps] = ev;
-                }
-                s.n_pps++;
-                s.pps_cnt++;
-              }
-            }
-          }
-          stereo = (tone * xd) * 2.0;
-          if (P.deemph_on_stereo) {
-            const double x0 = stereo - P.de_a1 * s.de_s_x1;
-            stereo = P.de_b0 * x0;
-            s.de_s_x1 = x0;
-          }
-        }
-        const double m0 = xd - P.de_a1 * s.de_m_x1;
-        const double mono = P.de_b0 * m0;
-        s.de_m_x1 = m0;
-        double2 o;
-        o.x = mono;
-        o.y = stereo;
-        orow[(t0lo + beg + (uint32_t)i) & omask] = o;
-      }
-    }
-    // per-call statistics (FmDecode.cpp:95,146-150)
-    {
-      const float *sv = stats + ((size_t)c * n_calls + b) * 3;
-      s.if_rms = sv[0];
-      s.baseband_mean = (float)(0.95 * (double)s.baseband_mean + 0.05 * (double)sv[1]);
-      s.baseband_level = (float)(0.95 * (double)s.baseband_level + 0.05 * (double)sv[2]);
-    }
-    if (P.stereo) {
-      // m_pilot_level is the value of the call's last sample (PilotPhaseLock.cpp:106)
-      s.pilot_level = sqrt(last_i * last_i + last_q * last_q);
-      // lock bookkeeping (PilotPhaseLock.cpp:153-170)
-      if (2 * s.pilot_level > P.minsignal) {
-        if (s.lock_cnt < P.lock_delay) s.lock_cnt += n;
-      } else {
-        s.lock_cnt = 0;
-      }
-      if (s.lock_cnt < P.lock_delay) {
-        s.pilot_periods = 0;
-        s.pps_cnt = 0;
-        // events of THIS call are dropped
-        while (s.n_pps > 0 && s.n_pps <= (uint32_t)kMaxPps &&
-               pps[(size_t)c * kMaxPps + s.n_pps - 1].block == (uint32_t)(b + block_off)) {
-          s.n_pps--;
-        }
-      }
-      s.sample_cnt += (unsigned long long)n;
-      s.stereo_detected = (s.lock_cnt >= P.lock_delay) ? 1 : 0;
-    }
-    flags[(size_t)c * n_calls + b] = (uint8_t)s.stereo_detected;
-  }
-  // Field-wise write-back of what this kernel owns: with the pipelined schedule the AGC kernel of
-  // the next time chunk (agc_gain) and the tail kernel of the previous one (dc_*) may be updating
-  // their own fields of the same struct concurrently.
-  {
-    FmChanState *o = st + c;
-    o->baseband_mean = s.baseband_mean;
-    o->baseband_level = s.baseband_level;
-    o->if_rms = s.if_rms;
-    o->stereo_detected = s.stereo_detected;
-    o->lock_cnt = s.lock_cnt;
-    o->pilot_periods = s.pilot_periods;
-    o->n_pps = s.n_pps;
-    o->pll_phase = s.pll_phase;
-    o->pll_freq = s.pll_freq;
-    o->bi_x1 = s.bi_x1;
-    o->bi_x2 = s.bi_x2;
-    o->bq_x1 = s.bq_x1;
-    o->bq_x2 = s.bq_x2;
-    o->lf_x1 = s.lf_x1;
-    o->pilot_level = s.pilot_level;
-    o->freq_err = s.freq_err;
-    o->pps_cnt = s.pps_cnt;
-    o->sample_cnt = s.sample_cnt;
-    o->de_m_x1 = s.de_m_x1;
-    o->de_s_x1 = s.de_s_x1;
-    o->decoder_calls = s.decoder_calls;
-  }
-}
-
 // ---------------------------------------------------------------------------------------
-// k_fm_pll2 — same block as k_fm_pll (PilotPhaseLock::process + demod_stereo + deemphasis), with
+// k_fm_pll2 — PilotPhaseLock::process + demod_stereo + deemphasis (PilotPhaseLock.cpp:60-180, FmDecode.cpp:152-170), with
 // the per-sample recurrence written for the shortest dependent chain. The loop
 //   phase -> (sin, cos) -> x*sin, x*cos -> biquads -> fast_atan2f -> loop filter -> freq -> phase
 // is strictly serial and one warp per SM sub-partition runs it, so its time is the latency of
-// the chain times the number of 384 kHz samples, whatever the channel count. Changes against
-// k_fm_pll, none of which alters a rounding that the reference performs in float:
+// the chain times the number of 384 kHz samples, whatever the channel count. Against a literal
+// transcription of the reference loop, none of which alters a rounding that the reference performs in float:
 //   * fast_atan2f without branches: min/max instead of the if/else quotient, the octant logic
 //     folded into one fused multiply-add  angle = K + sg*base  with K in {0, pi/2, pi} and
 //     sg = +-1 chosen from the signs while the division is still in flight (K + sg*base rounds

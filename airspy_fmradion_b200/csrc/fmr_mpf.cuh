@@ -77,7 +77,13 @@ __global__ void __launch_bounds__(32 * kMpfWarps, 4)
     bool ok = true;
     const uint32_t mask = kMpfRing - 1;
     // MultipathFilter::update_coeff (MultipathFilter.cpp:108-161) on the window `sv` and the output (yr, yi)
-    auto update = [&](const float2 (&sv)[J], float yr, float yi) -> bool {
+    // (the window registers of taps k >= N hold whatever older samples the ring has there: their coefficients are kept
+    // at zero HERE, so the output loops can run over whole rows without a per-tap test)
+    auto update = [&](float2 (&sv)[J], float yr, float yi) -> bool {
+#pragma unroll
+      for (int j = 0; j < J; j++) {
+        if (j >= jf && lane + 32 * j >= N) sv[j] = make_float2(0.f, 0.f);
+      }
       float m4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < J; j++) m4[j & 3] = fmaf(sv[j].y, sv[j].y, fmaf(sv[j].x, sv[j].x, m4[j & 3]));
@@ -119,7 +125,8 @@ __global__ void __launch_bounds__(32 * kMpfWarps, 4)
       float ar[2] = {0.f, 0.f}, ai[2] = {0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < J; j++) {
-        sv[j] = (j < jf || lane + 32 * j < N) ? w[32 * j] : make_float2(0.f, 0.f);
+        // (J = 32 only: the last row would read two slots past the mirrored ring)
+        sv[j] = (J < 32 || j < J - 1 || lane + 32 * j < N) ? w[32 * j] : make_float2(0.f, 0.f);
         ar[j & 1] = fmaf(-sv[j].y, cf[j].y, fmaf(sv[j].x, cf[j].x, ar[j & 1]));
         ai[j & 1] = fmaf(sv[j].y, cf[j].x, fmaf(sv[j].x, cf[j].y, ai[j & 1]));
       }
@@ -131,9 +138,12 @@ __global__ void __launch_bounds__(32 * kMpfWarps, 4)
     // sample 0 of the call: output with the carried coefficients, then the first update
     ok = step1(in.ld(c, tb), 0, true);
     int i = 1;
-    // batches of four: outputs i .. i+3 with the same coefficients, update after i+3 (i = 1 mod 4)
+    // batches of four: outputs i .. i+3 with the same coefficients, update after i+3 (i = 1 mod 4). Lanes 0..3 fetch the
+    // batch's samples one batch ahead, so the global-load latency hides behind the previous batch's arithmetic.
+    float2 xnext = (lane < 4 && 1 + lane < n) ? in.ld(c, tb + 1 + lane) : make_float2(0.f, 0.f);
     for (; ok && i + 3 < n; i += 4) {
-      const float2 xq = (lane < 4) ? in.ld(c, tb + i + lane) : make_float2(0.f, 0.f);
+      const float2 xq = xnext;
+      xnext = (lane < 4 && i + 4 + lane < n) ? in.ld(c, tb + i + 4 + lane) : make_float2(0.f, 0.f);
       if (lane < 4) {
         const uint32_t pz = (cnt + 1 + lane) & mask;
         ring[pz] = xq;
@@ -149,10 +159,9 @@ __global__ void __launch_bounds__(32 * kMpfWarps, 4)
       for (int d = 0; d < 4; d++) ar[d][0] = ar[d][1] = ai[d][0] = ai[d][1] = 0.f;
 #pragma unroll
       for (int j = 0; j < J; j++) {
-        const bool on = (j < jf || lane + 32 * j < N);
 #pragma unroll
         for (int d = 0; d < 4; d++) {
-          const float2 v = on ? w[32 * j + d] : make_float2(0.f, 0.f);
+          const float2 v = (J < 32 || j < J - 1 || lane + 32 * j < N) ? w[32 * j + d] : make_float2(0.f, 0.f);
           if (d == 3) sv[j] = v;
           ar[d][j & 1] = fmaf(-v.y, cf[j].y, fmaf(v.x, cf[j].x, ar[d][j & 1]));
           ai[d][j & 1] = fmaf(v.y, cf[j].x, fmaf(v.x, cf[j].y, ai[d][j & 1]));
@@ -187,8 +196,8 @@ __global__ void __launch_bounds__(32 * kMpfWarps, 4)
       }
       ok = update(sv, yr[3], yi[3]);
     }
-    // the last (n - 1) mod 4 samples of the call: outputs only
-    for (; ok && i < n; i++) ok = step1(in.ld(c, tb + i), i, false);
+    // the last (n - 1) mod 4 samples of the call: outputs only (already fetched: lane d holds sample i + d)
+    for (int d = 0; ok && i < n; i++, d++) ok = step1(make_float2(__shfl_sync(0xffffffffu, xnext.x, d), __shfl_sync(0xffffffffu, xnext.y, d)), i, false);
     if (!ok) {
       // FmDecode.cpp:114-123: reset coefficients, pass the call through unfiltered
 #pragma unroll

@@ -133,156 +133,5 @@ int main() {
   printf(ok ? "inplace fft: ok\n" : "FAIL\n");
   if (!ok) return 1;
 
-  // ---------------- shared-memory polyphase epilogue (fi_epilogue_smem) on the filtered block y, geometry of the
-  // 10 MHz chain: 192 phases x 18 taps, step 625/192; every "thread" in scrambled order, each output exactly once,
-  // bit-identical to the straightforward evaluation in the same summation order
-  {
-    const int instep = 625, outstep = 192, flen = 18;
-    const int lq = kN - klen + 1, cnt = (int)(((long long)(lq - flen - 8) * outstep) / instep);
-    std::vector<float> bankv((size_t)outstep * flen), sbank((size_t)fmr::kEpiMaxRows * fmr::kEpiRow, NAN);
-    for (auto &v : bankv) v = nd(rng);
-    for (int i = 0; i < outstep * flen; i++) sbank[(i / flen) * fmr::kEpiRow + i % flen] = bankv[i];
-    for (int rem_b : {0, 77, 191}) {
-      std::vector<int2> srow(outstep);
-      for (int p = 0; p < outstep; p++) srow[p] = fmr::epi_row(p, instep, outstep, rem_b);
-      std::vector<float2> got(cnt, mk(NAN, NAN));
-      std::vector<int> hits(cnt, 0);
-      for (int tid : order(512)) {
-        fmr::fi_epilogue_smem<18, 512>(tid, y.data(), sbank.data(), srow.data(), instep, outstep, klen, cnt,
-                                       [&](int i, float2 v) {
-                                         got[i] = v;
-                                         hits[i]++;
-                                       });
-      }
-      int bad = 0;
-      for (int i = 0; i < cnt; i++) {
-        const int prel = i * instep + rem_b, dip = prel / outstep, ph = prel - dip * outstep;
-        float ax = 0.f, ay = 0.f;
-        for (int k = 0; k < flen; k++) {
-          const float2 v = y[(klen - 1) + dip + k];
-          ax += bankv[(size_t)ph * flen + k] * v.x;
-          ay += bankv[(size_t)ph * flen + k] * v.y;
-        }
-        if (hits[i] != 1 || got[i].x != ax || got[i].y != ay) bad++;
-      }
-      printf("epilogue rem_b=%d: %d outputs, %d mismatches\n", rem_b, cnt, bad);
-      if (bad) {
-        printf("FAIL\n");
-        return 1;
-      }
-    }
-    printf("inplace epilogue: ok\n");
-  }
-
-  // ---------------- radix 32 x 32 x 16 form (ipfft32): same input, same taps
-  namespace r32 = fmr::ipfft32;
-  {
-    std::vector<int> seen(kN, 0);
-    for (int p = 0; p < kN; p++) seen[r32::freq_of_pos(p)]++;
-    for (int k = 0; k < kN; k++) {
-      if (seen[k] != 1) {
-        printf("FAIL: ipfft32::freq_of_pos is not a permutation\n");
-        return 1;
-      }
-    }
-  }
-  std::vector<float2> hrev32(kN), tab32(r32::kTabLen);
-  for (int p = 0; p < kN; p++) {
-    const cd v = hc[r32::freq_of_pos(p)] / (double)kN;
-    hrev32[p] = mk((float)v.real(), (float)v.imag());
-  }
-  for (int q = 0; q < 128; q++) {
-    tab32[q] = wv(128.0 * q, kN);
-    tab32[128 + q] = wv(q, kN);
-  }
-  std::vector<float2> buf32(r32::kBufLen, mk(NAN, NAN));
-  for (int i : order(512)) r32::dif_first(i, LdVec{x.data()}, buf32.data(), tab32.data());
-  for (int n = 0; n < kN; n++) {
-    if (std::isnan(buf32[pad(n)].x)) {
-      printf("FAIL: slot %d not written by the first radix-32 pass\n", n);
-      return 1;
-    }
-  }
-  for (int i : order(512)) r32::dif_16(i, buf32.data(), tab32.data());
-  for (int i : order(1024)) r32::mid_r16(i, buf32.data(), hrev32.data());
-  for (int i : order(512)) r32::dit_16(i, buf32.data(), tab32.data());
-  std::vector<float2> y32(kN);
-  for (int b : order(512)) {
-    float2 r[32];
-    r32::dit_last(b, buf32.data(), tab32.data(), r);
-    for (int a = 0; a < 32; a++) y32[b + 512 * a] = r[a];
-  }
-  int pads32 = 0;
-  for (int e = 0; e < r32::kBufLen; e++) pads32 += std::isnan(buf32[e].x) ? 1 : 0;
-  double maxerr32 = 0, maxdiff = 0;
-  for (int n = 0; n < kN; n += 3) {
-    cd acc(0, 0);
-    for (int j = 0; j < klen; j++) {
-      const float2 v = x[(n - j + kN) & (kN - 1)];
-      acc += h[j] * cd(v.x, v.y);
-    }
-    maxerr32 = std::max(maxerr32, std::abs(acc - cd(y32[n].x, y32[n].y)));
-    maxdiff = std::max(maxdiff, std::abs(cd(y[n].x, y[n].y) - cd(y32[n].x, y32[n].y)));
-  }
-  printf("radix-32 in-place FFT convolution: max |err| %.3e, vs the radix-16 form %.3e, poisoned pad words left %d of %d\n",
-         maxerr32, maxdiff, pads32, kN / 16);
-  const bool ok32 = maxerr32 < 2e-6 * std::max(1.0, maxref) * 4 && pads32 == kN / 16;
-  printf(ok32 ? "inplace fft32: ok\n" : "FAIL\n");
-  if (!ok32) return 1;
-
-  // ---------------- 8192-point form (ipfft8k), its own input block and a 1847-tap filter
-  namespace r8 = fmr::ipfft8k;
-  const int N8 = r8::kN, klen8 = 1847;
-  {
-    std::vector<int> seen(N8, 0);
-    for (int p = 0; p < N8; p++) seen[r8::freq_of_pos(p)]++;
-    for (int k = 0; k < N8; k++) {
-      if (seen[k] != 1) {
-        printf("FAIL: ipfft8k::freq_of_pos is not a permutation\n");
-        return 1;
-      }
-    }
-  }
-  std::vector<cd> hc8(N8, cd(0, 0));
-  for (int i = 0; i < klen8; i++) hc8[i] = h[i + (klen - klen8) / 2];
-  std::vector<double> h8(klen8);
-  for (int i = 0; i < klen8; i++) h8[i] = h[i + (klen - klen8) / 2];
-  host_fft(hc8);
-  std::vector<float2> hrev8(N8), tab8(r8::kTabLen);
-  for (int p = 0; p < N8; p++) {
-    const cd v = hc8[r8::freq_of_pos(p)] / (double)N8;
-    hrev8[p] = mk((float)v.real(), (float)v.imag());
-  }
-  for (int q = 0; q < 128; q++) {
-    tab8[q] = wv(128.0 * q, N8); // only q < 64 is ever read
-    tab8[128 + q] = wv(q, N8);
-  }
-  std::vector<float2> buf8(r8::kBufLen, mk(NAN, NAN));
-  for (int i : order(256)) r8::dif_first(i, LdVec{x.data()}, buf8.data(), tab8.data());
-  for (int i : order(512)) r8::dif_16(i, buf8.data(), tab8.data());
-  for (int i : order(512)) r8::mid_r16(i, buf8.data(), hrev8.data());
-  for (int i : order(512)) r8::dit_16(i, buf8.data(), tab8.data());
-  std::vector<float2> y8(N8);
-  for (int b : order(256)) {
-    float2 r[32];
-    r8::dit_last(b, buf8.data(), tab8.data(), r);
-    for (int a = 0; a < 32; a++) y8[b + 256 * a] = r[a];
-  }
-  int pads8 = 0;
-  for (int e = 0; e < r8::kBufLen; e++) pads8 += std::isnan(buf8[e].x) ? 1 : 0;
-  double maxerr8 = 0, maxref8 = 0;
-  for (int n = 0; n < N8; n += 3) {
-    cd acc(0, 0);
-    for (int j = 0; j < klen8; j++) {
-      const float2 v = x[(n - j + N8) & (N8 - 1)];
-      acc += h8[j] * cd(v.x, v.y);
-    }
-    maxerr8 = std::max(maxerr8, std::abs(acc - cd(y8[n].x, y8[n].y)));
-    maxref8 = std::max(maxref8, std::abs(acc));
-  }
-  printf("8192-point in-place FFT convolution: max |err| %.3e (signal max %.3e), poisoned pad words left %d of %d\n", maxerr8,
-         maxref8, pads8, N8 / 16);
-  const bool ok8 = maxerr8 < 2e-6 * std::max(1.0, maxref8) * 4 && pads8 == N8 / 16;
-  printf(ok8 ? "inplace fft8k: ok\n" : "FAIL\n");
-  return ok8 ? 0 : 1;
+  return 0;
 }

@@ -12,38 +12,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
+# every environment switch the library still reads (all select between paths the GPU suite covers)
+SWITCHES = ("FMR_FE", "FMR_FE_VARIANT", "FMR_FE_MIN_BLOCKS", "FMR_FDR", "FMR_FFT_INPLACE", "FMR_FFT_TW", "FMR_FFT_F64", "FMR_FFT",
+            "FMR_FUSE_FI", "FMR_HB_STREAM", "FMR_HBS_TMA", "FMR_CORE_FUSED")
+
 VARIANTS = [
     # name, env, blocks per step, channels
     ("all_on_329", {}, 329, 8192),
     ("all_on_128", {}, 128, 8192),
-    ("all_on_128_c1024", {}, 128, 1024),
-    ("all_on_128_c148", {}, 128, 148),
-    # time-chunk pipeline with the fused 384 kHz core (front end of chunk k+1 overlaps core + audio tail of chunk k)
-    ("tc2_fused", {"FMR_TIME_CHUNKS": "2", "FMR_FUSED_CHUNKS": "1"}, 329, 8192),
-    ("tc3_fused", {"FMR_TIME_CHUNKS": "3", "FMR_FUSED_CHUNKS": "1"}, 329, 8192),
-    ("tc4_fused", {"FMR_TIME_CHUNKS": "4", "FMR_FUSED_CHUNKS": "1"}, 329, 8192),
-    ("tc6_fused", {"FMR_TIME_CHUNKS": "6", "FMR_FUSED_CHUNKS": "1"}, 329, 8192),
-    ("tc4_unfused", {"FMR_TIME_CHUNKS": "4"}, 329, 8192),
-    ("tc4_fused_c2048", {"FMR_TIME_CHUNKS": "4", "FMR_FUSED_CHUNKS": "1"}, 329, 2048),
-    ("all_on_329_c2048", {}, 329, 2048),
-    ("fft_tw_off", {"FMR_FFT_TW": "0"}, 329, 8192),
-    ("fft_1024thr", {"FMR_FFT_THREADS": "1024"}, 329, 8192),
-    ("fft_inplace_512", {"FMR_FFT_INPLACE": "1"}, 329, 8192),
-    ("fft_inplace_1024", {"FMR_FFT_INPLACE": "1", "FMR_FFT_THREADS": "1024"}, 329, 8192),
-    ("fft_stockham", {"FMR_FFT_INPLACE": "0"}, 329, 8192),
-    ("fft_inplace_r32", {"FMR_FFT_INPLACE": "2"}, 329, 8192),
-    ("fft_epi_smem", {"FMR_FFT_EPI": "1"}, 329, 8192),
-    ("fft_inplace_r32_epi", {"FMR_FFT_INPLACE": "2", "FMR_FFT_EPI": "1"}, 329, 8192),
-    ("fft_inplace_8k", {"FMR_FFT_INPLACE8K": "1"}, 329, 8192),
-    ("fdr_off", {"FMR_FDR": "0"}, 329, 8192),
-    ("fe_off", {"FMR_FE": "0"}, 329, 8192),
-    ("fe_a", {"FMR_FE_VARIANT": "0"}, 329, 8192),
-    ("fe_b", {"FMR_FE_VARIANT": "1"}, 329, 8192),
-    ("fe_c", {"FMR_FE_VARIANT": "2"}, 329, 8192),
-    ("fe_s", {"FMR_FE_VARIANT": "3"}, 329, 8192),
-    ("fe_a_658", {"FMR_FE_VARIANT": "0"}, 658, 8192),
     ("all_on_329_c16384", {}, 329, 16384),
-    ("fft_inplace_r32_8k", {"FMR_FFT_INPLACE": "2", "FMR_FFT_INPLACE8K": "1"}, 329, 8192),
+    ("all_on_329_c2048", {}, 329, 2048),
+    ("all_on_329_c148", {}, 329, 148),
+    ("fe_off", {"FMR_FE": "0"}, 329, 8192),             # unfused front end: k_hb_stream_tma -> ring -> k_fdr
+    ("fe_split", {"FMR_FE_VARIANT": "1"}, 329, 8192),   # fused front end, real / imaginary part on two lanes
+    ("fdr_off", {"FMR_FE": "0", "FMR_FDR": "0"}, 329, 8192),  # time-domain form: 16384-point FFT low-pass + bank
+    ("fft_stockham", {"FMR_FE": "0", "FMR_FDR": "0", "FMR_FFT_INPLACE": "0"}, 329, 8192),
+    ("hb_tiled", {"FMR_FE": "0", "FMR_HB_STREAM": "0"}, 329, 8192),
+    ("hbs_cp_async", {"FMR_FE": "0", "FMR_HBS_TMA": "0"}, 329, 8192),
+    ("core_unfused", {"FMR_CORE_FUSED": "0"}, 329, 8192),
 ]
 
 
@@ -64,7 +50,7 @@ def main():
     iq = bench.gen_iq_device(torch, dev, fs, Cgen, Tmax, mode)
     stream = torch.cuda.current_stream()
     for name, env, nblk, C in variants:
-        for k in ("FMR_HB_STREAM", "FMR_FUSE_FI", "FMR_FFT_F64", "FMR_HBS_TILE", "FMR_FFT", "FMR_SERIAL_V2", "FMR_TIME_CHUNKS", "FMR_SERIAL_SMS", "FMR_CORE_FUSED", "FMR_HBS_STAGES", "FMR_HBS_L2PF", "FMR_HBS_TMA", "FMR_FFT_N", "FMR_CORE_ROT", "FMR_FUSED_CHUNKS", "FMR_CHUNK_MIN_BLOCKS", "FMR_FFT_TW", "FMR_FFT_THREADS", "FMR_FFT_INPLACE", "FMR_FFT_INPLACE8K", "FMR_FFT_REGCAP", "FMR_FFT_EPI", "FMR_FDR", "FMR_FE", "FMR_FE_VARIANT"):
+        for k in SWITCHES:
             os.environ.pop(k, None)
         os.environ.update(env)
         C = min(C, Cgen)
