@@ -35,6 +35,73 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// MultipathFilter::update_coeff (MultipathFilter.cpp:108-161) on the window `sv` and the output (yr, yi). A free
+// __forceinline__ function (not a lambda called from two places): the coefficient and window arrays must stay in
+// registers. The window registers of taps k >= N hold whatever older samples the ring has there: their coefficients are
+// kept at zero HERE, so the output loops can run over whole rows without a per-tap test.
+template <int J>
+__device__ __forceinline__ bool mpf_update(float2 (&cf)[J], float2 (&sv)[J], float yr, float yi, int lane, int N, int jf,
+                                           int ref_idx, double &err_keep) {
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    if (j >= jf && lane + 32 * j >= N) sv[j] = make_float2(0.f, 0.f);
+  }
+  float m4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < J; j++) m4[j & 3] = fmaf(sv[j].y, sv[j].y, fmaf(sv[j].x, sv[j].x, m4[j & 3]));
+  const float ms = warp_sum((m4[0] + m4[1]) + (m4[2] + m4[3]));
+  const double env = (double)(yr * yr + yi * yi);
+  const double err = 1.0 - env;
+  const float mu = (float)(0.1 / ((double)ms + 1e-10));
+  const float factor = (float)(err * (double)mu);
+  const float fr = factor * yr, fi = factor * yi;
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    cf[j].x = fmaf(fi, sv[j].y, fmaf(fr, sv[j].x, cf[j].x));
+    cf[j].y = fmaf(-fr, sv[j].y, fmaf(fi, sv[j].x, cf[j].y));
+  }
+  // the reference tap is pinned to 1+0j (MultipathFilter.cpp:158-160)
+  if (lane == (ref_idx & 31)) {
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+      if (j == (ref_idx >> 5)) cf[j] = make_float2(1.f, 0.f);
+    }
+  }
+  err_keep = err;
+  return isfinite(err);
+}
+
+// One sample: ring write, output, and the update when `upd`; false = the reference's failure path
+// (MultipathFilter.cpp:163-195). Free __forceinline__ function for the same reason as mpf_update.
+template <int J>
+__device__ __forceinline__ bool mpf_step1(float2 (&cf)[J], float2 *ring, uint32_t &cnt, float2 x, bool upd, int lane, int N,
+                                          int jf, int ref_idx, double &err_keep, Ring<float2> out, int c, int64_t t_out) {
+  constexpr uint32_t mask = kMpfRing - 1;
+  cnt++;
+  if (lane == 0) {
+    ring[cnt & mask] = x;
+    ring[(cnt & mask) + kMpfRing] = x;
+  }
+  __syncwarp();
+  // tap k = lane + 32 j reads the sample N-1-k steps behind the newest: contiguous from `w`
+  const float2 *__restrict__ w = ring + ((cnt - (uint32_t)(N - 1)) & mask) + lane;
+  float2 sv[J];
+  // (the same two accumulator chains per output as in the batch: a sample's value does not depend on which of the two
+  // paths the call partition sends it through)
+  float ar[2] = {0.f, 0.f}, ai[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    // (J = 32 only: the last row would read two slots past the mirrored ring)
+    sv[j] = (J < 32 || j < J - 1 || lane + 32 * j < N) ? w[32 * j] : make_float2(0.f, 0.f);
+    ar[j & 1] = fmaf(-sv[j].y, cf[j].y, fmaf(sv[j].x, cf[j].x, ar[j & 1]));
+    ai[j & 1] = fmaf(sv[j].y, cf[j].x, fmaf(sv[j].x, cf[j].y, ai[j & 1]));
+  }
+  const float yr = warp_sum(ar[0] + ar[1]), yi = warp_sum(ai[0] + ai[1]);
+  if (!isfinite(yr) || !isfinite(yi)) return false;
+  if (lane == 0) out.st(c, t_out, make_float2(yr, yi));
+  return upd ? mpf_update<J>(cf, sv, yr, yi, lane, N, jf, ref_idx, err_keep) : true;
+}
+
 template <int J>
 __global__ void __launch_bounds__(32 * kMpfWarps, 4)
     k_mpf(Ring<float2> in, Ring<float2> out, FmChanState *__restrict__ st, float2 *__restrict__ g_coeff,
@@ -76,67 +143,8 @@ __global__ void __launch_bounds__(32 * kMpfWarps, 4)
     }
     bool ok = true;
     const uint32_t mask = kMpfRing - 1;
-    // MultipathFilter::update_coeff (MultipathFilter.cpp:108-161) on the window `sv` and the output (yr, yi)
-    // (the window registers of taps k >= N hold whatever older samples the ring has there: their coefficients are kept
-    // at zero HERE, so the output loops can run over whole rows without a per-tap test)
-    auto update = [&](float2 (&sv)[J], float yr, float yi) -> bool {
-#pragma unroll
-      for (int j = 0; j < J; j++) {
-        if (j >= jf && lane + 32 * j >= N) sv[j] = make_float2(0.f, 0.f);
-      }
-      float m4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < J; j++) m4[j & 3] = fmaf(sv[j].y, sv[j].y, fmaf(sv[j].x, sv[j].x, m4[j & 3]));
-      const float ms = warp_sum((m4[0] + m4[1]) + (m4[2] + m4[3]));
-      const double env = (double)(yr * yr + yi * yi);
-      const double err = 1.0 - env;
-      const float mu = (float)(0.1 / ((double)ms + 1e-10));
-      const float factor = (float)(err * (double)mu);
-      const float fr = factor * yr, fi = factor * yi;
-      // taps beyond N keep a zero coefficient because their window sample was read as zero
-#pragma unroll
-      for (int j = 0; j < J; j++) {
-        cf[j].x = fmaf(fi, sv[j].y, fmaf(fr, sv[j].x, cf[j].x));
-        cf[j].y = fmaf(-fr, sv[j].y, fmaf(fi, sv[j].x, cf[j].y));
-      }
-      // the reference tap is pinned to 1+0j (MultipathFilter.cpp:158-160)
-      if (lane == (ref_idx & 31)) {
-#pragma unroll
-        for (int j = 0; j < J; j++) {
-          if (j == (ref_idx >> 5)) cf[j] = make_float2(1.f, 0.f);
-        }
-      }
-      err_keep = err;
-      return isfinite(err);
-    };
-    // one sample: output (and update when `upd`); false = the reference's failure path
-    auto step1 = [&](float2 x, int i, bool upd) -> bool {
-      cnt++;
-      if (lane == 0) {
-        ring[cnt & mask] = x;
-        ring[(cnt & mask) + kMpfRing] = x;
-      }
-      __syncwarp();
-      // tap k = lane + 32 j reads the sample N-1-k steps behind the newest: contiguous from `w`
-      const float2 *__restrict__ w = ring + ((cnt - (uint32_t)(N - 1)) & mask) + lane;
-      float2 sv[J];
-      // (the same two accumulator chains per output as in the batch below: a sample's value does not depend on which
-      // of the two paths the call partition sends it through)
-      float ar[2] = {0.f, 0.f}, ai[2] = {0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < J; j++) {
-        // (J = 32 only: the last row would read two slots past the mirrored ring)
-        sv[j] = (J < 32 || j < J - 1 || lane + 32 * j < N) ? w[32 * j] : make_float2(0.f, 0.f);
-        ar[j & 1] = fmaf(-sv[j].y, cf[j].y, fmaf(sv[j].x, cf[j].x, ar[j & 1]));
-        ai[j & 1] = fmaf(sv[j].y, cf[j].x, fmaf(sv[j].x, cf[j].y, ai[j & 1]));
-      }
-      const float yr = warp_sum(ar[0] + ar[1]), yi = warp_sum(ai[0] + ai[1]);
-      if (!isfinite(yr) || !isfinite(yi)) return false;
-      if (lane == 0) out.st(c, tb + i, make_float2(yr, yi));
-      return upd ? update(sv, yr, yi) : true;
-    };
     // sample 0 of the call: output with the carried coefficients, then the first update
-    ok = step1(in.ld(c, tb), 0, true);
+    ok = mpf_step1<J>(cf, ring, cnt, in.ld(c, tb), true, lane, N, jf, ref_idx, err_keep, out, c, tb);
     int i = 1;
     // batches of four: outputs i .. i+3 with the same coefficients, update after i+3 (i = 1 mod 4). Lanes 0..3 fetch the
     // batch's samples one batch ahead, so the global-load latency hides behind the previous batch's arithmetic.
@@ -194,10 +202,13 @@ __global__ void __launch_bounds__(32 * kMpfWarps, 4)
         }
         out.st(c, tb + i + lane, y);
       }
-      ok = update(sv, yr[3], yi[3]);
+      ok = mpf_update<J>(cf, sv, yr[3], yi[3], lane, N, jf, ref_idx, err_keep);
     }
     // the last (n - 1) mod 4 samples of the call: outputs only (already fetched: lane d holds sample i + d)
-    for (int d = 0; ok && i < n; i++, d++) ok = step1(make_float2(__shfl_sync(0xffffffffu, xnext.x, d), __shfl_sync(0xffffffffu, xnext.y, d)), i, false);
+    for (int d = 0; ok && i < n; i++, d++) {
+      const float2 x = make_float2(__shfl_sync(0xffffffffu, xnext.x, d), __shfl_sync(0xffffffffu, xnext.y, d));
+      ok = mpf_step1<J>(cf, ring, cnt, x, false, lane, N, jf, ref_idx, err_keep, out, c, tb + i);
+    }
     if (!ok) {
       // FmDecode.cpp:114-123: reset coefficients, pass the call through unfiltered
 #pragma unroll
