@@ -79,7 +79,9 @@ using CfgA = Cfg<4, 4, 60, 2, 208, 120>;  // 4 producer warps, long tiles (47 % 
 using CfgS = Cfg<8, 4, 60, 2, 128, 128, true>; // 8 producer warps on long tiles: real and imaginary part on two lanes
 
 struct Params {
-  const float2 *hb_ring; // 1.25 MHz ring (unfused path's output): samples shared with the block before the first one
+  float2 *hb_ring;       // 1.25 MHz ring: read for the samples the first block shares with its predecessor (the unfused
+                         // kernels or the previous call left them there), written from `ring_from` on (the last block's
+                         // final 2500 samples: what the NEXT block, which straddles the call boundary, shares with it)
   uint32_t hb_cap;
   float2 *out;           // 384 kHz ring
   uint32_t out_cap;
@@ -88,6 +90,7 @@ struct Params {
   int64_t j0;            // first block of the absolute grid this launch takes
   int n_blocks;          // blocks per channel
   int n_channels;
+  int64_t ring_from;     // first of the 2500 samples of the last block that the consumers copy to the ring
   float t1[8], t2[8], t3[8];
 };
 
@@ -284,6 +287,15 @@ __global__ void __launch_bounds__(CF::kThreads, 1) k_frontend_fused(const __grid
         mbar_wait_sleep(bar_bfull, bseq & 1);
         for (int b = ct; b < 625; b += kConsThreads) {
           fdr::fwd1(b, [&](int bb, int a) { return B[bb + 625 * ((o625 + a) & 15)]; }, A, P.tab);
+        }
+        if (blk == P.n_blocks - 1) {
+          // last block of the channel: its final 2500 samples are what the next block (which straddles the call boundary
+          // and goes through the unfused kernels, now or in the next call) shares with it — leave them in the 1.25 MHz ring
+          float2 *__restrict__ rrow = P.hb_ring + (size_t)ch * P.hb_cap;
+          for (int q = 2 * ct; q < 2 * fdr::kGuardIn; q += 2 * kConsThreads) {
+            const int64_t m = P.ring_from + q;
+            *reinterpret_cast<float4 *>(rrow + ((uint32_t)m & (P.hb_cap - 1))) = *reinterpret_cast<const float4 *>(B + (int)(m % fdr::kNin));
+          }
         }
         cons_sync();
         if (ct == 0) mbar_arrive(bar_bfree);

@@ -633,6 +633,7 @@ template <typename S> struct Resampler {
     P.j0 = ja;
     P.n_blocks = (int)(jb - ja + 1);
     P.n_channels = gcn;
+    P.ring_from = (jb + 1) * fdr::kAdvIn - fdr::kGuardIn;
     for (int k = 0; k < 8; k++) {
       P.t1[k] = hbt.t[0][k];
       P.t2[k] = hbt.t[1][k];
@@ -800,7 +801,8 @@ template <typename S> struct Resampler {
         // ja read (which includes the 2500 samples block ja shares with its predecessor), and everything from the first
         // sample of block jb + 1 on (history of the next call).
         const int64_t head_hi = fused ? std::min(h1, ja * fdr::kAdvIn + fdr::kGuardIn) : h1;
-        const int64_t tail_lo = fused ? std::max(h0, (jb + 1) * fdr::kAdvIn - fdr::kGuardIn) : h1;
+        // (the fused kernel itself writes the last block's final 2500 samples to the ring: the tail starts behind them)
+        const int64_t tail_lo = fused ? std::max(h0, (jb + 1) * fdr::kAdvIn + fdr::kGuardIn) : h1;
         if (fused && head_hi < tail_lo) {
           hb_range(h0, head_hi);
           hb_range(tail_lo, h1);
