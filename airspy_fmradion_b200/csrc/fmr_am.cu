@@ -382,6 +382,10 @@ struct fmr_am {
   // USB / LSB / CW / WSPR (AmDecode.cpp:103-137): FineTuner -> 2049-tap filter -> FineTuner
   Ring<float2> r_t1{nullptr, 0}, r_t2{nullptr, 0};
   float *d_cwfilter = nullptr, *d_ssbfilter = nullptr;
+  // FFT form of the channel filters (AM / DSB / SSB / CW; not NBFM): spectra of the causal taps padded to 2 K - 1
+  float2 *d_H_am = nullptr, *d_H_cw = nullptr, *d_H_ssb = nullptr;
+  float c0_am = 0.f, c0_cw = 0.f, c0_ssb = 0.f;
+  bool fft_filter = false; // FMR_AM_FFT_FILTER=0: direct form
   float2 *d_tab_cw = nullptr, *d_tab_up = nullptr, *d_tab_down = nullptr; // FineTuner tables (480 entries)
   uint32_t idx_cw = 0, idx_up = 0, idx_down = 0;                         // FineTuner m_index
   int p_tune = -1;
@@ -425,6 +429,22 @@ extern "C" fmr_status fmr_am_schedule(double input_rate, uint64_t start_sample, 
     audio_len[b] = (uint32_t)(cur - prev);
     prev = cur;
   }
+  return FMR_OK;
+}
+
+// FFT form of a causal FIR y[i] = sum_j c[j] x[i - j] for k_fir_fft<float, 8192, false>, which evaluates the centred
+// convolution y[q] = sum_j h[j] x[q + (klen - 1) / 2 - j]: h = K - 1 zeros followed by the taps, klen = 2 K - 1. Spectrum
+// in double, 1 / N folded in. K <= 2049 (the SSB / CW filters: half of every 8192-point block is payload).
+static fmr_status am_make_fft_filter(DevMem &mem, const float *c, int K, float2 **d_H) {
+  const int N = 8192;
+  if (2 * K - 1 > N / 2 + 1) return fail(FMR_ERR_UNSUPPORTED, "channel filter too long for the FFT form");
+  std::vector<std::complex<double>> hc(N, std::complex<double>(0.0, 0.0));
+  for (int j = 0; j < K; j++) hc[K - 1 + j] = (double)c[j];
+  host_fft(hc);
+  std::vector<float2> hf(N);
+  for (int i = 0; i < N; i++) hf[i] = make_float2((float)(hc[i].real() / N), (float)(hc[i].imag() / N));
+  FMR_CUDA(mem.alloc(d_H, (size_t)N, false));
+  FMR_CUDA(cudaMemcpy(*d_H, hf.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
   return FMR_OK;
 }
 
@@ -487,6 +507,16 @@ static fmr_status am_build(fmr_am *h) {
     }
     FMR_CUDA(h->mem.alloc(&h->d_amfilter, (size_t)h->amfilter_taps, false));
     FMR_CUDA(cudaMemcpy(h->d_amfilter, tbl, h->amfilter_taps * sizeof(float), cudaMemcpyHostToDevice));
+    // Long channel filters as overlap-save FFT + the head-loop correction (k_fir_head_fix). Not for NBFM: its
+    // discriminator needs the exact zeros the direct form keeps at stream start (atan2(0, 0)).
+    h->fft_filter = !h->nbfm && h->amfilter_taps >= 96 && h->amfilter_taps <= 2049 && !Resampler<float>::env_off("FMR_AM_FFT_FILTER");
+    if (h->fft_filter) {
+      fmr_status sf = am_make_fft_filter(h->mem, tbl, h->amfilter_taps, &h->d_H_am);
+      if (sf != FMR_OK) return sf;
+      h->c0_am = tbl[0];
+      FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<float, 8192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     FftCfg<float, 8192>::kSmemBytes)));
+    }
   }
   FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)fq_smem(h->amfilter_taps, sizeof(float2), sizeof(float))));
@@ -548,6 +578,15 @@ static fmr_status am_build(fmr_am *h) {
       FMR_CUDA(cudaMemcpy(h->d_ssbfilter, k_jj1bdx_ssb_48khz_1500hz, 2049 * sizeof(float), cudaMemcpyHostToDevice));
       FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)fq_smem(2049, sizeof(float2), sizeof(float))));
+      if (!Resampler<float>::env_off("FMR_AM_FFT_FILTER")) {
+        fmr_status sf = am_make_fft_filter(h->mem, k_jj1bdx_cw_48khz_500hz, 2049, &h->d_H_cw);
+        if (sf == FMR_OK) sf = am_make_fft_filter(h->mem, k_jj1bdx_ssb_48khz_1500hz, 2049, &h->d_H_ssb);
+        if (sf != FMR_OK) return sf;
+        h->c0_cw = k_jj1bdx_cw_48khz_500hz[0];
+        h->c0_ssb = k_jj1bdx_ssb_48khz_1500hz[0];
+        FMR_CUDA((cudaFuncSetAttribute(k_fir_fft<float, 8192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       FftCfg<float, 8192>::kSmemBytes)));
+      }
       // FineTuner::set_freq_shift (FineTuner.cpp:32-52): table_size 480 = 48000/100, shifts +5, +15, -15
       auto make_tab = [&](int shift, float2 **dst) -> cudaError_t {
         std::vector<float2> t(480);
@@ -713,6 +752,19 @@ extern "C" fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t
   }
   if (n48 > 0) {
     dim3 grid((n48 + kQTile - 1) / kQTile, C);
+    // K-tap causal channel filter as overlap-save FFT blocks (k_fir_fft with the padded taps, klen = 2 K - 1), then the
+    // head-loop quirk taken out of the outputs it applies to (LowPassFilterFirIQ::process, Filter.cpp:37-96)
+    auto fft_filter = [&](Ring<float2> a, Ring<float2> b, const float2 *H, int K, float c0) {
+      const int klen = 2 * K - 1, lq = 8192 - klen + 1;
+      FftFuse fz;
+      memset(&fz, 0, sizeof(fz));
+      dim3 fg((n48 + lq - 1) / lq, C);
+      k_fir_fft<float, 8192, false><<<fg, kFftThreads, FftCfg<float, 8192>::kSmemBytes, st>>>(a, b, H, klen, 1, t0, (int)n48,
+                                                                                            t0 + (int64_t)n48, lq, fz);
+      dim3 hg((n48 + 255) / 256, C);
+      k_fir_head_fix<float><<<hg, 256, 0, st>>>(a, b, c0, K - 1, t0, (int)n48, h->d_e48, (int)n_blocks);
+      launches++;
+    };
     const int mode = h->cfg.mode;
     if (mode >= 4 && mode <= 7) {
       // USB: down, ssb filter, up. LSB: up, ssb filter, down. CW: cw filter, cw tuner. WSPR: down, cw filter, up
@@ -724,8 +776,13 @@ extern "C" fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t
         launches++;
       };
       auto filt = [&](Ring<float2> a, Ring<float2> b, const float *taps) {
-        k_fir_quirk<float><<<grid, kQThreads, fq_smem(2049, sizeof(float2), sizeof(float)), st>>>(a, b, taps, 2049, t0, (int)n48,
-                                                                                             h->d_e48, (int)n_blocks);
+        const float2 *H = (taps == h->d_ssbfilter) ? h->d_H_ssb : h->d_H_cw;
+        if (H) {
+          fft_filter(a, b, H, 2049, (taps == h->d_ssbfilter) ? h->c0_ssb : h->c0_cw);
+        } else {
+          k_fir_quirk<float><<<grid, kQThreads, fq_smem(2049, sizeof(float2), sizeof(float)), st>>>(a, b, taps, 2049, t0, (int)n48,
+                                                                                               h->d_e48, (int)n_blocks);
+        }
       };
       pf.begin(h->p_tune, st);
       if (mode == 4 || mode == 7) tune(h->r_if, h->r_t1, h->d_tab_down, &h->idx_down);
@@ -739,8 +796,12 @@ extern "C" fmr_status fmr_am_process_device(fmr_am *h, const float *d_iq, size_t
       if (mode == 6) tune(h->r_t2, h->r_flt, h->d_tab_cw, &h->idx_cw);
     } else {
       pf.begin(h->p_flt, st);
-      k_fir_quirk<float><<<grid, kQThreads, fq_smem(h->amfilter_taps, sizeof(float2), sizeof(float)), st>>>(h->r_if, h->r_flt, h->d_amfilter, h->amfilter_taps, t0, (int)n48,
-                                               h->d_e48, (int)n_blocks);
+      if (h->fft_filter) {
+        fft_filter(h->r_if, h->r_flt, h->d_H_am, h->amfilter_taps, h->c0_am);
+      } else {
+        k_fir_quirk<float><<<grid, kQThreads, fq_smem(h->amfilter_taps, sizeof(float2), sizeof(float)), st>>>(
+            h->r_if, h->r_flt, h->d_amfilter, h->amfilter_taps, t0, (int)n48, h->d_e48, (int)n_blocks);
+      }
       pf.end(h->p_flt, st);
     }
     pf.begin(h->p_core, st);

@@ -582,6 +582,26 @@ __device__ __forceinline__ int find_call(const uint32_t *__restrict__ call_end, 
   return lo;
 }
 
+// The head-loop quirk as a correction of a full convolution (used behind the FFT form of the long channel filters,
+// fmr_am.cu): y[i] -= coeff[0] * x[i] for the outputs that fall into the first `order` samples of their reference call.
+template <typename S>
+__global__ void k_fir_head_fix(Ring<typename V2<S>::type> x, Ring<typename V2<S>::type> y, S c0, int order, int64_t j0, int n_out,
+                               const uint32_t *__restrict__ call_end, int n_calls) {
+  using V = typename V2<S>::type;
+  const uint32_t c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const int b = find_call(call_end, n_calls, (uint32_t)i);
+  const uint32_t cstart = (b == 0) ? 0u : call_end[b - 1];
+  if (i - (int)cstart < order) {
+    const V xv = x.ld(c, j0 + i);
+    V yv = y.ld(c, j0 + i);
+    yv.x -= c0 * xv.x;
+    yv.y -= c0 * xv.y;
+    y.st(c, j0 + i, yv);
+  }
+}
+
 constexpr int kQR = 4;        // consecutive outputs per thread
 constexpr int kQThreads = 64; // tile = 256 outputs
 constexpr int kQTile = kQR * kQThreads;

@@ -80,3 +80,33 @@ def test_switch_decodes_the_same_stream(env):
     e = np.abs(audio[1] - b["ref"]).max()
     print("%s: max |switch - default| %.3e, max |switch - oracle| %.3e" % (env, d, e))
     assert d <= 5e-6 and e <= 2e-5
+
+
+@pytest.mark.parametrize("mode", [2, 4, 6])  # AM, USB, CW (AmDecode.cpp:96-218)
+def test_am_direct_form_channel_filter_decodes_the_same_stream(mode):
+    """FMR_AM_FFT_FILTER=0: the 255- / 2049-tap channel filters in direct form instead of overlap-save FFT blocks + the
+    head-loop correction (fmr_am.cu)."""
+    from airspy_fmradion_b200 import AmDecoder
+    fs, blk, nblk = 48000.0, 2048, 24
+    iq = np.stack([siggen.am_iq(fs, blk * nblk, c) for c in range(2)])
+
+    def run(env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            dec = AmDecoder(amfilter=0, mode=mode, input_rate=fs, n_channels=2, max_samples_per_call=blk * nblk,
+                            max_blocks_per_call=nblk)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        return dec.process_blocks(iq, [blk] * nblk)
+
+    a1, l1 = run({})
+    a0, l0 = run({"FMR_AM_FFT_FILTER": "0"})
+    assert list(l1) == list(l0) and a1.shape[1] > 1000
+    d = np.abs(a1 - a0).max()
+    print("mode %d: max |fft form - direct form| %.3e" % (mode, d))
+    assert d <= 5e-6

@@ -14,7 +14,7 @@ import bench  # noqa: E402
 
 # every environment switch the library still reads (all select between paths the GPU suite covers)
 SWITCHES = ("FMR_FE", "FMR_FE_VARIANT", "FMR_FE_MIN_BLOCKS", "FMR_FDR", "FMR_FFT_INPLACE", "FMR_FFT_TW", "FMR_FFT_F64", "FMR_FFT",
-            "FMR_FUSE_FI", "FMR_HB_STREAM", "FMR_HBS_TMA", "FMR_CORE_FUSED")
+            "FMR_FUSE_FI", "FMR_HB_STREAM", "FMR_HBS_TMA", "FMR_CORE_FUSED", "FMR_AM_FFT_FILTER")
 
 VARIANTS = [
     # name, env, blocks per step, channels
