@@ -74,7 +74,7 @@ EXPORTS = [
     "fmr_fm_create", "fmr_fm_destroy", "fmr_fm_process_host", "fmr_fm_process_device",
     "fmr_fm_process_host_i16", "fmr_fm_process_device_i16",
     "fmr_fm_query_output", "fmr_fm_schedule", "fmr_am_schedule", "fmr_fm_stats", "fmr_fm_pps_events", "fmr_fm_coeffs",
-    "fmr_fm_block_flags", "fmr_fm_tap_if", "fmr_fm_last_launches", "fmr_fm_last_plan", "fmr_fm_set_profiling",
+    "fmr_fm_block_flags", "fmr_fm_tap_if", "fmr_fm_last_launches", "fmr_fm_last_plan", "fmr_fm_describe", "fmr_fm_set_profiling",
     "fmr_fm_stage_times",
     "fmr_am_create", "fmr_am_destroy", "fmr_am_process_host", "fmr_am_process_device",
     "fmr_am_query_output", "fmr_am_stats", "fmr_am_last_launches", "fmr_am_set_profiling",
@@ -116,6 +116,8 @@ def lib():
     L.fmr_fm_last_launches.argtypes = [vp]
     L.fmr_fm_last_launches.restype = C.c_uint32
     L.fmr_fm_last_plan.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.fmr_fm_describe.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.fmr_fm_describe.restype = C.c_size_t
     L.fmr_fm_set_profiling.argtypes = [vp, C.c_int]
     L.fmr_fm_stage_times.argtypes = [vp, vp, vp, C.c_uint32, u32p]
     L.fmr_am_set_profiling.argtypes = [vp, C.c_int]

@@ -905,6 +905,22 @@ extern "C" fmr_status fmr_fm_tap_if(fmr_fm *h, uint32_t channel, float *re_im, s
 
 extern "C" uint32_t fmr_fm_last_launches(fmr_fm *h) { return h ? h->last_launches : 0; }
 
+extern "C" size_t fmr_fm_describe(fmr_fm *h, char *buf, size_t cap) {
+  if (!h || !buf || cap == 0) return 0;
+  const Resampler<float> &r = h->ifres;
+  const int n = snprintf(buf, cap,
+                         "input_rate=%.0f channels=%d if_chain=%s frontend=%s lowpass=%s halfbands=%s core=%s audio_lowpass=%s "
+                         "multipath_stages=%u fmfilter=%d",
+                         h->cfg.input_rate, h->C, h->ifc ? "r8brain-tables" : "none",
+                         r.use_fe ? (r.fe_variant == 1 ? "fused(split-lanes)" : "fused") : "unfused",
+                         r.use_fdr ? (r.fdr_rl == 12 ? "fdr(3072)" : r.fdr_rl == 15 ? "fdr(3840)" : "fdr(2560)")
+                                   : (r.use_fft ? (r.fft_inplace ? "fft16384-inplace+bank" : "fft16384-stockham+bank") : "direct"),
+                         r.hb_stream ? (r.hbs_tma ? "stream(tma)" : "stream(cp.async)") : "tiled",
+                         (h->core_fused && h->cfg.stereo && h->cfg.multipath_stages == 0) ? "fused" : "agc|disc|pll",
+                         h->aures.use_fft ? "fft8192-f64" : "direct-f64", h->cfg.multipath_stages, h->cfg.fmfilter);
+  return (n < 0) ? 0 : ((size_t)n < cap ? (size_t)n : cap - 1);
+}
+
 extern "C" fmr_status fmr_fm_last_plan(fmr_fm *h, uint64_t plan[5]) {
   if (!h || !plan) return fail(FMR_ERR_INVALID, "null argument");
   for (int i = 0; i < 5; i++) plan[i] = h->ifc ? h->ifres.last_plan[i] : 0;

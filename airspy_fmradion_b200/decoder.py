@@ -246,6 +246,12 @@ class FmDecoder(_Base):
     def last_launches(self):
         return int(_capi.lib().fmr_fm_last_launches(self._h))
 
+    def describe(self):
+        """Which implementation of every stage this handle selected (fmr_fm_describe)."""
+        buf = C.create_string_buffer(512)
+        _capi.lib().fmr_fm_describe(self._h, buf, 512)
+        return buf.value.decode()
+
     def last_plan(self):
         """How the last call's IF front end ran, per channel (fmr_fm_last_plan)."""
         p = (C.c_uint64 * 5)()

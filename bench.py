@@ -69,28 +69,38 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t_start=None, t_end=None):
+        """Clocks over [t_start, t_end] (the timed region; the sampler itself is started before the warm-up so that
+        nvidia-smi is already polling when it begins). With no sample inside the window the nearest ones are used and
+        `samples_in_window` says 0."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        rows = []
+        for ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        inside = [r for r in rows if t_start is None or (t_start - 0.05 <= r[0] <= t_end + 0.05)]
+        n_in = len(inside)
+        if not inside and rows and t_end is not None:
+            inside = sorted(rows, key=lambda r: abs(r[0] - t_end))[:2]
+        sm, mx, reasons = [], [], set()
+        for _, a, b, flags in inside:
+            sm.append(a)
+            mx.append(b)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_window": n_in}
 
 
 def gen_iq_device(torch, dev, fs, C, T, mode, chunk=32):
@@ -321,6 +331,7 @@ def main():
         affinity = None
 
     dec = make_decoder(wl, C, T, nblk, dev_index)
+    impl_desc = dec.describe() if hasattr(dec, "describe") else None  # which kernels this handle selected
     iq = gen_iq_device(torch, dev, fs, C, T, mode)
     width = 2 if (mode == "fm" and stereo) else 1
     audio_cap = int(T * 48000.0 / fs) * width + 64
@@ -338,18 +349,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(dev_index)
+    sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
-    sampler = ClockSampler(dev_index)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         lens = step()
     e1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    t_end = time.time()
+    clocks = sampler.stop(t_start, t_end)
     ms = e0.elapsed_time(e1)
     launches = dec.last_launches() * args.steps
     if dist is not None:
@@ -554,6 +567,8 @@ def main():
                 "data": "synthetic",
                 "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+        if impl_desc:
+            line["implementation"] = impl_desc
         if isinstance(roof, dict) and "fp32" in roof:
             line["roofline_fp32"] = roof.pop("fp32")
         if single_homed is not None:

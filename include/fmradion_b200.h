@@ -162,6 +162,9 @@ uint32_t fmr_fm_last_launches(fmr_fm *h);
  * taken by the unfused kernel, plan[2] = 1.25 MHz samples the unfused half-band kernels produced, plan[3] = input
  * samples per block (60000 at 10 Msps), plan[4] = output samples per block (2304). All zero for chains without it. */
 fmr_status fmr_fm_last_plan(fmr_fm *h, uint64_t plan[5]);
+/* Which implementation of every stage this handle selected at creation (environment switches, sample rate), as one line
+ * of "key=value" words, so that a run can be audited. Returns the length written (without the terminating 0). */
+size_t fmr_fm_describe(fmr_fm *h, char *buf, size_t cap);
 /* Per-stage device timing (CUDA events on the launching stream). Enable, run a process
  * call, synchronise, then read: ms[i] is the duration of stage names[i] in the last call. */
 fmr_status fmr_fm_set_profiling(fmr_fm *h, int enable);
