@@ -912,7 +912,7 @@ extern "C" size_t fmr_fm_describe(fmr_fm *h, char *buf, size_t cap) {
                          "input_rate=%.0f channels=%d if_chain=%s frontend=%s lowpass=%s halfbands=%s core=%s audio_lowpass=%s "
                          "multipath_stages=%u fmfilter=%d",
                          h->cfg.input_rate, h->C, h->ifc ? "r8brain-tables" : "none",
-                         r.use_fe ? (r.fe_variant == 1 ? "fused(split-lanes)" : "fused") : "unfused",
+                         r.use_fe ? (r.fe_variant == 1 ? "fused(split-lanes)" : r.fe_variant == 2 ? "fused(8-consumer-warps,setmaxnreg)" : "fused") : "unfused",
                          r.use_fdr ? (r.fdr_rl == 12 ? "fdr(3072)" : r.fdr_rl == 15 ? "fdr(3840)" : "fdr(2560)")
                                    : (r.use_fft ? (r.fft_inplace ? "fft16384-inplace+bank" : "fft16384-stockham+bank") : "direct"),
                          r.hb_stream ? (r.hbs_tma ? "stream(tma)" : "stream(cp.async)") : "tiled",

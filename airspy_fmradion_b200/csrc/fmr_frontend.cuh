@@ -39,7 +39,7 @@ namespace fmr {
 namespace fe {
 
 using D = HbsDelays<4, 5, 8>;
-constexpr int kConsWarps = 8, kConsThreads = 32 * kConsWarps;
+constexpr int kConsWarpsDefault = 8;
 constexpr int kStages = 2;
 constexpr int kBlockIn = 8 * fdr::kAdvIn;                          // 60000 input samples between blocks
 // first input sample of (block j, tile 0, row 0): 16 * (((7500 j + 1250 + A3) >> 1) - kWarm) = 60000 j + kIn0
@@ -50,7 +50,8 @@ static_assert(fdr::kZLen <= fdr::kNin, "the 3072-point buffer aliases A");
 // stream tiles of TILE outputs, RS macro-steps per staged row, setmaxnreg budgets PREGS / CREGS.
 // SPLIT: a stream tile is run by TWO threads (even lane: real parts, odd lane: imaginary parts; the filters are real), i.e.
 // twice the warps for the same arithmetic, scalar FADD / FFMA instead of the packed forms, half the registers.
-template <int PW, int U_, int TILE, int RS, int PREGS, int CREGS, bool SPLIT = false> struct Cfg {
+template <int PW, int U_, int TILE, int RS, int PREGS, int CREGS, bool SPLIT = false, int CW = kConsWarpsDefault> struct Cfg {
+  static constexpr int kConsWarps = CW, kConsThreads = 32 * CW;
   static constexpr int kProdWarps = PW, kU = U_, kTile = TILE, kRowSteps = RS, kProdRegs = PREGS, kConsRegs = CREGS;
   static constexpr bool kSplit = SPLIT;
   static constexpr int kProdThreads = 32 * PW, kThreads = kProdThreads + kConsThreads;
@@ -77,6 +78,10 @@ template <int PW, int U_, int TILE, int RS, int PREGS, int CREGS, bool SPLIT = f
 // block steps of 32 or 16 samples - 87 % warm-up, register spills or twice the register moves - 13 % / 21 % slower)
 using CfgA = Cfg<4, 4, 60, 2, 208, 120>;  // 4 producer warps, long tiles (47 % warm-up), cascade block step of 64 samples
 using CfgS = Cfg<8, 4, 60, 2, 128, 128, true>; // 8 producer warps on long tiles: real and imaginary part on two lanes
+// DEFAULT: CfgA's producers with four consumer warps (one per scheduler) and one register budget for all eight warps
+// (220 registers, no setmaxnreg): the FFT takes twice as long per block but still fits the block period, and takes fewer
+// issue slots from the producer warp of its scheduler at any one time: 9.37 vs 9.74 ms (8192 channels)
+using CfgC4 = Cfg<4, 4, 60, 2, 232, 232, false, 4>;
 
 struct Params {
   float2 *hb_ring;       // 1.25 MHz ring: read for the samples the first block shares with its predecessor (the unfused
@@ -109,7 +114,7 @@ __device__ __forceinline__ void tma_load_5d(unsigned dst, const CUtensorMap *tm,
 __device__ __forceinline__ void mbar_arrive(unsigned a) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
 }
-__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory"); }
+template <int CT> __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }
 
 // The row that a producer warp requests next: rows of a tile follow each other through the blocks of a channel and
 // then through the CTA's channels, so the TMA pipeline never drains at a block or channel boundary.
@@ -278,6 +283,8 @@ __global__ void __launch_bounds__(CF::kThreads, 1) k_frontend_fused(const __grid
   } else {
     // =============================== consumers: B -> FFT -> 384 kHz ring ===============================
     if constexpr (CF::kProdRegs != CF::kConsRegs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CF::kConsRegs));
+    constexpr int CT = CF::kConsThreads;
+    constexpr int R3 = (400 + CT - 1) / CT; // rounds of the last forward pass (its outputs are held over a barrier)
     const int ct = tid - kProdThreads;
     uint32_t bseq = 0;
     for (int ch = blockIdx.x; ch < P.n_channels; ch += ch_step) {
@@ -285,44 +292,50 @@ __global__ void __launch_bounds__(CF::kThreads, 1) k_frontend_fused(const __grid
         const int64_t j = P.j0 + blk;
         const int o625 = (int)((12 * j + 14) & 15); // (7500 j - 1250) mod 10000 = 625 * o625
         mbar_wait_sleep(bar_bfull, bseq & 1);
-        for (int b = ct; b < 625; b += kConsThreads) {
+        for (int b = ct; b < 625; b += CT) {
           fdr::fwd1(b, [&](int bb, int a) { return B[bb + 625 * ((o625 + a) & 15)]; }, A, P.tab);
         }
         if (blk == P.n_blocks - 1) {
           // last block of the channel: its final 2500 samples are what the next block (which straddles the call boundary
           // and goes through the unfused kernels, now or in the next call) shares with it — leave them in the 1.25 MHz ring
           float2 *__restrict__ rrow = P.hb_ring + (size_t)ch * P.hb_cap;
-          for (int q = 2 * ct; q < 2 * fdr::kGuardIn; q += 2 * kConsThreads) {
+          for (int q = 2 * ct; q < 2 * fdr::kGuardIn; q += 2 * CT) {
             const int64_t m = P.ring_from + q;
             *reinterpret_cast<float4 *>(rrow + ((uint32_t)m & (P.hb_cap - 1))) = *reinterpret_cast<const float4 *>(B + (int)(m % fdr::kNin));
           }
         }
-        cons_sync();
+        cons_sync<CT>();
         if (ct == 0) mbar_arrive(bar_bfree);
-        for (int i = ct; i < 400; i += kConsThreads) fdr::fwd2(i, A, P.tab);
-        cons_sync();
+        for (int i = ct; i < 400; i += CT) fdr::fwd2(i, A, P.tab);
+        cons_sync<CT>();
         {
-          float2 o0[fdr::kKeep], o1[fdr::kKeep];
-          fdr::fwd3_compute<12>(ct, A, P.Hs, o0);
-          if (ct + kConsThreads < 400) fdr::fwd3_compute<12>(ct + kConsThreads, A, P.Hs, o1);
-          cons_sync(); // the 3072-point buffer aliases A: every butterfly has loaded before anyone stores
-          fdr::fwd3_store<12>(ct, A, o0);
-          if (ct + kConsThreads < 400) fdr::fwd3_store<12>(ct + kConsThreads, A, o1);
+          float2 o[R3][fdr::kKeep];
+#pragma unroll
+          for (int r = 0; r < R3; r++) {
+            if (ct + r * CT < 400) fdr::fwd3_compute<12>(ct + r * CT, A, P.Hs, o[r]);
+          }
+          cons_sync<CT>(); // the 3072-point buffer aliases A: every butterfly has loaded before anyone stores
+#pragma unroll
+          for (int r = 0; r < R3; r++) {
+            if (ct + r * CT < 400) fdr::fwd3_store<12>(ct + r * CT, A, o[r]);
+          }
         }
-        cons_sync();
-        if (ct < 192) fdr::inv1<12>(ct, A, P.tab);
-        cons_sync();
-        if (ct < 192) fdr::inv2<12>(ct, A, P.tab);
-        cons_sync();
+        cons_sync<CT>();
+        for (int b = ct; b < 192; b += CT) fdr::inv1<12>(b, A, P.tab);
+        cons_sync<CT>();
+        for (int b = ct; b < 192; b += CT) fdr::inv2<12>(b, A, P.tab);
+        cons_sync<CT>();
         {
           const int64_t mb = j * fdr::kAdvOut - fdr::kGuardOut;
           float2 *__restrict__ orow = P.out + (size_t)ch * P.out_cap;
           const uint32_t omask = P.out_cap - 1;
-          fdr::inv3<12>(ct, A, [&](int i, float2 v) {
-            if (i >= fdr::kGuardOut && i < fdr::kGuardOut + fdr::kAdvOut) orow[(uint32_t)(mb + i) & omask] = v;
-          });
+          for (int t = ct; t < 256; t += CT) {
+            fdr::inv3<12>(t, A, [&](int i, float2 v) {
+              if (i >= fdr::kGuardOut && i < fdr::kGuardOut + fdr::kAdvOut) orow[(uint32_t)(mb + i) & omask] = v;
+            });
+          }
         }
-        cons_sync(); // A is rewritten by pass 1 of the next block
+        cons_sync<CT>(); // A is rewritten by pass 1 of the next block
       }
     }
   }

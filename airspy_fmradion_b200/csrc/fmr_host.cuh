@@ -230,7 +230,7 @@ template <typename S> struct Resampler {
   float *d_fdr_Hs = nullptr;
   float2 *d_fdr_tab = nullptr;
   bool use_fe = false;                       // fused persistent front end (fmr_frontend.cuh); FMR_FE=0: off
-  int fe_variant = 0;                        // FMR_FE_VARIANT: 0 = CfgA, 1 = CfgS (fmr_frontend.cuh)
+  int fe_variant = 0;                        // FMR_FE_VARIANT: 0 = CfgC4 (default), 1 = CfgS, 2 = CfgA (fmr_frontend.cuh)
   int fe_min_blocks = 2;                     // fewer whole blocks inside the call's buffer: unfused kernels only
   int p_fe = -1;
   typedef CUresult (*TmEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -448,7 +448,7 @@ template <typename S> struct Resampler {
               qr == cudaDriverEntryPointSuccess) {
             tm_encode = reinterpret_cast<TmEncodeFn>(fn);
             CUtensorMap probe;
-            if (const char *ev = getenv("FMR_FE_VARIANT")) fe_variant = (atoi(ev) == 1) ? 1 : 0;
+            if (const char *ev = getenv("FMR_FE_VARIANT")) fe_variant = std::min(2, std::max(0, atoi(ev)));
             if (fe_encode(&probe, r_hb.base, 1, 1, (size_t)fe::kBlockIn)) {
               FMR_CUDA(fe_dispatch([&](auto cf) {
                 using CF = decltype(cf);
@@ -598,7 +598,8 @@ template <typename S> struct Resampler {
   }
   template <typename F> auto fe_dispatch(F &&f) const {
     if (fe_variant == 1) return f(fe::CfgS{});
-    return f(fe::CfgA{});
+    if (fe_variant == 2) return f(fe::CfgA{});
+    return f(fe::CfgC4{});
   }
   int fe_in_span() const {
     return fe_dispatch([](auto cf) { return decltype(cf)::kInSpan; });

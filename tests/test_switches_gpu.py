@@ -16,6 +16,7 @@ FS, BLK, CALLS = 1.0e7, 2048, [200, 40, 200, 150]  # 0.12 s: past both resampler
 SETTINGS = [
     {"FMR_FE": "0"},                                            # unfused front end
     {"FMR_FE_VARIANT": "1"},                                    # fused front end, split real / imaginary lanes
+    {"FMR_FE_VARIANT": "2"},                                    # fused front end, eight consumer warps + setmaxnreg
     {"FMR_FE_MIN_BLOCKS": "4"},
     {"FMR_FE": "0", "FMR_FDR": "0"},                            # time-domain low-pass + polyphase bank (in-place FFT)
     {"FMR_FE": "0", "FMR_FDR": "0", "FMR_FFT_INPLACE": "0"},    # ... Stockham FFT

@@ -25,6 +25,7 @@ VARIANTS = [
     ("all_on_329_c148", {}, 329, 148),
     ("fe_off", {"FMR_FE": "0"}, 329, 8192),             # unfused front end: k_hb_stream_tma -> ring -> k_fdr
     ("fe_split", {"FMR_FE_VARIANT": "1"}, 329, 8192),   # fused front end, real / imaginary part on two lanes
+    ("fe_cons8", {"FMR_FE_VARIANT": "2"}, 329, 8192),   # fused front end, eight consumer warps + setmaxnreg (CfgA)
     ("fdr_off", {"FMR_FE": "0", "FMR_FDR": "0"}, 329, 8192),  # time-domain form: 16384-point FFT low-pass + bank
     ("fft_stockham", {"FMR_FE": "0", "FMR_FDR": "0", "FMR_FFT_INPLACE": "0"}, 329, 8192),
     ("hb_tiled", {"FMR_FE": "0", "FMR_HB_STREAM": "0"}, 329, 8192),
