@@ -200,6 +200,7 @@ static fmr_status fm_build(fmr_fm *h) {
                                 (int)fq_smem(h->fmfilter_taps > 0 ? h->fmfilter_taps : 127, sizeof(float2), sizeof(float))));
   FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)fq_smem(127, sizeof(double2), sizeof(double))));
+  FMR_CUDA(cudaFuncSetAttribute(k_fm_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
   // initial state (constructors: FmDecode.cpp:25-83, PilotPhaseLock.cpp:35-54, IfSimpleAgc.cpp:22-32)
   {
     std::vector<FmChanState> st(C);
@@ -541,7 +542,7 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
                                                                                                  127, j0, (int)n48, d_e48, (int)nb);
       pf.end(h->p_pcut, st);
       pf.begin(h->p_tail, st);
-      k_fm_tail<<<cgrid, 32, 0, st>>>(h->r_48b, d_audio, audio_stride, h->d_state, d_flags, d_e48, (int)nb, j0, h->tail);
+      k_fm_tail<<<cgrid, kTailThreads, sizeof(TailSmem), st>>>(h->r_48b, d_audio, audio_stride, h->d_state, d_flags, d_e48, (int)nb, j0, h->tail);
       pf.end(h->p_tail, st);
       launches += 2;
     }

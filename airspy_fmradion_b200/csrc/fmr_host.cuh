@@ -253,7 +253,7 @@ template <typename S> struct Resampler {
     size_t total = 0;
     // levels 0 and 1 are live together; level 2 aliases level 0 (see k_hb_cascade)
     for (int s = 0; s < nst && s < 2; s++) {
-      total += 2 * (size_t)kHbR * hb_sub_len(hb_level_len(t.n, nst, s), (int)sizeof(V));
+      total += 2 * (size_t)kHbR * hb_sub_len(hb_level_len(t.n, nst, s, HbTile<S>::value), (int)sizeof(V));
     }
     return total * sizeof(V) + 16;
   }
@@ -294,7 +294,7 @@ template <typename S> struct Resampler {
       if (hbt.n[s] > 14) return fail(FMR_ERR_UNSUPPORTED, "half-band stage longer than 14 taps");
       for (int k = 0; k < hbt.n[s]; k++) hbt.t[s][k] = (S)d->hb[s].taps[k];
     }
-    for (int s = 0; s < d->n_hb; s++) hbt.sl[s] = hb_sub_len(hb_level_len(hbt.n, d->n_hb, s), (int)sizeof(V));
+    for (int s = 0; s < d->n_hb; s++) hbt.sl[s] = hb_sub_len(hb_level_len(hbt.n, d->n_hb, s, HbTile<S>::value), (int)sizeof(V));
     smem_hb = hb_smem(hbt, d->n_hb);
     cudaError_t e = cudaSuccess;
     const size_t smem_need = smem_hb;
@@ -784,7 +784,7 @@ template <typename S> struct Resampler {
         const size_t sm = smem_hb;
         auto tiled = [&](int64_t o0, int cnt) {
           if (cnt <= 0) return;
-          dim3 grid((cnt + kHbTile - 1) / kHbTile, gcn);
+          dim3 grid((cnt + HbTile<S>::value - 1) / HbTile<S>::value, gcn);
           hb_dispatch([&](auto kern) { kern<<<grid, kHbThreads, sm, st>>>(src, hb_out_ring, tp, o0, cnt, fs4); });
           (*launches)++;
         };

@@ -100,6 +100,12 @@ template <typename S> struct HbTaps {
 constexpr int kHbTile = FMR_HB_TILE;
 constexpr int kHbThreads = FMR_HB_THREADS;
 constexpr int kHbR = 4; // consecutive outputs per thread (register blocking)
+// Final-rate outputs per CTA. A stage hands groups of kHbR outputs to the kHbThreads threads; the FP64 cascade of the
+// audio resampler (7 + 13 taps) gets the tile for which both stages fill whole rounds of threads (255 and 121 groups
+// for 128 threads; with 256 the rounds were 141 and 64 groups: half of the thread slots idle).
+template <typename S> struct HbTile {
+  static constexpr int value = sizeof(S) == 8 ? 484 : kHbTile;
+};
 
 // Shared-memory layout of one level: even- and odd-indexed samples in two separate arrays
 // (E[m] = x[2m], O[j] = x[2j+1]) because a half-band output reads x[2m] and only ODD
@@ -107,8 +113,8 @@ constexpr int kHbR = 4; // consecutive outputs per thread (register blocking)
 // position j / kHbR) so that a thread that owns kHbR consecutive outputs, and whose window
 // of odd neighbours therefore advances kHbR elements per thread, still gives the warp
 // contiguous (bank-conflict-free) addresses for every window slot.
-__host__ __device__ inline int hb_level_len(const int *ntaps, int nst, int s) {
-  int full = kHbTile; // number of samples of level s needed by a full tile
+__host__ __device__ inline int hb_level_len(const int *ntaps, int nst, int s, int tile) {
+  int full = tile; // number of samples of level s needed by a full tile
   for (int q = nst; q > s; q--) full = 2 * full + 4 * ntaps[q - 1] - 3;
   return full;
 }
@@ -207,11 +213,12 @@ __global__ void __launch_bounds__(kHbThreads)
     k_hb_cascade(InSrc<typename V2<S>::type> in, Ring<typename V2<S>::type> out, HbTaps<S> taps,
                  int64_t o0, int n_out, int fs4) {
   using V = typename V2<S>::type;
+  constexpr int kTile = HbTile<S>::value;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t c = blockIdx.y;
-  const int64_t a_fin = o0 + (int64_t)blockIdx.x * kHbTile;
-  int cnt_fin = n_out - (int)(blockIdx.x * kHbTile);
-  if (cnt_fin > kHbTile) cnt_fin = kHbTile;
+  const int64_t a_fin = o0 + (int64_t)blockIdx.x * kTile;
+  int cnt_fin = n_out - (int)(blockIdx.x * kTile);
+  if (cnt_fin > kTile) cnt_fin = kTile;
   if (cnt_fin <= 0) return;
 
   if (NST == 0) { // plain copy (+ Fs/4 shift)
@@ -254,9 +261,9 @@ __global__ void __launch_bounds__(kHbThreads)
     const int npairs = (int)(((lo[0] + len[0] - 1) >> 1) - eb) + 1 + kHbR; // a few extra: window overrun
     constexpr int kN1 = (N1 > 0 ? N1 : 1), kN2 = (N2 > 0 ? N2 : 0), kN3 = (N3 > 0 ? N3 : 0);
     // level-0 samples of a full tile (compile time) -> loads per thread
-    constexpr int kLen0 = (NST == 1)   ? (2 * kHbTile + 4 * kN1 - 3)
-                          : (NST == 2) ? (2 * (2 * kHbTile + 4 * kN2 - 3) + 4 * kN1 - 3)
-                                       : (2 * (2 * (2 * kHbTile + 4 * kN3 - 3) + 4 * kN2 - 3) + 4 * kN1 - 3);
+    constexpr int kLen0 = (NST == 1)   ? (2 * kTile + 4 * kN1 - 3)
+                          : (NST == 2) ? (2 * (2 * kTile + 4 * kN2 - 3) + 4 * kN1 - 3)
+                                       : (2 * (2 * (2 * kTile + 4 * kN3 - 3) + 4 * kN2 - 3) + 4 * kN1 - 3);
     constexpr int kMaxPairs = kLen0 / 2 + 2 + kHbR;
     constexpr int kBatch = (kMaxPairs + kHbThreads - 1) / kHbThreads;
     bool fast = false;
@@ -326,17 +333,33 @@ __global__ void __launch_bounds__(kHbThreads)
       }
     }
     if (!fast) {
-      for (int i = threadIdx.x; i < npairs; i += kHbThreads) {
-        const int64_t a0 = 2 * (eb + i);
-        V v0 = src_ld<V, LINEAR>(in, c, a0);
-        V v1 = src_ld<V, LINEAR>(in, c, a0 + 1);
-        if (fs4) {
-          v0 = fs4_rot(v0, a0);
-          v1 = fs4_rot(v1, a0 + 1);
+      // generic source (ring, history, int16 at an odd offset, FP64): still all loads of a batch before the first
+      // store, so a thread pays one memory round trip per kGen pairs instead of one per pair
+      constexpr int kGen = 4;
+      for (int i0 = threadIdx.x; i0 < npairs; i0 += kGen * kHbThreads) {
+        V v0[kGen], v1[kGen];
+#pragma unroll
+        for (int q = 0; q < kGen; q++) {
+          const int i = i0 + q * kHbThreads;
+          const int64_t a0 = 2 * (eb + i);
+          if (i < npairs) {
+            v0[q] = src_ld<V, LINEAR>(in, c, a0);
+            v1[q] = src_ld<V, LINEAR>(in, c, a0 + 1);
+          }
         }
-        if (i / kHbR < sl[0]) {
-          E[0][hb_pos(i, sl[0])] = v0;
-          O[0][hb_pos(i, sl[0])] = v1;
+#pragma unroll
+        for (int q = 0; q < kGen; q++) {
+          const int i = i0 + q * kHbThreads;
+          const int64_t a0 = 2 * (eb + i);
+          if (i < npairs && i / kHbR < sl[0]) {
+            V w0 = v0[q], w1 = v1[q];
+            if (fs4) {
+              w0 = fs4_rot(w0, a0);
+              w1 = fs4_rot(w1, a0 + 1);
+            }
+            E[0][hb_pos(i, sl[0])] = w0;
+            O[0][hb_pos(i, sl[0])] = w1;
+          }
         }
       }
     }
@@ -602,7 +625,10 @@ __global__ void k_fir_head_fix(Ring<typename V2<S>::type> x, Ring<typename V2<S>
   }
 }
 
-constexpr int kQR = 4;        // consecutive outputs per thread
+#ifndef FMR_QR
+#define FMR_QR 4
+#endif
+constexpr int kQR = FMR_QR;   // consecutive outputs per thread
 constexpr int kQThreads = 64; // tile = 256 outputs
 constexpr int kQTile = kQR * kQThreads;
 
@@ -639,20 +665,44 @@ __global__ void __launch_bounds__(kQThreads)
   // stream start stay exact zeros, which the discriminator's atan2(0,0) depends on).
   V *xs = reinterpret_cast<V *>(smem_raw); // [kQR][LEN]
   S *hs = reinterpret_cast<S *>(xs + kQR * LEN); // hs[k'] = coeff[k' + 1]
+  // The reference call of this thread's oldest output (the others follow by stepping through call_end). The
+  // bisection is a chain of dependent loads: it runs before the tile's loads are issued, so that each step waits
+  // for a cache hit and not for the memory round trips queued behind it.
+  const int tid = threadIdx.x;
+  int bcall = find_call(call_end, n_calls, (uint32_t)(tile0 + kQTile - kQR * (tid + 1)));
+  uint32_t cend = call_end[bcall], cstart = (bcall == 0) ? 0u : call_end[bcall - 1];
   const int64_t E = j0 + tile0 + kQTile - 2;
   const int span = kQTile + ntp + kQR;
   const int64_t last = j0 + tile0 + cnt - 1; // newest sample this tile may read
-  for (int i = threadIdx.x; i < span; i += kQThreads) {
-    V v;
-    v.x = 0;
-    v.y = 0;
-    const int64_t xi = E - i;
-    if (xi <= last && i < kQTile + order) v = in.ld(c, xi);
-    if (i / kQR < LEN) xs[(i % kQR) * LEN + i / kQR] = v;
+  // the loads of a thread go out back to back (one memory round trip per kFill * kQThreads samples), then the stores
+  constexpr int kFill = 8;
+  for (int i0 = threadIdx.x; i0 < span; i0 += kFill * kQThreads) {
+    V v[kFill];
+#pragma unroll
+    for (int q = 0; q < kFill; q++) {
+      const int i = i0 + q * kQThreads;
+      v[q].x = 0;
+      v[q].y = 0;
+      const int64_t xi = E - i;
+      if (i < span && xi <= last && i < kQTile + order) v[q] = in.ld(c, xi);
+    }
+#pragma unroll
+    for (int q = 0; q < kFill; q++) {
+      const int i = i0 + q * kQThreads;
+      if (i < span && i / kQR < LEN) xs[(i % kQR) * LEN + i / kQR] = v[q];
+    }
   }
   for (int i = threadIdx.x; i < ntp; i += kQThreads) hs[i] = (i < order) ? coeff[i + 1] : (S)0;
+  // x[p] of every output for the coeff[0] term, fetched while the tile is in flight
+  V xp[kQR];
+#pragma unroll
+  for (int r = 0; r < kQR; r++) {
+    const int u = kQTile - 1 - (kQR * tid + r);
+    xp[r].x = 0;
+    xp[r].y = 0;
+    if (u < cnt) xp[r] = in.ld(c, j0 + tile0 + u);
+  }
   __syncthreads();
-  const int tid = threadIdx.x;
   V acc[kQR], w[kQR];
 #pragma unroll
   for (int r = 0; r < kQR; r++) {
@@ -676,18 +726,19 @@ __global__ void __launch_bounds__(kQThreads)
   }
   const S c0 = coeff[0];
 #pragma unroll
-  for (int r = 0; r < kQR; r++) {
+  for (int r = kQR - 1; r >= 0; r--) { // oldest output first: the call index only moves forward
     const int v = kQR * tid + r;
     const int u = kQTile - 1 - v;
     const int i = tile0 + u; // index within this launch
     if (u < cnt) {
-      const int b = find_call(call_end, n_calls, (uint32_t)i);
-      const uint32_t cstart = (b == 0) ? 0u : call_end[b - 1];
+      while ((uint32_t)i >= cend && bcall < n_calls - 1) {
+        cstart = cend;
+        cend = call_end[++bcall];
+      }
       V y = acc[r];
       if (i - (int)cstart >= order) { // outside the head loop of the reference: coeff[0]*x[p] is added
-        const V x = in.ld(c, j0 + i);
-        y.x += c0 * x.x;
-        y.y += c0 * x.y;
+        y.x += c0 * xp[r].x;
+        y.y += c0 * xp[r].y;
       }
       out.st(c, j0 + i, y);
     }
@@ -1182,79 +1233,149 @@ struct FmTailParams {
   int n_channels;
 };
 
-static __global__ void k_fm_tail(Ring<double2> in48, double *__restrict__ audio, size_t audio_stride,
-                          FmChanState *__restrict__ st, const uint8_t *__restrict__ flags,
-                          const uint32_t *__restrict__ call_end48, int n_calls, int64_t j0, FmTailParams P) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= P.n_channels) return;
-  double m1 = st[c].dc_m_x1, m2 = st[c].dc_m_x2, s1 = st[c].dc_s_x1, s2 = st[c].dc_s_x2;
-  double *o = audio + (size_t)c * audio_stride;
+// One CTA = 32 channels. Warp 0 runs the recurrences (lane = channel) and nothing else: a single warp pays the full
+// latency of every instruction it issues, so everything that is not on the dependent chain is done by the three
+// helper warps beside it. Warps 2 and 3 move tiles of kTailT samples between HBM and shared memory in rows (lane =
+// sample: 512 contiguous bytes of one channel per instruction, transposed through shared memory with a +1 pad), one
+// tile ahead of / behind the recurrence warp. Warp 1 looks up the stereo flag of (channel, reference call): lane =
+// sample steps to its call and gathers the 32 channels' flags into one word (a reference call is only ~10 samples
+// long at 48 kHz, so a per-channel lookup inside the recurrence would stall it every few samples). The lookups are a
+// chain of dependent loads and have a warp of their own: behind a batch of row loads every step of the chain would
+// wait for the whole batch.
+constexpr int kTailT = 32;
+constexpr int kTailThreads = 128;
+struct TailSmem {
+  double2 tin[2][32][kTailT + 1];
+  double2 tout[2][32][kTailT + 1];
+  uint32_t det[2][kTailT]; // [tile parity][sample]: bit r = stereo flag of channel c0 + r
+};
+
+static __global__ void __launch_bounds__(kTailThreads)
+k_fm_tail(Ring<double2> in48, double *__restrict__ audio, size_t audio_stride, FmChanState *__restrict__ st,
+          const uint8_t *__restrict__ flags, const uint32_t *__restrict__ call_end48, int n_calls, int64_t j0,
+          FmTailParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TailSmem &sm = *reinterpret_cast<TailSmem *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c0 = blockIdx.x * 32, c = c0 + lane;
+  const int rows = min(32, P.n_channels - c0);
   const int n_total = n_calls ? (int)call_end48[n_calls - 1] : 0;
-  int b = 0;
-  while (b < n_calls && call_end48[b] == 0) b++;
-  uint32_t end = (b < n_calls) ? call_end48[b] : 0;
-  int det = (b < n_calls) ? flags[(size_t)c * n_calls + b] : 0;
-  double2 nxt[kCoreChunk];
+  const int n_tiles = (n_total + kTailT - 1) / kTailT;
+  // 16-byte row stores need every channel row of the caller's buffer on a 16-byte boundary
+  const bool wide = P.stereo && (audio_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(audio) & 15) == 0;
+
+  // warp 1: stereo flags of tile k (lane = sample). Its call index only moves forward from tile to tile.
+  int fcall = 0;
+  auto flag_tile = [&](int k) {
+    const int par = k & 1, i = k * kTailT + lane;
+    uint32_t m = 0;
+    if (i < n_total && P.stereo) {
+      while (call_end48[fcall] <= (uint32_t)i) fcall++;
+      uint8_t f[32];
 #pragma unroll
-  for (int u = 0; u < kCoreChunk; u++) nxt[u] = (u < n_total) ? in48.ld(c, j0 + u) : make_double2(0.0, 0.0);
-  for (int i0 = 0; i0 < n_total; i0 += kCoreChunk) {
-    double2 xin[kCoreChunk];
+      for (int r = 0; r < 32; r++) f[r] = (r < rows) ? flags[(size_t)(c0 + r) * n_calls + fcall] : (uint8_t)0;
 #pragma unroll
-    for (int u = 0; u < kCoreChunk; u++) xin[u] = nxt[u];
+      for (int r = 0; r < 32; r++) m |= (f[r] ? 1u : 0u) << r;
+    }
+    sm.det[par][lane] = m;
+  };
+  // warps 2, 3: the even / odd rows of tile k (all loads of a warp in flight together)
+  auto load_tile = [&](int k) {
+    const int par = k & 1, i = k * kTailT + lane;
+    double2 v[16];
 #pragma unroll
-    for (int u = 0; u < kCoreChunk; u++) {
-      const int i = i0 + kCoreChunk + u;
-      nxt[u] = (i < n_total) ? in48.ld(c, j0 + i) : make_double2(0.0, 0.0);
+    for (int q = 0; q < 16; q++) {
+      const int r = (warp - 2) + 2 * q;
+      v[q] = (r < rows && i < n_total) ? in48.ld(c0 + r, j0 + i) : make_double2(0.0, 0.0);
     }
 #pragma unroll
-    for (int u = 0; u < kCoreChunk; u++) {
-      const uint32_t r = (uint32_t)(i0 + u);
-      if ((int)r >= n_total) break;
-      while (r >= end) { // next non-empty call (and its stereo flag)
-        b++;
-        end = call_end48[b];
-        det = flags[(size_t)c * n_calls + b];
-      }
-      const double2 x = xin[u];
-      const double m0 = x.x - (P.a1 * m1 + P.a2 * m2);
-      const double mono = P.b0 * m0 + P.b1 * m1 + P.b2 * m2;
-      m2 = m1;
-      m1 = m0;
+    for (int q = 0; q < 16; q++) sm.tin[par][(warp - 2) + 2 * q][lane] = v[q];
+  };
+  auto store_tile = [&](int k) { // warps 2, 3: the even / odd rows of tile k
+    const int par = k & 1;
+    const size_t i = (size_t)k * kTailT + lane;
+    if (i >= (size_t)n_total) return;
+    for (int r = warp - 2; r < rows; r += 2) {
+      double *o = audio + (size_t)(c0 + r) * audio_stride;
+      const double2 v = sm.tout[par][r][lane];
       if (!P.stereo) {
-        o[r] = mono;
-        continue;
-      }
-      const double s0 = x.y - (P.a1 * s1 + P.a2 * s2);
-      const double ster = P.b0 * s0 + P.b1 * s1 + P.b2 * s2;
-      s2 = s1;
-      s1 = s0;
-      double l, rr;
-      if (det) {
-        if (P.pilot_shift) {
-          l = ster;
-          rr = ster;
-        } else {
-          const double sb = 1.017 * ster;
-          l = mono + sb;
-          rr = mono - sb;
-        }
+        o[i] = v.x;
+      } else if (wide) {
+        *reinterpret_cast<double2 *>(o + 2 * i) = v;
       } else {
-        if (P.pilot_shift) {
-          l = 0.0;
-          rr = 0.0;
-        } else {
-          l = mono;
-          rr = mono;
-        }
+        o[2 * i] = v.x;
+        o[2 * i + 1] = v.y;
       }
-      o[2 * (size_t)r] = l;
-      o[2 * (size_t)r + 1] = rr;
     }
+  };
+
+  const bool live = warp == 0 && c < P.n_channels;
+  double m1 = 0.0, m2 = 0.0, s1 = 0.0, s2 = 0.0;
+  if (live) {
+    m1 = st[c].dc_m_x1;
+    m2 = st[c].dc_m_x2;
+    s1 = st[c].dc_s_x1;
+    s2 = st[c].dc_s_x2;
   }
-  st[c].dc_m_x1 = m1;
-  st[c].dc_m_x2 = m2;
-  st[c].dc_s_x1 = s1;
-  st[c].dc_s_x2 = s2;
+  if (n_tiles > 0) {
+    if (warp == 1) flag_tile(0);
+    if (warp >= 2) load_tile(0);
+  }
+  __syncthreads();
+  for (int k = 0; k < n_tiles; k++) {
+    const int par = k & 1;
+    if (warp == 1) {
+      if (k + 1 < n_tiles) flag_tile(k + 1);
+    } else if (warp >= 2) {
+      if (k + 1 < n_tiles) load_tile(k + 1);
+      if (k > 0) store_tile(k - 1);
+    } else if (live) {
+      const int nu = min(kTailT, n_total - k * kTailT);
+      for (int u = 0; u < nu; u++) {
+        const double2 x = sm.tin[par][lane][u];
+        const double m0 = x.x - (P.a1 * m1 + P.a2 * m2);
+        const double mono = P.b0 * m0 + P.b1 * m1 + P.b2 * m2;
+        m2 = m1;
+        m1 = m0;
+        if (!P.stereo) {
+          sm.tout[par][lane][u] = make_double2(mono, 0.0);
+          continue;
+        }
+        const double s0 = x.y - (P.a1 * s1 + P.a2 * s2);
+        const double ster = P.b0 * s0 + P.b1 * s1 + P.b2 * s2;
+        s2 = s1;
+        s1 = s0;
+        const bool det = (sm.det[par][u] >> lane) & 1u;
+        double l, rr;
+        if (det) {
+          if (P.pilot_shift) {
+            l = ster;
+            rr = ster;
+          } else {
+            const double sb = 1.017 * ster;
+            l = mono + sb;
+            rr = mono - sb;
+          }
+        } else {
+          if (P.pilot_shift) {
+            l = 0.0;
+            rr = 0.0;
+          } else {
+            l = mono;
+            rr = mono;
+          }
+        }
+        sm.tout[par][lane][u] = make_double2(l, rr);
+      }
+    }
+    __syncthreads();
+  }
+  if (warp >= 2 && n_tiles > 0) store_tile(n_tiles - 1);
+  if (live) {
+    st[c].dc_m_x1 = m1;
+    st[c].dc_m_x2 = m2;
+    st[c].dc_s_x1 = s1;
+    st[c].dc_s_x2 = s2;
+  }
 }
 
 // Keep the last kHist input samples of every channel for the next call's halo.
