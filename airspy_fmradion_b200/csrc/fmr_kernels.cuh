@@ -1237,17 +1237,20 @@ struct FmTailParams {
 // latency of every instruction it issues, so everything that is not on the dependent chain is done by the three
 // helper warps beside it. Warps 2 and 3 move tiles of kTailT samples between HBM and shared memory in rows (lane =
 // sample: 512 contiguous bytes of one channel per instruction, transposed through shared memory with a +1 pad), one
-// tile ahead of / behind the recurrence warp. Warp 1 looks up the stereo flag of (channel, reference call): lane =
-// sample steps to its call and gathers the 32 channels' flags into one word (a reference call is only ~10 samples
-// long at 48 kHz, so a per-channel lookup inside the recurrence would stall it every few samples). The lookups are a
-// chain of dependent loads and have a warp of their own: behind a batch of row loads every step of the chain would
-// wait for the whole batch.
+// tile ahead of / behind the recurrence warp. Warp 1 prepares, for the next tile, the list of reference calls that
+// intersect it: (end, stereo flags of the 32 channels as one word) — lane = channel loads the flag bytes of four calls
+// at a time and a ballot packs them. A reference call is only ~10 samples long at 48 kHz: a lookup inside the
+// recurrence would stall it every few samples, and behind a batch of row loads every lookup would wait for the batch.
+// The recurrence warp works in groups of eight samples: first only the two dependent chains (DC-block state of mono
+// and L-R, 2 FP64 operations per sample each), then the eight outputs, which are independent of each other.
 constexpr int kTailT = 32;
+constexpr int kTailG = 8;
 constexpr int kTailThreads = 128;
 struct TailSmem {
   double2 tin[2][32][kTailT + 1];
   double2 tout[2][32][kTailT + 1];
-  uint32_t det[2][kTailT]; // [tile parity][sample]: bit r = stereo flag of channel c0 + r
+  uint32_t ent_end[2][kTailT + 2];  // [tile parity][entry]: end (sample index of the launch) of a call of the tile
+  uint32_t ent_mask[2][kTailT + 2]; // bit r = stereo flag of channel c0 + r during that call
 };
 
 static __global__ void __launch_bounds__(kTailThreads)
@@ -1263,20 +1266,46 @@ k_fm_tail(Ring<double2> in48, double *__restrict__ audio, size_t audio_stride, F
   // 16-byte row stores need every channel row of the caller's buffer on a 16-byte boundary
   const bool wide = P.stereo && (audio_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(audio) & 15) == 0;
 
-  // warp 1: stereo flags of tile k (lane = sample). Its call index only moves forward from tile to tile.
-  int fcall = 0;
+  // warp 1: the calls of tile k in order; empty calls and calls that ended before the tile are left out, the last
+  // entry reaches the end of the tile
+  int bq = 0; // first call that may still intersect the next tile (warp-uniform)
   auto flag_tile = [&](int k) {
-    const int par = k & 1, i = k * kTailT + lane;
-    uint32_t m = 0;
-    if (i < n_total && P.stereo) {
-      while (call_end48[fcall] <= (uint32_t)i) fcall++;
-      uint8_t f[32];
+    if (!P.stereo) return;
+    const int par = k & 1;
+    const uint32_t t1 = (uint32_t)min((k + 1) * kTailT, n_total);
+    uint32_t pos = (uint32_t)(k * kTailT);
+    int n = 0;
+    const uint8_t *frow = flags + (size_t)min(c, P.n_channels - 1) * n_calls;
+    for (bool done = false; !done;) {
+      uint32_t e[4], m[4];
+      uint8_t f[4];
+      const int b0 = bq;
 #pragma unroll
-      for (int r = 0; r < 32; r++) f[r] = (r < rows) ? flags[(size_t)(c0 + r) * n_calls + fcall] : (uint8_t)0;
+      for (int q = 0; q < 4; q++) {
+        const int bb = min(b0 + q, n_calls - 1);
+        e[q] = call_end48[bb];
+        f[q] = frow[bb];
+      }
 #pragma unroll
-      for (int r = 0; r < 32; r++) m |= (f[r] ? 1u : 0u) << r;
+      for (int q = 0; q < 4; q++) m[q] = __ballot_sync(0xffffffffu, f[q] != 0 && lane < rows);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (done) break;
+        if (e[q] > pos) { // a call with samples in [pos, ..)
+          if (lane == 0) {
+            sm.ent_end[par][n] = e[q];
+            sm.ent_mask[par][n] = m[q];
+          }
+          n++;
+          pos = e[q];
+        }
+        if (e[q] >= t1) {
+          done = true; // this call may go on into the next tile: bq stays on it
+        } else {
+          bq++;
+        }
+      }
     }
-    sm.det[par][lane] = m;
   };
   // warps 2, 3: the even / odd rows of tile k (all loads of a warp in flight together)
   auto load_tile = [&](int k) {
@@ -1316,6 +1345,22 @@ k_fm_tail(Ring<double2> in48, double *__restrict__ audio, size_t audio_stride, F
     s1 = st[c].dc_s_x1;
     s2 = st[c].dc_s_x2;
   }
+  // one output pair from the filter states (m0, m1, m2 newest first), exactly the reference's expressions
+  auto emit = [&](double m0, double ma, double mb, double s0, double sa, double sb2, bool det) -> double2 {
+    const double mono = P.b0 * m0 + P.b1 * ma + P.b2 * mb;
+    if (!P.stereo) return make_double2(mono, 0.0);
+    const double ster = P.b0 * s0 + P.b1 * sa + P.b2 * sb2;
+    double l, rr;
+    if (P.pilot_shift) {
+      l = det ? ster : 0.0;
+      rr = l;
+    } else {
+      const double sb = 1.017 * ster;
+      l = det ? mono + sb : mono;
+      rr = det ? mono - sb : mono;
+    }
+    return make_double2(l, rr);
+  };
   if (n_tiles > 0) {
     if (warp == 1) flag_tile(0);
     if (warp >= 2) load_tile(0);
@@ -1330,41 +1375,63 @@ k_fm_tail(Ring<double2> in48, double *__restrict__ audio, size_t audio_stride, F
       if (k > 0) store_tile(k - 1);
     } else if (live) {
       const int nu = min(kTailT, n_total - k * kTailT);
-      for (int u = 0; u < nu; u++) {
+      int ej = 0;
+      uint32_t eend = P.stereo ? sm.ent_end[par][0] : 0xffffffffu, emask = P.stereo ? sm.ent_mask[par][0] : 0u;
+      int u0 = 0;
+      for (; u0 + kTailG <= nu; u0 += kTailG) {
+        double2 x[kTailG];
+        double mv[kTailG + 2], sv[kTailG + 2]; // [q + 2] = state after sample q; [1], [0] = the two before the group
+        bool det[kTailG];
+#pragma unroll
+        for (int q = 0; q < kTailG; q++) x[q] = sm.tin[par][lane][u0 + q];
+        mv[1] = m1;
+        mv[0] = m2;
+        sv[1] = s1;
+        sv[0] = s2;
+#pragma unroll
+        for (int q = 0; q < kTailG; q++) { // the dependent chains only
+          mv[q + 2] = x[q].x - (P.a1 * mv[q + 1] + P.a2 * mv[q]);
+          if (P.stereo) sv[q + 2] = x[q].y - (P.a1 * sv[q + 1] + P.a2 * sv[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kTailG; q++) {
+          const uint32_t i = (uint32_t)(k * kTailT + u0 + q);
+          while (i >= eend) {
+            ej++;
+            eend = sm.ent_end[par][ej];
+            emask = sm.ent_mask[par][ej];
+          }
+          det[q] = (emask >> lane) & 1u;
+        }
+#pragma unroll
+        for (int q = 0; q < kTailG; q++) {
+          sm.tout[par][lane][u0 + q] = emit(mv[q + 2], mv[q + 1], mv[q], sv[q + 2], sv[q + 1], sv[q], det[q]);
+        }
+        m1 = mv[kTailG + 1];
+        m2 = mv[kTailG];
+        if (P.stereo) {
+          s1 = sv[kTailG + 1];
+          s2 = sv[kTailG];
+        }
+      }
+      for (int u = u0; u < nu; u++) { // the last, shorter group of the launch
         const double2 x = sm.tin[par][lane][u];
         const double m0 = x.x - (P.a1 * m1 + P.a2 * m2);
-        const double mono = P.b0 * m0 + P.b1 * m1 + P.b2 * m2;
+        double s0 = 0.0;
+        if (P.stereo) s0 = x.y - (P.a1 * s1 + P.a2 * s2);
+        const uint32_t i = (uint32_t)(k * kTailT + u);
+        while (i >= eend) {
+          ej++;
+          eend = sm.ent_end[par][ej];
+          emask = sm.ent_mask[par][ej];
+        }
+        sm.tout[par][lane][u] = emit(m0, m1, m2, s0, s1, s2, (emask >> lane) & 1u);
         m2 = m1;
         m1 = m0;
-        if (!P.stereo) {
-          sm.tout[par][lane][u] = make_double2(mono, 0.0);
-          continue;
+        if (P.stereo) {
+          s2 = s1;
+          s1 = s0;
         }
-        const double s0 = x.y - (P.a1 * s1 + P.a2 * s2);
-        const double ster = P.b0 * s0 + P.b1 * s1 + P.b2 * s2;
-        s2 = s1;
-        s1 = s0;
-        const bool det = (sm.det[par][u] >> lane) & 1u;
-        double l, rr;
-        if (det) {
-          if (P.pilot_shift) {
-            l = ster;
-            rr = ster;
-          } else {
-            const double sb = 1.017 * ster;
-            l = mono + sb;
-            rr = mono - sb;
-          }
-        } else {
-          if (P.pilot_shift) {
-            l = 0.0;
-            rr = 0.0;
-          } else {
-            l = mono;
-            rr = mono;
-          }
-        }
-        sm.tout[par][lane][u] = make_double2(l, rr);
       }
     }
     __syncthreads();
