@@ -8,8 +8,9 @@
 A "step" is one pass of the hot path over one batch of synthetic IQ: every channel of the
 handle consumes `--blocks` source blocks of 2048 samples (FileSource's default block,
 FileSource.h:34) handed over as one super-block with its block partition. The default of 329
-blocks (673 792 samples, 67 ms of signal per channel) makes the overlap-save blocks of both
-resamplers come out whole (6 x 16384-point IF blocks, 1 x 8192-point audio block per channel).
+blocks (673 792 samples, 67 ms of signal per channel) fills one 8192-point block of the audio
+resampler's low-pass per channel and step; the IF resampler's 10000-point blocks lie on an absolute
+grid, ~11 per step, of which the fused front end takes those that lie inside the step.
 Streams are continuous across steps (filter/PLL/AGC state carries over).
 Metric = IQ Msamples/s consumed, summed over channels and GPUs (BASELINE.json).
 Prints ONE JSON line on rank 0.
@@ -263,12 +264,15 @@ def main():
 
     nblk = args.blocks
     T = nblk * BLK
-    # channels per GPU: as many as fit comfortably in 180 GB with their rings (the serial recurrences cost the same for
-    # 1 or 16384 channels, so throughput grows with the channel count); cfg4's 384 kHz rings are 10x larger per input
-    # sample; cfg3: 592 CTAs of 3 channels = one wave of the multipath kernel (4 CTAs/SM)
-    C = args.channels or {"cfg2_fm_stereo_10Msps": 16384, "cfg3_fm_stereo_10Msps_E200": 1776,
-                          "cfg4_fm_stereo_1Msps": 8192, "cfg5_am_384ksps": 8192}[wl]
-    Ce = min(C, 1024)  # channels of the end-to-end (host buffer) measurement: 16384 would need 88 GB of pinned memory
+    # channels per GPU: many (the serial recurrences cost the same for 1 or 14208 channels, so throughput grows with the
+    # channel count, and the input must exceed the L2), fitting 180 GB with their rings, and a multiple of
+    # 148 SMs x 32 channels per CTA of the lane-per-channel kernels, so that every SM holds the same number of their
+    # CTAs (3 for cfg2; with 16384 channels some SMs hold 4 and the 384 kHz core waits for those: 302 instead of
+    # 310 Gsamples/s). cfg4's 384 kHz rings are 10x larger per input sample; cfg3: 592 CTAs of 3 channels = one wave of
+    # the multipath kernel (4 CTAs/SM)
+    C = args.channels or {"cfg2_fm_stereo_10Msps": 14208, "cfg3_fm_stereo_10Msps_E200": 1776,
+                          "cfg4_fm_stereo_1Msps": 9472, "cfg5_am_384ksps": 9472}[wl]
+    Ce = min(C, 1024)  # channels of the end-to-end (host buffer) measurement: all of them would need 77 GB of pinned memory
     config = {"workload": wl, "channels_per_gpu": C, "samples_per_channel_per_step": T,
               "block": BLK, "blocks_per_step": nblk, "input_bytes_per_step": C * T * 8,
               "l2": "input per step (%.0f MB) exceeds the 126 MB L2" % (C * T * 8 / 1e6),

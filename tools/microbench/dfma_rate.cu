@@ -17,6 +17,28 @@ template <int CH> __global__ void k_dfma(double *out, int iters, double a, doubl
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FIR-shaped: acc[r] += h[q] * x[(r + q) % 8], every operand a different register (what a register-blocked FP64 FIR issues)
+__global__ void k_dfma_fir(double *out, const double *in, int iters) {
+  double acc[8], x[8], h[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    acc[i] = 0.0;
+    x[i] = in[threadIdx.x + 32 * i];
+    h[i] = in[threadIdx.x + 32 * i + 256];
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) acc[r] = fma(h[q], x[(r + q) % 8], acc[r]);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <int CH> __global__ void k_ffma(float *out, int iters, float a, float b) {
   float acc[CH];
 #pragma unroll
@@ -52,6 +74,20 @@ int main() {
       const double fma = (double)sms * threads * 8.0 * iters;
       if (rep) printf("DFMA threads/SM %4d: %.3f ms  %.2f TFLOP/s  %.1f FMA/clk/SM at %d MHz nominal\n", threads, ms,
                       2 * fma / ms * 1e-9, fma / (ms * 1e-3) / sms / (khz * 1e3), khz / 1000);
+    }
+  }
+  cudaMemset(d, 0, sizeof(double) * 1024);
+  for (int threads : {128, 256, 512}) {
+    for (int rep = 0; rep < 2; rep++) {
+      cudaEventRecord(e0);
+      k_dfma_fir<<<sms, threads>>>(d + 2048, d, iters / 8);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double fma = (double)sms * threads * 64.0 * (iters / 8);
+      if (rep) printf("DFMA (FIR-shaped, 3 register operands) threads/SM %4d: %.3f ms  %.2f TFLOP/s  %.1f FMA/clk/SM\n", threads, ms,
+                      2 * fma / ms * 1e-9, fma / (ms * 1e-3) / sms / (khz * 1e3));
     }
   }
   for (int threads : {512, 1024}) {

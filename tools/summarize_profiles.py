@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Turn what tools/collect_profiles.sh brought back in gpurun_out/ into the tracked summaries
-under profiles/ (run here, no GPU needed): key ncu metrics per captured kernel, DRAM traffic
-per input sample, launch shares, the bench sweep."""
+under profiles/ (run here, no GPU needed): key ncu metrics per captured kernel, launch shares,
+the bench sweep and the two bench lines. (profiles/traffic_rNN.json, the DRAM bytes per algorithmic
+byte of the kernel that streams the input, is written by hand from ncu_frontend_fused_rNN.txt.)"""
 import csv
 import glob
 import io
@@ -47,37 +48,16 @@ def raw_page(rep):
 
 
 def main():
-    traffic = {"note": "dram__bytes_read.sum + dram__bytes_write.sum per IQ input sample, one ncu --set full "
-                       "capture per kernel (profiles/ncu_*_%s.txt), C=1024 channels" % R}
-    # "fftip" (the in-place form, the default since the end of round 1) overrides "fft" (Stockham form) for the stage
-    stage_of = {"hbs": "if_halfband_cascade", "fft": "if_lowpass", "fftip": "if_lowpass", "core": "fm_core_fused"}
-    # samples per channel of the profiled run = bench default blocks
-    import re
-    blocks = int(re.search(r'"--blocks", type=int, default=(\d+)', open(os.path.join(ROOT, "bench.py")).read()).group(1))
-    n_in = 1024 * blocks * 2048
-    for tag, stage in stage_of.items():
-        rep = os.path.join(GO, "prof_%s_%s.ncu-rep" % (tag, R))
-        if not os.path.exists(rep):
-            continue
+    # key metrics of every full capture that came back (tools/collect_profiles.sh)
+    for rep in sorted(glob.glob(os.path.join(GO, "prof_*_%s.ncu-rep" % R))):
+        tag = os.path.basename(rep)[len("prof_"):-len("_%s.ncu-rep" % R)]
         ks, units = raw_page(rep)
         with open(os.path.join(OUT, "ncu_%s_%s.txt" % (tag, R)), "w") as f:
             for d in ks:
-                f.write("%-80s %s\n" % ("Kernel Name", d.get("Kernel Name")))
+                f.write("== %s  grid %s block %s\n" % (d.get("Kernel Name"), d.get("Grid Size"), d.get("Block Size")))
                 for k in KEYS:
                     if k in d:
-                        f.write("%-80s %s %s\n" % (k, d[k], units.get(k, "")))
-        # several launches may have been captured: take the kernel the stage is named after
-        want = {"fft": "k_fir_fft<float, 16384", "fftip": "k_fir_fft_ip"}.get(tag)
-        d = next((k for k in ks if want and want in k.get("Kernel Name", "")), ks[0])
-
-        def gb(k):
-            v = float(d[k].replace(",", ""))
-            u = units.get(k, "")
-            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
-        tot = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
-        traffic[stage] = {"kernel": d.get("Kernel Name", "")[:60], "dram_bytes": tot,
-                          "bytes_per_input_sample": tot / n_in, "input_samples": n_in}
-    json.dump(traffic, open(os.path.join(OUT, "traffic_%s.json" % R), "w"), indent=1)
+                        f.write("  %-80s %s %s\n" % (k, d[k], units.get(k, "")))
     # launch shares
     lc = os.path.join(GO, "launches_%s.csv" % R)
     if os.path.exists(lc):
@@ -98,7 +78,7 @@ def main():
         tot = sum(a[1] for a in agg.values())
         with open(os.path.join(OUT, "launch_shares_%s.txt" % R), "w") as f:
             f.write("kernel, launches, total (ncu gpu__time_duration.sum, unit as reported), share "
-                    "(C=1024, cold-cache serialised launches)\n")
+                    "(default bench, cold-cache serialised launches)\n")
             for name, a in sorted(agg.items(), key=lambda x: -x[1][1]):
                 f.write("%-70s %4d %12.1f %5.1f%%\n" % (name[:70], a[0], a[1], 100 * a[1] / tot))
         open(os.path.join(OUT, "launches_%s.csv" % R), "w").writelines(lines)
