@@ -426,6 +426,7 @@ __global__ void __launch_bounds__(kFirThreads)
   }
   const int base = threadIdx.x * down;
   const int rstep = kFirThreads * down;
+  if ((int)threadIdx.x >= cnt) return; // a short tile (the few outputs redone at stream start): no output in any round
   for (int k = 0; k < klen; k++) {
     const S h = hs[k];
 #pragma unroll
