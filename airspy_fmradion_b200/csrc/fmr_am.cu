@@ -518,8 +518,7 @@ static fmr_status am_build(fmr_am *h) {
                                      FftCfg<float, 8192>::kSmemBytes)));
     }
   }
-  FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)fq_smem(h->amfilter_taps, sizeof(float2), sizeof(float))));
+  FMR_CUDA(raise_smem_limit(k_fir_quirk<float>, fq_smem(h->amfilter_taps, sizeof(float2), sizeof(float))));
   FMR_CUDA(h->mem.alloc(&h->d_state, (size_t)C));
   FMR_CUDA(h->mem.alloc(&h->d_e48, (size_t)max_blocks));
   {
@@ -576,8 +575,7 @@ static fmr_status am_build(fmr_am *h) {
       FMR_CUDA(cudaMemcpy(h->d_cwfilter, k_jj1bdx_cw_48khz_500hz, 2049 * sizeof(float), cudaMemcpyHostToDevice));
       FMR_CUDA(h->mem.alloc(&h->d_ssbfilter, 2049, false));
       FMR_CUDA(cudaMemcpy(h->d_ssbfilter, k_jj1bdx_ssb_48khz_1500hz, 2049 * sizeof(float), cudaMemcpyHostToDevice));
-      FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)fq_smem(2049, sizeof(float2), sizeof(float))));
+      FMR_CUDA(raise_smem_limit(k_fir_quirk<float>, fq_smem(2049, sizeof(float2), sizeof(float))));
       if (!Resampler<float>::env_off("FMR_AM_FFT_FILTER")) {
         fmr_status sf = am_make_fft_filter(h->mem, k_jj1bdx_cw_48khz_500hz, 2049, &h->d_H_cw);
         if (sf == FMR_OK) sf = am_make_fft_filter(h->mem, k_jj1bdx_ssb_48khz_1500hz, 2049, &h->d_H_ssb);
@@ -620,8 +618,7 @@ static fmr_status am_build(fmr_am *h) {
     FMR_CUDA(h->mem.alloc(&h->r_aud.base, (size_t)C * h->r_aud.cap));
     FMR_CUDA(h->mem.alloc(&h->d_audiofilter, 63, false));
     FMR_CUDA(cudaMemcpy(h->d_audiofilter, k_jj1bdx_48khz_nbfmaudio, 63 * sizeof(double), cudaMemcpyHostToDevice));
-    FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)fq_smem(63, sizeof(double2), sizeof(double))));
+    FMR_CUDA(raise_smem_limit(k_fir_quirk<double>, fq_smem(63, sizeof(double2), sizeof(double))));
   }
   h->audio_cap = (size_t)max48;
   h->ifres.prof = &h->prof;

@@ -72,8 +72,9 @@ struct CfCalls {
   }
 };
 
+template <typename AV>
 static __global__ void __launch_bounds__(kCfThreads)
-    k_fm_core_fused(Ring<float2> if_raw, Ring<float2> iq_in, Ring<double2> out384, FmChanState *__restrict__ st,
+    k_fm_core_fused(Ring<float2> if_raw, Ring<float2> iq_in, Ring<AV> out384, FmChanState *__restrict__ st,
                     uint8_t *__restrict__ flags, PpsEventDev *__restrict__ pps, const uint32_t *__restrict__ call_end,
                     int n_calls, int64_t t0, FmCoreParams P, const float *__restrict__ atan_tbl, int block_off,
                     int reset_pps, int sm_count) {
@@ -211,7 +212,7 @@ static __global__ void __launch_bounds__(kCfThreads)
     double dem = sp->de_m_x1, des = sp->de_s_x1;
     const bool shift = P.pilot_shift != 0, de_st = P.deemph_on_stereo != 0;
     const double de_a1 = P.de_a1, de_b0 = P.de_b0;
-    double2 *__restrict__ orow = out384.base + (size_t)c * out384.cap;
+    AV *__restrict__ orow = out384.base + (size_t)c * out384.cap;
     const uint32_t omask = out384.cap - 1;
     cf_arrive(cf_empty(2, 0));
     cf_arrive(cf_empty(2, 1));
@@ -235,7 +236,7 @@ static __global__ void __launch_bounds__(kCfThreads)
         const double m0 = xd - de_a1 * dem;
         const double mono = de_b0 * m0;
         dem = m0;
-        if (act) orow[(t0lo + (uint32_t)(p0 + u)) & omask] = make_double2(mono, ster);
+        if (act) orow[(t0lo + (uint32_t)(p0 + u)) & omask] = aud_mk<AV>(mono, ster);
       }
       if (k + 2 < K) {
         cf_arrive(cf_empty(2, slot));

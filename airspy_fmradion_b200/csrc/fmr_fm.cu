@@ -20,6 +20,16 @@ using namespace fmr;
 constexpr int kMaxHostChunks = 8;       // time chunks of fmr_fm_process_host's copy/compute pipeline
 constexpr int kHostChunkMinBlocks = 16; // a chunk is at least this many source blocks
 
+// The FM audio chain between the 384 kHz core and the 48 kHz DC block, in sample type AS (see aud_mk in fmr_kernels.cuh).
+template <typename AS> struct AudioPath {
+  using AV = typename V2<AS>::type;
+  Resampler<AS> aures;       // 2x AudioResampler (mono, L-R as one complex stream)
+  Ring<AV> r_384{nullptr, 0}; // (mono, L-R) after deemphasis
+  Ring<AV> r_48a{nullptr, 0}; // audio resampler output
+  Ring<AV> r_48b{nullptr, 0}; // after pilot-cut FIR
+  AS *d_pilotcut = nullptr;
+};
+
 struct fmr_fm {
   fmr_fm_config cfg;
   bool core_fused = true; // FMR_CORE_FUSED=0: AGC / discriminator / PLL as separate launches
@@ -32,7 +42,6 @@ struct fmr_fm {
   cudaStream_t own_stream = nullptr;
 
   Resampler<float> ifres;
-  Resampler<double> aures;
   float2 *hist[2] = {nullptr, nullptr};
   int hist_cur = 0;
   Ring<float2> r_if{nullptr, 0};   // 384 kHz decoder input
@@ -41,16 +50,15 @@ struct fmr_fm {
   Ring<float2> r_mpf{nullptr, 0};  // after multipath filter
   Ring<float> r_mpx{nullptr, 0};   // discriminator output
   float *d_stats = nullptr;        // per (channel, block): if_rms, baseband mean, baseband rms
-  Ring<double2> r_384{nullptr, 0}; // (mono, L-R) after deemphasis
-  Ring<double2> r_48a{nullptr, 0}; // audio resampler output
-  Ring<double2> r_48b{nullptr, 0}; // after pilot-cut FIR
+  AudioPath<float> a32;   // the audio chain of this handle: FP32 filters (default) ...
+  AudioPath<double> a64;  // ... or the all-FP64 chain (FMR_AUDIO_FP64=1); only one of the two is initialised
+  bool audio_f64 = false;
   FmChanState *d_state = nullptr;
   uint8_t *d_flags = nullptr;
   PpsEventDev *d_pps = nullptr;
   uint32_t *d_e384 = nullptr, *d_e48 = nullptr;
   float *d_fmfilter = nullptr;
   int fmfilter_taps = 0;
-  double *d_pilotcut = nullptr;
   float *d_atan = nullptr;
   MpfDev mpf;
   Prof prof;
@@ -175,32 +183,40 @@ static fmr_status fm_build(fmr_fm *h) {
     fmr_status s = h->mpf.init(cfg.multipath_stages, C, h->mem);
     if (s != FMR_OK) return s;
   }
-  h->r_384.cap = pow2ceil((uint64_t)max384 + 512);
-  FMR_CUDA(h->mem.alloc(&h->r_384.base, (size_t)C * h->r_384.cap));
+  const int64_t max48 = max384 / 8 + 16;
+  if (const char *ev = getenv("FMR_AUDIO_FP64")) h->audio_f64 = atoi(ev) != 0;
+  auto init_audio = [&](auto &ap) -> fmr_status {
+    using AS = typename std::remove_reference<decltype(ap.aures)>::type::Scalar;
+    ap.r_384.cap = pow2ceil((uint64_t)max384 + 512);
+    FMR_CUDA(h->mem.alloc(&ap.r_384.base, (size_t)C * ap.r_384.cap));
+    fmr_status s = ap.aures.init(h->auc, C, max384, false, h->mem);
+    if (s != FMR_OK) return s;
+    ap.r_48a.cap = pow2ceil((uint64_t)max48 + 512);
+    FMR_CUDA(h->mem.alloc(&ap.r_48a.base, (size_t)C * ap.r_48a.cap));
+    ap.r_48b.cap = ap.r_48a.cap;
+    FMR_CUDA(h->mem.alloc(&ap.r_48b.base, (size_t)C * ap.r_48b.cap));
+    FMR_CUDA(h->mem.alloc(&ap.d_pilotcut, 127, false));
+    AS pc[127];
+    for (int i = 0; i < 127; i++) pc[i] = (AS)k_jj1bdx_48khz_fmaudio[i];
+    FMR_CUDA(cudaMemcpy(ap.d_pilotcut, pc, sizeof(pc), cudaMemcpyHostToDevice));
+    FMR_CUDA(cudaFuncSetAttribute(k_fm_tail<typename V2<AS>::type>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(TailSmem<typename V2<AS>::type>)));
+    return FMR_OK;
+  };
   {
-    fmr_status s = h->aures.init(h->auc, C, max384, false, h->mem);
+    const fmr_status s = h->audio_f64 ? init_audio(h->a64) : init_audio(h->a32);
     if (s != FMR_OK) return s;
   }
-  const int64_t max48 = max384 / 8 + 16;
-  h->r_48a.cap = pow2ceil((uint64_t)max48 + 512);
-  FMR_CUDA(h->mem.alloc(&h->r_48a.base, (size_t)C * h->r_48a.cap));
-  h->r_48b.cap = h->r_48a.cap;
-  FMR_CUDA(h->mem.alloc(&h->r_48b.base, (size_t)C * h->r_48b.cap));
   FMR_CUDA(h->mem.alloc(&h->d_state, (size_t)C));
   FMR_CUDA(h->mem.alloc(&h->d_flags, (size_t)C * max_blocks));
   FMR_CUDA(h->mem.alloc(&h->d_pps, (size_t)C * kMaxPps));
   FMR_CUDA(h->mem.alloc(&h->d_e384, (size_t)max_blocks));
   FMR_CUDA(h->mem.alloc(&h->d_e48, (size_t)max_blocks));
-  FMR_CUDA(h->mem.alloc(&h->d_pilotcut, 127, false));
-  FMR_CUDA(cudaMemcpy(h->d_pilotcut, k_jj1bdx_48khz_fmaudio, 127 * sizeof(double), cudaMemcpyHostToDevice));
   FMR_CUDA(h->mem.alloc(&h->d_atan, 257, false));
   FMR_CUDA(cudaMemcpy(h->d_atan, k_fast_atan_table, 257 * sizeof(float), cudaMemcpyHostToDevice));
 
-  FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)fq_smem(h->fmfilter_taps > 0 ? h->fmfilter_taps : 127, sizeof(float2), sizeof(float))));
-  FMR_CUDA(cudaFuncSetAttribute(k_fir_quirk<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)fq_smem(127, sizeof(double2), sizeof(double))));
-  FMR_CUDA(cudaFuncSetAttribute(k_fm_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
+  FMR_CUDA(raise_smem_limit(k_fir_quirk<float>, fq_smem(std::max(h->fmfilter_taps, 127), sizeof(float2), sizeof(float))));
+  FMR_CUDA(raise_smem_limit(k_fir_quirk<double>, fq_smem(127, sizeof(double2), sizeof(double))));
   // initial state (constructors: FmDecode.cpp:25-83, PilotPhaseLock.cpp:35-54, IfSimpleAgc.cpp:22-32)
   {
     std::vector<FmChanState> st(C);
@@ -263,9 +279,12 @@ static fmr_status fm_build(fmr_fm *h) {
   h->p_mpf = h->prof.add("fm_multipath");
   h->p_core = h->prof.add("fm_discriminator_stats");
   h->p_core2 = h->prof.add("fm_pll_stereo_deemph");
-  h->aures.prof = &h->prof;
-  h->aures.p_hb = h->prof.add("audio_halfband_cascade");
-  h->aures.p_bc = h->prof.add("audio_lowpass");
+  {
+    const int p_hb = h->prof.add("audio_halfband_cascade"), p_bc = h->prof.add("audio_lowpass");
+    h->a32.aures.prof = h->a64.aures.prof = &h->prof;
+    h->a32.aures.p_hb = h->a64.aures.p_hb = p_hb;
+    h->a32.aures.p_bc = h->a64.aures.p_bc = p_bc;
+  }
   h->p_pcut = h->prof.add("pilot_cut_fir");
   h->p_tail = h->prof.add("dcblock_matrix");
   return FMR_OK;
@@ -401,10 +420,24 @@ extern "C" fmr_status fmr_fm_process_device_i16(fmr_fm *h, const int16_t *d_iq, 
   return s;
 }
 
+template <typename AS>
+static fmr_status fm_process_device_t(fmr_fm *h, AudioPath<AS> &ap, const float *d_iq, size_t iq_stride,
+                                      const uint32_t *block_len, uint32_t n_blocks, double *d_audio, size_t audio_stride,
+                                      uint32_t *audio_len, void *stream);
+
 static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq_stride, const uint32_t *block_len,
                                          uint32_t n_blocks, double *d_audio, size_t audio_stride,
                                          uint32_t *audio_len, void *stream) {
   if (!h || !d_iq || !block_len || !d_audio) return fail(FMR_ERR_INVALID, "null argument");
+  return h->audio_f64 ? fm_process_device_t(h, h->a64, d_iq, iq_stride, block_len, n_blocks, d_audio, audio_stride, audio_len, stream)
+                      : fm_process_device_t(h, h->a32, d_iq, iq_stride, block_len, n_blocks, d_audio, audio_stride, audio_len, stream);
+}
+
+template <typename AS>
+static fmr_status fm_process_device_t(fmr_fm *h, AudioPath<AS> &ap, const float *d_iq, size_t iq_stride,
+                                      const uint32_t *block_len, uint32_t n_blocks, double *d_audio, size_t audio_stride,
+                                      uint32_t *audio_len, void *stream) {
+  using AV = typename V2<AS>::type;
   if (n_blocks == 0) return FMR_OK;
   if (n_blocks > h->cfg.max_blocks_per_call) return fail(FMR_ERR_CAPACITY, "n_blocks > max_blocks_per_call");
   FMR_CUDA(cudaSetDevice(h->cfg.device));
@@ -438,8 +471,8 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
   h->slots.commit(slot, st);
   h->ifres.gc0 = 0;
   h->ifres.gcn = C;
-  h->aures.gc0 = 0;
-  h->aures.gcn = C;
+  ap.aures.gc0 = 0;
+  ap.aures.gcn = C;
   const uint32_t flag_b0 = h->in_host_call ? h->host_b0 : 0;
   if (!h->in_host_call) h->last_chunks.clear();
   h->last_chunks.push_back(std::make_pair(flag_b0, n_blocks));
@@ -495,7 +528,7 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
     const int first = (flag_b0 == 0) ? 1 : 0;
     if (fused) {
       pf.begin(h->p_fused, st);
-      k_fm_core_fused<<<cgrid, kCfThreads, 0, st>>>(h->r_if, h->r_iff, h->r_384, h->d_state, d_flags, h->d_pps, d_e384, (int)nb, t0,
+      k_fm_core_fused<AV><<<cgrid, kCfThreads, 0, st>>>(h->r_if, h->r_iff, ap.r_384, h->d_state, d_flags, h->d_pps, d_e384, (int)nb, t0,
                                                    h->core, h->d_atan, (int)flag_b0, first, h->rot_sms);
       pf.end(h->p_fused, st);
       launches++;
@@ -521,28 +554,28 @@ static fmr_status fm_process_device_impl(fmr_fm *h, const float *d_iq, size_t iq
       }
       pf.end(h->p_core, st);
       pf.begin(h->p_core2, st);
-      k_fm_pll2<<<cgrid, 32, 0, st>>>(h->r_mpx, h->r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0, h->core,
+      k_fm_pll2<AV><<<cgrid, 32, 0, st>>>(h->r_mpx, ap.r_384, h->d_state, d_flags, h->d_pps, d_stats, d_e384, (int)nb, t0, h->core,
                                      h->d_atan, (int)flag_b0, first);
       pf.end(h->p_core2, st);
       launches += 3;
     }
     // ---- audio resamplers (mono and L-R in lock step, FmDecode.cpp:172-183)
-    InSrc<double2> asrc;
+    InSrc<AV> asrc;
     memset(&asrc, 0, sizeof(asrc));
-    asrc.ring = h->r_384;
+    asrc.ring = ap.r_384;
     int64_t a0, a1;
-    s = h->aures.run(asrc, (int64_t)n384, h->r_48a, 0, st, &a0, &a1, &launches, true);
+    s = ap.aures.run(asrc, (int64_t)n384, ap.r_48a, 0, st, &a0, &a1, &launches, true);
     if (s != FMR_OK) return s;
     if (a0 != j0 || a1 != j0 + n48) return fail(FMR_ERR_INVALID, "internal: audio schedule mismatch");
     if (n48 > 0) {
       // ---- pilot-cut FIR (FmDecode.cpp:190,196) then DC block + matrix
       dim3 grid((n48 + kQTile - 1) / kQTile, C);
       pf.begin(h->p_pcut, st);
-      k_fir_quirk<double><<<grid, kQThreads, fq_smem(127, sizeof(double2), sizeof(double)), st>>>(h->r_48a, h->r_48b, h->d_pilotcut,
+      k_fir_quirk<AS><<<grid, kQThreads, fq_smem(127, sizeof(AV), sizeof(AS)), st>>>(ap.r_48a, ap.r_48b, ap.d_pilotcut,
                                                                                                  127, j0, (int)n48, d_e48, (int)nb);
       pf.end(h->p_pcut, st);
       pf.begin(h->p_tail, st);
-      k_fm_tail<<<cgrid, kTailThreads, sizeof(TailSmem), st>>>(h->r_48b, d_audio, audio_stride, h->d_state, d_flags, d_e48, (int)nb, j0, h->tail);
+      k_fm_tail<AV><<<cgrid, kTailThreads, sizeof(TailSmem<AV>), st>>>(ap.r_48b, d_audio, audio_stride, h->d_state, d_flags, d_e48, (int)nb, j0, h->tail);
       pf.end(h->p_tail, st);
       launches += 2;
     }
@@ -918,7 +951,7 @@ extern "C" size_t fmr_fm_describe(fmr_fm *h, char *buf, size_t cap) {
                                    : (r.use_fft ? (r.fft_inplace ? "fft16384-inplace+bank" : "fft16384-stockham+bank") : "direct"),
                          r.hb_stream ? (r.hbs_tma ? "stream(tma)" : "stream(cp.async)") : "tiled",
                          (h->core_fused && h->cfg.stereo && h->cfg.multipath_stages == 0) ? "fused" : "agc|disc|pll",
-                         h->aures.use_fft ? "fft8192-f64" : "direct-f64", h->cfg.multipath_stages, h->cfg.fmfilter);
+                         h->audio_f64 ? (h->a64.aures.use_fft ? "fft8192-f64" : "direct-f64") : (h->a32.aures.use_fft ? "fft-f32" : "direct-f32"), h->cfg.multipath_stages, h->cfg.fmfilter);
   return (n < 0) ? 0 : ((size_t)n < cap ? (size_t)n : cap - 1);
 }
 

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +29,21 @@
 #include "fmr_tables.h"
 
 namespace fmr {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is ONE value per kernel (and device). Kernels that several resamplers or
+// handles of a process share (k_fir_long, k_frac_interp, k_fir_quirk) must never have it lowered by the one that is
+// created last and needs less: keep the largest request per (kernel, device) and set that.
+template <typename F> inline cudaError_t raise_smem_limit(F *func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, size_t> cur;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  size_t &v = cur[std::make_pair(reinterpret_cast<const void *>(func), dev)];
+  if (bytes > v) v = bytes;
+  return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v);
+}
+
 
 extern thread_local std::string g_err;
 
@@ -206,6 +223,7 @@ constexpr int kFftMinOutF64 = 500;
 
 template <typename S> struct Resampler {
   using V = typename V2<S>::type;
+  using Scalar = S;
   const ChainDesc *d = nullptr;
   int C = 0;
   bool linear_in = false;
@@ -253,7 +271,7 @@ template <typename S> struct Resampler {
     size_t total = 0;
     // levels 0 and 1 are live together; level 2 aliases level 0 (see k_hb_cascade)
     for (int s = 0; s < nst && s < 2; s++) {
-      total += 2 * (size_t)kHbR * hb_sub_len(hb_level_len(t.n, nst, s, HbTile<S>::value), (int)sizeof(V));
+      total += 2 * (size_t)kHbR * hb_sub_len(hb_level_len(t.n, nst, s, hb_tile_of(t.n[0], t.n[1])), (int)sizeof(V));
     }
     return total * sizeof(V) + 16;
   }
@@ -294,7 +312,7 @@ template <typename S> struct Resampler {
       if (hbt.n[s] > 14) return fail(FMR_ERR_UNSUPPORTED, "half-band stage longer than 14 taps");
       for (int k = 0; k < hbt.n[s]; k++) hbt.t[s][k] = (S)d->hb[s].taps[k];
     }
-    for (int s = 0; s < d->n_hb; s++) hbt.sl[s] = hb_sub_len(hb_level_len(hbt.n, d->n_hb, s, HbTile<S>::value), (int)sizeof(V));
+    for (int s = 0; s < d->n_hb; s++) hbt.sl[s] = hb_sub_len(hb_level_len(hbt.n, d->n_hb, s, hb_tile_of(hbt.n[0], hbt.n[1])), (int)sizeof(V));
     smem_hb = hb_smem(hbt, d->n_hb);
     cudaError_t e = cudaSuccess;
     const size_t smem_need = smem_hb;
@@ -410,7 +428,9 @@ template <typename S> struct Resampler {
         }
       }
       use_fft = true;
-      fft_min_out = (sizeof(S) == sizeof(float)) ? kFftMinOutF32 : kFftMinOutF64;
+      // fewer outputs than this: direct form (its cost grows with the outputs, an FFT block costs the same for any count;
+      // a decimating convolver sees `down` input samples per output)
+      fft_min_out = (sizeof(S) == sizeof(float)) ? kFftMinOutF32 / d->bc.down : kFftMinOutF64;
       fuse_fi = !env_off("FMR_FUSE_FI");
     }
     if constexpr (sizeof(S) == sizeof(float)) {
@@ -467,7 +487,7 @@ template <typename S> struct Resampler {
       use_dec2 = true;
     }
     smem_fir = ((size_t)(kFirTile - 1) * d->bc.down + d->bc.klen) * sizeof(V) + (size_t)d->bc.klen * sizeof(S);
-    FMR_CUDA(cudaFuncSetAttribute(k_fir_long<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fir));
+    FMR_CUDA(raise_smem_limit(k_fir_long<S>, smem_fir));
     if (d->has_fi) {
       int64_t max_bc = max_hb / d->bc.down + 4;
       // With the polyphase bank fused behind the FFT low-pass the intermediate ring only ever holds
@@ -482,7 +502,7 @@ template <typename S> struct Resampler {
       FMR_CUDA(mem.alloc(&d_fi, nt, false));
       FMR_CUDA(cudaMemcpy(d_fi, h.data(), nt * sizeof(S), cudaMemcpyHostToDevice));
       smem_fi = fi_smem(d->fi.instep, d->fi.outstep, d->fi.flen, sizeof(V), sizeof(S));
-      FMR_CUDA(cudaFuncSetAttribute(k_frac_interp<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fi));
+      FMR_CUDA(raise_smem_limit(k_frac_interp<S>, smem_fi));
     }
     return FMR_OK;
   }
@@ -784,7 +804,8 @@ template <typename S> struct Resampler {
         const size_t sm = smem_hb;
         auto tiled = [&](int64_t o0, int cnt) {
           if (cnt <= 0) return;
-          dim3 grid((cnt + HbTile<S>::value - 1) / HbTile<S>::value, gcn);
+          const int tile = hb_tile_of(hbt.n[0], hbt.n[1]);
+          dim3 grid((cnt + tile - 1) / tile, gcn);
           hb_dispatch([&](auto kern) { kern<<<grid, kHbThreads, sm, st>>>(src, hb_out_ring, tp, o0, cnt, fs4); });
           (*launches)++;
         };

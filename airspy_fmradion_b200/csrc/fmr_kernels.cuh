@@ -22,6 +22,17 @@ template <> struct V2<double> {
   using type = double2;
 };
 
+// Sample type AV of the FM audio chain between the 384 kHz core and the 48 kHz DC block (audio half-bands, 1621-tap
+// low-pass, pilot-cut FIR): float2 by default, double2 with FMR_AUDIO_FP64=1 at handle creation. The recurrences on
+// either side (PLL, deemphasis, DC block) are FP64 like the reference in both cases; the linear filters between them run
+// in FP32 like the IF resampler (audio error against the reference 1.5e-6 instead of 2e-7).
+template <typename AV> __host__ __device__ inline AV aud_mk(double a, double b) {
+  AV v;
+  v.x = (decltype(v.x))a;
+  v.y = (decltype(v.y))b;
+  return v;
+}
+
 template <typename V> struct Ring {
   V *base;
   uint32_t cap; // power of two, per channel
@@ -100,12 +111,10 @@ template <typename S> struct HbTaps {
 constexpr int kHbTile = FMR_HB_TILE;
 constexpr int kHbThreads = FMR_HB_THREADS;
 constexpr int kHbR = 4; // consecutive outputs per thread (register blocking)
-// Final-rate outputs per CTA. A stage hands groups of kHbR outputs to the kHbThreads threads; the FP64 cascade of the
-// audio resampler (7 + 13 taps) gets the tile for which both stages fill whole rounds of threads (255 and 121 groups
-// for 128 threads; with 256 the rounds were 141 and 64 groups: half of the thread slots idle).
-template <typename S> struct HbTile {
-  static constexpr int value = sizeof(S) == 8 ? 484 : kHbTile;
-};
+// Final-rate outputs per CTA. A stage hands groups of kHbR outputs to the kHbThreads threads; the cascade of the audio
+// resampler (7 + 13 taps) gets the tile for which both stages fill whole rounds of threads (255 and 121 groups for 128
+// threads; with 256 the rounds were 141 and 64 groups: half of the thread slots idle).
+__host__ __device__ constexpr int hb_tile_of(int n1, int n2) { return (n1 == 7 && n2 == 13) ? 484 : kHbTile; }
 
 // Shared-memory layout of one level: even- and odd-indexed samples in two separate arrays
 // (E[m] = x[2m], O[j] = x[2j+1]) because a half-band output reads x[2m] and only ODD
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(kHbThreads)
     k_hb_cascade(InSrc<typename V2<S>::type> in, Ring<typename V2<S>::type> out, HbTaps<S> taps,
                  int64_t o0, int n_out, int fs4) {
   using V = typename V2<S>::type;
-  constexpr int kTile = HbTile<S>::value;
+  constexpr int kTile = hb_tile_of(N1, N2);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t c = blockIdx.y;
   const int64_t a_fin = o0 + (int64_t)blockIdx.x * kTile;
@@ -1029,8 +1038,9 @@ __device__ __forceinline__ float fast_atan2f_bf_s(float y, float x, unsigned tab
   });
 }
 
+template <typename AV>
 static __global__ void __launch_bounds__(32)
-    k_fm_pll2(Ring<float> mpx, Ring<double2> out384, FmChanState *__restrict__ st, uint8_t *__restrict__ flags,
+    k_fm_pll2(Ring<float> mpx, Ring<AV> out384, FmChanState *__restrict__ st, uint8_t *__restrict__ flags,
               PpsEventDev *__restrict__ pps, const float *__restrict__ stats, const uint32_t *__restrict__ call_end,
               int n_calls, int64_t t0, FmCoreParams P, const float *__restrict__ atan_tbl, int block_off,
               int reset_pps) {
@@ -1047,7 +1057,7 @@ static __global__ void __launch_bounds__(32)
   sincos(f0, &sf0, &cf0);
   const int n_total = n_calls ? (int)call_end[n_calls - 1] : 0;
   const float *__restrict__ mrow = mpx.base + (size_t)c * mpx.cap;
-  double2 *__restrict__ orow = out384.base + (size_t)c * out384.cap;
+  AV *__restrict__ orow = out384.base + (size_t)c * out384.cap;
   const uint32_t mmask = mpx.cap - 1, omask = out384.cap - 1, t0lo = (uint32_t)t0;
   const bool stereo = P.stereo != 0, shift = P.pilot_shift != 0, de_st = P.deemph_on_stereo != 0;
   // loop constants pinned in registers (an operand fetched from the constant bank on the critical
@@ -1165,10 +1175,7 @@ static __global__ void __launch_bounds__(32)
         const double m0 = xd - P.de_a1 * dem;
         const double mono = P.de_b0 * m0;
         dem = m0;
-        double2 o;
-        o.x = mono;
-        o.y = ster;
-        orow[(t0lo + beg + (uint32_t)i) & omask] = o;
+        orow[(t0lo + beg + (uint32_t)i) & omask] = aud_mk<AV>(mono, ster);
       }
     }
     // per-call statistics (FmDecode.cpp:95,146-150)
@@ -1247,19 +1254,20 @@ struct FmTailParams {
 constexpr int kTailT = 32;
 constexpr int kTailG = 8;
 constexpr int kTailThreads = 128;
-struct TailSmem {
-  double2 tin[2][32][kTailT + 1];
+template <typename AV> struct TailSmem {
+  AV tin[2][32][kTailT + 1];
   double2 tout[2][32][kTailT + 1];
   uint32_t ent_end[2][kTailT + 2];  // [tile parity][entry]: end (sample index of the launch) of a call of the tile
   uint32_t ent_mask[2][kTailT + 2]; // bit r = stereo flag of channel c0 + r during that call
 };
 
+template <typename AV>
 static __global__ void __launch_bounds__(kTailThreads)
-k_fm_tail(Ring<double2> in48, double *__restrict__ audio, size_t audio_stride, FmChanState *__restrict__ st,
+k_fm_tail(Ring<AV> in48, double *__restrict__ audio, size_t audio_stride, FmChanState *__restrict__ st,
           const uint8_t *__restrict__ flags, const uint32_t *__restrict__ call_end48, int n_calls, int64_t j0,
           FmTailParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TailSmem &sm = *reinterpret_cast<TailSmem *>(smem_raw);
+  TailSmem<AV> &sm = *reinterpret_cast<TailSmem<AV> *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c0 = blockIdx.x * 32, c = c0 + lane;
   const int rows = min(32, P.n_channels - c0);
   const int n_total = n_calls ? (int)call_end48[n_calls - 1] : 0;
@@ -1311,11 +1319,11 @@ k_fm_tail(Ring<double2> in48, double *__restrict__ audio, size_t audio_stride, F
   // warps 2, 3: the even / odd rows of tile k (all loads of a warp in flight together)
   auto load_tile = [&](int k) {
     const int par = k & 1, i = k * kTailT + lane;
-    double2 v[16];
+    AV v[16];
 #pragma unroll
     for (int q = 0; q < 16; q++) {
       const int r = (warp - 2) + 2 * q;
-      v[q] = (r < rows && i < n_total) ? in48.ld(c0 + r, j0 + i) : make_double2(0.0, 0.0);
+      v[q] = (r < rows && i < n_total) ? in48.ld(c0 + r, j0 + i) : aud_mk<AV>(0.0, 0.0);
     }
 #pragma unroll
     for (int q = 0; q < 16; q++) sm.tin[par][(warp - 2) + 2 * q][lane] = v[q];
@@ -1380,7 +1388,7 @@ k_fm_tail(Ring<double2> in48, double *__restrict__ audio, size_t audio_stride, F
       uint32_t eend = P.stereo ? sm.ent_end[par][0] : 0xffffffffu, emask = P.stereo ? sm.ent_mask[par][0] : 0u;
       int u0 = 0;
       for (; u0 + kTailG <= nu; u0 += kTailG) {
-        double2 x[kTailG];
+        AV x[kTailG];
         double mv[kTailG + 2], sv[kTailG + 2]; // [q + 2] = state after sample q; [1], [0] = the two before the group
         bool det[kTailG];
 #pragma unroll
@@ -1391,8 +1399,8 @@ k_fm_tail(Ring<double2> in48, double *__restrict__ audio, size_t audio_stride, F
         sv[0] = s2;
 #pragma unroll
         for (int q = 0; q < kTailG; q++) { // the dependent chains only
-          mv[q + 2] = x[q].x - (P.a1 * mv[q + 1] + P.a2 * mv[q]);
-          if (P.stereo) sv[q + 2] = x[q].y - (P.a1 * sv[q + 1] + P.a2 * sv[q]);
+          mv[q + 2] = (double)x[q].x - (P.a1 * mv[q + 1] + P.a2 * mv[q]);
+          if (P.stereo) sv[q + 2] = (double)x[q].y - (P.a1 * sv[q + 1] + P.a2 * sv[q]);
         }
 #pragma unroll
         for (int q = 0; q < kTailG; q++) {
@@ -1416,10 +1424,10 @@ k_fm_tail(Ring<double2> in48, double *__restrict__ audio, size_t audio_stride, F
         }
       }
       for (int u = u0; u < nu; u++) { // the last, shorter group of the launch
-        const double2 x = sm.tin[par][lane][u];
-        const double m0 = x.x - (P.a1 * m1 + P.a2 * m2);
+        const AV x = sm.tin[par][lane][u];
+        const double m0 = (double)x.x - (P.a1 * m1 + P.a2 * m2);
         double s0 = 0.0;
-        if (P.stereo) s0 = x.y - (P.a1 * s1 + P.a2 * s2);
+        if (P.stereo) s0 = (double)x.y - (P.a1 * s1 + P.a2 * s2);
         const uint32_t i = (uint32_t)(k * kTailT + u);
         while (i >= eend) {
           ej++;

@@ -565,9 +565,16 @@ def main():
             cpu = {"error": str(ex)}
 
     if rank == 0:
+        # what the path computes in: linear filters FP32 (the FM audio filters FP64 with FMR_AUDIO_FP64=1), recurrences FP64
+        if mode == "fm" and os.environ.get("FMR_AUDIO_FP64", "0") not in ("", "0"):
+            dtype = "f32 (IF resampler) / f64 (PLL, deemphasis, audio filters, DC block)"
+        elif mode == "fm":
+            dtype = "f32 (IF resampler, audio filters) / f64 (PLL, deemphasis, DC block)"
+        else:
+            dtype = "f32 (IF resampler, channel filter) / f64 (audio)"
         line = {"metric": metric, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (IF) / f64 (PLL, audio)",
+                "scaling": "weak", "vs_baseline": None, "dtype": dtype,
                 "data": "synthetic",
                 "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}

@@ -1,6 +1,6 @@
 """Every environment switch the library still reads selects between two implementations of the same stage; each
-non-default setting must decode the same stream as the default path (they differ by FP32 rounding in the IF stages only)
-and as the oracle. One parametrised case per switch, so that a switch cannot rot.
+non-default setting must decode the same stream as the default path (they differ by FP32 rounding in the IF stages and,
+for FMR_AUDIO_FP64, in the audio filters) and as the oracle. One parametrised case per switch, so that a switch cannot rot.
 Switches: fmr_host.cuh (Resampler::init), fmr_fm.cu (fmr_fm_create)."""
 import os
 
@@ -25,7 +25,8 @@ SETTINGS = [
     {"FMR_FE": "0", "FMR_FDR": "0", "FMR_FFT": "0"},            # direct-form low-pass
     {"FMR_FE": "0", "FMR_HB_STREAM": "0"},                      # tiled half-band cascade
     {"FMR_FE": "0", "FMR_HBS_TMA": "0"},                        # streaming half-band cascade staged with cp.async
-    {"FMR_FFT_F64": "0"},                                       # audio low-pass as direct-form FIR
+    {"FMR_AUDIO_FP64": "1"},                                    # audio half-bands, low-pass and pilot cut in FP64
+    {"FMR_AUDIO_FP64": "1", "FMR_FFT_F64": "0"},                # ... with the audio low-pass as direct-form FIR
     {"FMR_CORE_FUSED": "0"},                                    # AGC / discriminator / PLL as separate launches
 ]
 
