@@ -17,9 +17,8 @@ cap() { timeout 600 ncu --set full --clock-control none --import-source on -k "r
 cap frontend_fused k_frontend_fused 2
 cap fdr k_fdr 2
 cap core k_fm_core_fused 2
-cap audio_hb "k_hb_cascade<double" 2
-cap audio_lowpass "k_fir_fft<double" 2
-cap pilot_cut "k_fir_quirk<double" 2
+cap audio_hb "k_hb_cascade<float, 2, 0, 7" 2
+cap pilot_cut "k_fir_quirk<float" 2
 cap tail k_fm_tail 2
 # 3. device-resident value over channel counts (multiples of 148 SMs x 32 channels, and the round-1 default) and workloads
 for ch in 148 1184 4736 9472 14208 16384 18944; do
@@ -31,4 +30,6 @@ timeout 400 $B --steps 4 --warmup 3 --blocks 128 --workload cfg5_am_384ksps 2>&1
 # 4. the default bench line (with e2e and the CPU reference on this box's cores) and the reference arm
 timeout 900 python bench.py 2>&1 | tail -1 > gpurun_out/bench_default_${R}.json
 timeout 900 python bench.py --impl reference 2>&1 | tail -1 > gpurun_out/bench_reference_${R}.json
+# 5. the all-FP64 audio chain (FMR_AUDIO_FP64=1) for comparison
+FMR_AUDIO_FP64=1 timeout 400 $B --steps 6 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_audio_fp64_${R}.json
 ls -la gpurun_out | head -60

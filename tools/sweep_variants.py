@@ -14,7 +14,7 @@ import bench  # noqa: E402
 
 # every environment switch the library still reads (all select between paths the GPU suite covers)
 SWITCHES = ("FMR_FE", "FMR_FE_VARIANT", "FMR_FE_MIN_BLOCKS", "FMR_FDR", "FMR_FFT_INPLACE", "FMR_FFT_TW", "FMR_FFT_F64", "FMR_FFT",
-            "FMR_FUSE_FI", "FMR_HB_STREAM", "FMR_HBS_TMA", "FMR_CORE_FUSED", "FMR_AM_FFT_FILTER")
+            "FMR_FUSE_FI", "FMR_HB_STREAM", "FMR_HBS_TMA", "FMR_CORE_FUSED", "FMR_AM_FFT_FILTER", "FMR_AUDIO_FP64")
 
 VARIANTS = [
     # name, env, blocks per step, channels
@@ -31,6 +31,7 @@ VARIANTS = [
     ("hb_tiled", {"FMR_FE": "0", "FMR_HB_STREAM": "0"}, 329, 8192),
     ("hbs_cp_async", {"FMR_FE": "0", "FMR_HBS_TMA": "0"}, 329, 8192),
     ("core_unfused", {"FMR_CORE_FUSED": "0"}, 329, 8192),
+    ("audio_fp64", {"FMR_AUDIO_FP64": "1"}, 329, 8192),  # audio half-bands, low-pass and pilot cut in FP64
 ]
 
 
