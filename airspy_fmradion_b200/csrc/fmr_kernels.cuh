@@ -635,10 +635,7 @@ __global__ void k_fir_head_fix(Ring<typename V2<S>::type> x, Ring<typename V2<S>
   }
 }
 
-#ifndef FMR_QR
-#define FMR_QR 4
-#endif
-constexpr int kQR = FMR_QR;   // consecutive outputs per thread
+constexpr int kQR = 4;        // consecutive outputs per thread (8 measured: no gain in FP32 or FP64, profiles/README.md)
 constexpr int kQThreads = 64; // tile = 256 outputs
 constexpr int kQTile = kQR * kQThreads;
 

@@ -96,6 +96,11 @@ typedef struct fmr_pps_event_t { /* PilotPhaseLock::PpsEvent + the block it fell
   uint32_t block; /* index into block_len[] of the last process call */
 } fmr_pps_event_t;
 
+/* Replaces the FmDecoder constructor (include/FmDecode.h:49-64) for cfg->n_channels independent streams.
+ * Arithmetic: every recurrence (PLL, deemphasis, DC block) in double like the reference; the linear filters (IF
+ * resampler, audio resamplers, pilot cut) in float. With FMR_AUDIO_FP64=1 in the environment at creation the audio
+ * resamplers and the pilot cut run in double as well (audio error against the reference 2e-7 instead of 1.5e-6 of
+ * full scale, about 7 % lower throughput). */
 fmr_status fmr_fm_create(const fmr_fm_config *cfg, fmr_fm **out);
 void fmr_fm_destroy(fmr_fm *h);
 
