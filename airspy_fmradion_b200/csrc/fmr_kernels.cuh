@@ -111,10 +111,12 @@ template <typename S> struct HbTaps {
 constexpr int kHbTile = FMR_HB_TILE;
 constexpr int kHbThreads = FMR_HB_THREADS;
 constexpr int kHbR = 4; // consecutive outputs per thread (register blocking)
-// Final-rate outputs per CTA. A stage hands groups of kHbR outputs to the kHbThreads threads; the cascade of the audio
-// resampler (7 + 13 taps) gets the tile for which both stages fill whole rounds of threads (255 and 121 groups for 128
+// Final-rate outputs per CTA. A stage hands groups of kHbR outputs to the kHbThreads threads; the two-stage cascades of
+// the 384 kHz -> 48 kHz chains (7 + 13 taps: FM audio resampler; 6 + 11: AM IF resampler) get the tile for which both stages fill whole rounds of threads (255 and 121 groups for 128
 // threads; with 256 the rounds were 141 and 64 groups: half of the thread slots idle).
-__host__ __device__ constexpr int hb_tile_of(int n1, int n2) { return (n1 == 7 && n2 == 13) ? 484 : kHbTile; }
+__host__ __device__ constexpr int hb_tile_of(int n1, int n2) {
+  return ((n1 == 7 && n2 == 13) || (n1 == 6 && n2 == 11)) ? 484 : kHbTile; // (6, 11): 253 and 121 groups
+}
 
 // Shared-memory layout of one level: even- and odd-indexed samples in two separate arrays
 // (E[m] = x[2m], O[j] = x[2j+1]) because a half-band output reads x[2m] and only ODD
