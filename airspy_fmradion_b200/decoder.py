@@ -161,7 +161,8 @@ class FmDecoder(_Base):
                  max_blocks_per_call=4096, device=0, fmfilter_coeff=None):
         """fmfilter: 0 none (FilterType Default/Wide), 1 medium, 2 narrow (main.cpp:785-810), or pass
         fmfilter_coeff (the reference's `fmfilter_coeff` vector); the other arguments are FmDecoder's
-        (FmDecode.h:49-64)."""
+        (FmDecode.h:49-64). Environment at creation: FMR_AUDIO_FP64=1 runs the audio resamplers and the pilot-cut FIR
+        in double (default float; the recurrences are double either way), see include/fmradion_b200.h."""
         L = _capi.lib()
         self._destroy, self._query = L.fmr_fm_destroy, L.fmr_fm_query_output
         self._process_host, self._process_device = L.fmr_fm_process_host, L.fmr_fm_process_device
