@@ -637,6 +637,14 @@ __global__ void k_fir_head_fix(Ring<typename V2<S>::type> x, Ring<typename V2<S>
   }
 }
 
+// acc += h * x on an (re, im) pair: one packed FFMA2 for float2 (the same rounding per lane as two FFMA), two DFMA for double2
+__device__ __forceinline__ float2 fir_mac(float2 acc, float h, float2 x) { return __ffma2_rn(make_float2(h, h), x, acc); }
+__device__ __forceinline__ double2 fir_mac(double2 acc, double h, double2 x) {
+  acc.x += h * x.x;
+  acc.y += h * x.y;
+  return acc;
+}
+
 constexpr int kQR = 4;        // consecutive outputs per thread (8 measured: no gain in FP32 or FP64, profiles/README.md)
 constexpr int kQThreads = 64; // tile = 256 outputs
 constexpr int kQTile = kQR * kQThreads;
@@ -725,11 +733,7 @@ __global__ void __launch_bounds__(kQThreads)
     for (int qq = 0; qq < kQR; qq++) {
       const S h = hs[q0 + qq];
 #pragma unroll
-      for (int r = 0; r < kQR; r++) {
-        const V x = w[(r + qq) % kQR];
-        acc[r].x += h * x.x;
-        acc[r].y += h * x.y;
-      }
+      for (int r = 0; r < kQR; r++) acc[r] = fir_mac(acc[r], h, w[(r + qq) % kQR]);
       w[qq] = xs[qq * LEN + tid + q0 / kQR + 1];
     }
   }
